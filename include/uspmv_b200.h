@@ -1,0 +1,169 @@
+/* uspmv_b200 — C ABI of the B200-native SELL-C-sigma SpMV/SpMMV engine.
+ *
+ * Drop-in boundary for the compute path of RRZE-HPC/Ultimate-SpMV.  The reference has no C ABI: its
+ * "interface" is a header of C++ templates (code/interface.hpp, API_doc.md) plus two std::function
+ * signatures inside the harness (code/classes_structs.hpp:283-333).  Every entry point below names the
+ * reference interface it replaces (file:line, paths relative to the reference checkout).  The C++ shim
+ * include/uspmv_interface.hpp re-creates the reference's template API (MtxData, ScsData,
+ * convert_to_scs, uspmv_scs_gpu, ...) on top of these calls; INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; uspmv_last_error() gives the message
+ *     (the reference prints and exit()s instead: classes_structs.hpp:33-41, kernels.hpp:295-299);
+ *   - ST = long, IT = int as in the reference (mmio.h:21, classes_structs.hpp:31);
+ *   - "_h" pointers are host memory, "_d" pointers are device memory of the context's GPU;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream);
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with an error.
+ */
+#ifndef USPMV_B200_H
+#define USPMV_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct uspmv_ctx uspmv_ctx; /* one GPU (one rank)                                         */
+typedef struct uspmv_coo uspmv_coo; /* device-resident MtxData (interface.hpp:16-56)              */
+typedef struct uspmv_scs uspmv_scs; /* device-resident ScsData (interface.hpp:58-80)              */
+typedef struct uspmv_halo uspmv_halo; /* per-rank halo plan (ContextData, classes_structs.hpp:156) */
+
+/* -dp / -sp / -hp (utilities.hpp:1190-1260) */
+enum { USPMV_F64 = 0, USPMV_F32 = 1, USPMV_F16 = 2 };
+/* BLOCK_VECTOR_LAYOUT colwise / rowwise (Makefile:17-31; kernels.hpp:352,358) */
+enum { USPMV_COLWISE = 0, USPMV_ROWWISE = 1 };
+/* -ap[dp_sp] / -ap[dp_hp] / -ap[sp_hp] / -ap[dp_sp_hp] (utilities.hpp:1262-1330) */
+enum { USPMV_AP_DP_SP = 0, USPMV_AP_DP_HP = 1, USPMV_AP_SP_HP = 2, USPMV_AP_DP_SP_HP = 3 };
+/* -seg_rows / -seg_nnz (mpi_funcs.hpp:446-493) */
+enum { USPMV_SEG_ROWS = 0, USPMV_SEG_NNZ = 1 };
+
+const char *uspmv_last_error(void);
+int uspmv_version(void);
+/* number of this library's kernel launches since load (bench.py's "gpu_launches" claim) */
+long uspmv_kernel_launches(void);
+
+/* ---- context and device memory --------------------------------------------------------------- */
+/* cudaSetDevice(rank % ndev) in the reference: main.cpp:1838-1842 */
+int uspmv_ctx_create(int device, uspmv_ctx **out);
+void uspmv_ctx_destroy(uspmv_ctx *ctx);
+int uspmv_ctx_sync(uspmv_ctx *ctx);
+/* cudaMalloc/cudaMemcpy staging of assign_spmv_kernel_gpu_data (utilities.hpp:3302-3815, 3720-3811) */
+int uspmv_malloc(uspmv_ctx *ctx, size_t bytes, void **out_d);
+int uspmv_free(uspmv_ctx *ctx, void *ptr_d);
+int uspmv_memcpy_h2d(uspmv_ctx *ctx, void *dst_d, const void *src_h, size_t bytes, void *stream);
+int uspmv_memcpy_d2h(uspmv_ctx *ctx, void *dst_h, const void *src_d, size_t bytes, void *stream);
+int uspmv_memset(uspmv_ctx *ctx, void *dst_d, int byte, size_t bytes, void *stream);
+/* pinned host staging (the harness uses pageable std::vector; pinned is what makes e2e copies fast) */
+int uspmv_host_alloc(size_t bytes, void **out_h);
+int uspmv_host_free(void *ptr_h);
+
+/* ---- MtxData (COO) ---------------------------------------------------------------------------- */
+/* MtxData filled by the caller (interface.hpp:16-56).  Values are `mt`-typed (USPMV_F64/F32/F16).
+ * Rows need not be sorted; within-row order of the input is preserved (utilities.hpp:2013-2036). */
+int uspmv_coo_from_host(uspmv_ctx *ctx, long n_rows, long n_cols, long nnz, const int *I_h, const int *J_h,
+                        const void *values_h, int mt, uspmv_coo **out);
+/* same, arrays already on the device (copied) */
+int uspmv_coo_from_device(uspmv_ctx *ctx, long n_rows, long n_cols, long nnz, const int *I_d, const int *J_d,
+                          const void *values_d, int mt, uspmv_coo **out);
+/* Synthetic stencil generated on the device (BASELINE.json configs 2/3/5): rows [row0, row1) of the
+ * nx*ny*nz grid, row = (z*ny + y)*nx + x, columns ascending, Dirichlet; points = 7 or 27; diagonal =
+ * points-1, off-diagonals -1; dp values.  I is made slab-local (I - row0), J stays global
+ * (localize_row_idx, mpi_funcs.hpp:862-877). */
+int uspmv_coo_stencil(uspmv_ctx *ctx, int points, long nx, long ny, long nz, long row0, long row1, uspmv_coo **out);
+int uspmv_coo_dims(const uspmv_coo *coo, long out3[3]); /* n_rows, n_cols, nnz */
+int uspmv_coo_export(const uspmv_coo *coo, int *I_h, int *J_h, void *values_h);
+void uspmv_coo_destroy(uspmv_coo *coo);
+
+/* ---- SELL-C-sigma construction ------------------------------------------------------------------ */
+/* convert_to_scs (utilities.hpp:1842-2104; interface.hpp:401-656), built on the device, bit-exact:
+ * sigma-window std::sort order (libstdc++ 13 introsort tie order), chunk_ptrs/chunk_lengths,
+ * padding (value 0, column 0), COO fill order, old_to_new / new_to_old.  fixed_perm_h (may be NULL)
+ * is the reference's `fixed_permutation` (n_rows ints).  CRS is C = 1, sigma = 1.  vt = value type of
+ * the stored matrix (MT -> VT conversion of utilities.hpp:2033 is a single rounding). */
+int uspmv_scs_build(uspmv_ctx *ctx, const uspmv_coo *coo, long C, long sigma, int vt, const int *fixed_perm_h,
+                    uspmv_scs **out);
+/* out8 = C, sigma, n_rows, n_cols, n_rows_padded, n_chunks, n_elements, nnz (ScsData scalars) */
+int uspmv_scs_dims(const uspmv_scs *scs, long out8[8]);
+/* Copy the arrays to the host (any pointer may be NULL).  Sizes: chunk_ptrs n_chunks+1, chunk_lengths
+ * n_chunks, col_idxs / values n_elements, old_to_new n_rows, new_to_old n_rows_padded.  Positions of
+ * new_to_old that no real row maps to are uninitialised in the reference (utilities.hpp:2060-2066);
+ * here they hold -1. */
+int uspmv_scs_export(const uspmv_scs *scs, int *chunk_ptrs_h, int *chunk_lengths_h, int *col_idxs_h, void *values_h,
+                     int *old_to_new_h, int *new_to_old_h);
+/* permute_scs_cols (utilities.hpp:1802-1831).  perm_h == NULL uses the struct's own old_to_new_idx
+ * (main.cpp:1308).  Columns >= n_rows (halo) are left alone; padding slots are permuted too. */
+int uspmv_scs_permute_cols(uspmv_scs *scs, const int *perm_h);
+/* Raw device pointers, for callers that keep the reference's kernel-argument style
+ * (OnePrecKernelArgs, classes_structs.hpp:213-236).  Any out pointer may be NULL. */
+int uspmv_scs_device_arrays(const uspmv_scs *scs, const int **chunk_ptrs_d, const int **chunk_lengths_d,
+                            const int **col_idxs_d, const void **values_d, const int **old_to_new_d,
+                            const int **new_to_old_d);
+void uspmv_scs_destroy(uspmv_scs *scs);
+
+/* ---- vector permutations ------------------------------------------------------------------------ */
+/* apply_permutation (utilities.hpp:1768-1782): out[i] = in[perm[i]], i < n; perm[i] < 0 gives 0. */
+int uspmv_apply_permutation(uspmv_ctx *ctx, void *out_d, const void *in_d, const int *perm_d, long n, int vt, void *stream);
+/* apply_strided_permutation (utilities.hpp:1784-1799) generalised to whole block rows:
+ * rowwise: out[i*bvs + v] = in[perm[i]*bvs + v]; colwise: out[i + v*ld] = in[perm[i] + v*ld]. */
+int uspmv_apply_permutation_block(uspmv_ctx *ctx, void *out_d, const void *in_d, const int *perm_d, long n, int vt,
+                                  int bvs, long ld, int layout, void *stream);
+
+/* ---- kernels ------------------------------------------------------------------------------------- */
+/* uspmv_scs_gpu / uspmv_csr_gpu (interface.hpp:1741-1867) == spmv_gpu_scs[_adv] / spmv_gpu_csr
+ * (kernels.hpp:579-775): raw device arrays, y has n_chunks*C entries in permuted order. */
+int uspmv_scs_gpu(uspmv_ctx *ctx, int vt, long C, long n_chunks, const int *chunk_ptrs_d, const int *chunk_lengths_d,
+                  const int *col_idxs_d, const void *values_d, const void *x_d, void *y_d, void *stream);
+int uspmv_csr_gpu(uspmv_ctx *ctx, int vt, long n_rows, const int *row_ptrs_d, const int *col_idxs_d, const void *values_d,
+                  const void *x_d, void *y_d, void *stream);
+/* SpmvKernel::execute on a built matrix (classes_structs.hpp:997-1035,1117): CRS kernel iff C == 1 and
+ * sigma == 1 (execute_uspmv's rule, interface.hpp:1911), else the SCS kernel. */
+int uspmv_spmv(const uspmv_scs *scs, const void *x_d, void *y_d, void *stream);
+/* Fused form (SURVEY §7 hard part 4): gathers x in ORIGINAL numbering through columns that have NOT
+ * been permuted and writes y[new_to_old[row]] — no separate apply_permutation passes. */
+int uspmv_spmv_unpermuted(const uspmv_scs *scs, const void *x_d, void *y_d, void *stream);
+/* block_spmv_{csr,scs} (kernels.hpp:68-154,306-398; GPU launchers are stubs in the reference,
+ * kernels.hpp:777-844).  bvs = block_vec_size, vec_length = n_local + per_vector_padding
+ * (classes_structs.hpp:1024), layout = USPMV_COLWISE / USPMV_ROWWISE. */
+int uspmv_spmmv(const uspmv_scs *scs, const void *X_d, void *Y_d, int bvs, long vec_length, int layout, void *stream);
+/* Host-buffer call (the reference-facing path measured as "e2e"): copies x to the device, runs the
+ * kernel, copies y (n_rows_padded entries) back, synchronises. */
+int uspmv_spmv_host(const uspmv_scs *scs, const void *x_h, long x_len, void *y_h, long y_len);
+
+/* ---- adaptive precision --------------------------------------------------------------------------- */
+/* partition_precisions (interface.hpp:690-978; utilities.hpp:2810-3123): order-preserving split of a
+ * COO matrix by abs(value) against t1 (and t2 for the 3-way split).  rowmax_h/colmax_h (NULL = not
+ * equilibrated) divide the thresholds (interface.hpp:908-936).  Outputs that the mode does not use are
+ * set to NULL.  dp part holds doubles, sp floats, hp halves. */
+int uspmv_partition_precisions(uspmv_ctx *ctx, const uspmv_coo *coo, int ap_mode, double t1, double t2,
+                               const double *rowmax_h, const double *colmax_h, uspmv_coo **dp, uspmv_coo **sp,
+                               uspmv_coo **hp);
+/* uspmv_scs_ap{dpsp,dphp,sphp,dpsphp} / uspmv_csr_ap* (interface.hpp:1129-1733; ap_kernels.hpp:24-953)
+ * as ONE fused pass.  Parts not used by the mode are NULL.  Modes 0,1,3: dp_x (double) in, y double.
+ * Mode 2 (sp_hp): sp_x (float) in, y float (interface.hpp:1620-1645). */
+int uspmv_ap_spmv(int ap_mode, const uspmv_scs *dp, const uspmv_scs *sp, const uspmv_scs *hp, const void *x_d, void *y_d,
+                  void *stream);
+
+/* ---- row partitioning and halo exchange (one rank per GPU) ------------------------------------------ */
+/* seg_work_sharing_arr (mpi_funcs.hpp:424-622): wsa_h has P+1 entries.  I_h is the row array of the
+ * row-sorted global COO. */
+int uspmv_seg_work_sharing_arr(int seg_method, long n_rows, long nnz, const int *I_h, int P, int *wsa_h);
+/* collect_local_needed_heri (mpi_funcs.hpp:242-415) on the device: rewrites the matrix' global
+ * columns to local/halo numbering (first-seen order, grouped by owner) and records the need lists. */
+int uspmv_halo_plan_create(uspmv_scs *scs, const int *wsa_h, int rank, int P, uspmv_halo **out);
+/* recv_counts_cumsum (P+1 ints) and the per-owner need lists, flattened; need_ptr has P+1 entries. */
+int uspmv_halo_plan_counts(const uspmv_halo *plan, int *recv_counts_cumsum_h, long *n_halo);
+int uspmv_halo_plan_need(const uspmv_halo *plan, int *need_flat_h, int *need_ptr_h);
+/* collect_comm_idxs (mpi_funcs.hpp:117-172): install what every peer needs from this rank
+ * (send_ptr P+1 entries, owner-local row ids). */
+int uspmv_halo_plan_set_send(uspmv_halo *plan, const int *send_flat_h, const int *send_ptr_h);
+/* pack_send_buf / pack_d_send_buf (classes_structs.hpp:786-831; kernels.hpp:554-577) for ALL peers in one
+ * launch: buf[send_ptr[p] + i] = x[perm[send_idx[p][i]]] (block vectors: bvs values per index). */
+int uspmv_halo_pack(const uspmv_halo *plan, const void *x_d, void *sendbuf_d, int vt, int bvs, long vec_length, int layout,
+                    void *stream);
+void uspmv_halo_destroy(uspmv_halo *plan);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* USPMV_B200_H */

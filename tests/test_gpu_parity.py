@@ -1,0 +1,276 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the oracle on the same seeded inputs.
+
+Bars: bit-exact for every index structure and for the stored values; y within 1e-12 (dp), 1e-5 (sp),
+1e-2 (hp) relative per element (BASELINE.json north_star) — and, for the SCS kernels, additionally
+bit-identical to the oracle because the per-row fused-multiply-add order is the same.
+"""
+import numpy as np
+import pytest
+
+from conftest import MATRIX_NAMES, load_matrix
+
+pytestmark = pytest.mark.gpu
+
+NPT = {"dp": np.float64, "sp": np.float32, "hp": np.float16}
+TOL = {"dp": 1e-12, "sp": 1e-5, "hp": 1e-2}
+STRUCT_KEYS = ("chunk_ptrs", "chunk_lengths", "col_idxs", "values", "old_to_new")
+
+
+def torch_():
+    import torch
+    return torch
+
+
+def assert_same_structure(got, ref, tag=""):
+    for k in ("n_rows_padded", "n_chunks", "n_elements", "nnz"):
+        assert getattr(got, k) == getattr(ref, k), f"{tag}: {k}"
+    for k in STRUCT_KEYS:
+        a, b = getattr(got, k), getattr(ref, k)
+        assert a.dtype == b.dtype and a.shape == b.shape, f"{tag}: {k} dtype/shape"
+        assert np.array_equal(a.view(np.uint8), b.view(np.uint8)), f"{tag}: {k} differs from the oracle"
+    assert np.array_equal(got.new_to_old, ref.new_to_old), f"{tag}: new_to_old"
+
+
+def rel_err(y, y_ref):
+    y = y.astype(np.float64)
+    y_ref = y_ref.astype(np.float64)
+    return float(np.max(np.abs(y - y_ref) / np.maximum(np.abs(y_ref), 1e-30))) if len(y) else 0.0
+
+
+def dev(a):
+    return torch_().from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def build_both(eng, orc, coo, C, sigma, vt, permute=True):
+    n, nc, I, J, V = coo
+    ref = orc.convert_to_scs(n, nc, I, J, V, C, sigma, vt)
+    mtx = eng.MtxData.from_host(n, nc, I, J, V)
+    scs = eng.convert_to_scs(mtx, C, sigma, vt)
+    if permute:
+        orc.permute_scs_cols(ref, ref.old_to_new)
+        eng.permute_scs_cols(scs)
+    return scs, ref
+
+
+def positive_coo(mats, n, avg, seed):
+    n, nc, I, J, V = mats.random_coo(n, avg, seed)
+    return n, nc, I, J, np.abs(V) + 0.25
+
+
+# ------------------------------------------------------------------------------------------------
+# convert_to_scs + permute_scs_cols: bit-exact structures
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", MATRIX_NAMES)
+@pytest.mark.parametrize("C,sigma", [(1, 1), (4, 8), (8, 1), (32, 512), (16, 64), (10, 30), (128, 256), (3, 7)])
+def test_build_fixture_matrices(eng, orc, name, C, sigma):
+    coo = load_matrix(name)
+    for vt in ("dp", "sp"):
+        scs, ref = build_both(eng, orc, coo, C, sigma, vt)
+        assert_same_structure(scs.export(), ref, f"{name} C={C} s={sigma} {vt}")
+
+
+@pytest.mark.parametrize("n", [1, 2, 31, 33, 1000, 20011])
+@pytest.mark.parametrize("C,sigma", [(1, 1), (2, 2), (32, 1), (32, 16), (32, 17), (32, 512), (64, 4096), (5, 1 << 20)])
+def test_build_random(eng, orc, mats, n, C, sigma):
+    coo = mats.random_coo(n, 6, seed=n * 131 + C + sigma)
+    if len(coo[2]) == 0:
+        pytest.skip("empty")
+    scs, ref = build_both(eng, orc, coo, C, sigma, "dp")
+    assert_same_structure(scs.export(), ref, f"random n={n} C={C} s={sigma}")
+
+
+def test_build_tie_heavy_and_adversarial(eng, orc):
+    """sigma-windows > 16 rows with many ties: the order is libstdc++'s introsort tie order (heapsort branch included)."""
+    z = np.load(__import__("os").path.join(__import__("conftest").GOLDEN, "ref_stdsort.npz"))
+    names = sorted({k.split("|")[0] for k in z.files})
+    before = orc.lib.orc_heapsort_calls()
+    for nm in names:
+        cnt = z[nm + "|cnt"].astype(np.int64)
+        n = len(cnt)
+        I = np.repeat(np.arange(n), cnt).astype(np.int32)
+        J = np.zeros(len(I), np.int32)
+        mtx = eng.MtxData.from_host(n, n, I, J, np.ones(len(I)))
+        got = eng.convert_to_scs(mtx, 1, n, "dp").export()
+        assert np.array_equal(got.old_to_new, z[nm + "|old_to_new"]), f"{nm}: differs from the reference's std::sort order"
+        ref = orc.convert_to_scs(n, n, I, J, np.ones(len(I)), 1, n)
+        assert np.array_equal(got.old_to_new, ref.old_to_new)
+
+
+def test_build_unsorted_coo(eng, orc, mats):
+    """Rows in arbitrary order: within-row order of the INPUT must be preserved (utilities.hpp:2013-2036)."""
+    n, nc, I, J, V = mats.random_coo(3000, 5, seed=5)
+    perm = np.random.default_rng(0).permutation(len(I))
+    Iu, Ju, Vu = I[perm], J[perm], V[perm]
+    ref = orc.convert_to_scs(n, nc, Iu, Ju, Vu, 16, 64)
+    mtx = eng.MtxData.from_host(n, nc, Iu, Ju, Vu)
+    got = eng.convert_to_scs(mtx, 16, 64, "dp").export()
+    assert_same_structure(got, ref, "unsorted COO")
+
+
+def test_build_fixed_permutation(eng, orc, mats):
+    n, nc, I, J, V = mats.random_coo(2048, 6, seed=9, empty_rows=False)
+    first = orc.convert_to_scs(n, nc, I, J, V, 32, 128)
+    sel = np.abs(V) < 0.5
+    ref = orc.convert_to_scs(n, nc, I[sel], J[sel], V[sel], 32, 128, "sp", fixed_perm=first.old_to_new)
+    mtx = eng.MtxData.from_host(n, nc, I[sel], J[sel], V[sel])
+    got = eng.convert_to_scs(mtx, 32, 128, "sp", fixed_permutation=first.old_to_new).export()
+    assert_same_structure(got, ref, "fixed_permutation")
+    assert np.array_equal(got.old_to_new, np.arange(n))
+
+
+def test_build_empty_and_errors(eng, pkg):
+    mtx = eng.MtxData.from_host(7, 7, np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(0))
+    s = eng.convert_to_scs(mtx, 4, 4, "dp")
+    e = s.export()
+    assert s.n_elements == 0 and s.n_chunks == 2 and np.all(e.chunk_lengths == 0) and np.all(e.chunk_ptrs == 0)
+    with pytest.raises(pkg.capi.UspmvError):
+        eng.convert_to_scs(mtx, 0, 1, "dp")
+    bad = eng.MtxData.from_host(3, 3, np.array([0, 5], np.int32), np.array([0, 1], np.int32), np.ones(2))
+    with pytest.raises(pkg.capi.UspmvError):
+        eng.convert_to_scs(bad, 1, 1, "dp")
+
+
+def test_stencil_generator_matches_host(eng, mats):
+    for pts, dims in ((7, (9, 7, 5)), (27, (6, 5, 7)), (7, (1, 1, 4)), (27, (2, 1, 3))):
+        n, nc, I, J, V = mats.stencil_coo(pts, *dims)
+        m = eng.MtxData.stencil(pts, *dims)
+        Id, Jd, Vd = m.to_host()
+        assert m.n_rows == n and m.nnz == len(I)
+        assert np.array_equal(Id, I) and np.array_equal(Jd, J) and np.array_equal(Vd, V)
+    # a slab: local rows, global columns
+    n, nc, I, J, V = mats.stencil_coo(27, 6, 5, 8, 60, 180)
+    m = eng.MtxData.stencil(27, 6, 5, 8, 60, 180)
+    Id, Jd, Vd = m.to_host()
+    assert np.array_equal(Id, I) and np.array_equal(Jd, J) and np.array_equal(Vd, V)
+
+
+# ------------------------------------------------------------------------------------------------
+# SpMV
+# ------------------------------------------------------------------------------------------------
+def run_spmv(eng, scs, ref, x_user, vt):
+    t = torch_()
+    xp = np.zeros(max(scs.n_rows_padded, scs.n_cols), NPT[vt])
+    xp[ref.old_to_new] = x_user.astype(NPT[vt])
+    yd = t.zeros(scs.n_rows_padded, dtype=eng.torch_dtype(scs.vt), device="cuda")
+    eng.spmv(scs, dev(xp), yd)
+    t.cuda.synchronize()
+    return xp, yd.cpu().numpy()
+
+
+@pytest.mark.parametrize("vt", ["dp", "sp", "hp"])
+@pytest.mark.parametrize("C,sigma", [(2, 1), (4, 8), (8, 8), (16, 64), (32, 1), (32, 512), (64, 64), (128, 256), (256, 256), (10, 30), (3, 1)])
+def test_spmv_scs_bit_exact(eng, orc, mats, vt, C, sigma):
+    coo = positive_coo(mats, 5000, 7, seed=C * 7 + sigma) if vt == "hp" else mats.random_coo(5000, 7, seed=C * 7 + sigma)
+    scs, ref = build_both(eng, orc, coo, C, sigma, vt)
+    x = np.random.default_rng(3).uniform(0.1 if vt == "hp" else -1.0, 1.0, coo[0])
+    xp, y = run_spmv(eng, scs, ref, x, vt)
+    y_ref = orc.spmv_scs(ref, xp)
+    assert rel_err(y, y_ref) <= TOL[vt]
+    assert np.array_equal(y.view(np.uint8), y_ref.view(np.uint8)), "SCS kernel is expected to be bit-identical to the oracle"
+
+
+@pytest.mark.parametrize("name", MATRIX_NAMES)
+def test_spmv_fixture_matrices_vs_coo(eng, orc, name):
+    """y in user order equals the plain COO sum (per-row order = COO order)."""
+    n, nc, I, J, V = load_matrix(name)
+    scs, ref = build_both(eng, orc, (n, nc, I, J, V), 32, 512, "dp")
+    x = np.random.default_rng(11).uniform(-1, 1, n)
+    xp, yp = run_spmv(eng, scs, ref, x, "dp")
+    y = yp[ref.old_to_new]
+    y_coo = np.zeros(n)
+    for i, j, v in zip(I, J, V):  # sequential, FMA-free reference sum
+        y_coo[i] += v * x[j]
+    scale = np.zeros(n)
+    np.add.at(scale, I, np.abs(V * x[J]))
+    assert np.all(np.abs(y - y_coo) <= 1e-12 * np.maximum(scale, 1e-300))
+
+
+@pytest.mark.parametrize("vt", ["dp", "sp", "hp"])
+def test_spmv_crs(eng, orc, mats, vt):
+    """C = 1, sigma = 1 dispatches to the CRS kernel (split-row reduction => tolerance, not bit-exactness)."""
+    coo = positive_coo(mats, 4000, 9, seed=21)
+    scs, ref = build_both(eng, orc, coo, 1, 1, vt)
+    x = np.random.default_rng(4).uniform(0.1, 1.0, coo[0])
+    xp, y = run_spmv(eng, scs, ref, x, vt)
+    y_ref = orc.spmv_csr(ref.n_rows, ref.chunk_ptrs, ref.col_idxs, ref.values, xp[:ref.n_cols])
+    assert rel_err(y, y_ref) <= TOL[vt]
+
+
+def test_spmv_raw_array_entry_points(eng, orc, mats):
+    """uspmv_scs_gpu / uspmv_csr_gpu with caller-owned device arrays (interface.hpp:1741-1793)."""
+    t = torch_()
+    coo = mats.random_coo(3000, 6, seed=2)
+    ref = orc.convert_to_scs(*coo, 32, 64)
+    x = np.random.default_rng(8).standard_normal(ref.n_rows_padded)
+    y = t.zeros(ref.n_rows_padded, dtype=t.float64, device="cuda")
+    eng.uspmv_scs_gpu(32, ref.n_chunks, dev(ref.chunk_ptrs), dev(ref.chunk_lengths), dev(ref.col_idxs), dev(ref.values), dev(x), y)
+    t.cuda.synchronize()
+    assert np.array_equal(y.cpu().numpy(), orc.spmv_scs(ref, x))
+    crs = orc.convert_to_scs(*coo, 1, 1)
+    y2 = t.zeros(crs.n_rows, dtype=t.float64, device="cuda")
+    eng.uspmv_csr_gpu(crs.n_rows, dev(crs.chunk_ptrs), dev(crs.col_idxs), dev(crs.values), dev(x[:crs.n_rows]), y2)
+    t.cuda.synchronize()
+    y_ref = orc.spmv_csr(crs.n_rows, crs.chunk_ptrs, crs.col_idxs, crs.values, x[:crs.n_rows])
+    scale = np.zeros(crs.n_rows)
+    np.add.at(scale, coo[2], np.abs(coo[4] * x[coo[3]]))
+    assert np.all(np.abs(y2.cpu().numpy() - y_ref) <= 1e-12 * np.maximum(scale, 1e-300))
+
+
+def test_spmv_unpermuted_fused(eng, orc, mats):
+    """Fused form: x and y in user numbering, columns not permuted, y[new_to_old[row]] written directly."""
+    t = torch_()
+    coo = mats.random_coo(4099, 6, seed=12)
+    scs, ref = build_both(eng, orc, coo, 32, 256, "dp", permute=False)
+    x = np.random.default_rng(5).standard_normal(coo[0])
+    y = t.full((coo[0],), 7.0, dtype=t.float64, device="cuda")
+    eng.spmv_unpermuted(scs, dev(x), y)
+    t.cuda.synchronize()
+    y_ref_perm = orc.spmv_scs(ref, np.concatenate([x, np.zeros(ref.n_rows_padded)]))
+    assert np.array_equal(y.cpu().numpy(), y_ref_perm[ref.old_to_new])
+
+
+def test_spmv_host_buffers(eng, orc, mats):
+    coo = mats.random_coo(2500, 6, seed=14)
+    scs, ref = build_both(eng, orc, coo, 32, 64, "dp")
+    xp = np.zeros(scs.n_rows_padded)
+    xp[ref.old_to_new] = np.random.default_rng(6).standard_normal(coo[0])
+    y = np.zeros(scs.n_rows_padded)
+    eng.spmv_host(scs, xp, y)
+    assert np.array_equal(y, orc.spmv_scs(ref, xp))
+
+
+def test_apply_permutation(eng, orc, mats):
+    t = torch_()
+    coo = mats.random_coo(1000, 4, seed=1)
+    scs, ref = build_both(eng, orc, coo, 8, 32, "dp")
+    x = np.random.default_rng(0).standard_normal(coo[0])
+    arrs = scs.device_arrays()
+    out = t.zeros(scs.n_rows_padded, dtype=t.float64, device="cuda")
+    eng.apply_permutation(out, dev(x), arrs["new_to_old"], scs.n_rows_padded)
+    t.cuda.synchronize()
+    exp = np.where(ref.new_to_old >= 0, x[np.maximum(ref.new_to_old, 0)], 0.0)
+    assert np.array_equal(out.cpu().numpy(), exp)
+
+
+# ------------------------------------------------------------------------------------------------
+# SpMMV
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("vt", ["dp", "sp", "hp"])
+@pytest.mark.parametrize("bvs", [2, 3, 4, 8, 16])
+@pytest.mark.parametrize("layout", ["rowwise", "colwise"])
+@pytest.mark.parametrize("C,sigma", [(32, 64), (1, 1), (4, 1)])
+def test_spmmv(eng, orc, mats, vt, bvs, layout, C, sigma):
+    t = torch_()
+    coo = positive_coo(mats, 1500, 6, seed=bvs + C) if vt == "hp" else mats.random_coo(1500, 6, seed=bvs + C)
+    scs, ref = build_both(eng, orc, coo, C, sigma, vt)
+    ld = scs.n_rows_padded + 5
+    rng = np.random.default_rng(9)
+    X = rng.uniform(0.1 if vt == "hp" else -1.0, 1.0, ld * bvs).astype(NPT[vt])
+    Y = t.zeros(ld * bvs, dtype=eng.torch_dtype(scs.vt), device="cuda")
+    eng.spmmv(scs, dev(X), Y, bvs, ld, layout)
+    t.cuda.synchronize()
+    lay = 1 if layout == "rowwise" else 0
+    Y_ref = orc.spmmv_scs(ref, X, bvs, ld, lay)
+    got = Y.cpu().numpy()
+    assert rel_err(got, Y_ref) <= TOL[vt]
+    assert np.array_equal(got.view(np.uint8), Y_ref.view(np.uint8))

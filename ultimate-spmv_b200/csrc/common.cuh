@@ -1,0 +1,138 @@
+// Shared internals of libuspmv_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+
+#include "../../include/uspmv_b200.h"
+
+namespace uspmv {
+
+// ---- error plumbing: C++ exceptions inside, int + message at the C boundary ---------------------
+void set_error(const std::string &msg);
+extern std::atomic<long> g_launches;
+
+struct Error : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+[[noreturn]] inline void fail(const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    throw Error(buf);
+}
+
+#define USPMV_CUDA(call)                                                                          \
+    do {                                                                                          \
+        cudaError_t e__ = (call);                                                                 \
+        if (e__ != cudaSuccess)                                                                   \
+            ::uspmv::fail("CUDA error %s at %s:%d: %s", cudaGetErrorName(e__), __FILE__, __LINE__, \
+                          cudaGetErrorString(e__));                                               \
+    } while (0)
+
+// every kernel launch goes through this so launches are counted and launch errors are not lost
+#define USPMV_LAUNCH_CHECK()                                  \
+    do {                                                      \
+        ::uspmv::g_launches.fetch_add(1, std::memory_order_relaxed); \
+        USPMV_CUDA(cudaGetLastError());                       \
+    } while (0)
+
+template <typename F>
+inline int guarded(F &&f) noexcept {
+    try {
+        f();
+        return 0;
+    } catch (const std::exception &e) {
+        set_error(e.what());
+        return 1;
+    } catch (...) {
+        set_error("unknown error");
+        return 2;
+    }
+}
+
+inline size_t vt_size(int vt) {
+    switch (vt) {
+    case USPMV_F64: return 8;
+    case USPMV_F32: return 4;
+    case USPMV_F16: return 2;
+    }
+    fail("invalid value type %d", vt);
+}
+
+inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// RAII device buffer
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    explicit DevBuf(size_t count) { alloc(count); }
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DevBuf &operator=(DevBuf &&o) noexcept {
+        if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+        return *this;
+    }
+    ~DevBuf() { release(); }
+    void alloc(size_t count) {
+        release();
+        n = count;
+        if (count) USPMV_CUDA(cudaMalloc(&p, count * sizeof(T)));
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+};
+
+inline int sm_count(int device) {
+    static int cached[64] = {0};
+    if (device >= 0 && device < 64 && cached[device]) return cached[device];
+    int n = 0;
+    USPMV_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device));
+    if (device >= 0 && device < 64) cached[device] = n;
+    return n;
+}
+
+}  // namespace uspmv
+
+// ---- opaque handle definitions ------------------------------------------------------------------
+struct uspmv_ctx {
+    int device = 0;
+    int n_sm = 0;
+};
+
+struct uspmv_coo {
+    uspmv_ctx *ctx = nullptr;
+    long n_rows = 0, n_cols = 0, nnz = 0;
+    int mt = USPMV_F64;
+    uspmv::DevBuf<int> I, J;
+    uspmv::DevBuf<unsigned char> values;  // nnz * vt_size(mt) bytes
+};
+
+struct uspmv_scs {
+    uspmv_ctx *ctx = nullptr;
+    long C = 1, sigma = 1, n_rows = 0, n_cols = 0, n_rows_padded = 0, n_chunks = 0, n_elements = 0, nnz = 0;
+    int vt = USPMV_F64;
+    bool cols_permuted = false;
+    uspmv::DevBuf<int> chunk_ptrs;     // n_chunks + 1
+    uspmv::DevBuf<int> chunk_lengths;  // n_chunks
+    uspmv::DevBuf<int> col_idxs;       // n_elements
+    uspmv::DevBuf<unsigned char> values;
+    uspmv::DevBuf<int> old_to_new;  // n_rows
+    uspmv::DevBuf<int> new_to_old;  // n_rows_padded, -1 where no real row lands
+    uspmv::DevBuf<unsigned char> h2d_stage_x, d2h_stage_y;  // device staging for the host-buffer call
+};

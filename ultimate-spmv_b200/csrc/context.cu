@@ -1,0 +1,102 @@
+// Context, error state and device-memory helpers of the C ABI (include/uspmv_b200.h).
+#include "common.cuh"
+
+namespace uspmv {
+static thread_local std::string t_error;
+std::atomic<long> g_launches{0};
+void set_error(const std::string &msg) { t_error = msg; }
+}  // namespace uspmv
+
+using namespace uspmv;
+
+extern "C" {
+
+const char *uspmv_last_error(void) { return t_error.c_str(); }
+int uspmv_version(void) { return 100; }
+long uspmv_kernel_launches(void) { return g_launches.load(); }
+
+int uspmv_ctx_create(int device, uspmv_ctx **out) {
+    return guarded([&] {
+        if (!out) fail("uspmv_ctx_create: out is NULL");
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || ndev == 0)
+            fail("uspmv_ctx_create: no CUDA device available (%s); this library has no CPU fallback",
+                 e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        if (device < 0 || device >= ndev) fail("uspmv_ctx_create: device %d out of range [0,%d)", device, ndev);
+        USPMV_CUDA(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        USPMV_CUDA(cudaGetDeviceProperties(&prop, device));
+        if (prop.major != 10)
+            fail("uspmv_ctx_create: device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major,
+                 prop.minor);
+        auto *ctx = new uspmv_ctx();
+        ctx->device = device;
+        ctx->n_sm = prop.multiProcessorCount;
+        *out = ctx;
+    });
+}
+
+void uspmv_ctx_destroy(uspmv_ctx *ctx) { delete ctx; }
+
+int uspmv_ctx_sync(uspmv_ctx *ctx) {
+    return guarded([&] {
+        if (!ctx) fail("uspmv_ctx_sync: ctx is NULL");
+        USPMV_CUDA(cudaSetDevice(ctx->device));
+        USPMV_CUDA(cudaDeviceSynchronize());
+    });
+}
+
+int uspmv_malloc(uspmv_ctx *ctx, size_t bytes, void **out_d) {
+    return guarded([&] {
+        if (!ctx || !out_d) fail("uspmv_malloc: NULL argument");
+        USPMV_CUDA(cudaSetDevice(ctx->device));
+        *out_d = nullptr;
+        if (bytes) USPMV_CUDA(cudaMalloc(out_d, bytes));
+    });
+}
+
+int uspmv_free(uspmv_ctx *ctx, void *ptr_d) {
+    return guarded([&] {
+        if (!ctx) fail("uspmv_free: ctx is NULL");
+        if (ptr_d) USPMV_CUDA(cudaFree(ptr_d));
+    });
+}
+
+int uspmv_memcpy_h2d(uspmv_ctx *ctx, void *dst_d, const void *src_h, size_t bytes, void *stream) {
+    return guarded([&] {
+        if (!ctx) fail("uspmv_memcpy_h2d: ctx is NULL");
+        USPMV_CUDA(cudaMemcpyAsync(dst_d, src_h, bytes, cudaMemcpyHostToDevice, as_stream(stream)));
+        USPMV_CUDA(cudaStreamSynchronize(as_stream(stream)));
+    });
+}
+
+int uspmv_memcpy_d2h(uspmv_ctx *ctx, void *dst_h, const void *src_d, size_t bytes, void *stream) {
+    return guarded([&] {
+        if (!ctx) fail("uspmv_memcpy_d2h: ctx is NULL");
+        USPMV_CUDA(cudaMemcpyAsync(dst_h, src_d, bytes, cudaMemcpyDeviceToHost, as_stream(stream)));
+        USPMV_CUDA(cudaStreamSynchronize(as_stream(stream)));
+    });
+}
+
+int uspmv_memset(uspmv_ctx *ctx, void *dst_d, int byte, size_t bytes, void *stream) {
+    return guarded([&] {
+        if (!ctx) fail("uspmv_memset: ctx is NULL");
+        USPMV_CUDA(cudaMemsetAsync(dst_d, byte, bytes, as_stream(stream)));
+    });
+}
+
+int uspmv_host_alloc(size_t bytes, void **out_h) {
+    return guarded([&] {
+        if (!out_h) fail("uspmv_host_alloc: out is NULL");
+        USPMV_CUDA(cudaMallocHost(out_h, bytes ? bytes : 1));
+    });
+}
+
+int uspmv_host_free(void *ptr_h) {
+    return guarded([&] {
+        if (ptr_h) USPMV_CUDA(cudaFreeHost(ptr_h));
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,676 @@
+// Device-side MtxData (COO) handling and SELL-C-sigma construction.
+//
+// Replaces, bit-exactly, the reference's serial host routines
+//   convert_to_scs     code/utilities.hpp:1842-2104  (library twin code/interface.hpp:401-656)
+//   permute_scs_cols   code/utilities.hpp:1802-1831
+// Pipeline (all on the GPU, int32 indices per rank like the reference's IT=int):
+//   [stable radix sort by row if the COO is not row-sorted]  -> row_ptr (boundary detection)
+//   -> per-row counts incl. zero-count padding rows
+//   -> one thread per sigma-window runs libstdc++-13's std::sort algorithm (introsort with the
+//      comparator `a.count > b.count`, utilities.hpp:1936-1940) so that the UNSTABLE tie order of
+//      the reference is reproduced exactly
+//   -> chunk_lengths = max count per chunk, chunk_ptrs = exclusive scan of len*C (64-bit, overflow checked)
+//   -> old_to_new / new_to_old
+//   -> gather-fill: one thread per padded row writes its slots j = 0..len-1 of the chunk, taking the
+//      row's COO elements in input order (utilities.hpp:2013-2036) and padding with value 0 / column 0
+//      (utilities.hpp:1991-2002).  Writes are coalesced across the C lanes of a chunk.
+#include "common.cuh"
+
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include <vector>
+
+using namespace uspmv;
+
+namespace {
+
+constexpr int TPB = 256;
+inline unsigned blocks_for(long n, int tpb = TPB) { return (unsigned)((n + tpb - 1) / tpb); }
+
+// ---------------------------------------------------------------------------------------------
+// small kernels
+// ---------------------------------------------------------------------------------------------
+__global__ void k_check_sorted(const int *__restrict__ I, long nnz, long n_rows, int *flags) {
+    long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (i >= nnz) return;
+    int r = I[i];
+    if (r < 0 || r >= n_rows) atomicOr(&flags[1], 1);
+    if (i > 0 && I[i - 1] > r) atomicOr(&flags[0], 1);
+}
+
+__global__ void k_check_cols(const int *__restrict__ J, long nnz, int *flags) {
+    long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (i < nnz && J[i] < 0) atomicOr(&flags[1], 1);
+}
+
+__global__ void k_iota(int *p, long n) {
+    long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (i < n) p[i] = (int)i;
+}
+
+// row_ptr[r] = first s with Isorted[s] >= r, for r in [0, n_ptr)
+__global__ void k_row_ptr(const int *__restrict__ Is, long nnz, long n_ptr, int *__restrict__ row_ptr) {
+    long s = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (s > nnz) return;
+    long lo = (s == 0) ? 0 : (long)Is[s - 1] + 1;
+    long hi = (s == nnz) ? n_ptr - 1 : (long)Is[s];
+    for (long r = lo; r <= hi; ++r) row_ptr[r] = (int)s;
+}
+
+struct RC {
+    int idx;  // original row
+    int cnt;  // stored elements in that row
+};
+static_assert(sizeof(RC) == 8, "RC must be one 64-bit word");
+
+__global__ void k_init_rc(const int *__restrict__ row_ptr, long n_rows, long n_pad, RC *__restrict__ rc) {
+    long r = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (r >= n_pad) return;
+    RC v;
+    v.idx = (int)r;
+    v.cnt = (r < n_rows) ? row_ptr[r + 1] - row_ptr[r] : 0;
+    rc[r] = v;
+}
+
+// fixed_permutation mode (utilities.hpp:1911-1928): position p holds the row i with fixed_perm[i] == p
+__global__ void k_scatter_fixed(const int *__restrict__ row_ptr, const int *__restrict__ fixed_perm, long n_rows, long n_pad,
+                                RC *__restrict__ rc, int *flags) {
+    long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (i >= n_rows) return;
+    int p = fixed_perm[i];
+    if (p < 0 || p >= n_pad) { atomicOr(&flags[1], 1); return; }
+    RC v;
+    v.idx = (int)i;
+    v.cnt = row_ptr[i + 1] - row_ptr[i];
+    rc[p] = v;
+}
+
+__global__ void k_fill_rc_empty(long n_pad, RC *rc) {
+    long r = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (r < n_pad) { RC v; v.idx = -1; v.cnt = 0; rc[r] = v; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// libstdc++ 13 std::sort on RC with comparator "longer rows first" — one thread per sigma window.
+// Algorithm (published in GCC's bits/stl_algo.h:1848-1951 and bits/stl_heap.h): __introsort_loop with
+// depth budget 2*floor(log2 n) and threshold 16, median-of-three pivot moved to `first`,
+// __unguarded_partition, heapsort when the budget is spent, then __final_insertion_sort.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool longer(const RC &a, const RC &b) { return a.cnt > b.cnt; }
+__device__ __forceinline__ void swp(RC *a, RC *b) { RC t = *a; *a = *b; *b = t; }
+
+__device__ void d_push_heap(RC *first, long hole, long top, RC value) {
+    long parent = (hole - 1) / 2;
+    while (hole > top && longer(first[parent], value)) {
+        first[hole] = first[parent];
+        hole = parent;
+        parent = (hole - 1) / 2;
+    }
+    first[hole] = value;
+}
+
+__device__ void d_adjust_heap(RC *first, long hole, long len, RC value) {
+    const long top = hole;
+    long child = hole;
+    while (child < (len - 1) / 2) {
+        child = 2 * (child + 1);
+        if (longer(first[child], first[child - 1])) child--;
+        first[hole] = first[child];
+        hole = child;
+    }
+    if ((len & 1) == 0 && child == (len - 2) / 2) {
+        child = 2 * (child + 1);
+        first[hole] = first[child - 1];
+        hole = child - 1;
+    }
+    d_push_heap(first, hole, top, value);
+}
+
+__device__ void d_heapsort(RC *first, long n) {
+    if (n >= 2) {
+        long parent = (n - 2) / 2;
+        for (;;) {
+            RC v = first[parent];
+            d_adjust_heap(first, parent, n, v);
+            if (parent == 0) break;
+            parent--;
+        }
+    }
+    long last = n;
+    while (last > 1) {
+        --last;
+        RC v = first[last];
+        first[last] = first[0];
+        d_adjust_heap(first, 0, last, v);
+    }
+}
+
+__device__ __forceinline__ void d_median_to_first(RC *result, RC *a, RC *b, RC *c) {
+    if (longer(*a, *b)) {
+        if (longer(*b, *c)) swp(result, b);
+        else if (longer(*a, *c)) swp(result, c);
+        else swp(result, a);
+    } else if (longer(*a, *c)) swp(result, a);
+    else if (longer(*b, *c)) swp(result, c);
+    else swp(result, b);
+}
+
+__device__ __forceinline__ RC *d_unguarded_partition(RC *first, RC *last, RC *pivot_p) {
+    const RC pivot = *pivot_p;  // the pivot slot (window[0]) is never written during the partition
+    for (;;) {
+        while (longer(*first, pivot)) ++first;
+        --last;
+        while (longer(pivot, *last)) --last;
+        if (!(first < last)) return first;
+        swp(first, last);
+        ++first;
+    }
+}
+
+__device__ __forceinline__ void d_unguarded_linear_insert(RC *last) {
+    RC val = *last;
+    RC *next = last - 1;
+    while (longer(val, *next)) {
+        *last = *next;
+        last = next;
+        --next;
+    }
+    *last = val;
+}
+
+__device__ void d_insertion_sort(RC *first, RC *last) {
+    if (first == last) return;
+    for (RC *i = first + 1; i != last; ++i) {
+        if (longer(*i, *first)) {
+            RC val = *i;
+            for (RC *p = i; p != first; --p) *p = *(p - 1);
+            *first = val;
+        } else
+            d_unguarded_linear_insert(i);
+    }
+}
+
+__device__ void d_std_sort(RC *first, long n) {
+    if (n <= 1) return;
+    long lg = 0;
+    for (long t = n; t > 1; t >>= 1) ++lg;
+    // __introsort_loop, recursion on the right part turned into an explicit stack (depth <= 2*lg)
+    struct Frame { RC *first, *last; long depth; };
+    Frame stack[130];
+    int sp = 0;
+    stack[sp++] = Frame{first, first + n, 2 * lg};
+    while (sp > 0) {
+        Frame f = stack[--sp];
+        while (f.last - f.first > 16) {
+            if (f.depth == 0) {
+                d_heapsort(f.first, f.last - f.first);
+                break;
+            }
+            --f.depth;
+            RC *mid = f.first + (f.last - f.first) / 2;
+            d_median_to_first(f.first, f.first + 1, mid, f.last - 1);
+            RC *cut = d_unguarded_partition(f.first + 1, f.last, f.first);
+            stack[sp++] = Frame{cut, f.last, f.depth};
+            f.last = cut;
+        }
+    }
+    if (n > 16) {
+        d_insertion_sort(first, first + 16);
+        for (RC *i = first + 16; i != first + n; ++i) d_unguarded_linear_insert(i);
+    } else
+        d_insertion_sort(first, first + n);
+}
+
+__global__ void k_sort_windows(RC *rc, long n_pad, long sigma, long n_windows) {
+    long w = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (w >= n_windows) return;
+    long begin = w * sigma;
+    long end = begin + sigma < n_pad ? begin + sigma : n_pad;
+    d_std_sort(rc + begin, end - begin);
+}
+
+// chunk_lengths[c] = max count in chunk; len64[c] = len*C
+__global__ void k_chunk_lengths(const RC *__restrict__ rc, long n_chunks, int C, int *__restrict__ chunk_lengths,
+                                long long *__restrict__ len64) {
+    long c = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (c >= n_chunks) return;
+    int mx = 0;
+    for (int i = 0; i < C; ++i) mx = max(mx, rc[c * C + i].cnt);
+    chunk_lengths[c] = mx;
+    len64[c] = (long long)mx * C;
+}
+
+__global__ void k_narrow_ptrs(const long long *__restrict__ ptr64, long n, int *__restrict__ ptr32) {
+    long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (i < n) ptr32[i] = (int)ptr64[i];
+}
+
+__global__ void k_perms(const RC *__restrict__ rc, long n_rows, long n_pad, bool identity, int *__restrict__ old_to_new,
+                        int *__restrict__ new_to_old) {
+    long p = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (p >= n_pad) return;
+    if (identity) {  // fixed_permutation mode: the struct's own permutation is the identity
+        if (p < n_rows) old_to_new[p] = (int)p;
+        new_to_old[p] = p < n_rows ? (int)p : -1;
+        return;
+    }
+    int old = rc[p].idx;
+    if (old >= 0 && old < n_rows) {
+        old_to_new[old] = (int)p;
+        new_to_old[p] = old;
+    } else
+        new_to_old[p] = -1;
+}
+
+template <typename T> struct Cvt;
+template <> struct Cvt<double> {
+    __device__ static double from(double v) { return v; }
+    __device__ static double from(float v) { return (double)v; }
+    __device__ static double from(__half v) { return (double)__half2float(v); }
+};
+template <> struct Cvt<float> {
+    __device__ static float from(double v) { return (float)v; }
+    __device__ static float from(float v) { return v; }
+    __device__ static float from(__half v) { return __half2float(v); }
+};
+template <> struct Cvt<__half> {
+    __device__ static __half from(double v) { return __double2half(v); }  // single rounding, like static_cast<_Float16>(double)
+    __device__ static __half from(float v) { return __float2half_rn(v); }
+    __device__ static __half from(__half v) { return v; }
+};
+
+// one thread per padded row position; lanes of a chunk are adjacent threads => coalesced stores
+template <typename MT, typename VT>
+__global__ void k_fill(const RC *__restrict__ rc, const int *__restrict__ row_ptr, const int *__restrict__ order,
+                       const int *__restrict__ J, const MT *__restrict__ vals, const int *__restrict__ chunk_ptrs,
+                       const int *__restrict__ chunk_lengths, long n_pad, int C, int *__restrict__ col_idxs,
+                       VT *__restrict__ values) {
+    long p = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (p >= n_pad) return;
+    long c = p / C;
+    int lane = (int)(p - c * C);
+    int len = chunk_lengths[c];
+    long e = (long)chunk_ptrs[c] + lane;
+    RC r = rc[p];
+    int src0 = (r.idx >= 0 && r.cnt > 0) ? row_ptr[r.idx] : 0;
+    for (int j = 0; j < len; ++j, e += C) {
+        int col = 0;
+        VT v = Cvt<VT>::from(MT(0.0));
+        if (j < r.cnt) {
+            int s = src0 + j;
+            if (order) s = order[s];
+            col = J[s];
+            v = Cvt<VT>::from(vals[s]);
+        }
+        col_idxs[e] = col;
+        values[e] = v;
+    }
+}
+
+__global__ void k_permute_cols(int *__restrict__ col_idxs, long n_elements, int n_rows, const int *__restrict__ perm) {
+    long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (i >= n_elements) return;
+    int c = col_idxs[i];
+    if (c < n_rows) col_idxs[i] = perm[c];
+}
+
+// ---- stencil generator ------------------------------------------------------------------------
+__device__ __forceinline__ int axis_cnt(long v, long n) { return 1 + (v > 0) + (v < n - 1); }
+
+__global__ void k_stencil_counts(int points, long nx, long ny, long nz, long row0, long n_local, long long *cnt) {
+    long r = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (r >= n_local) return;
+    long g = row0 + r;
+    long x = g % nx, y = (g / nx) % ny, z = g / (nx * ny);
+    int cx = axis_cnt(x, nx), cy = axis_cnt(y, ny), cz = axis_cnt(z, nz);
+    cnt[r] = points == 7 ? (cx + cy + cz - 2) : (long long)cx * cy * cz;
+}
+
+__global__ void k_stencil_fill(int points, long nx, long ny, long nz, long row0, long n_local, const long long *__restrict__ ptr,
+                               int *__restrict__ I, int *__restrict__ J, double *__restrict__ V) {
+    long r = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (r >= n_local) return;
+    long g = row0 + r;
+    long x = g % nx, y = (g / nx) % ny, z = g / (nx * ny);
+    long o = ptr[r];
+    for (int dz = -1; dz <= 1; ++dz) {
+        long zz = z + dz;
+        if (zz < 0 || zz >= nz) continue;
+        for (int dy = -1; dy <= 1; ++dy) {
+            long yy = y + dy;
+            if (yy < 0 || yy >= ny) continue;
+            for (int dx = -1; dx <= 1; ++dx) {
+                long xx = x + dx;
+                if (xx < 0 || xx >= nx) continue;
+                int nzd = (dx != 0) + (dy != 0) + (dz != 0);
+                if (points == 7 && nzd > 1) continue;
+                I[o] = (int)r;
+                J[o] = (int)((zz * ny + yy) * nx + xx);
+                V[o] = nzd == 0 ? (double)(points - 1) : -1.0;
+                ++o;
+            }
+        }
+    }
+}
+
+// ---- host helpers --------------------------------------------------------------------------------
+void exclusive_scan_i64(const long long *in, long long *out, long n, cudaStream_t st) {
+    size_t bytes = 0;
+    USPMV_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, (int)n, st));
+    DevBuf<unsigned char> tmp(bytes);
+    USPMV_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, bytes, in, out, (int)n, st));
+    g_launches.fetch_add(2);
+    USPMV_CUDA(cudaStreamSynchronize(st));
+}
+
+template <typename MT, typename VT>
+void launch_fill(const uspmv_coo *coo, uspmv_scs *s, const RC *rc, const int *row_ptr, const int *order) {
+    k_fill<MT, VT><<<blocks_for(s->n_rows_padded), TPB>>>(rc, row_ptr, order, coo->J.p, reinterpret_cast<const MT *>(coo->values.p),
+                                                        s->chunk_ptrs.p, s->chunk_lengths.p, s->n_rows_padded, (int)s->C,
+                                                        s->col_idxs.p, reinterpret_cast<VT *>(s->values.p));
+    USPMV_LAUNCH_CHECK();
+}
+
+template <typename MT>
+void dispatch_fill_vt(const uspmv_coo *coo, uspmv_scs *s, const RC *rc, const int *row_ptr, const int *order) {
+    switch (s->vt) {
+    case USPMV_F64: launch_fill<MT, double>(coo, s, rc, row_ptr, order); break;
+    case USPMV_F32: launch_fill<MT, float>(coo, s, rc, row_ptr, order); break;
+    default: launch_fill<MT, __half>(coo, s, rc, row_ptr, order); break;
+    }
+}
+
+void check_flags(DevBuf<int> &flags, int out[2]) {
+    USPMV_CUDA(cudaMemcpy(out, flags.p, 2 * sizeof(int), cudaMemcpyDeviceToHost));
+}
+
+}  // namespace
+
+extern "C" {
+
+// ---------------------------------------------------------------------------------------------
+// COO
+// ---------------------------------------------------------------------------------------------
+static void coo_common(uspmv_ctx *ctx, long n_rows, long n_cols, long nnz, int mt, uspmv_coo *c) {
+    if (!ctx) fail("coo: ctx is NULL");
+    if (n_rows < 0 || n_cols < 0 || nnz < 0) fail("coo: negative dimension");
+    if (n_rows > INT32_MAX - 1024 || nnz > INT32_MAX) fail("coo: n_rows/nnz exceed the reference's int index type (per rank)");
+    vt_size(mt);
+    USPMV_CUDA(cudaSetDevice(ctx->device));
+    c->ctx = ctx;
+    c->n_rows = n_rows;
+    c->n_cols = n_cols;
+    c->nnz = nnz;
+    c->mt = mt;
+    c->I.alloc(nnz);
+    c->J.alloc(nnz);
+    c->values.alloc(nnz * vt_size(mt));
+}
+
+int uspmv_coo_from_host(uspmv_ctx *ctx, long n_rows, long n_cols, long nnz, const int *I_h, const int *J_h, const void *values_h,
+                        int mt, uspmv_coo **out) {
+    return guarded([&] {
+        if (!out) fail("uspmv_coo_from_host: out is NULL");
+        if (nnz > 0 && (!I_h || !J_h || !values_h)) fail("uspmv_coo_from_host: NULL array");
+        auto c = new uspmv_coo();
+        try {
+            coo_common(ctx, n_rows, n_cols, nnz, mt, c);
+            if (nnz) {
+                USPMV_CUDA(cudaMemcpy(c->I.p, I_h, nnz * sizeof(int), cudaMemcpyHostToDevice));
+                USPMV_CUDA(cudaMemcpy(c->J.p, J_h, nnz * sizeof(int), cudaMemcpyHostToDevice));
+                USPMV_CUDA(cudaMemcpy(c->values.p, values_h, nnz * vt_size(mt), cudaMemcpyHostToDevice));
+            }
+        } catch (...) { delete c; throw; }
+        *out = c;
+    });
+}
+
+int uspmv_coo_from_device(uspmv_ctx *ctx, long n_rows, long n_cols, long nnz, const int *I_d, const int *J_d, const void *values_d,
+                          int mt, uspmv_coo **out) {
+    return guarded([&] {
+        if (!out) fail("uspmv_coo_from_device: out is NULL");
+        if (nnz > 0 && (!I_d || !J_d || !values_d)) fail("uspmv_coo_from_device: NULL array");
+        auto c = new uspmv_coo();
+        try {
+            coo_common(ctx, n_rows, n_cols, nnz, mt, c);
+            if (nnz) {
+                USPMV_CUDA(cudaMemcpy(c->I.p, I_d, nnz * sizeof(int), cudaMemcpyDeviceToDevice));
+                USPMV_CUDA(cudaMemcpy(c->J.p, J_d, nnz * sizeof(int), cudaMemcpyDeviceToDevice));
+                USPMV_CUDA(cudaMemcpy(c->values.p, values_d, nnz * vt_size(mt), cudaMemcpyDeviceToDevice));
+            }
+        } catch (...) { delete c; throw; }
+        *out = c;
+    });
+}
+
+int uspmv_coo_stencil(uspmv_ctx *ctx, int points, long nx, long ny, long nz, long row0, long row1, uspmv_coo **out) {
+    return guarded([&] {
+        if (!ctx || !out) fail("uspmv_coo_stencil: NULL argument");
+        if (points != 7 && points != 27) fail("uspmv_coo_stencil: points must be 7 or 27");
+        long n = nx * ny * nz;
+        if (nx <= 0 || ny <= 0 || nz <= 0 || row0 < 0 || row1 > n || row0 > row1) fail("uspmv_coo_stencil: bad grid / row range");
+        if (n > INT32_MAX) fail("uspmv_coo_stencil: grid exceeds int column indices");
+        USPMV_CUDA(cudaSetDevice(ctx->device));
+        long n_local = row1 - row0;
+        DevBuf<long long> cnt(n_local + 1), ptr(n_local + 1);
+        USPMV_CUDA(cudaMemset(cnt.p, 0, (n_local + 1) * sizeof(long long)));
+        if (n_local) {
+            k_stencil_counts<<<blocks_for(n_local), TPB>>>(points, nx, ny, nz, row0, n_local, cnt.p);
+            USPMV_LAUNCH_CHECK();
+        }
+        exclusive_scan_i64(cnt.p, ptr.p, n_local + 1, 0);
+        long long nnz = 0;
+        USPMV_CUDA(cudaMemcpy(&nnz, ptr.p + n_local, sizeof(long long), cudaMemcpyDeviceToHost));
+        auto c = new uspmv_coo();
+        try {
+            coo_common(ctx, n_local, n, (long)nnz, USPMV_F64, c);
+            if (n_local) {
+                k_stencil_fill<<<blocks_for(n_local), TPB>>>(points, nx, ny, nz, row0, n_local, ptr.p, c->I.p, c->J.p,
+                                                            reinterpret_cast<double *>(c->values.p));
+                USPMV_LAUNCH_CHECK();
+            }
+            USPMV_CUDA(cudaDeviceSynchronize());
+        } catch (...) { delete c; throw; }
+        *out = c;
+    });
+}
+
+int uspmv_coo_dims(const uspmv_coo *coo, long out3[3]) {
+    return guarded([&] {
+        if (!coo || !out3) fail("uspmv_coo_dims: NULL argument");
+        out3[0] = coo->n_rows; out3[1] = coo->n_cols; out3[2] = coo->nnz;
+    });
+}
+
+int uspmv_coo_export(const uspmv_coo *coo, int *I_h, int *J_h, void *values_h) {
+    return guarded([&] {
+        if (!coo) fail("uspmv_coo_export: coo is NULL");
+        USPMV_CUDA(cudaSetDevice(coo->ctx->device));
+        if (I_h && coo->nnz) USPMV_CUDA(cudaMemcpy(I_h, coo->I.p, coo->nnz * sizeof(int), cudaMemcpyDeviceToHost));
+        if (J_h && coo->nnz) USPMV_CUDA(cudaMemcpy(J_h, coo->J.p, coo->nnz * sizeof(int), cudaMemcpyDeviceToHost));
+        if (values_h && coo->nnz) USPMV_CUDA(cudaMemcpy(values_h, coo->values.p, coo->nnz * vt_size(coo->mt), cudaMemcpyDeviceToHost));
+    });
+}
+
+void uspmv_coo_destroy(uspmv_coo *coo) { delete coo; }
+
+// ---------------------------------------------------------------------------------------------
+// convert_to_scs
+// ---------------------------------------------------------------------------------------------
+int uspmv_scs_build(uspmv_ctx *ctx, const uspmv_coo *coo, long C, long sigma, int vt, const int *fixed_perm_h, uspmv_scs **out) {
+    return guarded([&] {
+        if (!ctx || !coo || !out) fail("uspmv_scs_build: NULL argument");
+        if (C < 1 || sigma < 1) fail("uspmv_scs_build: C and sigma must be >= 1 (got C=%ld sigma=%ld)", C, sigma);
+        vt_size(vt);
+        USPMV_CUDA(cudaSetDevice(ctx->device));
+        const long n_rows = coo->n_rows, nnz = coo->nnz;
+        const long n_chunks = (n_rows + C - 1) / C;
+        const long n_pad = n_chunks * C;
+        if (n_pad > INT32_MAX - 1024) fail("uspmv_scs_build: no. of padded rows exceeds the index type");
+
+        DevBuf<int> flags(2);
+        USPMV_CUDA(cudaMemset(flags.p, 0, 2 * sizeof(int)));
+        int hflags[2] = {0, 0};
+        if (nnz) {
+            k_check_sorted<<<blocks_for(nnz), TPB>>>(coo->I.p, nnz, n_rows, flags.p);
+            USPMV_LAUNCH_CHECK();
+            k_check_cols<<<blocks_for(nnz), TPB>>>(coo->J.p, nnz, flags.p);
+            USPMV_LAUNCH_CHECK();
+            check_flags(flags, hflags);
+            if (hflags[1]) fail("uspmv_scs_build: row index outside [0, n_rows) or negative column index");
+        }
+
+        // stable sort by row only if needed; `order` maps sorted position -> input position
+        DevBuf<int> Isorted, order;
+        const int *Is = coo->I.p;
+        const int *ord = nullptr;
+        if (hflags[0]) {
+            DevBuf<int> iota(nnz);
+            Isorted.alloc(nnz);
+            order.alloc(nnz);
+            k_iota<<<blocks_for(nnz), TPB>>>(iota.p, nnz);
+            USPMV_LAUNCH_CHECK();
+            int end_bit = 1;
+            while (end_bit < 31 && (1L << end_bit) < n_rows) ++end_bit;
+            size_t bytes = 0;
+            USPMV_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, coo->I.p, Isorted.p, iota.p, order.p, (int)nnz, 0, end_bit));
+            DevBuf<unsigned char> tmp(bytes);
+            USPMV_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, coo->I.p, Isorted.p, iota.p, order.p, (int)nnz, 0, end_bit));
+            g_launches.fetch_add(8);
+            USPMV_CUDA(cudaDeviceSynchronize());
+            Is = Isorted.p;
+            ord = order.p;
+        }
+
+        DevBuf<int> row_ptr(n_pad + 1);
+        k_row_ptr<<<blocks_for(nnz + 1), TPB>>>(Is, nnz, n_rows + 1, row_ptr.p);
+        USPMV_LAUNCH_CHECK();
+
+        DevBuf<RC> rc(n_pad + 1);
+        DevBuf<int> fixed_perm_d;
+        if (fixed_perm_h) {
+            fixed_perm_d.alloc(n_rows);
+            USPMV_CUDA(cudaMemcpy(fixed_perm_d.p, fixed_perm_h, n_rows * sizeof(int), cudaMemcpyHostToDevice));
+            if (n_pad) {
+                k_fill_rc_empty<<<blocks_for(n_pad), TPB>>>(n_pad, rc.p);
+                USPMV_LAUNCH_CHECK();
+            }
+            if (n_rows) {
+                k_scatter_fixed<<<blocks_for(n_rows), TPB>>>(row_ptr.p, fixed_perm_d.p, n_rows, n_pad, rc.p, flags.p);
+                USPMV_LAUNCH_CHECK();
+                check_flags(flags, hflags);
+                if (hflags[1]) fail("uspmv_scs_build: fixed_permutation entry outside [0, n_rows_padded)");
+            }
+        } else if (n_pad) {
+            k_init_rc<<<blocks_for(n_pad), TPB>>>(row_ptr.p, n_rows, n_pad, rc.p);
+            USPMV_LAUNCH_CHECK();
+            if (sigma > 1) {
+                long n_windows = (n_pad + sigma - 1) / sigma;
+                k_sort_windows<<<blocks_for(n_windows, 64), 64>>>(rc.p, n_pad, sigma, n_windows);
+                USPMV_LAUNCH_CHECK();
+            }
+        }
+
+        auto s = new uspmv_scs();
+        try {
+            s->ctx = ctx;
+            s->C = C; s->sigma = sigma; s->n_rows = n_rows; s->n_cols = coo->n_cols;
+            s->n_rows_padded = n_pad; s->n_chunks = n_chunks; s->nnz = nnz; s->vt = vt;
+            s->chunk_ptrs.alloc(n_chunks + 1);
+            s->chunk_lengths.alloc(n_chunks);
+            s->old_to_new.alloc(n_rows);
+            s->new_to_old.alloc(n_pad);
+            DevBuf<long long> len64(n_chunks + 1), ptr64(n_chunks + 1);
+            USPMV_CUDA(cudaMemset(len64.p, 0, (n_chunks + 1) * sizeof(long long)));
+            if (n_chunks) {
+                k_chunk_lengths<<<blocks_for(n_chunks), TPB>>>(rc.p, n_chunks, (int)C, s->chunk_lengths.p, len64.p);
+                USPMV_LAUNCH_CHECK();
+            }
+            exclusive_scan_i64(len64.p, ptr64.p, n_chunks + 1, 0);
+            long long n_el = 0;
+            USPMV_CUDA(cudaMemcpy(&n_el, ptr64.p + n_chunks, sizeof(long long), cudaMemcpyDeviceToHost));
+            if (n_el > INT32_MAX) fail("uspmv_scs_build: chunk_ptrs exceed index type (n_elements = %lld)", n_el);
+            s->n_elements = (long)n_el;
+            k_narrow_ptrs<<<blocks_for(n_chunks + 1), TPB>>>(ptr64.p, n_chunks + 1, s->chunk_ptrs.p);
+            USPMV_LAUNCH_CHECK();
+            if (n_pad) {
+                k_perms<<<blocks_for(n_pad), TPB>>>(rc.p, n_rows, n_pad, fixed_perm_h != nullptr, s->old_to_new.p, s->new_to_old.p);
+                USPMV_LAUNCH_CHECK();
+            }
+            s->col_idxs.alloc(s->n_elements);
+            s->values.alloc(s->n_elements * vt_size(vt));
+            if (n_pad && s->n_elements) {
+                switch (coo->mt) {
+                case USPMV_F64: dispatch_fill_vt<double>(coo, s, rc.p, row_ptr.p, ord); break;
+                case USPMV_F32: dispatch_fill_vt<float>(coo, s, rc.p, row_ptr.p, ord); break;
+                default: dispatch_fill_vt<__half>(coo, s, rc.p, row_ptr.p, ord); break;
+                }
+            }
+            USPMV_CUDA(cudaDeviceSynchronize());
+        } catch (...) { delete s; throw; }
+        *out = s;
+    });
+}
+
+int uspmv_scs_dims(const uspmv_scs *s, long o[8]) {
+    return guarded([&] {
+        if (!s || !o) fail("uspmv_scs_dims: NULL argument");
+        o[0] = s->C; o[1] = s->sigma; o[2] = s->n_rows; o[3] = s->n_cols;
+        o[4] = s->n_rows_padded; o[5] = s->n_chunks; o[6] = s->n_elements; o[7] = s->nnz;
+    });
+}
+
+int uspmv_scs_export(const uspmv_scs *s, int *chunk_ptrs_h, int *chunk_lengths_h, int *col_idxs_h, void *values_h, int *old_to_new_h,
+                     int *new_to_old_h) {
+    return guarded([&] {
+        if (!s) fail("uspmv_scs_export: scs is NULL");
+        USPMV_CUDA(cudaSetDevice(s->ctx->device));
+        auto d2h = [](void *dst, const void *src, size_t bytes) {
+            if (dst && bytes) USPMV_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+        };
+        d2h(chunk_ptrs_h, s->chunk_ptrs.p, (s->n_chunks + 1) * sizeof(int));
+        d2h(chunk_lengths_h, s->chunk_lengths.p, s->n_chunks * sizeof(int));
+        d2h(col_idxs_h, s->col_idxs.p, s->n_elements * sizeof(int));
+        d2h(values_h, s->values.p, s->n_elements * vt_size(s->vt));
+        d2h(old_to_new_h, s->old_to_new.p, s->n_rows * sizeof(int));
+        d2h(new_to_old_h, s->new_to_old.p, s->n_rows_padded * sizeof(int));
+    });
+}
+
+int uspmv_scs_permute_cols(uspmv_scs *s, const int *perm_h) {
+    return guarded([&] {
+        if (!s) fail("uspmv_scs_permute_cols: scs is NULL");
+        USPMV_CUDA(cudaSetDevice(s->ctx->device));
+        DevBuf<int> perm_d;
+        const int *perm = s->old_to_new.p;
+        if (perm_h) {
+            perm_d.alloc(s->n_rows);
+            USPMV_CUDA(cudaMemcpy(perm_d.p, perm_h, s->n_rows * sizeof(int), cudaMemcpyHostToDevice));
+            perm = perm_d.p;
+        }
+        if (s->n_elements) {
+            k_permute_cols<<<blocks_for(s->n_elements), TPB>>>(s->col_idxs.p, s->n_elements, (int)s->n_rows, perm);
+            USPMV_LAUNCH_CHECK();
+        }
+        USPMV_CUDA(cudaDeviceSynchronize());
+        s->cols_permuted = true;
+    });
+}
+
+int uspmv_scs_device_arrays(const uspmv_scs *s, const int **chunk_ptrs_d, const int **chunk_lengths_d, const int **col_idxs_d,
+                            const void **values_d, const int **old_to_new_d, const int **new_to_old_d) {
+    return guarded([&] {
+        if (!s) fail("uspmv_scs_device_arrays: scs is NULL");
+        if (chunk_ptrs_d) *chunk_ptrs_d = s->chunk_ptrs.p;
+        if (chunk_lengths_d) *chunk_lengths_d = s->chunk_lengths.p;
+        if (col_idxs_d) *col_idxs_d = s->col_idxs.p;
+        if (values_d) *values_d = s->values.p;
+        if (old_to_new_d) *old_to_new_d = s->old_to_new.p;
+        if (new_to_old_d) *new_to_old_d = s->new_to_old.p;
+    });
+}
+
+void uspmv_scs_destroy(uspmv_scs *s) { delete s; }
+
+}  // extern "C"

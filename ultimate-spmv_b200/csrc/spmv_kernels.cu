@@ -1,0 +1,466 @@
+// SpMV / SpMMV kernels for sm_100a and their C-ABI launchers.
+//
+// Replaces the reference's kernels
+//   spmv_gpu_scs / spmv_gpu_scs_adv / scs_impl_gpu<C>   code/kernels.hpp:579-775
+//   spmv_gpu_csr                                         code/kernels.hpp:631-680
+//   block_spmv_gpu_*_launcher (stubs in the reference)   code/kernels.hpp:777-844
+//   CPU semantics of the block kernels                   code/kernels.hpp:68-154,306-398
+//
+// Design (HBM-bound, CUDA cores — see DESIGN.md):
+//   * SCS: one thread per padded row, lanes of a chunk are adjacent threads, so for C >= 32/sizeof-ratio
+//     every `j` step of a warp is one fully coalesced 32*sizeof(VT) + 128 B request.  The value and
+//     column streams are read exactly once with streaming (evict-first, no L1 allocate) loads, all
+//     loads of an unrolled group of U slots are issued before the first use (memory-level
+//     parallelism), x is gathered through the read-only path so neighbouring rows share L1/L2 lines.
+//   * The per-row accumulation order is j = 0..len-1 with one fused multiply-add per slot — the same
+//     order and rounding as the reference's CPU loop (kernels.hpp:242-246 built with -O3 on an FMA
+//     machine), so dp/sp/hp results are bit-identical to the oracle, padding slots included.
+//   * hp accumulates in fp16 with product+sum formed in fp32 and rounded once per step, which is what
+//     g++ -std=c++23 emits for `_Float16 tmp += v * x` on x86 without AVX512-FP16.
+#include "common.cuh"
+
+using namespace uspmv;
+
+namespace {
+
+constexpr int TPB = 256;
+
+// ---- per-precision arithmetic --------------------------------------------------------------------
+template <typename VT> struct Arith;
+template <> struct Arith<double> {
+    using acc_t = double;
+    __device__ static __forceinline__ acc_t zero() { return 0.0; }
+    __device__ static __forceinline__ acc_t mad(double v, double x, acc_t a) { return fma(v, x, a); }
+    __device__ static __forceinline__ double out(acc_t a) { return a; }
+    __device__ static __forceinline__ acc_t add(acc_t a, acc_t b) { return a + b; }
+};
+template <> struct Arith<float> {
+    using acc_t = float;
+    __device__ static __forceinline__ acc_t zero() { return 0.0f; }
+    __device__ static __forceinline__ acc_t mad(float v, float x, acc_t a) { return fmaf(v, x, a); }
+    __device__ static __forceinline__ float out(acc_t a) { return a; }
+    __device__ static __forceinline__ acc_t add(acc_t a, acc_t b) { return a + b; }
+};
+template <> struct Arith<__half> {
+    using acc_t = __half;
+    __device__ static __forceinline__ acc_t zero() { return __float2half_rn(0.0f); }
+    __device__ static __forceinline__ acc_t mad(__half v, __half x, acc_t a) {
+        return __float2half_rn(fmaf(__half2float(v), __half2float(x), __half2float(a)));
+    }
+    __device__ static __forceinline__ __half out(acc_t a) { return a; }
+    __device__ static __forceinline__ acc_t add(acc_t a, acc_t b) { return __float2half_rn(__half2float(a) + __half2float(b)); }
+};
+
+// streaming loads for the matrix (read once), read-only cached loads for x
+template <typename T> __device__ __forceinline__ T ld_stream(const T *p) { return __ldcs(p); }
+template <typename T> __device__ __forceinline__ T ld_x(const T *p) { return __ldg(p); }
+
+// ---------------------------------------------------------------------------------------------
+// SCS SpMV.  CT > 0: compile-time chunk height; CT == 0: runtime C (any C > 0, like spmv_gpu_scs).
+// UNPERM: fused un-permuted write y[new_to_old[row]] (columns must be in original numbering).
+// ---------------------------------------------------------------------------------------------
+template <typename VT, int CT, int U, bool UNPERM>
+__global__ void __launch_bounds__(TPB)
+k_scs_spmv(long n_pad, int Crt, const int *__restrict__ chunk_ptrs, const int *__restrict__ chunk_lengths,
+           const int *__restrict__ col_idxs, const VT *__restrict__ values, const VT *__restrict__ x, VT *__restrict__ y,
+           const int *__restrict__ new_to_old) {
+    using A = Arith<VT>;
+    const long row = blockIdx.x * (long)TPB + threadIdx.x;
+    if (row >= n_pad) return;
+    const int C = CT > 0 ? CT : Crt;
+    const long c = row / C;
+    const int lane = (int)(row - c * C);
+    const int len = chunk_lengths[c];
+    long e = (long)chunk_ptrs[c] + lane;
+    typename A::acc_t acc = A::zero();
+    for (int j = 0; j < len; j += U) {
+        int col[U];
+        VT v[U], xv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (j + u < len) {
+                col[u] = ld_stream(col_idxs + e + (long)u * C);
+                v[u] = ld_stream(values + e + (long)u * C);
+            }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (j + u < len) xv[u] = ld_x(x + col[u]);
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (j + u < len) acc = A::mad(v[u], xv[u], acc);
+        e += (long)U * C;
+    }
+    if (UNPERM) {
+        const int o = new_to_old[row];
+        if (o >= 0) y[o] = A::out(acc);
+    } else
+        y[row] = A::out(acc);
+}
+
+// ---------------------------------------------------------------------------------------------
+// CRS SpMV (C = 1, sigma = 1): T adjacent lanes share one row, rows of a warp are contiguous in
+// memory so the value/column streams stay coalesced; partial sums are combined by a shuffle tree.
+// (Summation order differs from the sequential CPU loop => compared within tolerance, not bit-exact.)
+// ---------------------------------------------------------------------------------------------
+template <typename VT, int T>
+__global__ void __launch_bounds__(TPB)
+k_csr_spmv(long n_rows, const int *__restrict__ row_ptrs, const int *__restrict__ col_idxs, const VT *__restrict__ values,
+           const VT *__restrict__ x, VT *__restrict__ y) {
+    using A = Arith<VT>;
+    const long gt = blockIdx.x * (long)TPB + threadIdx.x;
+    const long row = gt / T;
+    const int t = (int)(gt % T);
+    typename A::acc_t acc = A::zero();
+    if (row < n_rows) {
+        const int beg = row_ptrs[row], end = row_ptrs[row + 1];
+        for (int j = beg + t; j < end; j += T) acc = A::mad(ld_stream(values + j), ld_x(x + ld_stream(col_idxs + j)), acc);
+    }
+#pragma unroll
+    for (int off = T / 2; off > 0; off >>= 1) {
+        typename A::acc_t other = __shfl_down_sync(0xffffffffu, acc, off, T);
+        acc = A::add(acc, other);
+    }
+    if (row < n_rows && t == 0) y[row] = A::out(acc);
+}
+
+// ---------------------------------------------------------------------------------------------
+// SpMMV: one thread per padded row, BVS accumulators in registers.
+//   rowwise: X[col*bvs + v]  — the bvs values of a gathered row are contiguous => vector loads
+//   colwise: X[col + v*ld]
+// BT > 0: compile-time block width; BT == 0: runtime bvs <= 16.
+// ---------------------------------------------------------------------------------------------
+// vectorised access to one row of a row-major block vector (BT*sizeof(VT) bytes, naturally aligned)
+template <typename VT, int BT, typename W>
+__device__ __forceinline__ void load_row_as(const VT *__restrict__ src, VT *xv) {
+    constexpr int PER = sizeof(W) / sizeof(VT);
+    const W *p = reinterpret_cast<const W *>(src);
+#pragma unroll
+    for (int k = 0; k < BT / PER; ++k) {
+        alignas(sizeof(W)) VT tmp[PER];
+        *reinterpret_cast<W *>(tmp) = __ldg(p + k);
+#pragma unroll
+        for (int m = 0; m < PER; ++m) xv[k * PER + m] = tmp[m];
+    }
+}
+
+template <typename VT, int BT, typename W>
+__device__ __forceinline__ void store_row_as(VT *__restrict__ dst, const VT *yv) {
+    constexpr int PER = sizeof(W) / sizeof(VT);
+    W *p = reinterpret_cast<W *>(dst);
+#pragma unroll
+    for (int k = 0; k < BT / PER; ++k) {
+        alignas(sizeof(W)) VT tmp[PER];
+#pragma unroll
+        for (int m = 0; m < PER; ++m) tmp[m] = yv[k * PER + m];
+        p[k] = *reinterpret_cast<W *>(tmp);
+    }
+}
+
+template <typename VT, int BT>
+__device__ __forceinline__ void load_block_row(const VT *__restrict__ X, long col, int bvs, VT *xv) {
+    constexpr int BYTES = BT * (int)sizeof(VT);
+    if constexpr (BT > 0 && BYTES % 16 == 0) load_row_as<VT, BT, int4>(X + col * BT, xv);
+    else if constexpr (BT > 0 && BYTES % 8 == 0) load_row_as<VT, BT, int2>(X + col * BT, xv);
+    else if constexpr (BT > 0 && BYTES % 4 == 0) load_row_as<VT, BT, int>(X + col * BT, xv);
+    else {
+        const int n = BT > 0 ? BT : bvs;
+#pragma unroll
+        for (int v = 0; v < (BT > 0 ? BT : 16); ++v)
+            if (v < n) xv[v] = ld_x(X + col * n + v);
+    }
+}
+
+template <typename VT, int BT>
+__device__ __forceinline__ void store_block_row(VT *__restrict__ Y, long row, int bvs, const VT *yv) {
+    constexpr int BYTES = BT * (int)sizeof(VT);
+    if constexpr (BT > 0 && BYTES % 16 == 0) store_row_as<VT, BT, int4>(Y + row * BT, yv);
+    else if constexpr (BT > 0 && BYTES % 8 == 0) store_row_as<VT, BT, int2>(Y + row * BT, yv);
+    else if constexpr (BT > 0 && BYTES % 4 == 0) store_row_as<VT, BT, int>(Y + row * BT, yv);
+    else {
+        const int n = BT > 0 ? BT : bvs;
+#pragma unroll
+        for (int v = 0; v < (BT > 0 ? BT : 16); ++v)
+            if (v < n) Y[row * n + v] = yv[v];
+    }
+}
+
+template <typename VT, int BT, int LAYOUT>
+__global__ void __launch_bounds__(TPB)
+k_scs_spmmv(long n_pad, int C, const int *__restrict__ chunk_ptrs, const int *__restrict__ chunk_lengths,
+            const int *__restrict__ col_idxs, const VT *__restrict__ values, const VT *__restrict__ X, VT *__restrict__ Y, int bvs_rt,
+            long ld) {
+    using A = Arith<VT>;
+    constexpr int NB = BT > 0 ? BT : 16;
+    const int bvs = BT > 0 ? BT : bvs_rt;
+    const long row = blockIdx.x * (long)TPB + threadIdx.x;
+    if (row >= n_pad) return;
+    const long c = row / C;
+    const int lane = (int)(row - c * C);
+    const int len = chunk_lengths[c];
+    long e = (long)chunk_ptrs[c] + lane;
+    typename A::acc_t acc[NB];
+#pragma unroll
+    for (int v = 0; v < NB; ++v) acc[v] = A::zero();
+    for (int j = 0; j < len; ++j, e += C) {
+        const int col = ld_stream(col_idxs + e);
+        const VT val = ld_stream(values + e);
+        VT xv[NB];
+        if (LAYOUT == USPMV_ROWWISE) {
+            load_block_row<VT, BT>(X, (long)col, bvs, xv);
+        } else {
+#pragma unroll
+            for (int v = 0; v < NB; ++v)
+                if (v < bvs) xv[v] = ld_x(X + col + v * ld);
+        }
+#pragma unroll
+        for (int v = 0; v < NB; ++v)
+            if (v < bvs) acc[v] = A::mad(val, xv[v], acc[v]);
+    }
+    if (LAYOUT == USPMV_ROWWISE) {
+        VT yv[NB];
+#pragma unroll
+        for (int v = 0; v < NB; ++v) yv[v] = A::out(acc[v]);
+        store_block_row<VT, BT>(Y, row, bvs, yv);
+    } else {
+#pragma unroll
+        for (int v = 0; v < NB; ++v)
+            if (v < bvs) Y[row + v * ld] = A::out(acc[v]);
+    }
+}
+
+// ---- launch helpers ----------------------------------------------------------------------------
+inline unsigned blocks_for(long n) { return (unsigned)((n + TPB - 1) / TPB); }
+
+template <typename VT, bool UNPERM>
+void launch_scs(long C, long n_chunks, const int *cp, const int *cl, const int *ci, const void *vals, const void *x, void *y,
+                const int *n2o, cudaStream_t st) {
+    const long n_pad = n_chunks * C;
+    if (n_pad == 0) return;
+    const VT *v = static_cast<const VT *>(vals);
+    const VT *xx = static_cast<const VT *>(x);
+    VT *yy = static_cast<VT *>(y);
+    const unsigned g = blocks_for(n_pad);
+#define USPMV_SCS_CASE(CC)                                                                                              \
+    case CC: k_scs_spmv<VT, CC, 8, UNPERM><<<g, TPB, 0, st>>>(n_pad, (int)C, cp, cl, ci, v, xx, yy, n2o); break;
+    switch (C) {
+        USPMV_SCS_CASE(1)
+        USPMV_SCS_CASE(2)
+        USPMV_SCS_CASE(4)
+        USPMV_SCS_CASE(8)
+        USPMV_SCS_CASE(16)
+        USPMV_SCS_CASE(32)
+        USPMV_SCS_CASE(64)
+        USPMV_SCS_CASE(128)
+        USPMV_SCS_CASE(256)
+    default: k_scs_spmv<VT, 0, 8, UNPERM><<<g, TPB, 0, st>>>(n_pad, (int)C, cp, cl, ci, v, xx, yy, n2o);
+    }
+#undef USPMV_SCS_CASE
+    USPMV_LAUNCH_CHECK();
+}
+
+template <typename VT>
+void launch_csr(long n_rows, long nnz_hint, const int *rp, const int *ci, const void *vals, const void *x, void *y, cudaStream_t st) {
+    if (n_rows == 0) return;
+    const VT *v = static_cast<const VT *>(vals);
+    const VT *xx = static_cast<const VT *>(x);
+    VT *yy = static_cast<VT *>(y);
+    const double avg = nnz_hint >= 0 ? (double)nnz_hint / (double)n_rows : 8.0;
+    int T = 2;
+    while (T < 32 && T < avg) T *= 2;
+    const unsigned g = blocks_for(n_rows * T);
+    switch (T) {
+    case 2: k_csr_spmv<VT, 2><<<g, TPB, 0, st>>>(n_rows, rp, ci, v, xx, yy); break;
+    case 4: k_csr_spmv<VT, 4><<<g, TPB, 0, st>>>(n_rows, rp, ci, v, xx, yy); break;
+    case 8: k_csr_spmv<VT, 8><<<g, TPB, 0, st>>>(n_rows, rp, ci, v, xx, yy); break;
+    case 16: k_csr_spmv<VT, 16><<<g, TPB, 0, st>>>(n_rows, rp, ci, v, xx, yy); break;
+    default: k_csr_spmv<VT, 32><<<g, TPB, 0, st>>>(n_rows, rp, ci, v, xx, yy); break;
+    }
+    USPMV_LAUNCH_CHECK();
+}
+
+template <typename VT, int LAYOUT>
+void launch_spmmv_l(const uspmv_scs *s, const void *X, void *Y, int bvs, long ld, cudaStream_t st) {
+    const long n_pad = s->n_rows_padded;
+    if (n_pad == 0) return;
+    const VT *v = reinterpret_cast<const VT *>(s->values.p);
+    const VT *xx = static_cast<const VT *>(X);
+    VT *yy = static_cast<VT *>(Y);
+    const unsigned g = blocks_for(n_pad);
+    const int C = (int)s->C;
+#define USPMV_MMV_CASE(BB)                                                                                                      \
+    case BB: k_scs_spmmv<VT, BB, LAYOUT><<<g, TPB, 0, st>>>(n_pad, C, s->chunk_ptrs.p, s->chunk_lengths.p, s->col_idxs.p, v, xx, yy, \
+                                                           bvs, ld); break;
+    switch (bvs) {
+        USPMV_MMV_CASE(2)
+        USPMV_MMV_CASE(4)
+        USPMV_MMV_CASE(8)
+        USPMV_MMV_CASE(16)
+    default: k_scs_spmmv<VT, 0, LAYOUT><<<g, TPB, 0, st>>>(n_pad, C, s->chunk_ptrs.p, s->chunk_lengths.p, s->col_idxs.p, v, xx, yy, bvs, ld);
+    }
+#undef USPMV_MMV_CASE
+    USPMV_LAUNCH_CHECK();
+}
+
+template <typename VT>
+void launch_spmmv(const uspmv_scs *s, const void *X, void *Y, int bvs, long ld, int layout, cudaStream_t st) {
+    if (layout == USPMV_ROWWISE) launch_spmmv_l<VT, USPMV_ROWWISE>(s, X, Y, bvs, ld, st);
+    else launch_spmmv_l<VT, USPMV_COLWISE>(s, X, Y, bvs, ld, st);
+}
+
+// ---- permutation kernels -----------------------------------------------------------------------
+template <typename VT>
+__global__ void k_apply_perm(VT *__restrict__ out, const VT *__restrict__ in, const int *__restrict__ perm, long n) {
+    long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int p = perm[i];
+    out[i] = p >= 0 ? in[p] : VT(0.0);
+}
+
+template <typename VT>
+__global__ void k_apply_perm_block(VT *__restrict__ out, const VT *__restrict__ in, const int *__restrict__ perm, long n, int bvs,
+                                   long ld, int layout) {
+    long t = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (t >= n * bvs) return;
+    long i, v;
+    if (layout == USPMV_ROWWISE) { i = t / bvs; v = t % bvs; }
+    else { v = t / n; i = t % n; }
+    int p = perm[i];
+    VT val = VT(0.0);
+    if (p >= 0) val = layout == USPMV_ROWWISE ? in[(long)p * bvs + v] : in[(long)p + v * ld];
+    if (layout == USPMV_ROWWISE) out[i * bvs + v] = val;
+    else out[i + v * ld] = val;
+}
+
+}  // namespace
+
+extern "C" {
+
+int uspmv_scs_gpu(uspmv_ctx *ctx, int vt, long C, long n_chunks, const int *cp, const int *cl, const int *ci, const void *vals,
+                  const void *x, void *y, void *stream) {
+    return guarded([&] {
+        if (!ctx) fail("uspmv_scs_gpu: ctx is NULL");
+        if (C < 1) fail("uspmv_scs_gpu: C must be >= 1");
+        cudaStream_t st = as_stream(stream);
+        switch (vt) {
+        case USPMV_F64: launch_scs<double, false>(C, n_chunks, cp, cl, ci, vals, x, y, nullptr, st); break;
+        case USPMV_F32: launch_scs<float, false>(C, n_chunks, cp, cl, ci, vals, x, y, nullptr, st); break;
+        case USPMV_F16: launch_scs<__half, false>(C, n_chunks, cp, cl, ci, vals, x, y, nullptr, st); break;
+        default: fail("uspmv_scs_gpu: invalid value type %d", vt);
+        }
+    });
+}
+
+int uspmv_csr_gpu(uspmv_ctx *ctx, int vt, long n_rows, const int *rp, const int *ci, const void *vals, const void *x, void *y,
+                  void *stream) {
+    return guarded([&] {
+        if (!ctx) fail("uspmv_csr_gpu: ctx is NULL");
+        cudaStream_t st = as_stream(stream);
+        switch (vt) {
+        case USPMV_F64: launch_csr<double>(n_rows, -1, rp, ci, vals, x, y, st); break;
+        case USPMV_F32: launch_csr<float>(n_rows, -1, rp, ci, vals, x, y, st); break;
+        case USPMV_F16: launch_csr<__half>(n_rows, -1, rp, ci, vals, x, y, st); break;
+        default: fail("uspmv_csr_gpu: invalid value type %d", vt);
+        }
+    });
+}
+
+int uspmv_spmv(const uspmv_scs *s, const void *x, void *y, void *stream) {
+    return guarded([&] {
+        if (!s) fail("uspmv_spmv: scs is NULL");
+        if (s->n_rows_padded && (!x || !y)) fail("uspmv_spmv: NULL vector");
+        cudaStream_t st = as_stream(stream);
+        const bool crs = (s->C == 1 && s->sigma == 1);  // execute_uspmv's rule, interface.hpp:1911
+        switch (s->vt) {
+        case USPMV_F64:
+            if (crs) launch_csr<double>(s->n_rows, s->nnz, s->chunk_ptrs.p, s->col_idxs.p, s->values.p, x, y, st);
+            else launch_scs<double, false>(s->C, s->n_chunks, s->chunk_ptrs.p, s->chunk_lengths.p, s->col_idxs.p, s->values.p, x, y, nullptr, st);
+            break;
+        case USPMV_F32:
+            if (crs) launch_csr<float>(s->n_rows, s->nnz, s->chunk_ptrs.p, s->col_idxs.p, s->values.p, x, y, st);
+            else launch_scs<float, false>(s->C, s->n_chunks, s->chunk_ptrs.p, s->chunk_lengths.p, s->col_idxs.p, s->values.p, x, y, nullptr, st);
+            break;
+        default:
+            if (crs) launch_csr<__half>(s->n_rows, s->nnz, s->chunk_ptrs.p, s->col_idxs.p, s->values.p, x, y, st);
+            else launch_scs<__half, false>(s->C, s->n_chunks, s->chunk_ptrs.p, s->chunk_lengths.p, s->col_idxs.p, s->values.p, x, y, nullptr, st);
+        }
+    });
+}
+
+int uspmv_spmv_unpermuted(const uspmv_scs *s, const void *x, void *y, void *stream) {
+    return guarded([&] {
+        if (!s) fail("uspmv_spmv_unpermuted: scs is NULL");
+        if (s->cols_permuted) fail("uspmv_spmv_unpermuted: columns were already permuted (permute_scs_cols); use uspmv_spmv");
+        cudaStream_t st = as_stream(stream);
+        switch (s->vt) {
+        case USPMV_F64: launch_scs<double, true>(s->C, s->n_chunks, s->chunk_ptrs.p, s->chunk_lengths.p, s->col_idxs.p, s->values.p, x, y, s->new_to_old.p, st); break;
+        case USPMV_F32: launch_scs<float, true>(s->C, s->n_chunks, s->chunk_ptrs.p, s->chunk_lengths.p, s->col_idxs.p, s->values.p, x, y, s->new_to_old.p, st); break;
+        default: launch_scs<__half, true>(s->C, s->n_chunks, s->chunk_ptrs.p, s->chunk_lengths.p, s->col_idxs.p, s->values.p, x, y, s->new_to_old.p, st);
+        }
+    });
+}
+
+int uspmv_spmmv(const uspmv_scs *s, const void *X, void *Y, int bvs, long vec_length, int layout, void *stream) {
+    return guarded([&] {
+        if (!s) fail("uspmv_spmmv: scs is NULL");
+        if (bvs < 1 || bvs > 16) fail("uspmv_spmmv: block_vec_size must be in [1,16] (got %d)", bvs);
+        if (layout != USPMV_COLWISE && layout != USPMV_ROWWISE) fail("uspmv_spmmv: invalid layout %d", layout);
+        if (layout == USPMV_COLWISE && vec_length < s->n_rows_padded) fail("uspmv_spmmv: vec_length %ld < n_rows_padded %ld", vec_length, s->n_rows_padded);
+        cudaStream_t st = as_stream(stream);
+        switch (s->vt) {
+        case USPMV_F64: launch_spmmv<double>(s, X, Y, bvs, vec_length, layout, st); break;
+        case USPMV_F32: launch_spmmv<float>(s, X, Y, bvs, vec_length, layout, st); break;
+        default: launch_spmmv<__half>(s, X, Y, bvs, vec_length, layout, st);
+        }
+    });
+}
+
+int uspmv_spmv_host(const uspmv_scs *s_, const void *x_h, long x_len, void *y_h, long y_len) {
+    return guarded([&] {
+        uspmv_scs *s = const_cast<uspmv_scs *>(s_);
+        if (!s || !x_h || !y_h) fail("uspmv_spmv_host: NULL argument");
+        if (y_len < s->n_rows_padded) fail("uspmv_spmv_host: y_len %ld < n_rows_padded %ld", y_len, s->n_rows_padded);
+        USPMV_CUDA(cudaSetDevice(s->ctx->device));
+        const size_t es = vt_size(s->vt);
+        if (s->h2d_stage_x.n < (size_t)x_len * es) s->h2d_stage_x.alloc((size_t)x_len * es);
+        if (s->d2h_stage_y.n < (size_t)s->n_rows_padded * es) s->d2h_stage_y.alloc((size_t)s->n_rows_padded * es);
+        USPMV_CUDA(cudaMemcpyAsync(s->h2d_stage_x.p, x_h, (size_t)x_len * es, cudaMemcpyHostToDevice, 0));
+        if (uspmv_spmv(s, s->h2d_stage_x.p, s->d2h_stage_y.p, nullptr)) throw Error(uspmv_last_error());
+        USPMV_CUDA(cudaMemcpyAsync(y_h, s->d2h_stage_y.p, (size_t)s->n_rows_padded * es, cudaMemcpyDeviceToHost, 0));
+        USPMV_CUDA(cudaStreamSynchronize(0));
+    });
+}
+
+int uspmv_apply_permutation(uspmv_ctx *ctx, void *out, const void *in, const int *perm, long n, int vt, void *stream) {
+    return guarded([&] {
+        if (!ctx) fail("uspmv_apply_permutation: ctx is NULL");
+        if (n == 0) return;
+        cudaStream_t st = as_stream(stream);
+        const unsigned g = blocks_for(n);
+        switch (vt) {
+        case USPMV_F64: k_apply_perm<double><<<g, TPB, 0, st>>>((double *)out, (const double *)in, perm, n); break;
+        case USPMV_F32: k_apply_perm<float><<<g, TPB, 0, st>>>((float *)out, (const float *)in, perm, n); break;
+        case USPMV_F16: k_apply_perm<__half><<<g, TPB, 0, st>>>((__half *)out, (const __half *)in, perm, n); break;
+        default: fail("uspmv_apply_permutation: invalid value type %d", vt);
+        }
+        USPMV_LAUNCH_CHECK();
+    });
+}
+
+int uspmv_apply_permutation_block(uspmv_ctx *ctx, void *out, const void *in, const int *perm, long n, int vt, int bvs, long ld,
+                                  int layout, void *stream) {
+    return guarded([&] {
+        if (!ctx) fail("uspmv_apply_permutation_block: ctx is NULL");
+        if (n == 0 || bvs == 0) return;
+        cudaStream_t st = as_stream(stream);
+        const unsigned g = blocks_for(n * bvs);
+        switch (vt) {
+        case USPMV_F64: k_apply_perm_block<double><<<g, TPB, 0, st>>>((double *)out, (const double *)in, perm, n, bvs, ld, layout); break;
+        case USPMV_F32: k_apply_perm_block<float><<<g, TPB, 0, st>>>((float *)out, (const float *)in, perm, n, bvs, ld, layout); break;
+        case USPMV_F16: k_apply_perm_block<__half><<<g, TPB, 0, st>>>((__half *)out, (const __half *)in, perm, n, bvs, ld, layout); break;
+        default: fail("uspmv_apply_permutation_block: invalid value type %d", vt);
+        }
+        USPMV_LAUNCH_CHECK();
+    });
+}
+
+}  // extern "C"

@@ -42,6 +42,11 @@ const char *uspmv_last_error(void);
 int uspmv_version(void);
 /* number of this library's kernel launches since load (bench.py's "gpu_launches" claim) */
 long uspmv_kernel_launches(void);
+/* Kernel-selection knobs (no reference counterpart; THREADS_PER_BLOCK is the closest, config.mk:20):
+ *   "scs_stream" 0/1          C = 32: bulk-copy (TMA) streamed kernel (default 1) or the direct-load kernel
+ *   "stream_variant" 0..5     (slots per piece, ring depth, warps per CTA) instantiation
+ *   "stream_blocks_per_sm"    persistent CTAs per SM */
+int uspmv_set_option(const char *name, long value);
 
 /* ---- context and device memory --------------------------------------------------------------- */
 /* cudaSetDevice(rank % ndev) in the reference: main.cpp:1838-1842 */

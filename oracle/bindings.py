@@ -55,6 +55,15 @@ class Oracle:
         self.lib = L = C.CDLL(path)
         L.orc_scs_structure.restype = C.c_long
         L.orc_collect_halo.restype = C.c_long
+        L.orc_stencil_coo.restype = C.c_long
+
+    def stencil_coo(self, points, nx, ny, nz, row0=0, row1=None):
+        row1 = nx * ny * nz if row1 is None else row1
+        args = (C.c_int(points), C.c_long(nx), C.c_long(ny), C.c_long(nz), C.c_long(row0), C.c_long(row1))
+        nnz = self.lib.orc_stencil_coo(*args, None, None, None)
+        I, J, V = np.empty(nnz, np.int32), np.empty(nnz, np.int32), np.empty(nnz, np.float64)
+        self.lib.orc_stencil_coo(*args, _p(I), _p(J), _p(V))
+        return row1 - row0, nx * ny * nz, I, J, V
 
     # -- std::sort restatement ---------------------------------------------------------------
     def sort_window(self, cnt):

@@ -529,3 +529,35 @@ long orc_collect_halo(long n_elements, int *col_idxs, const int *wsa, int rank, 
 void orc_pack_f64(long n, const int *send_idxs, const int *perm, const double *x, double *buf) {
     for (long i = 0; i < n; ++i) buf[i] = x[perm[send_idxs[i]]];
 }
+
+/* Synthetic stencil COO (BASELINE.json configs 2/3/5): rows [row0,row1) of an nx*ny*nz
+ * grid, row = (z*ny + y)*nx + x, columns ascending, Dirichlet, diagonal = points-1, off-diagonals -1; local row
+ * ids, global column ids.  Call with I == NULL to get the count.  Used to feed the reference's own builder in
+ * bench.py's CPU legs; the product has its own device generator (uspmv_coo_stencil). */
+long orc_stencil_coo(int points, long nx, long ny, long nz, long row0, long row1, int *I, int *J, double *V) {
+    long o = 0;
+    for (long g = row0; g < row1; ++g) {
+        long x = g % nx, y = (g / nx) % ny, z = g / (nx * ny);
+        for (int dz = -1; dz <= 1; ++dz) {
+            long zz = z + dz;
+            if (zz < 0 || zz >= nz) continue;
+            for (int dy = -1; dy <= 1; ++dy) {
+                long yy = y + dy;
+                if (yy < 0 || yy >= ny) continue;
+                for (int dx = -1; dx <= 1; ++dx) {
+                    long xx = x + dx;
+                    if (xx < 0 || xx >= nx) continue;
+                    int nzd = (dx != 0) + (dy != 0) + (dz != 0);
+                    if (points == 7 && nzd > 1) continue;
+                    if (I) {
+                        I[o] = (int)(g - row0);
+                        J[o] = (int)((zz * ny + yy) * nx + xx);
+                        V[o] = nzd == 0 ? (double)(points - 1) : -1.0;
+                    }
+                    ++o;
+                }
+            }
+        }
+    }
+    return o;
+}

@@ -33,6 +33,7 @@ lib.uspmv_kernel_launches.restype = C.c_long
 
 vp = C.c_void_p
 _sigs = {
+    "uspmv_set_option": [C.c_char_p, C.c_long],
     "uspmv_ctx_create": [C.c_int, C.POINTER(vp)],
     "uspmv_ctx_sync": [vp],
     "uspmv_malloc": [vp, C.c_size_t, C.POINTER(vp)],
@@ -88,6 +89,10 @@ def check(rc: int) -> None:
 
 def call(name: str, *args) -> None:
     check(getattr(lib, name)(*args))
+
+
+def set_option(name: str, value: int) -> None:
+    call("uspmv_set_option", name.encode(), int(value))
 
 
 def kernel_launches() -> int:

@@ -1,0 +1,192 @@
+// SELL-32-sigma SpMV for sm_100a with the matrix streamed through shared memory by the bulk-copy (TMA) engine.
+//
+// Why: a thread-per-row kernel that loads values/columns straight into registers is latency-bound on B200
+// (ncu r01a: 45 % occupancy, 90 % "no eligible warp", 2.4 TB/s) because the bytes in flight are tied to
+// registers x resident threads and every thread walks a 3-deep dependent chain (chunk meta -> col/val -> x).
+// Here each warp owns a private ring of D shared-memory stages that lane 0 keeps full with
+// `cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes` copies (SASS: UBLKCP), so the matrix
+// stream (the 84 % of the traffic that is perfectly contiguous: a chunk's values and column indices are
+// `len*32` consecutive elements) is decoupled from the register file; the lanes only do shared-memory reads,
+// the x gathers and the fused multiply-adds.  In-flight bytes per SM = warps x D x piece size (~170 KB).
+//
+// Work split: warp gw takes chunks gw, gw + W, gw + 2W, ... (W = warps in the grid), so all SMs advance as one
+// front over the rows and the x lines shared by neighbouring chunks are hit in L1/L2 (measured DRAM traffic ==
+// algorithmic bytes).  A chunk of length len is cut into pieces of <= LMAX slots (contiguous because SELL
+// chunks are slot-major); piece headers {ns, chunk, first/last} live next to the stage.  Per-row accumulation
+// order is j = 0..len-1 with one FMA per slot: bit-identical to the direct kernel and to the oracle.
+#pragma once
+#include <cstdint>
+
+namespace uspmv {
+namespace stream {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+// global -> shared bulk copy (bytes % 16 == 0, both addresses 16 B aligned), completion on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst_smem)),
+        "l"(__cvta_generic_to_global(src_gmem)), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+
+struct PieceHdr {
+    int ns;     // slots in this piece (0 with flags != 0: empty chunk; flags == 0 && ns == 0: end of stream)
+    int flags;  // bit0 first piece of the chunk, bit1 last piece, bit2 valid
+    int chunk;
+    int pad;
+};
+
+template <typename VT, int LMAX, int D>
+struct WarpRing {
+    static constexpr int STAGE_ELEMS = LMAX * 32;
+    static constexpr int VAL_BYTES = STAGE_ELEMS * (int)sizeof(VT);
+    static constexpr int COL_BYTES = STAGE_ELEMS * 4;
+    static constexpr int STAGE_BYTES = VAL_BYTES + COL_BYTES;
+    static constexpr int BYTES = D * STAGE_BYTES + D * 8 + D * (int)sizeof(PieceHdr);  // stages + mbarriers + headers
+    static constexpr int BYTES_ALIGNED = (BYTES + 127) / 128 * 128;
+};
+
+template <typename VT, typename A, int LMAX, int D, int WARPS, bool UNPERM>
+__global__ void __launch_bounds__(WARPS * 32)
+k_scs32_stream(long n_chunks, const int *__restrict__ chunk_ptrs, const int *__restrict__ chunk_lengths,
+               const int *__restrict__ col_idxs, const VT *__restrict__ values, const VT *__restrict__ x, VT *__restrict__ y,
+               const int *__restrict__ new_to_old) {
+    using R = WarpRing<VT, LMAX, D>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char *base = smem_raw + (size_t)warp * R::BYTES_ALIGNED;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(base + D * R::STAGE_BYTES);
+    PieceHdr *hdrs = reinterpret_cast<PieceHdr *>(base + D * R::STAGE_BYTES + D * 8);
+
+    const long W = (long)gridDim.x * WARPS;
+    const long gw = (long)blockIdx.x * WARPS + warp;
+
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < D; ++s) mbar_init(&bars[s], 1);
+        fence_barrier_init();
+    }
+    __syncwarp();
+    const uint64_t pol = policy_evict_first();
+
+    // ---- producer state (meaningful in lane 0 only) --------------------------------------------------
+    long pc = gw;  // chunk of the next piece
+    int pj = 0, plen = 0, pcs = 0;
+    if (lane == 0 && pc < n_chunks) {
+        plen = chunk_lengths[pc];
+        pcs = chunk_ptrs[pc];
+    }
+    auto issue = [&](int s) {  // lane 0: fill stage s with the next piece of this warp's stream
+        PieceHdr h;
+        if (pc >= n_chunks) {
+            h.ns = 0; h.flags = 0; h.chunk = 0; h.pad = 0;
+            hdrs[s] = h;
+            return;
+        }
+        const int ns = min(LMAX, plen - pj);
+        h.ns = ns;
+        h.flags = 4 | (pj == 0 ? 1 : 0) | (pj + ns >= plen ? 2 : 0);
+        h.chunk = (int)pc;
+        h.pad = 0;
+        hdrs[s] = h;
+        if (ns > 0) {
+            const long e0 = (long)pcs + (long)pj * 32;
+            const uint32_t vb = (uint32_t)ns * 32u * (uint32_t)sizeof(VT), cb = (uint32_t)ns * 128u;
+            unsigned char *st = base + s * R::STAGE_BYTES;
+            mbar_expect_tx(&bars[s], vb + cb);
+            bulk_g2s(st, values + e0, vb, &bars[s], pol);
+            bulk_g2s(st + R::VAL_BYTES, col_idxs + e0, cb, &bars[s], pol);
+        }
+        pj += ns;
+        if (pj >= plen) {
+            pc += W;
+            pj = 0;
+            if (pc < n_chunks) {
+                plen = chunk_lengths[pc];
+                pcs = chunk_ptrs[pc];
+            }
+        }
+    };
+
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < D; ++s) issue(s);
+    }
+    __syncwarp();
+
+    // ---- consumer -----------------------------------------------------------------------------------------
+    uint32_t phase_bits = 0;  // one parity bit per stage, flipped after every completed wait
+    typename A::acc_t acc = A::zero();
+    for (int s = 0;; s = (s + 1 == D) ? 0 : s + 1) {
+        const PieceHdr h = hdrs[s];
+        if (h.flags == 0) break;
+        if (h.flags & 1) acc = A::zero();
+        if (h.ns > 0) {
+            mbar_wait(&bars[s], (phase_bits >> s) & 1u);
+            phase_bits ^= (1u << s);
+            const VT *sv = reinterpret_cast<const VT *>(base + s * R::STAGE_BYTES) + lane;
+            const int *sc = reinterpret_cast<const int *>(base + s * R::STAGE_BYTES + R::VAL_BYTES) + lane;
+            VT v[LMAX], xv[LMAX];
+            int col[LMAX];
+#pragma unroll
+            for (int j = 0; j < LMAX; ++j)
+                if (j < h.ns) col[j] = sc[j * 32];
+#pragma unroll
+            for (int j = 0; j < LMAX; ++j)
+                if (j < h.ns) xv[j] = __ldg(x + col[j]);
+#pragma unroll
+            for (int j = 0; j < LMAX; ++j)
+                if (j < h.ns) v[j] = sv[j * 32];
+#pragma unroll
+            for (int j = 0; j < LMAX; ++j)
+                if (j < h.ns) acc = A::mad(v[j], xv[j], acc);
+        }
+        if (h.flags & 2) {
+            const long row = (long)h.chunk * 32 + lane;
+            if (UNPERM) {
+                const int o = new_to_old[row];
+                if (o >= 0) y[o] = A::out(acc);
+            } else
+                y[row] = A::out(acc);
+        }
+        __syncwarp();  // every lane is done with stage s (data and header) before it is refilled
+        if (lane == 0) issue(s);
+        __syncwarp();
+    }
+}
+
+}  // namespace stream
+}  // namespace uspmv

@@ -18,6 +18,10 @@
 //   * hp accumulates in fp16 with product+sum formed in fp32 and rounded once per step, which is what
 //     g++ -std=c++23 emits for `_Float16 tmp += v * x` on x86 without AVX512-FP16.
 #include "common.cuh"
+#include "scs_stream.cuh"
+
+#include <cstdlib>
+#include <cstring>
 
 using namespace uspmv;
 
@@ -231,6 +235,61 @@ k_scs_spmmv(long n_pad, int C, const int *__restrict__ chunk_ptrs, const int *__
 // ---- launch helpers ----------------------------------------------------------------------------
 inline unsigned blocks_for(long n) { return (unsigned)((n + TPB - 1) / TPB); }
 
+// ---- C = 32: bulk-copy (TMA) streamed kernel, see scs_stream.cuh -----------------------------------------
+struct StreamCfg {
+    int variant;         // index into the instantiated (LMAX, D, WARPS) table
+    int blocks_per_sm;   // persistent CTAs per SM
+    bool enabled;
+};
+
+inline StreamCfg &stream_cfg() {
+    static StreamCfg cfg = [] {
+        StreamCfg c{0, 2, true};
+        if (const char *e = std::getenv("USPMV_SCS_KERNEL")) c.enabled = std::strcmp(e, "direct") != 0;
+        if (const char *e = std::getenv("USPMV_STREAM_VARIANT")) c.variant = std::atoi(e);
+        if (const char *e = std::getenv("USPMV_STREAM_BPS")) c.blocks_per_sm = std::max(1, std::atoi(e));
+        return c;
+    }();
+    return cfg;
+}
+
+template <typename VT, bool UNPERM, int LMAX, int D, int WARPS>
+void launch_stream_v(long n_chunks, const int *cp, const int *cl, const int *ci, const VT *v, const VT *x, VT *y, const int *n2o,
+                     cudaStream_t st, int bps) {
+    using R = stream::WarpRing<VT, LMAX, D>;
+    auto kern = stream::k_scs32_stream<VT, Arith<VT>, LMAX, D, WARPS, UNPERM>;
+    constexpr int smem = WARPS * R::BYTES_ALIGNED;
+    static bool configured = false;
+    if (!configured) {
+        USPMV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    int dev = 0;
+    USPMV_CUDA(cudaGetDevice(&dev));
+    long grid = (long)sm_count(dev) * bps;
+    const long need = (n_chunks + WARPS - 1) / WARPS;
+    if (grid > need) grid = need;
+    kern<<<(unsigned)grid, WARPS * 32, smem, st>>>(n_chunks, cp, cl, ci, v, x, y, n2o);
+}
+
+template <typename VT, bool UNPERM>
+void launch_stream(long n_chunks, const int *cp, const int *cl, const int *ci, const VT *v, const VT *x, VT *y, const int *n2o,
+                   cudaStream_t st) {
+    const StreamCfg c = stream_cfg();
+    switch (c.variant) {
+    case 1: launch_stream_v<VT, UNPERM, 8, 3, 8>(n_chunks, cp, cl, ci, v, x, y, n2o, st, c.blocks_per_sm); break;
+    case 2: launch_stream_v<VT, UNPERM, 8, 4, 8>(n_chunks, cp, cl, ci, v, x, y, n2o, st, c.blocks_per_sm); break;
+    case 3: launch_stream_v<VT, UNPERM, 4, 4, 16>(n_chunks, cp, cl, ci, v, x, y, n2o, st, c.blocks_per_sm); break;
+    case 4: launch_stream_v<VT, UNPERM, 4, 3, 16>(n_chunks, cp, cl, ci, v, x, y, n2o, st, c.blocks_per_sm); break;
+    case 5: launch_stream_v<VT, UNPERM, 4, 2, 16>(n_chunks, cp, cl, ci, v, x, y, n2o, st, c.blocks_per_sm); break;
+    case 6: launch_stream_v<VT, UNPERM, 8, 2, 8>(n_chunks, cp, cl, ci, v, x, y, n2o, st, c.blocks_per_sm); break;
+    case 7: launch_stream_v<VT, UNPERM, 16, 2, 8>(n_chunks, cp, cl, ci, v, x, y, n2o, st, c.blocks_per_sm); break;
+    case 8: launch_stream_v<VT, UNPERM, 8, 2, 32>(n_chunks, cp, cl, ci, v, x, y, n2o, st, c.blocks_per_sm); break;
+    case 9: launch_stream_v<VT, UNPERM, 2, 4, 16>(n_chunks, cp, cl, ci, v, x, y, n2o, st, c.blocks_per_sm); break;
+    default: launch_stream_v<VT, UNPERM, 8, 2, 16>(n_chunks, cp, cl, ci, v, x, y, n2o, st, c.blocks_per_sm); break;
+    }
+}
+
 template <typename VT, bool UNPERM>
 void launch_scs(long C, long n_chunks, const int *cp, const int *cl, const int *ci, const void *vals, const void *x, void *y,
                 const int *n2o, cudaStream_t st) {
@@ -239,6 +298,11 @@ void launch_scs(long C, long n_chunks, const int *cp, const int *cl, const int *
     const VT *v = static_cast<const VT *>(vals);
     const VT *xx = static_cast<const VT *>(x);
     VT *yy = static_cast<VT *>(y);
+    if (C == 32 && stream_cfg().enabled) {
+        launch_stream<VT, UNPERM>(n_chunks, cp, cl, ci, v, xx, yy, n2o, st);
+        USPMV_LAUNCH_CHECK();
+        return;
+    }
     const unsigned g = blocks_for(n_pad);
 #define USPMV_SCS_CASE(CC)                                                                                              \
     case CC: k_scs_spmv<VT, CC, 8, UNPERM><<<g, TPB, 0, st>>>(n_pad, (int)C, cp, cl, ci, v, xx, yy, n2o); break;
@@ -334,6 +398,17 @@ __global__ void k_apply_perm_block(VT *__restrict__ out, const VT *__restrict__ 
 }  // namespace
 
 extern "C" {
+
+int uspmv_set_option(const char *name, long value) {
+    return guarded([&] {
+        if (!name) fail("uspmv_set_option: name is NULL");
+        StreamCfg &c = stream_cfg();
+        if (!std::strcmp(name, "scs_stream")) c.enabled = value != 0;
+        else if (!std::strcmp(name, "stream_variant")) c.variant = (int)value;
+        else if (!std::strcmp(name, "stream_blocks_per_sm")) c.blocks_per_sm = (int)std::max(1L, value);
+        else fail("uspmv_set_option: unknown option '%s'", name);
+    });
+}
 
 int uspmv_scs_gpu(uspmv_ctx *ctx, int vt, long C, long n_chunks, const int *cp, const int *cl, const int *ci, const void *vals,
                   const void *x, void *y, void *stream) {

@@ -66,7 +66,7 @@ class Context:
         call("uspmv_ctx_sync", self.h)
 
     def __del__(self):
-        if getattr(self, "h", None):
+        if getattr(self, "h", None) and capi is not None:
             capi.lib.uspmv_ctx_destroy(self.h)
             self.h = None
 
@@ -121,7 +121,7 @@ class MtxData:
         return I, J, V
 
     def __del__(self):
-        if getattr(self, "h", None):
+        if getattr(self, "h", None) and capi is not None:
             capi.lib.uspmv_coo_destroy(self.h)
             self.h = None
 
@@ -156,7 +156,7 @@ class ScsData:
         return dict(zip(("chunk_ptrs", "chunk_lengths", "col_idxs", "values", "old_to_new", "new_to_old"), ptrs))
 
     def __del__(self):
-        if getattr(self, "h", None):
+        if getattr(self, "h", None) and capi is not None:
             capi.lib.uspmv_scs_destroy(self.h)
             self.h = None
 
@@ -290,3 +290,69 @@ class SpmvKernel:
     def swap_local_vectors(x, y):
         """classes_structs.hpp:1130-1165: y becomes the next x."""
         return y, x
+
+
+def spmv_host_ptr(scs: ScsData, x_ptr: int, x_len: int, y_ptr: int, y_len: int) -> None:
+    """uspmv_spmv_host on raw host addresses (e.g. pinned torch tensors)."""
+    call("uspmv_spmv_host", scs.h, vp(x_ptr), int(x_len), vp(y_ptr), int(y_len))
+
+
+class SingleGpuSpmv:
+    """bench.py's N = 1 runner: stencil matrix generated and converted on the device, the harness' bench-mode
+    protocol (bench_spmv, main.cpp:380-527): x = 5.0 in permuted space, repeated execute()."""
+
+    kernel_name = "k_scs32_stream"
+
+    def __init__(self, ctx: Context, points: int, n: int, C_: int, sigma: int, vt: str):
+        t = _torch()
+        self.ctx = ctx
+        mtx = MtxData.stencil(points, n, n, n, ctx=ctx)
+        if vt != "dp":  # the stencil generator emits doubles; convert_to_scs narrows (MT -> VT)
+            pass
+        self.scs = convert_to_scs(mtx, C_, sigma, vt)
+        permute_scs_cols(self.scs)
+        del mtx
+        s = self.scs
+        self.nnz, self.n_elements, self.n_chunks = s.nnz, s.n_elements, s.n_chunks
+        self.n_rows, self.n_rows_padded, self.n_cols_local, self.n_halo = s.n_rows, s.n_rows_padded, s.n_cols, 0
+        dt = torch_dtype(s.vt)
+        self.x = t.full((max(s.n_rows_padded, s.n_cols),), 5.0, dtype=dt, device=f"cuda:{ctx.device}")
+        self.y = t.zeros(s.n_rows_padded, dtype=dt, device=f"cuda:{ctx.device}")
+        self.e2e_h2d_bytes = self.x.numel() * self.x.element_size()
+        self.e2e_d2h_bytes = self.y.numel() * self.y.element_size()
+        if s.C == 1 and s.sigma == 1:
+            self.kernel_name = "k_csr_spmv"
+        elif s.C != 32:
+            self.kernel_name = "k_scs_spmv"
+
+    def step(self):
+        spmv(self.scs, self.x, self.y)
+
+    def time_kernel(self, steps: int) -> float:
+        """Average device time of the SpMV kernel (ms), CUDA events on the launching stream."""
+        t = _torch()
+        e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+        t.cuda.synchronize()
+        e0.record()
+        for _ in range(steps):
+            spmv(self.scs, self.x, self.y)
+        e1.record()
+        t.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+
+    def time_e2e(self, steps: int, barrier) -> float:
+        """Seconds per step through the host-buffer C-ABI call with pinned host x / y."""
+        import time
+        t = _torch()
+        xh = t.full((self.x.numel(),), 5.0, dtype=self.x.dtype).pin_memory()
+        yh = t.zeros(self.y.numel(), dtype=self.y.dtype).pin_memory()
+        for _ in range(2):
+            spmv_host_ptr(self.scs, xh.data_ptr(), xh.numel(), yh.data_ptr(), yh.numel())
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            spmv_host_ptr(self.scs, xh.data_ptr(), xh.numel(), yh.data_ptr(), yh.numel())
+        barrier()
+        dt = (time.perf_counter() - t0) / steps
+        self.e2e_checksum = float(yh[: self.n_rows].double().sum())
+        return dt

@@ -162,6 +162,11 @@ int uspmv_halo_plan_need(const uspmv_halo *plan, int *need_flat_h, int *need_ptr
 /* collect_comm_idxs (mpi_funcs.hpp:117-172): install what every peer needs from this rank
  * (send_ptr P+1 entries, owner-local row ids). */
 int uspmv_halo_plan_set_send(uspmv_halo *plan, const int *send_flat_h, const int *send_ptr_h);
+/* Overlap support (the reference has none, main.cpp:464-468: begin -> finish -> execute): classify the chunks of a
+ * halo-renumbered matrix into interior (no column >= n_rows) and boundary ones WITHOUT reordering them, and run the
+ * SpMV on one class: which = 0 all, 1 interior, 2 boundary.  Rows of the other class are not written. */
+int uspmv_scs_split_chunks(uspmv_scs *scs, long *n_interior, long *n_boundary);
+int uspmv_spmv_part(const uspmv_scs *scs, int which, const void *x_d, void *y_d, void *stream);
 /* pack_send_buf / pack_d_send_buf (classes_structs.hpp:786-831; kernels.hpp:554-577) for ALL peers in one
  * launch: buf[send_ptr[p] + i] = x[perm[send_idx[p][i]]] (block vectors: bvs values per index). */
 int uspmv_halo_pack(const uspmv_halo *plan, const void *x_d, void *sendbuf_d, int vt, int bvs, long vec_length, int layout,

@@ -158,6 +158,13 @@ class Oracle:
                                           _p(rowmax), _p(colmax), _p(part), _p(counts))
         return part, counts
 
+    def largest_elems(self, n_rows, n_cols, I, J, vals):
+        I, J = _i32(I), _i32(J)
+        vals = np.ascontiguousarray(vals, np.float64)
+        rm, cm = np.zeros(n_rows), np.zeros(n_cols)
+        self.lib.orc_largest_elems(C.c_long(len(I)), _p(I), _p(J), _p(vals), _p(rm), _p(cm))
+        return rm, cm
+
     def seg_work_sharing_arr(self, method, n_rows, I, P):
         I = _i32(I)
         wsa = np.zeros(P + 1, np.int32)

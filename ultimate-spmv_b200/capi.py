@@ -68,6 +68,8 @@ _sigs = {
     "uspmv_halo_plan_counts": [vp, vp, C.POINTER(C.c_long)],
     "uspmv_halo_plan_need": [vp, vp, vp],
     "uspmv_halo_plan_set_send": [vp, vp, vp],
+    "uspmv_scs_split_chunks": [vp, C.POINTER(C.c_long), C.POINTER(C.c_long)],
+    "uspmv_spmv_part": [vp, C.c_int, vp, vp, vp],
     "uspmv_halo_pack": [vp, vp, vp, C.c_int, C.c_int, C.c_long, C.c_int, vp],
 }
 for _name, _args in _sigs.items():

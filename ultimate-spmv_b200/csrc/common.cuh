@@ -135,4 +135,6 @@ struct uspmv_scs {
     uspmv::DevBuf<int> old_to_new;  // n_rows
     uspmv::DevBuf<int> new_to_old;  // n_rows_padded, -1 where no real row lands
     uspmv::DevBuf<unsigned char> h2d_stage_x, d2h_stage_y;  // device staging for the host-buffer call
+    bool chunks_split = false;
+    uspmv::DevBuf<int> interior_chunks, boundary_chunks;  // chunk ids without / with halo columns (order kept)
 };

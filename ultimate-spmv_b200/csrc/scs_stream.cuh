@@ -81,9 +81,10 @@ struct WarpRing {
 
 template <typename VT, typename A, int LMAX, int D, int WARPS, bool UNPERM>
 __global__ void __launch_bounds__(WARPS * 32)
-k_scs32_stream(long n_chunks, const int *__restrict__ chunk_ptrs, const int *__restrict__ chunk_lengths,
-               const int *__restrict__ col_idxs, const VT *__restrict__ values, const VT *__restrict__ x, VT *__restrict__ y,
-               const int *__restrict__ new_to_old) {
+k_scs32_stream(long n_items, const int *__restrict__ chunk_list, const int *__restrict__ chunk_ptrs,
+               const int *__restrict__ chunk_lengths, const int *__restrict__ col_idxs, const VT *__restrict__ values,
+               const VT *__restrict__ x, VT *__restrict__ y, const int *__restrict__ new_to_old) {
+    // work item k is chunk chunk_list[k] (or chunk k when no list is given: all chunks)
     using R = WarpRing<VT, LMAX, D>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -103,15 +104,16 @@ k_scs32_stream(long n_chunks, const int *__restrict__ chunk_ptrs, const int *__r
     const uint64_t pol = policy_evict_first();
 
     // ---- producer state (meaningful in lane 0 only) --------------------------------------------------
-    long pc = gw;  // chunk of the next piece
-    int pj = 0, plen = 0, pcs = 0;
-    if (lane == 0 && pc < n_chunks) {
-        plen = chunk_lengths[pc];
-        pcs = chunk_ptrs[pc];
+    long pc = gw;  // work item of the next piece
+    int pj = 0, plen = 0, pcs = 0, pchunk = 0;
+    if (lane == 0 && pc < n_items) {
+        pchunk = chunk_list ? chunk_list[pc] : (int)pc;
+        plen = chunk_lengths[pchunk];
+        pcs = chunk_ptrs[pchunk];
     }
     auto issue = [&](int s) {  // lane 0: fill stage s with the next piece of this warp's stream
         PieceHdr h;
-        if (pc >= n_chunks) {
+        if (pc >= n_items) {
             h.ns = 0; h.flags = 0; h.chunk = 0; h.pad = 0;
             hdrs[s] = h;
             return;
@@ -119,7 +121,7 @@ k_scs32_stream(long n_chunks, const int *__restrict__ chunk_ptrs, const int *__r
         const int ns = min(LMAX, plen - pj);
         h.ns = ns;
         h.flags = 4 | (pj == 0 ? 1 : 0) | (pj + ns >= plen ? 2 : 0);
-        h.chunk = (int)pc;
+        h.chunk = pchunk;
         h.pad = 0;
         hdrs[s] = h;
         if (ns > 0) {
@@ -134,9 +136,10 @@ k_scs32_stream(long n_chunks, const int *__restrict__ chunk_ptrs, const int *__r
         if (pj >= plen) {
             pc += W;
             pj = 0;
-            if (pc < n_chunks) {
-                plen = chunk_lengths[pc];
-                pcs = chunk_ptrs[pc];
+            if (pc < n_items) {
+                pchunk = chunk_list ? chunk_list[pc] : (int)pc;
+                plen = chunk_lengths[pchunk];
+                pcs = chunk_ptrs[pchunk];
             }
         }
     };

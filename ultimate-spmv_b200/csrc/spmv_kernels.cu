@@ -22,6 +22,7 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 using namespace uspmv;
 
@@ -65,15 +66,17 @@ template <typename T> __device__ __forceinline__ T ld_x(const T *p) { return __l
 // ---------------------------------------------------------------------------------------------
 template <typename VT, int CT, int U, bool UNPERM>
 __global__ void __launch_bounds__(TPB)
-k_scs_spmv(long n_pad, int Crt, const int *__restrict__ chunk_ptrs, const int *__restrict__ chunk_lengths,
-           const int *__restrict__ col_idxs, const VT *__restrict__ values, const VT *__restrict__ x, VT *__restrict__ y,
-           const int *__restrict__ new_to_old) {
+k_scs_spmv(long n_pad, int Crt, const int *__restrict__ chunk_list, const int *__restrict__ chunk_ptrs,
+           const int *__restrict__ chunk_lengths, const int *__restrict__ col_idxs, const VT *__restrict__ values,
+           const VT *__restrict__ x, VT *__restrict__ y, const int *__restrict__ new_to_old) {
     using A = Arith<VT>;
-    const long row = blockIdx.x * (long)TPB + threadIdx.x;
+    long row = blockIdx.x * (long)TPB + threadIdx.x;  // n_pad = (#work items) * C
     if (row >= n_pad) return;
     const int C = CT > 0 ? CT : Crt;
-    const long c = row / C;
-    const int lane = (int)(row - c * C);
+    const long item = row / C;
+    const int lane = (int)(row - item * C);
+    const long c = chunk_list ? chunk_list[item] : item;
+    row = c * C + lane;
     const int len = chunk_lengths[c];
     long e = (long)chunk_ptrs[c] + lane;
     typename A::acc_t acc = A::zero();
@@ -232,6 +235,19 @@ k_scs_spmmv(long n_pad, int C, const int *__restrict__ chunk_ptrs, const int *__
     }
 }
 
+// a chunk is "boundary" if any of its slots references a halo column (>= n_local)
+__global__ void k_flag_boundary_chunks(long n_chunks, int C, int n_local, const int *__restrict__ chunk_ptrs,
+                                       const int *__restrict__ chunk_lengths, const int *__restrict__ col_idxs, int *__restrict__ flag) {
+    const long w = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= n_chunks) return;
+    const long beg = chunk_ptrs[w], end = beg + (long)chunk_lengths[w] * C;
+    int hit = 0;
+    for (long e = beg + lane; e < end; e += 32) hit |= col_idxs[e] >= n_local;
+    hit = __any_sync(0xffffffffu, hit);
+    if (lane == 0) flag[w] = hit;
+}
+
 // ---- launch helpers ----------------------------------------------------------------------------
 inline unsigned blocks_for(long n) { return (unsigned)((n + TPB - 1) / TPB); }
 
@@ -254,8 +270,8 @@ inline StreamCfg &stream_cfg() {
 }
 
 template <typename VT, bool UNPERM, int LMAX, int D, int WARPS>
-void launch_stream_v(long n_chunks, const int *cp, const int *cl, const int *ci, const VT *v, const VT *x, VT *y, const int *n2o,
-                     cudaStream_t st, int bps) {
+void launch_stream_v(long n_chunks, const int *list, const int *cp, const int *cl, const int *ci, const VT *v, const VT *x, VT *y,
+                     const int *n2o, cudaStream_t st, int bps) {
     using R = stream::WarpRing<VT, LMAX, D>;
     auto kern = stream::k_scs32_stream<VT, Arith<VT>, LMAX, D, WARPS, UNPERM>;
     constexpr int smem = WARPS * R::BYTES_ALIGNED;
@@ -269,43 +285,44 @@ void launch_stream_v(long n_chunks, const int *cp, const int *cl, const int *ci,
     long grid = (long)sm_count(dev) * bps;
     const long need = (n_chunks + WARPS - 1) / WARPS;
     if (grid > need) grid = need;
-    kern<<<(unsigned)grid, WARPS * 32, smem, st>>>(n_chunks, cp, cl, ci, v, x, y, n2o);
+    kern<<<(unsigned)grid, WARPS * 32, smem, st>>>(n_chunks, list, cp, cl, ci, v, x, y, n2o);
 }
 
 template <typename VT, bool UNPERM>
-void launch_stream(long n_chunks, const int *cp, const int *cl, const int *ci, const VT *v, const VT *x, VT *y, const int *n2o,
-                   cudaStream_t st) {
+void launch_stream(long n_chunks, const int *list, const int *cp, const int *cl, const int *ci, const VT *v, const VT *x, VT *y,
+                   const int *n2o, cudaStream_t st) {
     const StreamCfg c = stream_cfg();
     switch (c.variant) {
-    case 1: launch_stream_v<VT, UNPERM, 8, 3, 8>(n_chunks, cp, cl, ci, v, x, y, n2o, st, c.blocks_per_sm); break;
-    case 2: launch_stream_v<VT, UNPERM, 8, 4, 8>(n_chunks, cp, cl, ci, v, x, y, n2o, st, c.blocks_per_sm); break;
-    case 3: launch_stream_v<VT, UNPERM, 4, 4, 16>(n_chunks, cp, cl, ci, v, x, y, n2o, st, c.blocks_per_sm); break;
-    case 4: launch_stream_v<VT, UNPERM, 4, 3, 16>(n_chunks, cp, cl, ci, v, x, y, n2o, st, c.blocks_per_sm); break;
-    case 5: launch_stream_v<VT, UNPERM, 4, 2, 16>(n_chunks, cp, cl, ci, v, x, y, n2o, st, c.blocks_per_sm); break;
-    case 6: launch_stream_v<VT, UNPERM, 8, 2, 8>(n_chunks, cp, cl, ci, v, x, y, n2o, st, c.blocks_per_sm); break;
-    case 7: launch_stream_v<VT, UNPERM, 16, 2, 8>(n_chunks, cp, cl, ci, v, x, y, n2o, st, c.blocks_per_sm); break;
-    case 8: launch_stream_v<VT, UNPERM, 8, 2, 32>(n_chunks, cp, cl, ci, v, x, y, n2o, st, c.blocks_per_sm); break;
-    case 9: launch_stream_v<VT, UNPERM, 2, 4, 16>(n_chunks, cp, cl, ci, v, x, y, n2o, st, c.blocks_per_sm); break;
-    default: launch_stream_v<VT, UNPERM, 8, 2, 16>(n_chunks, cp, cl, ci, v, x, y, n2o, st, c.blocks_per_sm); break;
+    case 1: launch_stream_v<VT, UNPERM, 8, 3, 8>(n_chunks, list, cp, cl, ci, v, x, y, n2o, st, c.blocks_per_sm); break;
+    case 2: launch_stream_v<VT, UNPERM, 8, 4, 8>(n_chunks, list, cp, cl, ci, v, x, y, n2o, st, c.blocks_per_sm); break;
+    case 3: launch_stream_v<VT, UNPERM, 4, 4, 16>(n_chunks, list, cp, cl, ci, v, x, y, n2o, st, c.blocks_per_sm); break;
+    case 4: launch_stream_v<VT, UNPERM, 4, 3, 16>(n_chunks, list, cp, cl, ci, v, x, y, n2o, st, c.blocks_per_sm); break;
+    case 5: launch_stream_v<VT, UNPERM, 4, 2, 16>(n_chunks, list, cp, cl, ci, v, x, y, n2o, st, c.blocks_per_sm); break;
+    case 6: launch_stream_v<VT, UNPERM, 8, 2, 8>(n_chunks, list, cp, cl, ci, v, x, y, n2o, st, c.blocks_per_sm); break;
+    case 7: launch_stream_v<VT, UNPERM, 16, 2, 8>(n_chunks, list, cp, cl, ci, v, x, y, n2o, st, c.blocks_per_sm); break;
+    case 8: launch_stream_v<VT, UNPERM, 8, 2, 32>(n_chunks, list, cp, cl, ci, v, x, y, n2o, st, c.blocks_per_sm); break;
+    case 9: launch_stream_v<VT, UNPERM, 2, 4, 16>(n_chunks, list, cp, cl, ci, v, x, y, n2o, st, c.blocks_per_sm); break;
+    default: launch_stream_v<VT, UNPERM, 8, 2, 16>(n_chunks, list, cp, cl, ci, v, x, y, n2o, st, c.blocks_per_sm); break;
     }
 }
 
 template <typename VT, bool UNPERM>
 void launch_scs(long C, long n_chunks, const int *cp, const int *cl, const int *ci, const void *vals, const void *x, void *y,
-                const int *n2o, cudaStream_t st) {
+                const int *n2o, cudaStream_t st, const int *list = nullptr) {
+    // n_chunks = number of work items: all chunks, or the length of `list`
     const long n_pad = n_chunks * C;
     if (n_pad == 0) return;
     const VT *v = static_cast<const VT *>(vals);
     const VT *xx = static_cast<const VT *>(x);
     VT *yy = static_cast<VT *>(y);
     if (C == 32 && stream_cfg().enabled) {
-        launch_stream<VT, UNPERM>(n_chunks, cp, cl, ci, v, xx, yy, n2o, st);
+        launch_stream<VT, UNPERM>(n_chunks, list, cp, cl, ci, v, xx, yy, n2o, st);
         USPMV_LAUNCH_CHECK();
         return;
     }
     const unsigned g = blocks_for(n_pad);
 #define USPMV_SCS_CASE(CC)                                                                                              \
-    case CC: k_scs_spmv<VT, CC, 8, UNPERM><<<g, TPB, 0, st>>>(n_pad, (int)C, cp, cl, ci, v, xx, yy, n2o); break;
+    case CC: k_scs_spmv<VT, CC, 8, UNPERM><<<g, TPB, 0, st>>>(n_pad, (int)C, list, cp, cl, ci, v, xx, yy, n2o); break;
     switch (C) {
         USPMV_SCS_CASE(1)
         USPMV_SCS_CASE(2)
@@ -316,7 +333,7 @@ void launch_scs(long C, long n_chunks, const int *cp, const int *cl, const int *
         USPMV_SCS_CASE(64)
         USPMV_SCS_CASE(128)
         USPMV_SCS_CASE(256)
-    default: k_scs_spmv<VT, 0, 8, UNPERM><<<g, TPB, 0, st>>>(n_pad, (int)C, cp, cl, ci, v, xx, yy, n2o);
+    default: k_scs_spmv<VT, 0, 8, UNPERM><<<g, TPB, 0, st>>>(n_pad, (int)C, list, cp, cl, ci, v, xx, yy, n2o);
     }
 #undef USPMV_SCS_CASE
     USPMV_LAUNCH_CHECK();
@@ -457,6 +474,51 @@ int uspmv_spmv(const uspmv_scs *s, const void *x, void *y, void *stream) {
         default:
             if (crs) launch_csr<__half>(s->n_rows, s->nnz, s->chunk_ptrs.p, s->col_idxs.p, s->values.p, x, y, st);
             else launch_scs<__half, false>(s->C, s->n_chunks, s->chunk_ptrs.p, s->chunk_lengths.p, s->col_idxs.p, s->values.p, x, y, nullptr, st);
+        }
+    });
+}
+
+int uspmv_scs_split_chunks(uspmv_scs *s, long *n_interior, long *n_boundary) {
+    return guarded([&] {
+        if (!s) fail("uspmv_scs_split_chunks: scs is NULL");
+        USPMV_CUDA(cudaSetDevice(s->ctx->device));
+        const long nc = s->n_chunks;
+        DevBuf<int> flag(nc + 1), pos(nc + 1);
+        USPMV_CUDA(cudaMemset(flag.p, 0, (nc + 1) * sizeof(int)));
+        if (nc) {
+            k_flag_boundary_chunks<<<blocks_for(nc * 32), TPB>>>(nc, (int)s->C, (int)s->n_rows, s->chunk_ptrs.p, s->chunk_lengths.p, s->col_idxs.p, flag.p);
+            USPMV_LAUNCH_CHECK();
+        }
+        std::vector<int> fh(nc + 1);
+        USPMV_CUDA(cudaMemcpy(fh.data(), flag.p, (nc + 1) * sizeof(int), cudaMemcpyDeviceToHost));
+        std::vector<int> in, bd;
+        for (long c = 0; c < nc; ++c) (fh[c] ? bd : in).push_back((int)c);  // order preserved: classify, do not reorder
+        s->interior_chunks.alloc(in.size());
+        s->boundary_chunks.alloc(bd.size());
+        if (!in.empty()) USPMV_CUDA(cudaMemcpy(s->interior_chunks.p, in.data(), in.size() * sizeof(int), cudaMemcpyHostToDevice));
+        if (!bd.empty()) USPMV_CUDA(cudaMemcpy(s->boundary_chunks.p, bd.data(), bd.size() * sizeof(int), cudaMemcpyHostToDevice));
+        s->chunks_split = true;
+        if (n_interior) *n_interior = (long)in.size();
+        if (n_boundary) *n_boundary = (long)bd.size();
+    });
+}
+
+int uspmv_spmv_part(const uspmv_scs *s, int which, const void *x, void *y, void *stream) {
+    return guarded([&] {
+        if (!s) fail("uspmv_spmv_part: scs is NULL");
+        if (which == 0) {
+            if (uspmv_spmv(s, x, y, stream)) throw Error(uspmv_last_error());
+            return;
+        }
+        if (which != 1 && which != 2) fail("uspmv_spmv_part: which must be 0 (all), 1 (interior) or 2 (boundary)");
+        if (!s->chunks_split) fail("uspmv_spmv_part: call uspmv_scs_split_chunks first");
+        const DevBuf<int> &l = which == 1 ? s->interior_chunks : s->boundary_chunks;
+        if (l.n == 0) return;
+        cudaStream_t st = as_stream(stream);
+        switch (s->vt) {
+        case USPMV_F64: launch_scs<double, false>(s->C, (long)l.n, s->chunk_ptrs.p, s->chunk_lengths.p, s->col_idxs.p, s->values.p, x, y, nullptr, st, l.p); break;
+        case USPMV_F32: launch_scs<float, false>(s->C, (long)l.n, s->chunk_ptrs.p, s->chunk_lengths.p, s->col_idxs.p, s->values.p, x, y, nullptr, st, l.p); break;
+        default: launch_scs<__half, false>(s->C, (long)l.n, s->chunk_ptrs.p, s->chunk_lengths.p, s->col_idxs.p, s->values.p, x, y, nullptr, st, l.p);
         }
     });
 }

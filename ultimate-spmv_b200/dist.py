@@ -1,0 +1,193 @@
+"""One process per GPU: row partitioning, comm schedule and halo exchange (replaces the reference's MPI layer,
+code/mpi_funcs.hpp + SpmvKernel::{init,finalize}_halo_exchange, classes_structs.hpp:857-995).
+
+torch.distributed is the plumbing (NCCL over NVLink on GPUs, gloo on CPU for the host-logic tests); the pack
+kernel and the SpMV kernels are the library's own.  Per SpMV (comm_halos = 1):
+
+    comm stream : pack (one launch for all peers) -> isend/irecv per neighbour, receiving IN PLACE at the tail of x
+    main stream : interior chunks (no halo column)  ... wait for the exchange ... boundary chunks
+
+The reference does begin -> finish -> execute with no overlap (main.cpp:464-468).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .capi import call, vp
+
+
+def seg_rows_equal(n_rows_total: int, world: int) -> np.ndarray:
+    """seg-rows work_sharing_arr for a matrix whose last row is non-empty (mpi_funcs.hpp:446-465)."""
+    per = n_rows_total // world
+    wsa = np.arange(world + 1, dtype=np.int64) * per
+    wsa[world] = n_rows_total
+    return wsa.astype(np.int32)
+
+
+def comm_schedule(need_lists, rank: int, world: int, group=None):
+    """collect_comm_idxs (mpi_funcs.hpp:117-172): every rank tells every owner which owner-local x indices it needs.
+    need_lists[p] = indices this rank needs from owner p.  Returns send_lists[q] = indices rank q needs from us."""
+    import torch.distributed as dist
+    gathered = [None] * world
+    dist.all_gather_object(gathered, [np.asarray(a, np.int32) for a in need_lists], group=group)
+    return [np.asarray(gathered[q][rank], np.int32) for q in range(world)]
+
+
+class HaloExchange:
+    """begin/finish_communicate_halo_elements (mpi_funcs.hpp:16-66) on torch tensors (CPU/gloo or CUDA/nccl).
+    sendbuf holds the packed elements for all peers back to back (send_ptr); the halo of peer p is received in place
+    at x[n_local + recv_cumsum[p] : n_local + recv_cumsum[p+1]]."""
+
+    def __init__(self, rank, world, n_local, recv_cumsum, send_ptr, group=None):
+        self.rank, self.world, self.n_local, self.group = rank, world, int(n_local), group
+        self.recv_cumsum = [int(v) for v in recv_cumsum]
+        self.send_ptr = [int(v) for v in send_ptr]
+        self.non_zero_senders = [p for p in range(world) if self.recv_cumsum[p + 1] > self.recv_cumsum[p]]
+        self.non_zero_receivers = [p for p in range(world) if self.send_ptr[p + 1] > self.send_ptr[p]]
+
+    def begin(self, x, sendbuf):
+        import torch.distributed as dist
+        ops = []
+        for p in self.non_zero_senders:
+            ops.append(dist.P2POp(dist.irecv, x[self.n_local + self.recv_cumsum[p]: self.n_local + self.recv_cumsum[p + 1]], p, self.group))
+        for p in self.non_zero_receivers:
+            ops.append(dist.P2POp(dist.isend, sendbuf[self.send_ptr[p]: self.send_ptr[p + 1]], p, self.group))
+        return dist.batch_isend_irecv(ops) if ops else []
+
+    @staticmethod
+    def finish(reqs):
+        for r in reqs:
+            r.wait()
+
+
+class HaloPlan:
+    """Device-side collect_local_needed_heri + comm schedule for one rank."""
+
+    def __init__(self, scs, wsa, rank, world, group=None):
+        from .engine import _hp
+        self.scs, self.rank, self.world = scs, rank, world
+        wsa = np.ascontiguousarray(wsa, np.int32)
+        h = vp()
+        call("uspmv_halo_plan_create", scs.h, _hp(wsa), int(rank), int(world), C.byref(h))
+        self.h = h
+        cum = np.zeros(world + 1, np.int32)
+        nh = C.c_long(0)
+        call("uspmv_halo_plan_counts", self.h, _hp(cum), C.byref(nh))
+        self.recv_cumsum, self.n_halo = cum, int(nh.value)
+        flat = np.zeros(max(self.n_halo, 1), np.int32)
+        ptr = np.zeros(world + 1, np.int32)
+        call("uspmv_halo_plan_need", self.h, _hp(flat), _hp(ptr))
+        self.need_lists = [flat[ptr[p]:ptr[p + 1]].copy() for p in range(world)]
+        self.send_lists = None
+        self.send_ptr = None
+
+    def set_send(self, send_lists):
+        from .engine import _hp
+        self.send_lists = send_lists
+        ptr = np.cumsum([0] + [len(a) for a in send_lists]).astype(np.int32)
+        flat = np.ascontiguousarray(np.concatenate(send_lists) if ptr[-1] else np.zeros(1, np.int32), np.int32)
+        call("uspmv_halo_plan_set_send", self.h, _hp(flat), _hp(ptr))
+        self.send_ptr = ptr
+        self.n_send = int(ptr[-1])
+
+    def pack(self, x, sendbuf, bvs=1, vec_length=0, layout=capi.COLWISE):
+        from .engine import _dp, _stream
+        vt = {8: capi.F64, 4: capi.F32, 2: capi.F16}[x.element_size()]
+        call("uspmv_halo_pack", self.h, _dp(x), _dp(sendbuf), vt, int(bvs), int(vec_length), int(layout), _stream())
+
+    def __del__(self):
+        if getattr(self, "h", None) and capi is not None:
+            capi.lib.uspmv_halo_destroy(self.h)
+            self.h = None
+
+
+class DistributedSpmv:
+    """bench.py's N > 1 runner (weak scaling): every rank owns an n^3 z-slab of an n x n x (n*world) stencil grid.
+    Harness order (main.cpp:1104-1128,1271-1308): slab -> convert_to_scs -> halo discovery -> permute_scs_cols."""
+
+    kernel_name = "k_scs32_stream"
+
+    def __init__(self, ctx, points, n, C_, sigma, vt, rank, world, overlap=True, group=None):
+        import torch
+        import torch.distributed as dist
+        from . import engine as eng
+        self.ctx, self.rank, self.world, self.overlap = ctx, rank, world, overlap
+        rows_per = n * n * n
+        wsa = seg_rows_equal(rows_per * world, world)
+        mtx = eng.MtxData.stencil(points, n, n, n * world, int(wsa[rank]), int(wsa[rank + 1]), ctx=ctx)
+        self.scs = eng.convert_to_scs(mtx, C_, sigma, vt)
+        del mtx
+        self.plan = HaloPlan(self.scs, wsa, rank, world)
+        eng.permute_scs_cols(self.scs)
+        self.plan.set_send(comm_schedule(self.plan.need_lists, rank, world, group))
+        ni, nb = C.c_long(0), C.c_long(0)
+        call("uspmv_scs_split_chunks", self.scs.h, C.byref(ni), C.byref(nb))
+        self.n_interior_chunks, self.n_boundary_chunks = int(ni.value), int(nb.value)
+        s = self.scs
+        self.nnz, self.n_elements, self.n_chunks = s.nnz, s.n_elements, s.n_chunks
+        self.n_rows, self.n_rows_padded, self.n_cols_local, self.n_halo = s.n_rows, s.n_rows_padded, s.n_rows, self.plan.n_halo
+        dt = eng.torch_dtype(s.vt)
+        dev = f"cuda:{ctx.device}"
+        # vector length n_local + max(scs_padding, halo_count) (main.cpp:1405-1420)
+        self.x = torch.full((s.n_rows + max(s.n_rows_padded - s.n_rows, self.n_halo),), 5.0, dtype=dt, device=dev)
+        self.y = torch.zeros(s.n_rows_padded, dtype=dt, device=dev)
+        self.sendbuf = torch.zeros(max(self.plan.n_send, 1), dtype=dt, device=dev)
+        self.ex = HaloExchange(rank, world, s.n_rows, self.plan.recv_cumsum, self.plan.send_ptr, group)
+        self.comm_stream = torch.cuda.Stream(device=dev)
+        self.e2e_h2d_bytes = s.n_rows * self.x.element_size()
+        self.e2e_d2h_bytes = s.n_rows_padded * self.y.element_size()
+        self._torch, self._eng = torch, eng
+        dist.barrier()
+
+    def step(self):
+        torch, eng = self._torch, self._eng
+        main = torch.cuda.current_stream()
+        if not self.overlap:
+            self.plan.pack(self.x, self.sendbuf)
+            HaloExchange.finish(self.ex.begin(self.x, self.sendbuf))
+            eng.spmv(self.scs, self.x, self.y)
+            return
+        self.comm_stream.wait_stream(main)  # x (and last step's boundary SpMV, which reads the halo) are done
+        with torch.cuda.stream(self.comm_stream):
+            self.plan.pack(self.x, self.sendbuf)
+            reqs = self.ex.begin(self.x, self.sendbuf)
+        call("uspmv_spmv_part", self.scs.h, 1, vp(self.x.data_ptr()), vp(self.y.data_ptr()), vp(main.cuda_stream))
+        with torch.cuda.stream(self.comm_stream):
+            HaloExchange.finish(reqs)
+        main.wait_stream(self.comm_stream)
+        call("uspmv_spmv_part", self.scs.h, 2, vp(self.x.data_ptr()), vp(self.y.data_ptr()), vp(main.cuda_stream))
+
+    def time_kernel(self, steps):
+        torch, eng = self._torch, self._eng
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(steps):
+            eng.spmv(self.scs, self.x, self.y)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+
+    def time_e2e(self, steps, barrier):
+        """Host-buffer step: H2D of this rank's x slab, halo exchange + SpMV, D2H of y."""
+        import time
+        torch = self._torch
+        n = self.scs.n_rows
+        xh = torch.full((n,), 5.0, dtype=self.x.dtype).pin_memory()
+        yh = torch.zeros(self.y.numel(), dtype=self.y.dtype).pin_memory()
+
+        def one():
+            self.x[:n].copy_(xh, non_blocking=True)
+            self.step()
+            yh.copy_(self.y, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        one()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            one()
+        barrier()
+        return (time.perf_counter() - t0) / steps

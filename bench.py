@@ -41,6 +41,8 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=8.0, help="CPU baseline time box")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="N>1: exchange first, then one full SpMV (the reference's order)")
+    ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"], help="N>1: NVLink peer stores + epoch flags, or NCCL send/recv")
     return ap.parse_args()
 
 
@@ -208,7 +210,7 @@ def run_ours(args):
     if world == 1:
         runner = pkg.engine.SingleGpuSpmv(ctx, pts, n, args.C, args.sigma, vt)
     else:
-        runner = pkg.dist.DistributedSpmv(ctx, pts, n, args.C, args.sigma, vt, rank, world)
+        runner = pkg.dist.DistributedSpmv(ctx, pts, n, args.C, args.sigma, vt, rank, world, halo=args.halo, overlap=not args.no_overlap)
     nnz_local = runner.nnz
     bytes_local = algorithmic_bytes(runner.n_elements, runner.n_chunks, runner.n_cols_local + runner.n_halo, runner.n_rows_padded, vsize)
 
@@ -283,7 +285,7 @@ def run_ours(args):
             "dtype": {"dp": "f64", "sp": "f32", "hp": "f16"}[vt], "data": "synthetic",
             "config": {"workload": f"{args.workload}: {pts}-point stencil on a {n}^3 grid per GPU, scs C={args.C} sigma={args.sigma} {vt} SpMV",
                        "rows_per_gpu": runner.n_rows, "nnz_per_gpu": int(nnz_local), "n_elements_per_gpu": int(runner.n_elements),
-                       "partition": "none" if world == 1 else f"seg_rows z-slabs x{world}, halo exchange every step (comm_halos=1)",
+                       "partition": "none" if world == 1 else f"seg_rows z-slabs x{world}, halo exchange every step (comm_halos=1) via {args.halo}",
                        "l2": "inputs (>= 1.4 GB per GPU) are larger than the 126 MB L2; no explicit flush",
                        "x": "constant 5.0 (reference default)"},
             "gbs": bytes_total / sec_per_step / 1e9,

@@ -45,7 +45,10 @@ long uspmv_kernel_launches(void);
 /* Kernel-selection knobs (no reference counterpart; THREADS_PER_BLOCK is the closest, config.mk:20):
  *   "scs_stream" 0/1          C = 32: bulk-copy (TMA) streamed kernel (default 1) or the direct-load kernel
  *   "stream_variant" 0..5     (slots per piece, ring depth, warps per CTA) instantiation
- *   "stream_blocks_per_sm"    persistent CTAs per SM */
+ *   "stream_blocks_per_sm"    persistent CTAs per SM
+ *   "strict_reference_halo"   0 (default): padding slots stay local (column 0 of the rank); 1: replicate the reference,
+ *                             where padding's column 0 is GLOBAL column 0 and so becomes one spurious halo element
+ *                             received from rank 0 on every rank > 0 (utilities.hpp:1991-2002, mpi_funcs.hpp:279-283) */
 int uspmv_set_option(const char *name, long value);
 
 /* ---- context and device memory --------------------------------------------------------------- */
@@ -172,6 +175,24 @@ int uspmv_spmv_part(const uspmv_scs *scs, int which, const void *x_d, void *y_d,
 int uspmv_halo_pack(const uspmv_halo *plan, const void *x_d, void *sendbuf_d, int vt, int bvs, long vec_length, int layout,
                     void *stream);
 void uspmv_halo_destroy(uspmv_halo *plan);
+
+/* NVLink peer-to-peer halo exchange for one-process-per-GPU runs (replaces MPI_Isend/Irecv/Waitall in
+ * init/finalize_halo_exchange, classes_structs.hpp:857-995, which assume CUDA-aware MPI).  Every rank allocates an
+ * "arena" (its x vector + epoch flags), shares it through a 64-byte CUDA IPC handle, and the pack kernel of the
+ * neighbours stores their elements straight into the tail of x.  The caller all-gathers the handles (any transport)
+ * and passes, per peer q, the size of q's x region and the element offset where this rank's data starts in q's x
+ * (q.n_local + q.recv_counts_cumsum[rank]). */
+typedef struct uspmv_p2p uspmv_p2p;
+int uspmv_p2p_create(uspmv_halo *plan, int vt, long x_len, uspmv_p2p **out, void *ipc_handle64, void **x_d);
+int uspmv_p2p_connect(uspmv_p2p *p2p, const void *all_handles, const long *peer_x_bytes, const long *peer_halo_base);
+/* one SpMV incl. halo exchange, overlapped: push + wait on comm_stream, interior chunks on stream, then boundary */
+int uspmv_p2p_spmv(uspmv_p2p *p2p, const uspmv_scs *scs, void *y_d, void *stream, void *comm_stream);
+/* mode 2 (default, C = 32): ONE fused kernel per SpMV — push to the peers, interior chunks, wait for the own halo, boundary
+ * chunks, acknowledge; mode 1: separate push/wait kernels on comm_stream next to the interior kernel; mode 0: exchange,
+ * then one full SpMV (the reference's begin -> finish -> execute order, main.cpp:464-468) */
+int uspmv_p2p_set_overlap(uspmv_p2p *p2p, int overlap);
+int uspmv_p2p_status(uspmv_p2p *p2p, int *error_flag, long *epoch);
+void uspmv_p2p_destroy(uspmv_p2p *p2p);
 
 #ifdef __cplusplus
 }

@@ -145,9 +145,27 @@ def _rank_slab(I, J, V, wsa, r):
     return (I[sel] - wsa[r]).astype(np.int32), J[sel], V[sel]
 
 
+def _pad_mask(ref, lI, n_loc):
+    """True for the padding slots of an SCS structure (slot j >= stored elements of the row at that position)."""
+    cnt_row = np.bincount(lI, minlength=n_loc)
+    cnt_pos = np.zeros(ref.n_rows_padded, np.int64)
+    cnt_pos[ref.old_to_new] = cnt_row
+    mask = np.zeros(ref.n_elements, bool)
+    C = ref.C
+    for c in range(ref.n_chunks):
+        L = int(ref.chunk_lengths[c])
+        if L == 0:
+            continue
+        j = np.repeat(np.arange(L), C)
+        lane = np.tile(np.arange(C), L)
+        mask[ref.chunk_ptrs[c]: ref.chunk_ptrs[c] + L * C] = j >= cnt_pos[c * C + lane]
+    return mask
+
+
+@pytest.mark.parametrize("strict", [True, False])
 @pytest.mark.parametrize("P", [2, 4])
 @pytest.mark.parametrize("C,sigma", [(1, 1), (8, 16), (32, 64)])
-def test_halo_plan_pack_and_distributed_spmv(eng, pkg, orc, mats, P, C, sigma):
+def test_halo_plan_pack_and_distributed_spmv(eng, pkg, orc, mats, P, C, sigma, strict):
     """P ranks emulated on one GPU: bit-exact halo renumbering / need lists, pack, interior+boundary == full SpMV,
     and the assembled distributed result equals the single-rank result."""
     t = torch_()
@@ -156,10 +174,15 @@ def test_halo_plan_pack_and_distributed_spmv(eng, pkg, orc, mats, P, C, sigma):
     x_glob = np.random.default_rng(2).standard_normal(n)
     wsa = eng.seg_work_sharing_arr("seg-nnz", n, I, P)
     ranks = []
+    # strict: padding's column 0 is GLOBAL column 0 -> a halo element from rank 0 on ranks > 0 (the reference);
+    # default: padding stays local (column 0 of the rank)
+    pkg.capi.set_option("strict_reference_halo", 1 if strict else 0)
     for r in range(P):
         lI, lJ, lV = _rank_slab(I, J, V, wsa, r)
         n_loc = int(wsa[r + 1] - wsa[r])
         ref = orc.convert_to_scs(n_loc, n, lI, lJ, lV, C, sigma)
+        if not strict:
+            ref.col_idxs[_pad_mask(ref, lI, n_loc)] = wsa[r]
         need_ref, cum_ref = orc.collect_halo(ref.col_idxs, wsa, r)
         orc.permute_scs_cols(ref, ref.old_to_new)
         mtx = eng.MtxData.from_host(n_loc, n, lI, lJ, lV)
@@ -172,6 +195,7 @@ def test_halo_plan_pack_and_distributed_spmv(eng, pkg, orc, mats, P, C, sigma):
         for a, b in zip(plan.need_lists, need_ref):
             assert np.array_equal(a, b)
         ranks.append(dict(scs=scs, plan=plan, ref=ref, n_loc=n_loc))
+    pkg.capi.set_option("strict_reference_halo", 0)
     # comm schedule = transpose of the need lists (collect_comm_idxs)
     for r in range(P):
         ranks[r]["plan"].set_send([ranks[q]["plan"].need_lists[r] for q in range(P)])

@@ -70,6 +70,11 @@ _sigs = {
     "uspmv_halo_plan_set_send": [vp, vp, vp],
     "uspmv_scs_split_chunks": [vp, C.POINTER(C.c_long), C.POINTER(C.c_long)],
     "uspmv_spmv_part": [vp, C.c_int, vp, vp, vp],
+    "uspmv_p2p_create": [vp, C.c_int, C.c_long, C.POINTER(vp), vp, C.POINTER(vp)],
+    "uspmv_p2p_connect": [vp, vp, vp, vp],
+    "uspmv_p2p_spmv": [vp, vp, vp, vp, vp],
+    "uspmv_p2p_set_overlap": [vp, C.c_int],
+    "uspmv_p2p_status": [vp, C.POINTER(C.c_int), C.POINTER(C.c_long)],
     "uspmv_halo_pack": [vp, vp, vp, C.c_int, C.c_int, C.c_long, C.c_int, vp],
 }
 for _name, _args in _sigs.items():
@@ -77,7 +82,7 @@ for _name, _args in _sigs.items():
     if _fn is not None:  # symbol presence is asserted by tests/test_capi_symbols.py against the header
         _fn.argtypes = _args
         _fn.restype = C.c_int
-for _name in ("uspmv_ctx_destroy", "uspmv_coo_destroy", "uspmv_scs_destroy", "uspmv_halo_destroy"):
+for _name in ("uspmv_ctx_destroy", "uspmv_coo_destroy", "uspmv_scs_destroy", "uspmv_halo_destroy", "uspmv_p2p_destroy"):
     _fn = getattr(lib, _name, None)
     if _fn is not None:
         _fn.argtypes = [vp]

@@ -98,6 +98,15 @@ struct DevBuf {
     }
 };
 
+// run-time knobs (uspmv_set_option / environment), defined in context.cu
+struct Options {
+    bool scs_stream = true;      // C = 32: bulk-copy streamed kernel (false: direct-load kernel)
+    int stream_variant = 0;      // (slots per piece, ring depth, warps per CTA) instantiation
+    int stream_blocks_per_sm = 2;
+    bool strict_reference_halo = false;  // true: padding slots (column 0) become a halo element on ranks > 0, like the reference
+};
+Options &options();
+
 inline int sm_count(int device) {
     static int cached[64] = {0};
     if (device >= 0 && device < 64 && cached[device]) return cached[device];
@@ -134,7 +143,10 @@ struct uspmv_scs {
     uspmv::DevBuf<unsigned char> values;
     uspmv::DevBuf<int> old_to_new;  // n_rows
     uspmv::DevBuf<int> new_to_old;  // n_rows_padded, -1 where no real row lands
+    uspmv::DevBuf<int> row_lengths; // n_rows_padded: stored elements of the row at each (permuted) position
     uspmv::DevBuf<unsigned char> h2d_stage_x, d2h_stage_y;  // device staging for the host-buffer call
     bool chunks_split = false;
     uspmv::DevBuf<int> interior_chunks, boundary_chunks;  // chunk ids without / with halo columns (order kept)
+    bool interior_contig = false, boundary_contig = false;
+    int interior_off = 0, boundary_off = 0;
 };

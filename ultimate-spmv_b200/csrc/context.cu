@@ -1,10 +1,25 @@
 // Context, error state and device-memory helpers of the C ABI (include/uspmv_b200.h).
 #include "common.cuh"
 
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
 namespace uspmv {
 static thread_local std::string t_error;
 std::atomic<long> g_launches{0};
 void set_error(const std::string &msg) { t_error = msg; }
+Options &options() {
+    static Options o = [] {
+        Options c;
+        if (const char *e = std::getenv("USPMV_SCS_KERNEL")) c.scs_stream = std::strcmp(e, "direct") != 0;
+        if (const char *e = std::getenv("USPMV_STREAM_VARIANT")) c.stream_variant = std::atoi(e);
+        if (const char *e = std::getenv("USPMV_STREAM_BPS")) c.stream_blocks_per_sm = std::max(1, std::atoi(e));
+        if (const char *e = std::getenv("USPMV_STRICT_REFERENCE_HALO")) c.strict_reference_halo = std::atoi(e) != 0;
+        return c;
+    }();
+    return o;
+}
 }  // namespace uspmv
 
 using namespace uspmv;
@@ -14,6 +29,18 @@ extern "C" {
 const char *uspmv_last_error(void) { return t_error.c_str(); }
 int uspmv_version(void) { return 100; }
 long uspmv_kernel_launches(void) { return g_launches.load(); }
+
+int uspmv_set_option(const char *name, long value) {
+    return guarded([&] {
+        if (!name) fail("uspmv_set_option: name is NULL");
+        Options &c = options();
+        if (!std::strcmp(name, "scs_stream")) c.scs_stream = value != 0;
+        else if (!std::strcmp(name, "stream_variant")) c.stream_variant = (int)value;
+        else if (!std::strcmp(name, "stream_blocks_per_sm")) c.stream_blocks_per_sm = (int)std::max(1L, value);
+        else if (!std::strcmp(name, "strict_reference_halo")) c.strict_reference_halo = value != 0;
+        else fail("uspmv_set_option: unknown option '%s'", name);
+    });
+}
 
 int uspmv_ctx_create(int device, uspmv_ctx **out) {
     return guarded([&] {

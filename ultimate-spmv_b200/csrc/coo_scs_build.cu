@@ -247,9 +247,10 @@ __global__ void k_narrow_ptrs(const long long *__restrict__ ptr64, long n, int *
 }
 
 __global__ void k_perms(const RC *__restrict__ rc, long n_rows, long n_pad, bool identity, int *__restrict__ old_to_new,
-                        int *__restrict__ new_to_old) {
+                        int *__restrict__ new_to_old, int *__restrict__ row_lengths) {
     long p = blockIdx.x * (long)blockDim.x + threadIdx.x;
     if (p >= n_pad) return;
+    row_lengths[p] = rc[p].cnt;
     if (identity) {  // fixed_permutation mode: the struct's own permutation is the identity
         if (p < n_rows) old_to_new[p] = (int)p;
         new_to_old[p] = p < n_rows ? (int)p : -1;
@@ -581,6 +582,7 @@ int uspmv_scs_build(uspmv_ctx *ctx, const uspmv_coo *coo, long C, long sigma, in
             s->chunk_lengths.alloc(n_chunks);
             s->old_to_new.alloc(n_rows);
             s->new_to_old.alloc(n_pad);
+            s->row_lengths.alloc(n_pad);
             DevBuf<long long> len64(n_chunks + 1), ptr64(n_chunks + 1);
             USPMV_CUDA(cudaMemset(len64.p, 0, (n_chunks + 1) * sizeof(long long)));
             if (n_chunks) {
@@ -595,7 +597,7 @@ int uspmv_scs_build(uspmv_ctx *ctx, const uspmv_coo *coo, long C, long sigma, in
             k_narrow_ptrs<<<blocks_for(n_chunks + 1), TPB>>>(ptr64.p, n_chunks + 1, s->chunk_ptrs.p);
             USPMV_LAUNCH_CHECK();
             if (n_pad) {
-                k_perms<<<blocks_for(n_pad), TPB>>>(rc.p, n_rows, n_pad, fixed_perm_h != nullptr, s->old_to_new.p, s->new_to_old.p);
+                k_perms<<<blocks_for(n_pad), TPB>>>(rc.p, n_rows, n_pad, fixed_perm_h != nullptr, s->old_to_new.p, s->new_to_old.p, s->row_lengths.p);
                 USPMV_LAUNCH_CHECK();
             }
             s->col_idxs.alloc(s->n_elements);

@@ -79,37 +79,81 @@ struct WarpRing {
     static constexpr int BYTES_ALIGNED = (BYTES + 127) / 128 * 128;
 };
 
-template <typename VT, typename A, int LMAX, int D, int WARPS, bool UNPERM>
-__global__ void __launch_bounds__(WARPS * 32)
-k_scs32_stream(long n_items, const int *__restrict__ chunk_list, const int *__restrict__ chunk_ptrs,
-               const int *__restrict__ chunk_lengths, const int *__restrict__ col_idxs, const VT *__restrict__ values,
-               const VT *__restrict__ x, VT *__restrict__ y, const int *__restrict__ new_to_old) {
-    // work item k is chunk chunk_list[k] (or chunk k when no list is given: all chunks)
-    using R = WarpRing<VT, LMAX, D>;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    unsigned char *base = smem_raw + (size_t)warp * R::BYTES_ALIGNED;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(base + D * R::STAGE_BYTES);
-    PieceHdr *hdrs = reinterpret_cast<PieceHdr *>(base + D * R::STAGE_BYTES + D * 8);
+// ---- fused halo exchange (one process per GPU, NVLink peer memory) -------------------------------------------
+// With FUSED the SAME kernel (a) gathers this rank's send elements and stores them straight into the neighbours'
+// x tails, then raises their `arrived` epoch flags, (b) runs the interior chunks, (c) waits for its own `arrived`
+// flags and runs the boundary chunks (the only ones that read halo columns), (d) the last warp acknowledges
+// consumption to the senders and bumps the epoch.  One launch per distributed SpMV, transfer overlapped with
+// the interior math, no collective call and no host round trip.  Flags live in the IPC arena (halo.cu).
+struct FusedArgs {
+    long n_int, n_bnd;            // interior items first, then boundary items
+    const int *int_list, *bnd_list;
+    int int_off, bnd_off;
+    int P, my_rank;
+    long n_send;
+    const int *send_ptr, *is_receiver, *is_sender, *send_idx, *perm;
+    const unsigned long long *peer_x_dst, *peer_arrived, *peer_acked;
+    unsigned int *acked, *arrived, *epoch, *error, *counters;  // counters[0] push warps done, [1] warps finished
+};
 
-    const long W = (long)gridDim.x * WARPS;
-    const long gw = (long)blockIdx.x * WARPS + warp;
-
-    if (lane == 0) {
-#pragma unroll
-        for (int s = 0; s < D; ++s) mbar_init(&bars[s], 1);
-        fence_barrier_init();
+__device__ __forceinline__ unsigned int ld_flag(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long gtimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// lane p (< P, selected) spins until flags[p] >= target; bounded (10 s) so that a lost peer cannot hang the GPU
+__device__ __forceinline__ void warp_wait_flags(const unsigned int *flags, const int *select, int P, unsigned int target, int lane,
+                                                unsigned int *error) {
+    if (lane < P && select[lane]) {
+        const unsigned long long t0 = gtimer_ns();
+        while (ld_flag(flags + lane) < target) {
+            if (gtimer_ns() - t0 > 10000000000ull) {
+                atomicExch(error, 1u);
+                break;
+            }
+            __nanosleep(100);
+        }
     }
     __syncwarp();
-    const uint64_t pol = policy_evict_first();
+}
+template <typename T> __device__ __forceinline__ T ld_x_coherent(const T *p) { return __ldcg(p); }  // L2 (coherent with peer stores)
+
+// The streaming loop of one warp over work items first, first + W, ... < n_items (item k -> chunk list[k] or k + off).
+// COHERENT: x is read through L2 only (ld.global.cg) because a peer GPU wrote part of it during this kernel.
+template <typename VT, typename A, int LMAX, int D, bool UNPERM, bool COHERENT>
+__device__ __forceinline__ void stream_items(unsigned char *base, uint64_t *bars, PieceHdr *hdrs, uint32_t &phase_bits, const long W,
+                                             const long first, const int lane, const long n_items, const int *__restrict__ chunk_list,
+                                             const int chunk_offset, const int *__restrict__ chunk_ptrs,
+                                             const int *__restrict__ chunk_lengths, const int *__restrict__ col_idxs,
+                                             const VT *__restrict__ values, const VT *__restrict__ x, VT *__restrict__ y,
+                                             const int *__restrict__ new_to_old, const uint64_t pol) {
+    using R = WarpRing<VT, LMAX, D>;
+    auto item_chunk = [&](long k) -> int { return chunk_list ? chunk_list[k] : (int)k + chunk_offset; };
 
     // ---- producer state (meaningful in lane 0 only) --------------------------------------------------
-    long pc = gw;  // work item of the next piece
-    int pj = 0, plen = 0, pcs = 0, pchunk = 0;
-    if (lane == 0 && pc < n_items) {
-        pchunk = chunk_list ? chunk_list[pc] : (int)pc;
-        plen = chunk_lengths[pchunk];
-        pcs = chunk_ptrs[pchunk];
+    // Three-deep metadata lookahead so that no load issued by lane 0 is consumed in the same piece:
+    //   cur  = (pchunk, plen, pcs)  item being cut into pieces
+    //   nxt  = (nchunk, nlen, ncs)  item pc + W, loaded when cur became current
+    //   n2chunk                     chunk id of item pc + 2W (only needed with a chunk list)
+    long pc = first;  // work item of the next piece
+    int pj = 0, plen = 0, pcs = 0, pchunk = 0, nlen = 0, ncs = 0, nchunk = 0, n2chunk = 0;
+    if (lane == 0) {
+        if (pc < n_items) {
+            pchunk = item_chunk(pc);
+            plen = chunk_lengths[pchunk];
+            pcs = chunk_ptrs[pchunk];
+        }
+        if (pc + W < n_items) {
+            nchunk = item_chunk(pc + W);
+            nlen = chunk_lengths[nchunk];
+            ncs = chunk_ptrs[nchunk];
+        }
+        if (pc + 2 * W < n_items) n2chunk = item_chunk(pc + 2 * W);
     }
     auto issue = [&](int s) {  // lane 0: fill stage s with the next piece of this warp's stream
         PieceHdr h;
@@ -133,14 +177,16 @@ k_scs32_stream(long n_items, const int *__restrict__ chunk_list, const int *__re
             bulk_g2s(st + R::VAL_BYTES, col_idxs + e0, cb, &bars[s], pol);
         }
         pj += ns;
-        if (pj >= plen) {
+        if (pj >= plen) {  // advance: nxt -> cur, start the loads for the new nxt
             pc += W;
             pj = 0;
-            if (pc < n_items) {
-                pchunk = chunk_list ? chunk_list[pc] : (int)pc;
-                plen = chunk_lengths[pchunk];
-                pcs = chunk_ptrs[pchunk];
+            pchunk = nchunk; plen = nlen; pcs = ncs;
+            nchunk = n2chunk;
+            if (pc + W < n_items) {
+                nlen = chunk_lengths[nchunk];
+                ncs = chunk_ptrs[nchunk];
             }
+            if (pc + 2 * W < n_items) n2chunk = item_chunk(pc + 2 * W);
         }
     };
 
@@ -151,7 +197,6 @@ k_scs32_stream(long n_items, const int *__restrict__ chunk_list, const int *__re
     __syncwarp();
 
     // ---- consumer -----------------------------------------------------------------------------------------
-    uint32_t phase_bits = 0;  // one parity bit per stage, flipped after every completed wait
     typename A::acc_t acc = A::zero();
     for (int s = 0;; s = (s + 1 == D) ? 0 : s + 1) {
         const PieceHdr h = hdrs[s];
@@ -169,7 +214,7 @@ k_scs32_stream(long n_items, const int *__restrict__ chunk_list, const int *__re
                 if (j < h.ns) col[j] = sc[j * 32];
 #pragma unroll
             for (int j = 0; j < LMAX; ++j)
-                if (j < h.ns) xv[j] = __ldg(x + col[j]);
+                if (j < h.ns) xv[j] = COHERENT ? __ldcg(x + col[j]) : __ldg(x + col[j]);
 #pragma unroll
             for (int j = 0; j < LMAX; ++j)
                 if (j < h.ns) v[j] = sv[j * 32];
@@ -188,6 +233,93 @@ k_scs32_stream(long n_items, const int *__restrict__ chunk_list, const int *__re
         __syncwarp();  // every lane is done with stage s (data and header) before it is refilled
         if (lane == 0) issue(s);
         __syncwarp();
+    }
+}
+
+template <typename VT, typename A, int LMAX, int D, int WARPS, bool UNPERM, bool FUSED>
+__global__ void __launch_bounds__(WARPS * 32, (1024 / (WARPS * 32)) > 0 ? (1024 / (WARPS * 32)) : 1)  // <= 64 registers: 32 warps/SM
+k_scs32_stream(long n_items, const int *__restrict__ chunk_list, int chunk_offset, const int *__restrict__ chunk_ptrs,
+               const int *__restrict__ chunk_lengths, const int *__restrict__ col_idxs, const VT *__restrict__ values,
+               const VT *__restrict__ x, VT *__restrict__ y, const int *__restrict__ new_to_old, const FusedArgs fa) {
+    using R = WarpRing<VT, LMAX, D>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char *base = smem_raw + (size_t)warp * R::BYTES_ALIGNED;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(base + D * R::STAGE_BYTES);
+    PieceHdr *hdrs = reinterpret_cast<PieceHdr *>(base + D * R::STAGE_BYTES + D * 8);
+    const long W = (long)gridDim.x * WARPS;
+    const long gw = (long)blockIdx.x * WARPS + warp;
+
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < D; ++s) mbar_init(&bars[s], 1);
+        fence_barrier_init();
+    }
+    __syncwarp();
+    const uint64_t pol = policy_evict_first();
+    uint32_t phase_bits = 0;  // one parity bit per stage, flipped after every completed wait
+
+    if constexpr (!FUSED) {
+        stream_items<VT, A, LMAX, D, UNPERM, false>(base, bars, hdrs, phase_bits, W, gw, lane, n_items, chunk_list, chunk_offset, chunk_ptrs,
+                                                    chunk_lengths, col_idxs, values, x, y, new_to_old, pol);
+    } else {
+        // (a) push: warp pw handles send elements [32 pw, 32 pw + 32)
+        const unsigned int epoch_e = ld_flag(fa.epoch) + 1u;
+        const long n_push_warps = (fa.n_send + 31) / 32;
+        for (long pw = gw; pw < n_push_warps; pw += W) {
+            warp_wait_flags(fa.acked, fa.is_receiver, fa.P, epoch_e - 1u, lane, fa.error);  // receivers consumed step e-1
+            const long i = pw * 32 + lane;
+            if (i < fa.n_send) {
+                int q = 0;
+                while (i >= fa.send_ptr[q + 1]) ++q;
+                VT *dst = reinterpret_cast<VT *>(fa.peer_x_dst[q]);
+                dst[i - fa.send_ptr[q]] = x[fa.perm[fa.send_idx[i]]];
+            }
+            __threadfence_system();
+            __syncwarp();
+            unsigned int last = 0;
+            if (lane == 0) last = (atomicAdd(&fa.counters[0], 1u) == (unsigned int)(n_push_warps - 1));
+            last = __shfl_sync(0xffffffffu, last, 0);
+            if (last) {
+                __threadfence_system();
+                if (lane < fa.P && fa.is_receiver[lane]) {
+                    volatile unsigned int *f = reinterpret_cast<volatile unsigned int *>(fa.peer_arrived[lane]);
+                    *f = epoch_e;
+                }
+                __threadfence_system();
+            }
+        }
+        // (b) interior chunks: no halo column, identical code path to the single-GPU kernel
+        stream_items<VT, A, LMAX, D, UNPERM, false>(base, bars, hdrs, phase_bits, W, gw, lane, fa.n_int, fa.int_list, fa.int_off, chunk_ptrs,
+                                                    chunk_lengths, col_idxs, values, x, y, new_to_old, pol);
+        // (c) boundary chunks once the neighbours' elements for this step have landed in our x tail
+        if (gw < fa.n_bnd) {
+            warp_wait_flags(fa.arrived, fa.is_sender, fa.P, epoch_e, lane, fa.error);
+            stream_items<VT, A, LMAX, D, UNPERM, true>(base, bars, hdrs, phase_bits, W, gw, lane, fa.n_bnd, fa.bnd_list, fa.bnd_off, chunk_ptrs,
+                                                       chunk_lengths, col_idxs, values, x, y, new_to_old, pol);
+        }
+        // (d) the last warp of the grid acknowledges consumption to the senders and closes the epoch
+        __syncwarp();
+        unsigned int last = 0;
+        if (lane == 0) {
+            __threadfence();
+            last = (atomicAdd(&fa.counters[1], 1u) == (unsigned int)(W - 1));
+        }
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last) {
+            if (fa.n_bnd == 0) warp_wait_flags(fa.arrived, fa.is_sender, fa.P, epoch_e, lane, fa.error);  // keep epochs in step
+            if (lane < fa.P && fa.is_sender[lane]) {
+                volatile unsigned int *f = reinterpret_cast<volatile unsigned int *>(fa.peer_acked[lane]);
+                *f = epoch_e;
+            }
+            __threadfence_system();
+            if (lane == 0) {
+                fa.counters[0] = 0;
+                fa.counters[1] = 0;
+                *reinterpret_cast<volatile unsigned int *>(fa.epoch) = epoch_e;
+                __threadfence();
+            }
+        }
     }
 }
 

@@ -66,7 +66,7 @@ template <typename T> __device__ __forceinline__ T ld_x(const T *p) { return __l
 // ---------------------------------------------------------------------------------------------
 template <typename VT, int CT, int U, bool UNPERM>
 __global__ void __launch_bounds__(TPB)
-k_scs_spmv(long n_pad, int Crt, const int *__restrict__ chunk_list, const int *__restrict__ chunk_ptrs,
+k_scs_spmv(long n_pad, int Crt, const int *__restrict__ chunk_list, int chunk_offset, const int *__restrict__ chunk_ptrs,
            const int *__restrict__ chunk_lengths, const int *__restrict__ col_idxs, const VT *__restrict__ values,
            const VT *__restrict__ x, VT *__restrict__ y, const int *__restrict__ new_to_old) {
     using A = Arith<VT>;
@@ -75,7 +75,7 @@ k_scs_spmv(long n_pad, int Crt, const int *__restrict__ chunk_list, const int *_
     const int C = CT > 0 ? CT : Crt;
     const long item = row / C;
     const int lane = (int)(row - item * C);
-    const long c = chunk_list ? chunk_list[item] : item;
+    const long c = chunk_list ? chunk_list[item] : item + chunk_offset;
     row = c * C + lane;
     const int len = chunk_lengths[c];
     long e = (long)chunk_ptrs[c] + lane;
@@ -252,28 +252,11 @@ __global__ void k_flag_boundary_chunks(long n_chunks, int C, int n_local, const 
 inline unsigned blocks_for(long n) { return (unsigned)((n + TPB - 1) / TPB); }
 
 // ---- C = 32: bulk-copy (TMA) streamed kernel, see scs_stream.cuh -----------------------------------------
-struct StreamCfg {
-    int variant;         // index into the instantiated (LMAX, D, WARPS) table
-    int blocks_per_sm;   // persistent CTAs per SM
-    bool enabled;
-};
-
-inline StreamCfg &stream_cfg() {
-    static StreamCfg cfg = [] {
-        StreamCfg c{0, 2, true};
-        if (const char *e = std::getenv("USPMV_SCS_KERNEL")) c.enabled = std::strcmp(e, "direct") != 0;
-        if (const char *e = std::getenv("USPMV_STREAM_VARIANT")) c.variant = std::atoi(e);
-        if (const char *e = std::getenv("USPMV_STREAM_BPS")) c.blocks_per_sm = std::max(1, std::atoi(e));
-        return c;
-    }();
-    return cfg;
-}
-
 template <typename VT, bool UNPERM, int LMAX, int D, int WARPS>
-void launch_stream_v(long n_chunks, const int *list, const int *cp, const int *cl, const int *ci, const VT *v, const VT *x, VT *y,
+void launch_stream_v(long n_chunks, const int *list, int off, const int *cp, const int *cl, const int *ci, const VT *v, const VT *x, VT *y,
                      const int *n2o, cudaStream_t st, int bps) {
     using R = stream::WarpRing<VT, LMAX, D>;
-    auto kern = stream::k_scs32_stream<VT, Arith<VT>, LMAX, D, WARPS, UNPERM>;
+    auto kern = stream::k_scs32_stream<VT, Arith<VT>, LMAX, D, WARPS, UNPERM, false>;
     constexpr int smem = WARPS * R::BYTES_ALIGNED;
     static bool configured = false;
     if (!configured) {
@@ -285,44 +268,81 @@ void launch_stream_v(long n_chunks, const int *list, const int *cp, const int *c
     long grid = (long)sm_count(dev) * bps;
     const long need = (n_chunks + WARPS - 1) / WARPS;
     if (grid > need) grid = need;
-    kern<<<(unsigned)grid, WARPS * 32, smem, st>>>(n_chunks, list, cp, cl, ci, v, x, y, n2o);
+    kern<<<(unsigned)grid, WARPS * 32, smem, st>>>(n_chunks, list, off, cp, cl, ci, v, x, y, n2o, stream::FusedArgs{});
 }
 
 template <typename VT, bool UNPERM>
-void launch_stream(long n_chunks, const int *list, const int *cp, const int *cl, const int *ci, const VT *v, const VT *x, VT *y,
+void launch_stream(long n_chunks, const int *list, int off, const int *cp, const int *cl, const int *ci, const VT *v, const VT *x, VT *y,
                    const int *n2o, cudaStream_t st) {
-    const StreamCfg c = stream_cfg();
-    switch (c.variant) {
-    case 1: launch_stream_v<VT, UNPERM, 8, 3, 8>(n_chunks, list, cp, cl, ci, v, x, y, n2o, st, c.blocks_per_sm); break;
-    case 2: launch_stream_v<VT, UNPERM, 8, 4, 8>(n_chunks, list, cp, cl, ci, v, x, y, n2o, st, c.blocks_per_sm); break;
-    case 3: launch_stream_v<VT, UNPERM, 4, 4, 16>(n_chunks, list, cp, cl, ci, v, x, y, n2o, st, c.blocks_per_sm); break;
-    case 4: launch_stream_v<VT, UNPERM, 4, 3, 16>(n_chunks, list, cp, cl, ci, v, x, y, n2o, st, c.blocks_per_sm); break;
-    case 5: launch_stream_v<VT, UNPERM, 4, 2, 16>(n_chunks, list, cp, cl, ci, v, x, y, n2o, st, c.blocks_per_sm); break;
-    case 6: launch_stream_v<VT, UNPERM, 8, 2, 8>(n_chunks, list, cp, cl, ci, v, x, y, n2o, st, c.blocks_per_sm); break;
-    case 7: launch_stream_v<VT, UNPERM, 16, 2, 8>(n_chunks, list, cp, cl, ci, v, x, y, n2o, st, c.blocks_per_sm); break;
-    case 8: launch_stream_v<VT, UNPERM, 8, 2, 32>(n_chunks, list, cp, cl, ci, v, x, y, n2o, st, c.blocks_per_sm); break;
-    case 9: launch_stream_v<VT, UNPERM, 2, 4, 16>(n_chunks, list, cp, cl, ci, v, x, y, n2o, st, c.blocks_per_sm); break;
-    default: launch_stream_v<VT, UNPERM, 8, 2, 16>(n_chunks, list, cp, cl, ci, v, x, y, n2o, st, c.blocks_per_sm); break;
+    const Options &c = options();
+    switch (c.stream_variant) {
+    case 1: launch_stream_v<VT, UNPERM, 8, 3, 8>(n_chunks, list, off, cp, cl, ci, v, x, y, n2o, st, c.stream_blocks_per_sm); break;
+    case 2: launch_stream_v<VT, UNPERM, 8, 4, 8>(n_chunks, list, off, cp, cl, ci, v, x, y, n2o, st, c.stream_blocks_per_sm); break;
+    case 3: launch_stream_v<VT, UNPERM, 4, 4, 16>(n_chunks, list, off, cp, cl, ci, v, x, y, n2o, st, c.stream_blocks_per_sm); break;
+    case 4: launch_stream_v<VT, UNPERM, 4, 3, 16>(n_chunks, list, off, cp, cl, ci, v, x, y, n2o, st, c.stream_blocks_per_sm); break;
+    case 5: launch_stream_v<VT, UNPERM, 4, 2, 16>(n_chunks, list, off, cp, cl, ci, v, x, y, n2o, st, c.stream_blocks_per_sm); break;
+    case 6: launch_stream_v<VT, UNPERM, 8, 2, 8>(n_chunks, list, off, cp, cl, ci, v, x, y, n2o, st, c.stream_blocks_per_sm); break;
+    case 7: launch_stream_v<VT, UNPERM, 16, 2, 8>(n_chunks, list, off, cp, cl, ci, v, x, y, n2o, st, c.stream_blocks_per_sm); break;
+    case 8: launch_stream_v<VT, UNPERM, 8, 2, 32>(n_chunks, list, off, cp, cl, ci, v, x, y, n2o, st, c.stream_blocks_per_sm); break;
+    case 9: launch_stream_v<VT, UNPERM, 2, 4, 16>(n_chunks, list, off, cp, cl, ci, v, x, y, n2o, st, c.stream_blocks_per_sm); break;
+    default: launch_stream_v<VT, UNPERM, 8, 2, 16>(n_chunks, list, off, cp, cl, ci, v, x, y, n2o, st, c.stream_blocks_per_sm); break;
     }
 }
 
+}  // namespace
+
+namespace uspmv {
+// One-launch distributed SpMV (C = 32): push + interior + wait + boundary + ack, see scs_stream.cuh.
+template <typename VT>
+static void launch_fused_t(const uspmv_scs *s, const void *x, void *y, const stream::FusedArgs &fa, cudaStream_t st) {
+    constexpr int LMAX = 8, D = 2, WARPS = 16;
+    using R = stream::WarpRing<VT, LMAX, D>;
+    auto kern = stream::k_scs32_stream<VT, Arith<VT>, LMAX, D, WARPS, false, true>;
+    constexpr int smem = WARPS * R::BYTES_ALIGNED;
+    static bool configured = false;
+    if (!configured) {
+        USPMV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    int dev = 0;
+    USPMV_CUDA(cudaGetDevice(&dev));
+    // every CTA must be resident at once (warps spin on peer flags): never more than 2 CTAs per SM
+    const long grid = (long)sm_count(dev) * 2;
+    kern<<<(unsigned)grid, WARPS * 32, smem, st>>>(fa.n_int + fa.n_bnd, nullptr, 0, s->chunk_ptrs.p, s->chunk_lengths.p, s->col_idxs.p,
+                                                 reinterpret_cast<const VT *>(s->values.p), static_cast<const VT *>(x), static_cast<VT *>(y),
+                                                 nullptr, fa);
+    USPMV_LAUNCH_CHECK();
+}
+
+void launch_scs32_fused(const uspmv_scs *s, const void *x, void *y, const stream::FusedArgs &fa, cudaStream_t st) {
+    if (s->C != 32) fail("fused halo exchange kernel needs C = 32 (got %ld)", s->C);
+    switch (s->vt) {
+    case USPMV_F64: launch_fused_t<double>(s, x, y, fa, st); break;
+    case USPMV_F32: launch_fused_t<float>(s, x, y, fa, st); break;
+    default: launch_fused_t<__half>(s, x, y, fa, st);
+    }
+}
+}  // namespace uspmv
+
+namespace {
+
 template <typename VT, bool UNPERM>
 void launch_scs(long C, long n_chunks, const int *cp, const int *cl, const int *ci, const void *vals, const void *x, void *y,
-                const int *n2o, cudaStream_t st, const int *list = nullptr) {
+                const int *n2o, cudaStream_t st, const int *list = nullptr, int off = 0) {
     // n_chunks = number of work items: all chunks, or the length of `list`
     const long n_pad = n_chunks * C;
     if (n_pad == 0) return;
     const VT *v = static_cast<const VT *>(vals);
     const VT *xx = static_cast<const VT *>(x);
     VT *yy = static_cast<VT *>(y);
-    if (C == 32 && stream_cfg().enabled) {
-        launch_stream<VT, UNPERM>(n_chunks, list, cp, cl, ci, v, xx, yy, n2o, st);
+    if (C == 32 && options().scs_stream) {
+        launch_stream<VT, UNPERM>(n_chunks, list, off, cp, cl, ci, v, xx, yy, n2o, st);
         USPMV_LAUNCH_CHECK();
         return;
     }
     const unsigned g = blocks_for(n_pad);
 #define USPMV_SCS_CASE(CC)                                                                                              \
-    case CC: k_scs_spmv<VT, CC, 8, UNPERM><<<g, TPB, 0, st>>>(n_pad, (int)C, list, cp, cl, ci, v, xx, yy, n2o); break;
+    case CC: k_scs_spmv<VT, CC, 8, UNPERM><<<g, TPB, 0, st>>>(n_pad, (int)C, list, off, cp, cl, ci, v, xx, yy, n2o); break;
     switch (C) {
         USPMV_SCS_CASE(1)
         USPMV_SCS_CASE(2)
@@ -333,7 +353,7 @@ void launch_scs(long C, long n_chunks, const int *cp, const int *cl, const int *
         USPMV_SCS_CASE(64)
         USPMV_SCS_CASE(128)
         USPMV_SCS_CASE(256)
-    default: k_scs_spmv<VT, 0, 8, UNPERM><<<g, TPB, 0, st>>>(n_pad, (int)C, list, cp, cl, ci, v, xx, yy, n2o);
+    default: k_scs_spmv<VT, 0, 8, UNPERM><<<g, TPB, 0, st>>>(n_pad, (int)C, list, off, cp, cl, ci, v, xx, yy, n2o);
     }
 #undef USPMV_SCS_CASE
     USPMV_LAUNCH_CHECK();
@@ -416,17 +436,6 @@ __global__ void k_apply_perm_block(VT *__restrict__ out, const VT *__restrict__ 
 
 extern "C" {
 
-int uspmv_set_option(const char *name, long value) {
-    return guarded([&] {
-        if (!name) fail("uspmv_set_option: name is NULL");
-        StreamCfg &c = stream_cfg();
-        if (!std::strcmp(name, "scs_stream")) c.enabled = value != 0;
-        else if (!std::strcmp(name, "stream_variant")) c.variant = (int)value;
-        else if (!std::strcmp(name, "stream_blocks_per_sm")) c.blocks_per_sm = (int)std::max(1L, value);
-        else fail("uspmv_set_option: unknown option '%s'", name);
-    });
-}
-
 int uspmv_scs_gpu(uspmv_ctx *ctx, int vt, long C, long n_chunks, const int *cp, const int *cl, const int *ci, const void *vals,
                   const void *x, void *y, void *stream) {
     return guarded([&] {
@@ -498,6 +507,10 @@ int uspmv_scs_split_chunks(uspmv_scs *s, long *n_interior, long *n_boundary) {
         if (!in.empty()) USPMV_CUDA(cudaMemcpy(s->interior_chunks.p, in.data(), in.size() * sizeof(int), cudaMemcpyHostToDevice));
         if (!bd.empty()) USPMV_CUDA(cudaMemcpy(s->boundary_chunks.p, bd.data(), bd.size() * sizeof(int), cudaMemcpyHostToDevice));
         s->chunks_split = true;
+        // a contiguous class (typical for slab partitions) needs no index list: chunk = k + offset
+        auto contiguous = [](const std::vector<int> &v) { return !v.empty() && (long)v.back() - v.front() + 1 == (long)v.size(); };
+        s->interior_contig = contiguous(in); s->interior_off = in.empty() ? 0 : in.front();
+        s->boundary_contig = contiguous(bd); s->boundary_off = bd.empty() ? 0 : bd.front();
         if (n_interior) *n_interior = (long)in.size();
         if (n_boundary) *n_boundary = (long)bd.size();
     });
@@ -514,11 +527,14 @@ int uspmv_spmv_part(const uspmv_scs *s, int which, const void *x, void *y, void 
         if (!s->chunks_split) fail("uspmv_spmv_part: call uspmv_scs_split_chunks first");
         const DevBuf<int> &l = which == 1 ? s->interior_chunks : s->boundary_chunks;
         if (l.n == 0) return;
+        const bool contig = which == 1 ? s->interior_contig : s->boundary_contig;
+        const int off = contig ? (which == 1 ? s->interior_off : s->boundary_off) : 0;
+        const int *lp = contig ? nullptr : l.p;
         cudaStream_t st = as_stream(stream);
         switch (s->vt) {
-        case USPMV_F64: launch_scs<double, false>(s->C, (long)l.n, s->chunk_ptrs.p, s->chunk_lengths.p, s->col_idxs.p, s->values.p, x, y, nullptr, st, l.p); break;
-        case USPMV_F32: launch_scs<float, false>(s->C, (long)l.n, s->chunk_ptrs.p, s->chunk_lengths.p, s->col_idxs.p, s->values.p, x, y, nullptr, st, l.p); break;
-        default: launch_scs<__half, false>(s->C, (long)l.n, s->chunk_ptrs.p, s->chunk_lengths.p, s->col_idxs.p, s->values.p, x, y, nullptr, st, l.p);
+        case USPMV_F64: launch_scs<double, false>(s->C, (long)l.n, s->chunk_ptrs.p, s->chunk_lengths.p, s->col_idxs.p, s->values.p, x, y, nullptr, st, lp, off); break;
+        case USPMV_F32: launch_scs<float, false>(s->C, (long)l.n, s->chunk_ptrs.p, s->chunk_lengths.p, s->col_idxs.p, s->values.p, x, y, nullptr, st, lp, off); break;
+        default: launch_scs<__half, false>(s->C, (long)l.n, s->chunk_ptrs.p, s->chunk_lengths.p, s->col_idxs.p, s->values.p, x, y, nullptr, st, lp, off);
         }
     });
 }

@@ -104,13 +104,59 @@ class HaloPlan:
             self.h = None
 
 
+class _DevArray:
+    """Zero-copy torch view of library-owned device memory (the P2P arena's x)."""
+
+    def __init__(self, ptr, n, np_dtype):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": np.dtype(np_dtype).str, "data": (int(ptr), False), "version": 3}
+
+
+class P2PHalo:
+    """NVLink peer-to-peer exchange (uspmv_p2p_*): arena with x + epoch flags, IPC handles all-gathered over
+    torch.distributed at setup; no collective call inside the SpMV loop."""
+
+    def __init__(self, plan: HaloPlan, vt: int, x_len: int, rank: int, world: int, group=None):
+        import torch
+        import torch.distributed as dist
+        from .engine import NP_OF
+        self.plan = plan
+        h, xptr = vp(), vp()
+        handle = (C.c_ubyte * 64)()
+        call("uspmv_p2p_create", plan.h, int(vt), int(x_len), C.byref(h), handle, C.byref(xptr))
+        self.h = h
+        es = {capi.F64: 8, capi.F32: 4, capi.F16: 2}[vt]
+        x_bytes = (x_len * es + 255) // 256 * 256
+        info = {"handle": bytes(handle), "x_bytes": x_bytes, "n_local": plan.scs.n_rows, "recv_cumsum": [int(v) for v in plan.recv_cumsum]}
+        infos = [None] * world
+        dist.all_gather_object(infos, info, group=group)
+        handles = b"".join(i["handle"] for i in infos)
+        peer_x_bytes = (C.c_long * world)(*[i["x_bytes"] for i in infos])
+        peer_base = (C.c_long * world)(*[i["n_local"] + i["recv_cumsum"][rank] for i in infos])
+        call("uspmv_p2p_connect", self.h, handles, peer_x_bytes, peer_base)
+        self.x = torch.as_tensor(_DevArray(xptr.value, x_len, NP_OF[vt]), device=f"cuda:{plan.scs.ctx.device}")
+        dist.barrier(group=group)
+
+    def spmv(self, scs, y, main_stream, comm_stream):
+        call("uspmv_p2p_spmv", self.h, scs.h, vp(y.data_ptr()), vp(main_stream.cuda_stream), vp(comm_stream.cuda_stream))
+
+    def status(self):
+        err, ep = C.c_int(0), C.c_long(0)
+        call("uspmv_p2p_status", self.h, C.byref(err), C.byref(ep))
+        return int(err.value), int(ep.value)
+
+    def __del__(self):
+        if getattr(self, "h", None) and capi is not None:
+            capi.lib.uspmv_p2p_destroy(self.h)
+            self.h = None
+
+
 class DistributedSpmv:
     """bench.py's N > 1 runner (weak scaling): every rank owns an n^3 z-slab of an n x n x (n*world) stencil grid.
     Harness order (main.cpp:1104-1128,1271-1308): slab -> convert_to_scs -> halo discovery -> permute_scs_cols."""
 
     kernel_name = "k_scs32_stream"
 
-    def __init__(self, ctx, points, n, C_, sigma, vt, rank, world, overlap=True, group=None):
+    def __init__(self, ctx, points, n, C_, sigma, vt, rank, world, overlap=True, group=None, halo="p2p"):
         import torch
         import torch.distributed as dist
         from . import engine as eng
@@ -132,7 +178,16 @@ class DistributedSpmv:
         dt = eng.torch_dtype(s.vt)
         dev = f"cuda:{ctx.device}"
         # vector length n_local + max(scs_padding, halo_count) (main.cpp:1405-1420)
-        self.x = torch.full((s.n_rows + max(s.n_rows_padded - s.n_rows, self.n_halo),), 5.0, dtype=dt, device=dev)
+        x_len = s.n_rows + max(s.n_rows_padded - s.n_rows, self.n_halo)
+        self.halo = halo
+        self.p2p = None
+        if halo == "p2p":
+            self.p2p = P2PHalo(self.plan, s.vt, x_len, rank, world, group)
+            call("uspmv_p2p_set_overlap", self.p2p.h, {True: 2, False: 0}.get(overlap, overlap))
+            self.x = self.p2p.x
+            self.x.fill_(5.0)
+        else:
+            self.x = torch.full((x_len,), 5.0, dtype=dt, device=dev)
         self.y = torch.zeros(s.n_rows_padded, dtype=dt, device=dev)
         self.sendbuf = torch.zeros(max(self.plan.n_send, 1), dtype=dt, device=dev)
         self.ex = HaloExchange(rank, world, s.n_rows, self.plan.recv_cumsum, self.plan.send_ptr, group)
@@ -145,6 +200,9 @@ class DistributedSpmv:
     def step(self):
         torch, eng = self._torch, self._eng
         main = torch.cuda.current_stream()
+        if self.p2p is not None:
+            self.p2p.spmv(self.scs, self.y, main, self.comm_stream)
+            return
         if not self.overlap:
             self.plan.pack(self.x, self.sendbuf)
             HaloExchange.finish(self.ex.begin(self.x, self.sendbuf))

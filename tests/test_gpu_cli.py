@@ -1,0 +1,85 @@
+"""The C++ host side on a GPU: `uspmv` harness clone (same CLI / report file as the reference) and the
+interface.hpp-style shim example."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import load_matrix
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "ultimate-spmv_b200", "bin")
+
+
+def write_mtx(path, name):
+    n, nc, I, J, V = load_matrix(name)
+    with open(path, "w") as f:
+        f.write("%%MatrixMarket matrix coordinate real general\n")
+        f.write(f"{n} {nc} {len(I)}\n")
+        for i, j, v in zip(I, J, V):
+            f.write(f"{i + 1} {j + 1} {float(v)!r}\n")
+    return path
+
+
+def run(args, cwd):
+    return subprocess.run([os.path.join(BIN, "uspmv")] + args, cwd=cwd, capture_output=True, text=True, timeout=300)
+
+
+def test_interface_shim_example(eng):
+    r = subprocess.run([os.path.join(BIN, "example_interface")], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "max|y - y_coo|" in r.stdout
+
+
+@pytest.mark.parametrize("fmt_args", [["scs", "-c", "32", "-s", "512"], ["scs", "-c", "16", "-s", "64"], ["crs"], ["scs", "-c", "4", "-s", "1"]])
+@pytest.mark.parametrize("vt", ["-dp", "-sp"])
+def test_cli_solve_mode_validates(eng, tmp_path, fmt_args, vt):
+    m = write_mtx(str(tmp_path / "bcsstk13.mtx"), "bcsstk13")
+    r = run([m] + fmt_args + [vt, "-mode", "s", "-rev", "2", "-rand_x", "1"], str(tmp_path))
+    assert r.returncode == 0, r.stdout + r.stderr
+    m_ = re.search(r"max relative difference ([0-9.e+-]+) -> (\w+)", r.stdout)
+    assert m_, r.stdout
+    # single precision on this ill-scaled matrix cancels heavily after two revisions: WARNING (> 1e-4) is acceptable there,
+    # ERROR (> 1e-2, the reference's failure threshold, write_results.hpp:422-428) never is
+    assert m_.group(2) == "OK" if vt == "-dp" else m_.group(2) in ("OK", "WARNING")
+    assert float(m_.group(1)) < (1e-10 if vt == "-dp" else 1e-2)
+
+
+def test_cli_bench_mode_report_file(eng, tmp_path):
+    m = write_mtx(str(tmp_path / "bcsstk13.mtx"), "bcsstk13")
+    r = run([m, "scs", "-c", "32", "-s", "512", "-dp", "-mode", "b", "-bench_time", "0.2"], str(tmp_path))
+    assert r.returncode == 0, r.stdout + r.stderr
+    rep = open(tmp_path / "spmv_bench.txt").read()
+    # same layout as write_bench_to_file (write_results.hpp:43-157); scripts/scrape_perf.py greps "Total Gflops:"
+    assert re.search(r"bcsstk13\.mtx with \d+ block\(s\), and \d+ thread\(s\) per block", rep)
+    assert re.search(r"kernel: scs, block_vec_size: 1, C: 32 sigma: 512, beta: 0\.\d{8}, block_vec_layout: colwise, data_type: double, revisions: \d+", rep)
+    assert "Total Gflops:" in rep and "Total Walltime:" in rep
+    # beta of the reference for this matrix / C / sigma (n_elements = 88 672)
+    assert "beta: 0.94599197" in rep
+
+
+def test_cli_spmmv_ap_and_generator(eng, tmp_path):
+    m = write_mtx(str(tmp_path / "impcol_e.mtx"), "impcol_e")
+    for extra in (["-block_vec_size", "4", "-block_vec_layout", "rowwise"], ["-block_vec_size", "3"]):
+        r = run([m, "scs", "-c", "8", "-s", "16", "-dp", "-mode", "s", "-rand_x", "1"] + extra, str(tmp_path))
+        assert r.returncode == 0 and "-> OK" in r.stdout, r.stdout + r.stderr
+    r = run([m, "scs", "-c", "8", "-s", "16", "-ap[dp_sp_hp]", "-apt1", "10", "-apt2", "0.1", "-mode", "s", "-rand_x", "1"], str(tmp_path))
+    assert r.returncode == 0 and ("-> OK" in r.stdout or "-> WARNING" in r.stdout), r.stdout + r.stderr
+    r = run(["gen:laplace7:64", "scs", "-c", "32", "-s", "1", "-dp", "-mode", "b", "-bench_time", "0.1"], str(tmp_path))
+    assert r.returncode == 0 and "Total Gflops" in r.stdout, r.stdout + r.stderr
+    assert "262144 rows, 1810432 nnz" in r.stdout
+
+
+def test_cli_rejections(eng, tmp_path):
+    m = write_mtx(str(tmp_path / "m.mtx"), "myMat")
+    for args, msg in ((["scs", "-c", "0"], "chunk size must be >= 1"),
+                      (["scs", "-block_vec_size", "2", "-ap[dp_sp]"], "SpMMV is not yet implemented for AP kernels"),
+                      (["scs", "-block_vec_layout", "rowwise"], "Row-wise block vector layout selected, but block vector width is 1"),
+                      (["ell"], "kernel format not recognized"),
+                      (["scs", "-ap[dp_sp_hp]", "-apt1", "1", "-apt2", "2"], "second threshold is larger than the first"),
+                      (["scs", "-bogus"], "unknown argument")):
+        r = run([m] + args, str(tmp_path))
+        assert r.returncode != 0 and msg in r.stderr, (args, r.stderr)

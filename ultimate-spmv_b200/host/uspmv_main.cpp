@@ -1,0 +1,462 @@
+// uspmv — harness CLI clone of the reference's benchmark driver (code/main.cpp) on top of libuspmv_b200.so.
+//
+//   ./uspmv <matrix.mtx | gen:laplace7:<n> | gen:stencil27:<n>> <crs|csr|scs> [options]
+//
+// Same positional arguments, flags (dash and underscore spellings), defaults, rejections and report file
+// (spmv_bench.txt, write_results.hpp:43-157) as the reference (utilities.hpp:983-1545, classes_structs.hpp:47-153).
+// Host side is plain C++ (no CUDA headers); everything numerical goes through the C ABI (include/uspmv_b200.h).
+// Protocol of bench mode (main.cpp:380-527): x = 5.0 (or random / matrix mean) in permuted space, 100 warm-up SpMVs,
+// then n_iter = 2,4,8,... until one loop takes >= bench_time; Gflops = 2*nnz*block_vec_size / (t / n_iter) / 1e9.
+// Solve mode (main.cpp:528-631): `rev` x { SpMV ; y becomes the next x }, result un-permuted and compared with a
+// host-side COO product (the reference needs MKL for this step, write_results.hpp:442-556).
+// Single process = single GPU here; the multi-GPU path is launched with torchrun (bench.py / dist.py).
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <fstream>
+#include <iomanip>
+#include <iostream>
+#include <numeric>
+#include <random>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "../../include/uspmv_b200.h"
+
+using ST = long;
+
+namespace {
+
+struct Config {  // classes_structs.hpp:47-153
+    long chunk_size = 1, sigma = 1;
+    char random_init_x = '0';
+    unsigned long n_repetitions = 1;
+    int validate_result = 1, verbose = 0, block_vec_size = 1, comm_halos = 1, ba_synch = 1, par_pack = 0, no_pack = 0, print_comm_vol = 0,
+        equilibrate = 0;
+    char mode = 'b';
+    double bench_time = 5.0, ap_threshold_1 = 0.0, ap_threshold_2 = 0.0, dropout = 0, dropout_threshold = 0.0;
+    double matrix_min = 1.0, matrix_mean = 1.0, matrix_max = 1.0;
+    std::string matrix_file_name, seg_method = "seg-rows", value_type = "dp", kernel_format = "scs", block_vec_layout = "colwise";
+    std::string output_filename_bench = "spmv_bench.txt";
+};
+
+[[noreturn]] void die(const char *msg) {
+    fprintf(stderr, "%s\n", msg);
+    exit(1);
+}
+void ck(int rc) {
+    if (rc) {
+        fprintf(stderr, "uspmv ERROR: %s\n", uspmv_last_error());
+        exit(1);
+    }
+}
+
+void usage(const char *argv0, const Config &c) {
+    fprintf(stderr,
+            "Usage: %s <martix-market-filename | gen:laplace7:<n> | gen:stencil27:<n>> <kernel-format> [options]\n "
+            "options [defaults] (description): \n"
+            "-block_vec_size [%i] (int: width of block vectors for SpMMV) \n"
+            "-block_vec_layout [%s] (colwise/rowwise: block vector layout; a compile-time switch in the reference) \n"
+            "-c [%li] (int: chunk size (required for scs)) \n"
+            "-s [%li] (int: sigma (required for scs)) \n"
+            "-rev [%li] (int: number of back-to-back revisions to perform) \n"
+            "-rand_x [%c] (0/1: random x vector option) \n"
+            "-dp / sp / hp / ap[dp_sp] / ap[dp_hp] / ap[sp_hp] / ap[dp_sp_hp] [%s] (numerical precision of matrix data) \n"
+            "-seg_metis / seg_nnz / seg_rows [%s] (global matrix partitioning; multi-GPU runs use torchrun + bench.py) \n"
+            "-validate [%i] (0/1: check result against a host COO product in solve mode) \n"
+            "-verbose [%i] (0/1: verbose validation of results) \n"
+            "-mode [%c] ('s'/'b': either in solve mode or bench mode) \n"
+            "-bench_time [%g] (float: minimum number of seconds for SpMV benchmark) \n"
+            "-ba_synch [%i] -comm_halos [%i] -par_pack [%i] -no_pack [%i] (accepted for compatibility; single process) \n"
+            "-equilibrate [%i] (0/1: normalize rows of matrix) \n"
+            "--------------------------- Adaptive Precision Options --------------------------- \n"
+            "-ap_threshold_1 [%f] (float: threshold for two-way matrix partitioning for adaptive precision `-ap`) \n"
+            "-ap_threshold_2 [%f] (float: threshold for three-way matrix partitioning for adaptive precision `-ap`) \n"
+            "-dropout[%f] (0/1: enable dropout of elements below theh designated threshold) \n"
+            "-dropout_threshold [%f] (float: remove matrix elements below this range) \n\n",
+            argv0, c.block_vec_size, c.block_vec_layout.c_str(), c.chunk_size, c.sigma, (long)c.n_repetitions, c.random_init_x,
+            c.value_type.c_str(), c.seg_method.c_str(), c.validate_result, c.verbose, c.mode, c.bench_time, c.ba_synch, c.comm_halos,
+            c.par_pack, c.no_pack, c.equilibrate, c.ap_threshold_1, c.ap_threshold_2, c.dropout, c.dropout_threshold);
+}
+
+bool is_ap(const std::string &v) { return v.rfind("ap[", 0) == 0; }
+
+void parse_cli(int argc, char **argv, Config &c) {  // utilities.hpp:1047-1545
+    if (argc < 3) { usage(argv[0], c); exit(1); }
+    c.matrix_file_name = argv[1];
+    c.kernel_format = argv[2];
+    auto need = [&](int &i) -> const char * {
+        if (i + 1 >= argc) { fprintf(stderr, "ERROR: missing value for %s\n", argv[i]); usage(argv[0], c); exit(1); }
+        return argv[++i];
+    };
+    auto bad = [&](const char *m) { fprintf(stderr, "%s\n", m); usage(argv[0], c); exit(1); };
+    for (int i = 3; i < argc; ++i) {
+        std::string a = argv[i];
+        std::replace(a.begin() + 1, a.end(), '-', '_');  // "-bench-time" == "-bench_time"
+        if (a == "-c") { c.chunk_size = atoi(need(i)); if (c.chunk_size < 1) bad("ERROR: chunk size must be >= 1."); }
+        else if (a == "-s") { c.sigma = atoi(need(i)); if (c.sigma < 1) bad("ERROR: sigma must be >= 1."); }
+        else if (a == "-block_vec_size") { c.block_vec_size = atoi(need(i)); if (c.block_vec_size < 1) bad("ERROR: block_vec_size must be >= 1."); }
+        else if (a == "-block_vec_layout") { c.block_vec_layout = need(i); if (c.block_vec_layout != "colwise" && c.block_vec_layout != "rowwise") bad("ERROR: block_vec_layout must be colwise or rowwise."); }
+        else if (a == "-bench_time") { c.bench_time = atof(need(i)); if (c.bench_time < 0) bad("ERROR: bench_time must be > 0."); }
+        else if (a == "-rev") { long r = atol(need(i)); if (r < 1) bad("ERROR: revisions must be >= 1."); c.n_repetitions = r; }
+        else if (a == "-verbose") { c.verbose = atoi(need(i)); if (c.verbose != 0 && c.verbose != 1) bad("ERROR: Only validation verbosity levels 0 and 1 are supported."); }
+        else if (a == "-validate") { c.validate_result = atoi(need(i)); if (c.validate_result != 0 && c.validate_result != 1) bad("ERROR: You can only choose to validate result (1, i.e. yes) or not (0, i.e. no)."); }
+        else if (a == "-mode") { c.mode = need(i)[0]; if (c.mode != 'b' && c.mode != 's') bad("ERROR: Only bench (b) and solve (s) modes are supported."); }
+        else if (a == "-rand_x") { c.random_init_x = need(i)[0]; if (c.random_init_x != '0' && c.random_init_x != '1' && c.random_init_x != 'm') bad("ERROR: You can only choose to initialize x randomly (1), with the default value (0) or the matrix mean (m)."); }
+        else if (a == "-comm_halos") c.comm_halos = atoi(need(i));
+        else if (a == "-ba_synch") c.ba_synch = atoi(need(i));
+        else if (a == "-par_pack") c.par_pack = atoi(need(i));
+        else if (a == "-no_pack") c.no_pack = atoi(need(i));
+        else if (a == "-print_comm_vol") c.print_comm_vol = atoi(need(i));
+        else if (a == "-ap_threshold_1" || a == "-apt1") { c.ap_threshold_1 = atof(need(i)); if (c.ap_threshold_1 < 0) bad("ERROR: ap_threshold_1 must be nonnegative."); }
+        else if (a == "-ap_threshold_2" || a == "-apt2") { c.ap_threshold_2 = atof(need(i)); if (c.ap_threshold_2 < 0) bad("ERROR: ap_threshold_2 must be nonnegative."); }
+        else if (a == "-dropout" || a == "-do") c.dropout = atof(need(i));
+        else if (a == "-dropout_threshold" || a == "-dt") c.dropout_threshold = atof(need(i));
+        else if (a == "-equilibrate") c.equilibrate = atoi(need(i));
+        else if (a == "-dp" || a == "-sp" || a == "-hp") c.value_type = a.substr(1);
+        else if (a == "-ap[dp_sp]" || a == "-ap[sp_hp]" || a == "-ap[dp_hp]" || a == "-ap[dp_sp_hp]") c.value_type = a.substr(1);
+        else if (a == "-seg_rows") c.seg_method = "seg-rows";
+        else if (a == "-seg_nnz") c.seg_method = "seg-nnz";
+        else if (a == "-seg_metis") c.seg_method = "seg-metis";
+        else { fprintf(stderr, "ERROR: unknown argument: %s\n", argv[i]); usage(argv[0], c); exit(1); }
+    }
+    // sanity checks, utilities.hpp:1371-1545
+    if (c.block_vec_layout == "rowwise" && c.block_vec_size == 1)
+        die("ERROR: Row-wise block vector layout selected, but block vector width is 1.\n Please choose colwise block vector layout if using SpMV.");
+    if (c.block_vec_size > 1 && is_ap(c.value_type)) die("ERROR: SpMMV is not yet implemented for AP kernels.");
+    if (c.block_vec_size > 16) die("ERROR: block_vec_size > 16 is not supported by the GPU SpMMV kernels.");
+    if (c.seg_method == "seg-metis") die("ERROR: seg-metis selected, but USE_METIS not defined in Makefile.");
+    if (!is_ap(c.value_type) && c.ap_threshold_1 > 0.0) fprintf(stderr, "WARNING: First adaptive precision threshold entered, but not used.\n");
+    if (c.value_type != "ap[dp_sp_hp]" && c.ap_threshold_2 > 0.0)
+        fprintf(stderr, "WARNING: Second adaptive precision threshold entered, but three-way partitioning is not used.\n");
+    if ((c.value_type == "ap[dp_sp]" || c.value_type == "ap[sp_hp]" || c.value_type == "ap[dp_hp]") && c.ap_threshold_1 == 0.0)
+        fprintf(stderr, "WARNING: Two-way adaptive precision used, but the first threshold is not entered.\n");
+    if (c.value_type == "ap[dp_sp_hp]") {
+        if (c.ap_threshold_1 == 0.0) fprintf(stderr, "WARNING: Three-way adaptive precision used, but the first threshold is not entered.\n");
+        if (c.ap_threshold_2 == 0.0) fprintf(stderr, "WARNING: Three-way adaptive precision used, but the second threshold is not entered.\n");
+        if (c.ap_threshold_1 <= c.ap_threshold_2) die("ERROR: Three-way adaptive precision used, but the second threshold is larger than the first.");
+    }
+    if (c.dropout && c.dropout_threshold == 0.0) fprintf(stderr, "WARNING: Dropout selected, but dropout_threshold is 0.\n");
+    if (c.kernel_format != "crs" && c.kernel_format != "csr" && c.kernel_format != "scs") die("ERROR: kernel format not recognized.");
+    if (c.kernel_format != "scs") { c.chunk_size = 1; c.sigma = 1; }  // CRS is the C = 1, sigma = 1 instance
+    printf("Single process: forcing comm_halos = 0.\n");
+    c.comm_halos = 0;
+}
+
+struct Coo {
+    ST n_rows = 0, n_cols = 0;
+    std::vector<int> I, J;
+    std::vector<double> V;
+};
+
+// read_mtx (utilities.hpp:2148-2309 + mmio.h:138-263): real/integer/pattern, general/symmetric; symmetric entries expanded as
+// (i,j) immediately followed by (j,i); stable sort by row.
+Coo read_mtx(const std::string &path) {
+    std::ifstream f(path);
+    if (!f) die("Unable to open file");
+    std::string line;
+    std::getline(f, line);
+    std::istringstream b(line);
+    std::string banner, obj, fmt, field, symm;
+    b >> banner >> obj >> fmt >> field >> symm;
+    auto lower = [](std::string s) { std::transform(s.begin(), s.end(), s.begin(), ::tolower); return s; };
+    obj = lower(obj); fmt = lower(fmt); field = lower(field); symm = lower(symm);
+    if (banner != "%%MatrixMarket") die("mm_read_unsymetric: Could not process Matrix Market banner");
+    if (obj != "matrix" || fmt != "coordinate") die("The matrix market file provided is not supported.\n Reason :\n * matrix has to be sparse");
+    if (field != "real" && field != "integer" && field != "pattern") die("The matrix market file provided is not supported.\n Reason :\n * matrix has to be real or pattern");
+    if (symm != "general" && symm != "symmetric") die("The matrix market file provided is not supported.\n Reason :\n * matrix has to be either general or symmetric");
+    do { if (!std::getline(f, line)) die("read_unsymmetric_sparse(): could not parse matrix size."); } while (line.empty() || line[0] == '%');
+    long M, N, nz;
+    { std::istringstream s(line); if (!(s >> M >> N >> nz)) die("read_unsymmetric_sparse(): could not parse matrix size."); }
+    if (M != N) die("Matrix not square. Currently only square matrices are supported");
+    std::vector<int> I, J;
+    std::vector<double> V;
+    I.reserve(nz * 2); J.reserve(nz * 2); V.reserve(nz * 2);
+    const bool pattern = field == "pattern", sym = symm == "symmetric";
+    for (long k = 0; k < nz; ++k) {
+        long i, j;
+        double v = 0.01;  // pattern matrices: mmio.h:195-203
+        if (!(f >> i >> j)) die("Error in file reading");
+        if (!pattern && !(f >> v)) die("Error in file reading");
+        I.push_back((int)i - 1); J.push_back((int)j - 1); V.push_back(v);
+        if (sym && i != j) { I.push_back((int)j - 1); J.push_back((int)i - 1); V.push_back(v); }
+    }
+    std::vector<int> perm(I.size());
+    std::iota(perm.begin(), perm.end(), 0);
+    std::stable_sort(perm.begin(), perm.end(), [&](int a, int c) { return I[a] < I[c]; });
+    Coo m;
+    m.n_rows = M; m.n_cols = N;
+    m.I.resize(I.size()); m.J.resize(I.size()); m.V.resize(I.size());
+    for (size_t k = 0; k < perm.size(); ++k) { m.I[k] = I[perm[k]]; m.J[k] = J[perm[k]]; m.V[k] = V[perm[k]]; }
+    return m;
+}
+
+double now() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);  // timing.c:3-8
+    return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+
+size_t vt_bytes(int vt) { return vt == USPMV_F64 ? 8 : vt == USPMV_F32 ? 4 : 2; }
+
+// double -> fp16 bits (round to nearest even), for uploading x in half precision without _Float16 support
+unsigned short f2h(double d) {
+#if defined(__FLT16_MAX__)
+    _Float16 h = (_Float16)d;
+    unsigned short b;
+    memcpy(&b, &h, 2);
+    return b;
+#else
+    float f = (float)d;
+    unsigned int x;
+    memcpy(&x, &f, 4);
+    unsigned int sign = (x >> 16) & 0x8000u;
+    int e = (int)((x >> 23) & 0xff) - 127 + 15;
+    unsigned int m = x & 0x7fffffu;
+    if (e <= 0) return (unsigned short)sign;
+    if (e >= 31) return (unsigned short)(sign | 0x7c00u);
+    unsigned int h = sign | (e << 10) | (m >> 13);
+    if ((m & 0x1000u) && ((m & 0x2fffu) != 0)) ++h;
+    return (unsigned short)h;
+#endif
+}
+double h2d(unsigned short b) {
+#if defined(__FLT16_MAX__)
+    _Float16 h;
+    memcpy(&h, &b, 2);
+    return (double)h;
+#else
+    int s = (b >> 15) & 1, e = (b >> 10) & 31, m = b & 1023;
+    double v = e == 0 ? std::ldexp((double)m, -24) : e == 31 ? (m ? NAN : INFINITY) : std::ldexp((double)(m + 1024), e - 25);
+    return s ? -v : v;
+#endif
+}
+
+void upload(uspmv_ctx *ctx, void *dst, const std::vector<double> &src, int vt) {
+    const size_t n = src.size();
+    if (vt == USPMV_F64) ck(uspmv_memcpy_h2d(ctx, dst, src.data(), n * 8, nullptr));
+    else if (vt == USPMV_F32) { std::vector<float> t(src.begin(), src.end()); ck(uspmv_memcpy_h2d(ctx, dst, t.data(), n * 4, nullptr)); }
+    else { std::vector<unsigned short> t(n); for (size_t i = 0; i < n; ++i) t[i] = f2h(src[i]); ck(uspmv_memcpy_h2d(ctx, dst, t.data(), n * 2, nullptr)); }
+}
+std::vector<double> download(uspmv_ctx *ctx, const void *src, size_t n, int vt) {
+    std::vector<double> out(n);
+    if (vt == USPMV_F64) ck(uspmv_memcpy_d2h(ctx, out.data(), src, n * 8, nullptr));
+    else if (vt == USPMV_F32) { std::vector<float> t(n); ck(uspmv_memcpy_d2h(ctx, t.data(), src, n * 4, nullptr)); std::copy(t.begin(), t.end(), out.begin()); }
+    else { std::vector<unsigned short> t(n); ck(uspmv_memcpy_d2h(ctx, t.data(), src, n * 2, nullptr)); for (size_t i = 0; i < n; ++i) out[i] = h2d(t[i]); }
+    return out;
+}
+
+}  // namespace
+
+int main(int argc, char **argv) {
+    Config cfg;
+    parse_cli(argc, argv, cfg);
+    uspmv_ctx *ctx = nullptr;
+    ck(uspmv_ctx_create(0, &ctx));
+
+    // ---- matrix ------------------------------------------------------------------------------------------------------
+    uspmv_coo *coo = nullptr;
+    Coo host;  // kept only when a file was read (needed for validation / x statistics)
+    bool have_host = false;
+    if (cfg.matrix_file_name.rfind("gen:", 0) == 0) {
+        char kind[32];
+        long n = 0;
+        if (sscanf(cfg.matrix_file_name.c_str(), "gen:%31[^:]:%ld", kind, &n) != 2 || n < 1) die("ERROR: generator syntax is gen:laplace7:<n> or gen:stencil27:<n>");
+        int pts = !strcmp(kind, "laplace7") ? 7 : !strcmp(kind, "stencil27") ? 27 : 0;
+        if (!pts) die("ERROR: unknown generator");
+        ck(uspmv_coo_stencil(ctx, pts, n, n, n, 0, n * n * n, &coo));
+        cfg.matrix_min = -1.0; cfg.matrix_max = pts - 1.0; cfg.matrix_mean = 0.0;
+    } else {
+        host = read_mtx(cfg.matrix_file_name);
+        have_host = true;
+        if (host.V.empty()) die("ERROR: empty matrix");
+        if (cfg.dropout) {  // -dropout: remove elements below the threshold (utilities.hpp, -dt)
+            Coo k; k.n_rows = host.n_rows; k.n_cols = host.n_cols;
+            for (size_t i = 0; i < host.V.size(); ++i)
+                if (std::fabs(host.V[i]) >= cfg.dropout_threshold) { k.I.push_back(host.I[i]); k.J.push_back(host.J[i]); k.V.push_back(host.V[i]); }
+            host = k;
+        }
+        cfg.matrix_min = *std::min_element(host.V.begin(), host.V.end());
+        cfg.matrix_max = *std::max_element(host.V.begin(), host.V.end());
+        cfg.matrix_mean = std::accumulate(host.V.begin(), host.V.end(), 0.0) / host.V.size();
+        ck(uspmv_coo_from_host(ctx, host.n_rows, host.n_cols, (long)host.V.size(), host.I.data(), host.J.data(), host.V.data(), USPMV_F64, &coo));
+    }
+    long cd[3];
+    ck(uspmv_coo_dims(coo, cd));
+    const long n_rows = cd[0], nnz = cd[2];
+
+    // ---- format conversion (convert_to_scs, partition_precisions, permute_scs_cols; main.cpp:1128-1221,1308) ---------
+    const bool ap = is_ap(cfg.value_type);
+    const int ap_mode = cfg.value_type == "ap[dp_sp]" ? USPMV_AP_DP_SP : cfg.value_type == "ap[dp_hp]" ? USPMV_AP_DP_HP
+                        : cfg.value_type == "ap[sp_hp]" ? USPMV_AP_SP_HP : USPMV_AP_DP_SP_HP;
+    const int vt = cfg.value_type == "sp" ? USPMV_F32 : cfg.value_type == "hp" ? USPMV_F16 : USPMV_F64;
+    uspmv_scs *scs = nullptr, *part[3] = {nullptr, nullptr, nullptr};
+    long dims[8];
+    double t0 = now();
+    long part_nnz[3] = {0, 0, 0};
+    if (!ap) {
+        ck(uspmv_scs_build(ctx, coo, cfg.chunk_size, cfg.sigma, vt, nullptr, &scs));
+        ck(uspmv_scs_permute_cols(scs, nullptr));
+        ck(uspmv_scs_dims(scs, dims));
+    } else {
+        uspmv_coo *pc[3] = {nullptr, nullptr, nullptr};
+        ck(uspmv_partition_precisions(ctx, coo, ap_mode, cfg.ap_threshold_1, cfg.ap_threshold_2, nullptr, nullptr, &pc[0], &pc[1], &pc[2]));
+        const int first = ap_mode == USPMV_AP_SP_HP ? 1 : 0;
+        const int vts[3] = {USPMV_F64, USPMV_F32, USPMV_F16};
+        ck(uspmv_scs_build(ctx, pc[first], cfg.chunk_size, cfg.sigma, vts[first], nullptr, &part[first]));
+        ck(uspmv_scs_dims(part[first], dims));
+        std::vector<int> perm(dims[2]);
+        ck(uspmv_scs_export(part[first], nullptr, nullptr, nullptr, nullptr, perm.data(), nullptr));
+        for (int p = 0; p < 3; ++p) {
+            if (!pc[p]) continue;
+            long d3[3];
+            ck(uspmv_coo_dims(pc[p], d3));
+            part_nnz[p] = d3[2];
+            if (p != first) ck(uspmv_scs_build(ctx, pc[p], cfg.chunk_size, cfg.sigma, vts[p], perm.data(), &part[p]));  // fixed_permutation, main.cpp:1175-1219
+            uspmv_coo_destroy(pc[p]);
+        }
+        // the AP structs keep ORIGINAL column numbering (they are never column-permuted in the reference either,
+        // main.cpp:1308-1332); x is therefore used un-permuted and only y comes out in permuted row order.
+    }
+    const double t_convert = now() - t0;
+    const long n_pad = dims[4], n_chunks = dims[5];
+    long n_elements = dims[6];
+    if (ap) { n_elements = 0; for (int p = 0; p < 3; ++p) if (part[p]) { long d[8]; ck(uspmv_scs_dims(part[p], d)); n_elements += d[6]; } }
+    const double beta = n_elements ? (double)nnz / (double)n_elements : 0.0;
+    printf("matrix: %ld rows, %ld nnz; C=%ld sigma=%ld: %ld chunks, %ld elements, beta=%.8f; conversion on device took %.3f s\n", n_rows, nnz,
+           cfg.chunk_size, cfg.sigma, n_chunks, n_elements, beta, t_convert);
+
+    // ---- vectors (main.cpp:1405-1431; utilities.hpp:880-981) -------------------------------------------------------------
+    const int bvs = cfg.block_vec_size;
+    const int layout = cfg.block_vec_layout == "rowwise" ? USPMV_ROWWISE : USPMV_COLWISE;
+    const long vec_length = std::max(n_pad, n_rows);  // n_local + per_vector_padding (no halo in a single process)
+    const int xvt = ap ? (ap_mode == USPMV_AP_SP_HP ? USPMV_F32 : USPMV_F64) : vt;
+    std::vector<double> x_user(vec_length * bvs, 0.0);
+    {
+        std::mt19937 engine;  // default-seeded, like random_init (utilities.hpp:880-912)
+        std::uniform_real_distribution<double> dist(cfg.matrix_min, cfg.matrix_max);
+        for (long i = 0; i < vec_length * bvs; ++i) {
+            double v = cfg.random_init_x == '1' ? dist(engine) : cfg.random_init_x == 'm' ? cfg.matrix_mean : 5.0;  // DefaultValues x = 5.0
+            const long r = layout == USPMV_ROWWISE ? i / bvs : i % vec_length;
+            x_user[i] = r < n_rows ? v : 0.0;  // padding slots zeroed (utilities.hpp:948-981)
+        }
+    }
+    std::vector<int> old_to_new(n_rows), new_to_old(n_pad);
+    ck(uspmv_scs_export(ap ? part[ap_mode == USPMV_AP_SP_HP ? 1 : 0] : scs, nullptr, nullptr, nullptr, nullptr, old_to_new.data(), new_to_old.data()));
+    // x_perm[i] = x[new_to_old[i]] (main.cpp:86-102); AP: x stays in user order (see above)
+    std::vector<double> x_perm(vec_length * bvs, 0.0);
+    for (long v = 0; v < bvs; ++v)
+        for (long i = 0; i < n_rows; ++i) {
+            const long dst = ap ? i : old_to_new[i];
+            if (layout == USPMV_ROWWISE) x_perm[dst * bvs + v] = x_user[i * bvs + v];
+            else x_perm[dst + v * vec_length] = x_user[i + v * vec_length];
+        }
+    void *x_d = nullptr, *y_d = nullptr;
+    ck(uspmv_malloc(ctx, vec_length * bvs * vt_bytes(xvt), &x_d));
+    ck(uspmv_malloc(ctx, vec_length * bvs * vt_bytes(xvt), &y_d));
+    ck(uspmv_memset(ctx, y_d, 0, vec_length * bvs * vt_bytes(xvt), nullptr));
+    upload(ctx, x_d, x_perm, xvt);
+
+    auto execute = [&]() {  // SpmvKernel::execute (classes_structs.hpp:997-1127)
+        if (ap) ck(uspmv_ap_spmv(ap_mode, part[0], part[1], part[2], x_d, y_d, nullptr));
+        else if (bvs > 1) ck(uspmv_spmmv(scs, x_d, y_d, bvs, vec_length, layout, nullptr));
+        else ck(uspmv_spmv(scs, x_d, y_d, nullptr));
+    };
+
+    if (cfg.mode == 'b') {
+        const int WARM_UP_REPS = 100;  // main.cpp:22
+        ck(uspmv_ctx_sync(ctx));
+        double tw = now();
+        for (int k = 0; k < WARM_UP_REPS; ++k) execute();
+        ck(uspmv_ctx_sync(ctx));
+        std::cout << "warm up time: " << now() - tw << std::endl;
+        long n_iter = 2;
+        double runtime = 0.0;
+        do {
+            ck(uspmv_ctx_sync(ctx));
+            const double tb = now();
+            for (long k = 0; k < n_iter; ++k) execute();
+            ck(uspmv_ctx_sync(ctx));
+            runtime = now() - tb;
+            n_iter *= 2;
+        } while (runtime < cfg.bench_time);
+        n_iter /= 2;
+        const double t_kernel = runtime / n_iter;
+        const double gflops = (double)nnz * 2.0 * bvs / t_kernel / 1e9;  // "only count useful flops", main.cpp:521-526
+        const size_t vs = vt_bytes(vt);
+        const double bytes = ap ? 0.0 : (double)n_elements * (vs + 4) + 8.0 * n_chunks + (double)bvs * vs * (n_rows + n_pad);
+        printf("Total Gflops: %.6f   time per SpM(M)V: %.3f us   revisions: %ld", gflops, t_kernel * 1e6, n_iter);
+        if (!ap) printf("   model bandwidth: %.1f GB/s", bytes / t_kernel / 1e9);
+        printf("\n");
+        // ---- spmv_bench.txt, same layout as write_bench_to_file (write_results.hpp:43-157, nvcc branch) ----
+        std::fstream out(cfg.output_filename_bench, std::fstream::in | std::fstream::out | std::fstream::app);
+        const int width = 32;
+        out << cfg.matrix_file_name << " with " << (n_pad + 255) / 256 << " block(s), and " << 256 << " thread(s) per block" << std::endl;
+        out << "kernel: " << cfg.kernel_format << ", block_vec_size: " << bvs;
+        if (cfg.kernel_format == "scs") out << ", C: " << cfg.chunk_size << " sigma: " << cfg.sigma << std::fixed << std::setprecision(8) << ", beta: " << beta;
+        out << ", block_vec_layout: " << cfg.block_vec_layout;
+        const double pct[3] = {nnz ? 100.0 * part_nnz[0] / nnz : 0, nnz ? 100.0 * part_nnz[1] / nnz : 0, nnz ? 100.0 * part_nnz[2] / nnz : 0};
+        out << std::fixed << std::setprecision(2);
+        if (cfg.value_type == "ap[dp_sp]") out << ", data_type: ap[dp_sp], threshold: " << cfg.ap_threshold_1 << ", % dp elems: " << pct[0] << ", % sp elems: " << pct[1];
+        else if (cfg.value_type == "ap[dp_hp]") out << ", data_type: ap[dp_hp], threshold: " << cfg.ap_threshold_1 << ", % dp elems: " << pct[0] << ", % hp elems: " << pct[2];
+        else if (cfg.value_type == "ap[sp_hp]") out << ", data_type: ap[sp_hp], threshold: " << cfg.ap_threshold_1 << ", % sp elems: " << pct[1] << ", % hp elems: " << pct[2];
+        else if (cfg.value_type == "ap[dp_sp_hp]") out << ", data_type: ap[dp_sp_hp], threshold 1: " << cfg.ap_threshold_1 << ", threshold 2: " << cfg.ap_threshold_2 << ", % dp elems: " << pct[0] << ", % sp elems: " << pct[1] << ", % hp elems: " << pct[2];
+        else out << ", data_type: " << (cfg.value_type == "dp" ? "double" : cfg.value_type == "sp" ? "float" : "half");
+        out << ", revisions: " << n_iter << std::endl << std::endl;
+        out << std::left << std::setw(width) << "Total Gflops:" << std::left << std::setw(width) << "Total Walltime:" << std::endl;
+        out << std::left << std::setw(width) << "-------------" << std::left << std::setw(width) << "-------------" << std::endl;
+        out << std::left << std::setprecision(16) << std::left << std::setw(width) << gflops << std::left << std::setw(width) << runtime << std::endl;
+        out << std::endl << std::endl;
+    } else {
+        // ---- solve mode: rev x { SpMV; swap } then un-permute and validate -------------------------------------------
+        if (ap && cfg.n_repetitions > 1) die("ERROR: solve mode with adaptive precision supports -rev 1 only (x stays in user order)");
+        for (unsigned long it = 0; it < cfg.n_repetitions; ++it) {
+            execute();
+            if (it + 1 < cfg.n_repetitions) std::swap(x_d, y_d);  // swap_local_vectors, classes_structs.hpp:1130-1165
+        }
+        ck(uspmv_ctx_sync(ctx));
+        std::vector<double> y_perm = download(ctx, y_d, vec_length * bvs, xvt);
+        std::vector<double> y(n_rows * bvs);  // sorted_y[i] = y_perm[old_to_new[i]] (utilities.hpp:3856-3868)
+        for (long v = 0; v < bvs; ++v)
+            for (long i = 0; i < n_rows; ++i)
+                y[i + v * n_rows] = layout == USPMV_ROWWISE ? y_perm[(long)old_to_new[i] * bvs + v] : y_perm[old_to_new[i] + v * vec_length];
+        printf("solve mode: %lu revision(s); y[0..3] =", cfg.n_repetitions);
+        for (long i = 0; i < std::min<long>(4, n_rows); ++i) printf(" %.10g", y[i]);
+        printf("\n");
+        if (cfg.validate_result && have_host) {
+            // host-side COO reference in double (stands in for the reference's MKL validator, write_results.hpp:442-556)
+            double max_rel = 0.0;
+            for (long v = 0; v < bvs; ++v) {
+                std::vector<double> xa(n_rows), ya(n_rows);
+                for (long i = 0; i < n_rows; ++i) xa[i] = layout == USPMV_ROWWISE ? x_user[i * bvs + v] : x_user[i + v * vec_length];
+                for (unsigned long it = 0; it < cfg.n_repetitions; ++it) {
+                    std::fill(ya.begin(), ya.end(), 0.0);
+                    for (size_t k = 0; k < host.V.size(); ++k) ya[host.I[k]] += host.V[k] * xa[host.J[k]];
+                    if (it + 1 < cfg.n_repetitions) std::swap(xa, ya);
+                }
+                for (long i = 0; i < n_rows; ++i) {
+                    const double d = std::fabs(y[i + v * n_rows] - ya[i]) / std::max(std::fabs(ya[i]), 1e-300);
+                    if (ya[i] != 0.0 && d > max_rel) max_rel = d;
+                }
+            }
+            // thresholds of write_result_to_file (write_results.hpp:378-383,422-428)
+            const char *verdict = max_rel > 1e-2 ? "ERROR" : max_rel > 1e-4 ? "WARNING" : "OK";
+            printf("validation vs host COO product: max relative difference %.3e -> %s\n", max_rel, verdict);
+            std::ofstream vf("spmv_validate_" + (ap ? std::string("ap") : cfg.value_type) + ".txt", std::ios::app);
+            vf << cfg.matrix_file_name << " kernel: " << cfg.kernel_format << " C: " << cfg.chunk_size << " sigma: " << cfg.sigma << " data_type: "
+               << cfg.value_type << " block_vec_size: " << bvs << " revisions: " << cfg.n_repetitions << " max_rel_diff: " << max_rel << " " << verdict << std::endl;
+            if (max_rel > 1e-2 && cfg.value_type == "dp") return 2;
+        }
+    }
+    uspmv_free(ctx, x_d);
+    uspmv_free(ctx, y_d);
+    if (scs) uspmv_scs_destroy(scs);
+    for (auto *p : part) if (p) uspmv_scs_destroy(p);
+    uspmv_coo_destroy(coo);
+    uspmv_ctx_destroy(ctx);
+    return 0;
+}

@@ -103,6 +103,8 @@ struct Options {
     bool scs_stream = true;      // C = 32: bulk-copy streamed kernel (false: direct-load kernel)
     int stream_variant = 0;      // (slots per piece, ring depth, warps per CTA) instantiation
     int stream_blocks_per_sm = 2;
+    int mmv_variant = 0;         // SpMMV streamed kernel: 0 = tuned default, 1..4 force a variant (see spmv_kernels.cu)
+    int mmv_blocks_per_sm = 0;   // SpMMV streamed kernel: CTAs (8 warps) per SM, 0 = as many as fit
     bool strict_reference_halo = false;  // true: padding slots (column 0) become a halo element on ranks > 0, like the reference
 };
 Options &options();

@@ -37,6 +37,8 @@ int uspmv_set_option(const char *name, long value) {
         if (!std::strcmp(name, "scs_stream")) c.scs_stream = value != 0;
         else if (!std::strcmp(name, "stream_variant")) c.stream_variant = (int)value;
         else if (!std::strcmp(name, "stream_blocks_per_sm")) c.stream_blocks_per_sm = (int)std::max(1L, value);
+        else if (!std::strcmp(name, "mmv_variant")) c.mmv_variant = (int)std::max(0L, value);
+        else if (!std::strcmp(name, "mmv_blocks_per_sm")) c.mmv_blocks_per_sm = (int)std::max(0L, value);
         else if (!std::strcmp(name, "strict_reference_halo")) c.strict_reference_halo = value != 0;
         else fail("uspmv_set_option: unknown option '%s'", name);
     });

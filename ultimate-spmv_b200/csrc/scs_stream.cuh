@@ -123,15 +123,201 @@ __device__ __forceinline__ void warp_wait_flags(const unsigned int *flags, const
 }
 template <typename T> __device__ __forceinline__ T ld_x_coherent(const T *p) { return __ldcg(p); }  // L2 (coherent with peer stores)
 
+// ---- per-piece arithmetic ("bodies") ----------------------------------------------------------------------------
+// A body owns the accumulators of the 32 rows of the current chunk (one row per lane):
+//   begin_chunk()                       reset
+//   piece(ns, sv, sc)                   consume ns slots: sv/sc point at this lane's value / column of slot 0 (stride 32)
+//   end_chunk(chunk)                    write the rows of `chunk`
+// SpMV: y = A x.  COHERENT: x through L2 only (ld.global.cg) because a peer GPU wrote part of it during this kernel.
+template <typename VT, typename A, int LMAX, bool UNPERM, bool COHERENT>
+struct SpmvBody {
+    const VT *__restrict__ x;
+    VT *__restrict__ y;
+    const int *__restrict__ new_to_old;
+    int lane;
+    typename A::acc_t acc;
+    __device__ __forceinline__ void begin_chunk() { acc = A::zero(); }
+    __device__ __forceinline__ void piece(const int ns, const VT *sv, const int *sc) {
+        VT v[LMAX], xv[LMAX];
+        int col[LMAX];
+#pragma unroll
+        for (int j = 0; j < LMAX; ++j)
+            if (j < ns) col[j] = sc[j * 32];
+#pragma unroll
+        for (int j = 0; j < LMAX; ++j)
+            if (j < ns) xv[j] = COHERENT ? __ldcg(x + col[j]) : __ldg(x + col[j]);
+#pragma unroll
+        for (int j = 0; j < LMAX; ++j)
+            if (j < ns) v[j] = sv[j * 32];
+#pragma unroll
+        for (int j = 0; j < LMAX; ++j)
+            if (j < ns) acc = A::mad(v[j], xv[j], acc);
+    }
+    __device__ __forceinline__ void end_chunk(const int chunk) {
+        const long row = (long)chunk * 32 + lane;
+        if (UNPERM) {
+            const int o = new_to_old[row];
+            if (o >= 0) y[o] = A::out(acc);
+        } else
+            y[row] = A::out(acc);
+    }
+};
+
+// SpMMV: Y = A X with BVS right-hand sides.  ROWWISE: X[col*BVS + v] (one vector load per gathered row); else X[col + v*ld].
+// Slots are consumed SB at a time so that SB*BVS gathered values are in flight per lane without blowing the register file.
+template <typename VT, typename A, int LMAX, int BVS, bool ROWWISE>
+struct SpmmvBody {
+    static constexpr int SB = (BVS * (int)sizeof(VT) >= 64) ? 2 : (BVS * (int)sizeof(VT) >= 32 ? 4 : 8);
+    const VT *__restrict__ X;
+    VT *__restrict__ Y;
+    long ld;
+    int lane;
+    typename A::acc_t acc[BVS];
+    __device__ __forceinline__ void begin_chunk() {
+#pragma unroll
+        for (int v = 0; v < BVS; ++v) acc[v] = A::zero();
+    }
+    __device__ __forceinline__ void load_row(const long col, VT *xv) const {
+        if constexpr (ROWWISE) {
+            constexpr int BYTES = BVS * (int)sizeof(VT);
+            if constexpr (BYTES % 16 == 0) {
+                const int4 *p = reinterpret_cast<const int4 *>(X + col * BVS);
+#pragma unroll
+                for (int k = 0; k < BYTES / 16; ++k) reinterpret_cast<int4 *>(xv)[k] = __ldg(p + k);
+            } else if constexpr (BYTES % 8 == 0) {
+                const int2 *p = reinterpret_cast<const int2 *>(X + col * BVS);
+#pragma unroll
+                for (int k = 0; k < BYTES / 8; ++k) reinterpret_cast<int2 *>(xv)[k] = __ldg(p + k);
+            } else {
+#pragma unroll
+                for (int v = 0; v < BVS; ++v) xv[v] = __ldg(X + col * BVS + v);
+            }
+        } else {
+#pragma unroll
+            for (int v = 0; v < BVS; ++v) xv[v] = __ldg(X + col + v * ld);
+        }
+    }
+    __device__ __forceinline__ void piece(const int ns, const VT *sv, const int *sc) {
+#pragma unroll
+        for (int j0 = 0; j0 < LMAX; j0 += SB) {
+            if (j0 < ns) {
+                alignas(16) VT xv[SB][BVS];
+                VT v[SB];
+#pragma unroll
+                for (int u = 0; u < SB; ++u)
+                    if (j0 + u < ns) load_row((long)sc[(j0 + u) * 32], xv[u]);
+#pragma unroll
+                for (int u = 0; u < SB; ++u)
+                    if (j0 + u < ns) v[u] = sv[(j0 + u) * 32];
+#pragma unroll
+                for (int u = 0; u < SB; ++u)
+                    if (j0 + u < ns) {
+#pragma unroll
+                        for (int w = 0; w < BVS; ++w) acc[w] = A::mad(v[u], xv[u][w], acc[w]);
+                    }
+            }
+        }
+    }
+    __device__ __forceinline__ void end_chunk(const int chunk) {
+        const long row = (long)chunk * 32 + lane;
+        if constexpr (ROWWISE) {
+            alignas(16) VT yv[BVS];
+#pragma unroll
+            for (int v = 0; v < BVS; ++v) yv[v] = A::out(acc[v]);
+            constexpr int BYTES = BVS * (int)sizeof(VT);
+            if constexpr (BYTES % 16 == 0) {
+#pragma unroll
+                for (int k = 0; k < BYTES / 16; ++k) reinterpret_cast<int4 *>(Y + row * BVS)[k] = reinterpret_cast<const int4 *>(yv)[k];
+            } else if constexpr (BYTES % 8 == 0) {
+#pragma unroll
+                for (int k = 0; k < BYTES / 8; ++k) reinterpret_cast<int2 *>(Y + row * BVS)[k] = reinterpret_cast<const int2 *>(yv)[k];
+            } else {
+#pragma unroll
+                for (int v = 0; v < BVS; ++v) Y[row * BVS + v] = yv[v];
+            }
+        } else {
+#pragma unroll
+            for (int v = 0; v < BVS; ++v) Y[row + v * ld] = A::out(acc[v]);
+        }
+    }
+};
+
+// Row-major SpMMV with wide block rows (BVS*sizeof(VT) = 32..128 B): T = bytes/16 adjacent lanes fetch ONE gathered row with
+// one 128-bit load each, so every warp-wide load touches whole 128-byte lines (a lane-per-row int4 load touches 32 different
+// lines per instruction and is L1-wavefront bound: measured 0.47 of peak for dp bvs 8).  Lane l owns the 16-byte slice
+// (l % T) of the rows l/T + (32/T)*k, k = 0..T-1 of the chunk; per (row, vector) the FMA order is unchanged (slot order).
+template <typename VT, typename A, int LMAX, int BVS>
+struct SpmmvBodyRowWide {
+    static constexpr int PER = 16 / (int)sizeof(VT);            // values per 128-bit load
+    static constexpr int T = BVS * (int)sizeof(VT) / 16;        // lanes per row == rows per lane
+    static constexpr int RPI = 32 / T;                          // rows covered by one warp-wide load
+    static constexpr int SB = (T >= 8) ? 1 : (T == 4 ? 2 : 4);  // slots in flight per lane (SB*T 128-bit loads)
+    const VT *__restrict__ X;
+    VT *__restrict__ Y;
+    int lane;
+    typename A::acc_t acc[T][PER];
+    __device__ __forceinline__ void begin_chunk() {
+#pragma unroll
+        for (int k = 0; k < T; ++k)
+#pragma unroll
+            for (int m = 0; m < PER; ++m) acc[k][m] = A::zero();
+    }
+    // sv / sc arrive offset by `lane`; rebase to the chunk's lane 0
+    __device__ __forceinline__ void piece(const int ns, const VT *sv, const int *sc) {
+        const VT *v0 = sv - lane;
+        const int *c0 = sc - lane;
+        const int r0 = lane / T, part = lane % T;
+#pragma unroll
+        for (int j0 = 0; j0 < LMAX; j0 += SB) {
+            if (j0 < ns) {
+                alignas(16) VT xv[SB][T][PER];
+                VT v[SB][T];
+#pragma unroll
+                for (int u = 0; u < SB; ++u)
+                    if (j0 + u < ns) {
+#pragma unroll
+                        for (int k = 0; k < T; ++k) {
+                            const long col = c0[(j0 + u) * 32 + r0 + RPI * k];
+                            *reinterpret_cast<int4 *>(xv[u][k]) = __ldg(reinterpret_cast<const int4 *>(X + col * BVS) + part);
+                        }
+                    }
+#pragma unroll
+                for (int u = 0; u < SB; ++u)
+                    if (j0 + u < ns) {
+#pragma unroll
+                        for (int k = 0; k < T; ++k) v[u][k] = v0[(j0 + u) * 32 + r0 + RPI * k];
+                    }
+#pragma unroll
+                for (int u = 0; u < SB; ++u)
+                    if (j0 + u < ns) {
+#pragma unroll
+                        for (int k = 0; k < T; ++k)
+#pragma unroll
+                            for (int m = 0; m < PER; ++m) acc[k][m] = A::mad(v[u][k], xv[u][k][m], acc[k][m]);
+                    }
+            }
+        }
+    }
+    __device__ __forceinline__ void end_chunk(const int chunk) {
+        const int r0 = lane / T, part = lane % T;
+#pragma unroll
+        for (int k = 0; k < T; ++k) {
+            alignas(16) VT yv[PER];
+#pragma unroll
+            for (int m = 0; m < PER; ++m) yv[m] = A::out(acc[k][m]);
+            const long row = (long)chunk * 32 + r0 + RPI * k;
+            reinterpret_cast<int4 *>(Y + row * BVS)[part] = *reinterpret_cast<const int4 *>(yv);
+        }
+    }
+};
+
 // The streaming loop of one warp over work items first, first + W, ... < n_items (item k -> chunk list[k] or k + off).
-// COHERENT: x is read through L2 only (ld.global.cg) because a peer GPU wrote part of it during this kernel.
-template <typename VT, typename A, int LMAX, int D, bool UNPERM, bool COHERENT>
+template <typename VT, int LMAX, int D, typename Body>
 __device__ __forceinline__ void stream_items(unsigned char *base, uint64_t *bars, PieceHdr *hdrs, uint32_t &phase_bits, const long W,
                                              const long first, const int lane, const long n_items, const int *__restrict__ chunk_list,
                                              const int chunk_offset, const int *__restrict__ chunk_ptrs,
                                              const int *__restrict__ chunk_lengths, const int *__restrict__ col_idxs,
-                                             const VT *__restrict__ values, const VT *__restrict__ x, VT *__restrict__ y,
-                                             const int *__restrict__ new_to_old, const uint64_t pol) {
+                                             const VT *__restrict__ values, Body &body, const uint64_t pol) {
     using R = WarpRing<VT, LMAX, D>;
     auto item_chunk = [&](long k) -> int { return chunk_list ? chunk_list[k] : (int)k + chunk_offset; };
 
@@ -197,39 +383,19 @@ __device__ __forceinline__ void stream_items(unsigned char *base, uint64_t *bars
     __syncwarp();
 
     // ---- consumer -----------------------------------------------------------------------------------------
-    typename A::acc_t acc = A::zero();
+    body.begin_chunk();
     for (int s = 0;; s = (s + 1 == D) ? 0 : s + 1) {
         const PieceHdr h = hdrs[s];
         if (h.flags == 0) break;
-        if (h.flags & 1) acc = A::zero();
+        if (h.flags & 1) body.begin_chunk();
         if (h.ns > 0) {
             mbar_wait(&bars[s], (phase_bits >> s) & 1u);
             phase_bits ^= (1u << s);
             const VT *sv = reinterpret_cast<const VT *>(base + s * R::STAGE_BYTES) + lane;
             const int *sc = reinterpret_cast<const int *>(base + s * R::STAGE_BYTES + R::VAL_BYTES) + lane;
-            VT v[LMAX], xv[LMAX];
-            int col[LMAX];
-#pragma unroll
-            for (int j = 0; j < LMAX; ++j)
-                if (j < h.ns) col[j] = sc[j * 32];
-#pragma unroll
-            for (int j = 0; j < LMAX; ++j)
-                if (j < h.ns) xv[j] = COHERENT ? __ldcg(x + col[j]) : __ldg(x + col[j]);
-#pragma unroll
-            for (int j = 0; j < LMAX; ++j)
-                if (j < h.ns) v[j] = sv[j * 32];
-#pragma unroll
-            for (int j = 0; j < LMAX; ++j)
-                if (j < h.ns) acc = A::mad(v[j], xv[j], acc);
+            body.piece(h.ns, sv, sc);
         }
-        if (h.flags & 2) {
-            const long row = (long)h.chunk * 32 + lane;
-            if (UNPERM) {
-                const int o = new_to_old[row];
-                if (o >= 0) y[o] = A::out(acc);
-            } else
-                y[row] = A::out(acc);
-        }
+        if (h.flags & 2) body.end_chunk(h.chunk);
         __syncwarp();  // every lane is done with stage s (data and header) before it is refilled
         if (lane == 0) issue(s);
         __syncwarp();
@@ -260,8 +426,9 @@ k_scs32_stream(long n_items, const int *__restrict__ chunk_list, int chunk_offse
     uint32_t phase_bits = 0;  // one parity bit per stage, flipped after every completed wait
 
     if constexpr (!FUSED) {
-        stream_items<VT, A, LMAX, D, UNPERM, false>(base, bars, hdrs, phase_bits, W, gw, lane, n_items, chunk_list, chunk_offset, chunk_ptrs,
-                                                    chunk_lengths, col_idxs, values, x, y, new_to_old, pol);
+        SpmvBody<VT, A, LMAX, UNPERM, false> body{x, y, new_to_old, lane, A::zero()};
+        stream_items<VT, LMAX, D>(base, bars, hdrs, phase_bits, W, gw, lane, n_items, chunk_list, chunk_offset,
+                                  chunk_ptrs, chunk_lengths, col_idxs, values, body, pol);
     } else {
         // (a) push: warp pw handles send elements [32 pw, 32 pw + 32)
         const unsigned int epoch_e = ld_flag(fa.epoch) + 1u;
@@ -290,13 +457,17 @@ k_scs32_stream(long n_items, const int *__restrict__ chunk_list, int chunk_offse
             }
         }
         // (b) interior chunks: no halo column, identical code path to the single-GPU kernel
-        stream_items<VT, A, LMAX, D, UNPERM, false>(base, bars, hdrs, phase_bits, W, gw, lane, fa.n_int, fa.int_list, fa.int_off, chunk_ptrs,
-                                                    chunk_lengths, col_idxs, values, x, y, new_to_old, pol);
+        {
+            SpmvBody<VT, A, LMAX, UNPERM, false> body{x, y, new_to_old, lane, A::zero()};
+            stream_items<VT, LMAX, D>(base, bars, hdrs, phase_bits, W, gw, lane, fa.n_int, fa.int_list, fa.int_off,
+                                      chunk_ptrs, chunk_lengths, col_idxs, values, body, pol);
+        }
         // (c) boundary chunks once the neighbours' elements for this step have landed in our x tail
         if (gw < fa.n_bnd) {
             warp_wait_flags(fa.arrived, fa.is_sender, fa.P, epoch_e, lane, fa.error);
-            stream_items<VT, A, LMAX, D, UNPERM, true>(base, bars, hdrs, phase_bits, W, gw, lane, fa.n_bnd, fa.bnd_list, fa.bnd_off, chunk_ptrs,
-                                                       chunk_lengths, col_idxs, values, x, y, new_to_old, pol);
+            SpmvBody<VT, A, LMAX, UNPERM, true> body{x, y, new_to_old, lane, A::zero()};
+            stream_items<VT, LMAX, D>(base, bars, hdrs, phase_bits, W, gw, lane, fa.n_bnd, fa.bnd_list, fa.bnd_off, chunk_ptrs,
+                                      chunk_lengths, col_idxs, values, body, pol);
         }
         // (d) the last warp of the grid acknowledges consumption to the senders and closes the epoch
         __syncwarp();
@@ -320,6 +491,41 @@ k_scs32_stream(long n_items, const int *__restrict__ chunk_list, int chunk_offse
                 __threadfence();
             }
         }
+    }
+}
+
+// SELL-32 SpMMV through the same per-warp bulk-copy ring (smaller stages: the block vectors want the L1 capacity).
+template <typename VT, typename A, int LMAX, int D, int WARPS, int BVS, bool ROWWISE, bool WIDE>
+__global__ void __launch_bounds__(WARPS * 32)  // ~80 registers, 24 warps/SM: capping at 64 spills and is 30-50 % slower (measured)
+k_scs32_stream_mmv(long n_items, const int *__restrict__ chunk_ptrs, const int *__restrict__ chunk_lengths, const int *__restrict__ col_idxs,
+                   const VT *__restrict__ values, const VT *__restrict__ X, VT *__restrict__ Y, long ld) {
+    using R = WarpRing<VT, LMAX, D>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char *base = smem_raw + (size_t)warp * R::BYTES_ALIGNED;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(base + D * R::STAGE_BYTES);
+    PieceHdr *hdrs = reinterpret_cast<PieceHdr *>(base + D * R::STAGE_BYTES + D * 8);
+    const long W = (long)gridDim.x * WARPS;
+    const long gw = (long)blockIdx.x * WARPS + warp;
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < D; ++s) mbar_init(&bars[s], 1);
+        fence_barrier_init();
+    }
+    __syncwarp();
+    const uint64_t pol = policy_evict_first();
+    uint32_t phase_bits = 0;
+    constexpr int ROW_BYTES = BVS * (int)sizeof(VT);
+    if constexpr (WIDE && ROWWISE && ROW_BYTES >= 32 && ROW_BYTES <= 128 && (ROW_BYTES & (ROW_BYTES - 1)) == 0) {
+        SpmmvBodyRowWide<VT, A, LMAX, BVS> body;
+        body.X = X; body.Y = Y; body.lane = lane;
+        stream_items<VT, LMAX, D>(base, bars, hdrs, phase_bits, W, gw, lane, n_items, nullptr, 0, chunk_ptrs,
+                                  chunk_lengths, col_idxs, values, body, pol);
+    } else {
+        SpmmvBody<VT, A, LMAX, BVS, ROWWISE> body;
+        body.X = X; body.Y = Y; body.ld = ld; body.lane = lane;
+        stream_items<VT, LMAX, D>(base, bars, hdrs, phase_bits, W, gw, lane, n_items, nullptr, 0, chunk_ptrs,
+                                  chunk_lengths, col_idxs, values, body, pol);
     }
 }
 

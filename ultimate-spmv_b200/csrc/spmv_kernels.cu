@@ -20,6 +20,7 @@
 #include "common.cuh"
 #include "scs_stream.cuh"
 
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -248,6 +249,12 @@ __global__ void k_flag_boundary_chunks(long n_chunks, int C, int n_local, const 
     if (lane == 0) flag[w] = hit;
 }
 
+// measured best SpMMV variant (scripts/tune_mmv.py on B200); 1 = lane per row, 2 = T lanes per row ("wide")
+inline int mmv_default_variant(size_t vsize, int bvs, bool rowwise) {
+    if (!rowwise) return 1;
+    return (long)vsize * bvs >= 64 ? 2 : 1;
+}
+
 // ---- launch helpers ----------------------------------------------------------------------------
 inline unsigned blocks_for(long n) { return (unsigned)((n + TPB - 1) / TPB); }
 
@@ -379,6 +386,44 @@ void launch_csr(long n_rows, long nnz_hint, const int *rp, const int *ci, const 
     USPMV_LAUNCH_CHECK();
 }
 
+// C = 32 and bvs in {2,4,8,16}: streamed kernel
+template <typename VT, int BVS, bool ROWWISE, int LMAX, int WARPS, bool WIDE>
+void launch_spmmv_stream_v(const uspmv_scs *s, const VT *X, VT *Y, long ld, cudaStream_t st) {
+    constexpr int D = 2;
+    using R = stream::WarpRing<VT, LMAX, D>;
+    auto kern = stream::k_scs32_stream_mmv<VT, Arith<VT>, LMAX, D, WARPS, BVS, ROWWISE, WIDE>;
+    constexpr int smem = WARPS * R::BYTES_ALIGNED;
+    static bool configured = false;
+    static int blocks_per_sm = 1;
+    if (!configured) {
+        USPMV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        USPMV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, WARPS * 32, smem));
+        if (blocks_per_sm < 1) blocks_per_sm = 1;
+        configured = true;
+    }
+    int dev = 0;
+    USPMV_CUDA(cudaGetDevice(&dev));
+    const int bps = options().mmv_blocks_per_sm > 0 ? std::min(options().mmv_blocks_per_sm, blocks_per_sm) : blocks_per_sm;
+    long grid = (long)sm_count(dev) * bps;
+    const long need = (s->n_chunks + WARPS - 1) / WARPS;
+    if (grid > need) grid = need;
+    kern<<<(unsigned)grid, WARPS * 32, smem, st>>>(s->n_chunks, s->chunk_ptrs.p, s->chunk_lengths.p, s->col_idxs.p,
+                                                  reinterpret_cast<const VT *>(s->values.p), X, Y, ld);
+}
+
+// variant: 0 = tuned default per (precision, bvs, layout); 1..4 force (wide body?, slots per stage)
+template <typename VT, int BVS, bool ROWWISE>
+void launch_spmmv_stream(const uspmv_scs *s, const VT *X, VT *Y, long ld, cudaStream_t st) {
+    int v = options().mmv_variant;
+    if (v == 0) v = mmv_default_variant(sizeof(VT), BVS, ROWWISE);
+    switch (v) {
+    case 2: launch_spmmv_stream_v<VT, BVS, ROWWISE, 8, 8, true>(s, X, Y, ld, st); break;
+    case 3: launch_spmmv_stream_v<VT, BVS, ROWWISE, 4, 8, false>(s, X, Y, ld, st); break;
+    case 4: launch_spmmv_stream_v<VT, BVS, ROWWISE, 4, 8, true>(s, X, Y, ld, st); break;
+    default: launch_spmmv_stream_v<VT, BVS, ROWWISE, 8, 8, false>(s, X, Y, ld, st); break;
+    }
+}
+
 template <typename VT, int LAYOUT>
 void launch_spmmv_l(const uspmv_scs *s, const void *X, void *Y, int bvs, long ld, cudaStream_t st) {
     const long n_pad = s->n_rows_padded;
@@ -386,6 +431,17 @@ void launch_spmmv_l(const uspmv_scs *s, const void *X, void *Y, int bvs, long ld
     const VT *v = reinterpret_cast<const VT *>(s->values.p);
     const VT *xx = static_cast<const VT *>(X);
     VT *yy = static_cast<VT *>(Y);
+    if (s->C == 32 && options().scs_stream && (bvs == 2 || bvs == 4 || bvs == 8 || bvs == 16)) {
+        constexpr bool RW = LAYOUT == USPMV_ROWWISE;
+        switch (bvs) {
+        case 2: launch_spmmv_stream<VT, 2, RW>(s, xx, yy, ld, st); break;
+        case 4: launch_spmmv_stream<VT, 4, RW>(s, xx, yy, ld, st); break;
+        case 8: launch_spmmv_stream<VT, 8, RW>(s, xx, yy, ld, st); break;
+        default: launch_spmmv_stream<VT, 16, RW>(s, xx, yy, ld, st);
+        }
+        USPMV_LAUNCH_CHECK();
+        return;
+    }
     const unsigned g = blocks_for(n_pad);
     const int C = (int)s->C;
 #define USPMV_MMV_CASE(BB)                                                                                                      \

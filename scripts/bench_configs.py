@@ -63,30 +63,31 @@ if "ap" in which:
     J = np.concatenate([p[3] for p in parts]); V = np.concatenate([p[4] for p in parts]); del parts
     print(f"power-law matrix: {n} rows, {len(I)} nnz generated on the host in {time.time()-t0:.1f} s", flush=True)
     mtx = eng.MtxData.from_host(n, n, I, J, V); nnz = len(I); del I, J, V
+    SIG = int(os.environ.get("PL_SIGMA", "512"))
     for mode in ("ap[dp_sp_hp]", "ap[dp_sp]", None):
         if mode is None:
-            scs = eng.convert_to_scs(mtx, 32, 512, "dp")
+            t0 = time.time(); scs = eng.convert_to_scs(mtx, 32, SIG, "dp"); torch.cuda.synchronize(); print(f"plain build {time.time()-t0:.2f} s")
             x = torch.full((scs.n_rows_padded,), 1.0, dtype=torch.float64, device="cuda"); y = torch.zeros_like(x)
             sec = timeit(lambda: eng.spmv_unpermuted(scs, x, y) if False else eng.spmv(scs, x, y), 20)
             nb = scs.n_elements * 12 + 8 * scs.n_chunks + 16 * scs.n_rows_padded
-            report(f"powerlaw {n} plain dp C32 s512 (beta {scs.nnz/scs.n_elements:.3f})", sec, nb, 2.0 * nnz)
+            report(f"powerlaw {n} plain dp C32 s{SIG} (beta {scs.nnz/scs.n_elements:.3f})", sec, nb, 2.0 * nnz)
             continue
         t0 = time.time()
         coos = eng.partition_precisions(mtx, mode, 1.0, 1e-2)
         used = [k for k in range(3) if coos[k] is not None]
         vts = ("dp", "sp", "hp")
         P = [None] * 3
-        P[used[0]] = eng.convert_to_scs(coos[used[0]], 32, 512, vts[used[0]])
+        P[used[0]] = eng.convert_to_scs(coos[used[0]], 32, SIG, vts[used[0]])
         perm = P[used[0]].export().old_to_new
         for k in used[1:]:
-            P[k] = eng.convert_to_scs(coos[k], 32, 512, vts[k], fixed_permutation=perm)
+            P[k] = eng.convert_to_scs(coos[k], 32, SIG, vts[k], fixed_permutation=perm)
         torch.cuda.synchronize(); tb = time.time() - t0
         n_pad = P[used[0]].n_rows_padded
         x = torch.full((max(n_pad, n),), 1.0, dtype=torch.float64, device="cuda"); y = torch.zeros(n_pad, dtype=torch.float64, device="cuda")
         sec = timeit(lambda: eng.ap_spmv(mode, P[0], P[1], P[2], x, y), 20)
         nb = sum(P[k].n_elements * ((8, 4, 2)[k] + 4) + 8 * P[k].n_chunks for k in used) + 16 * n_pad
         frac = [coos[k].nnz / nnz if coos[k] is not None else 0 for k in range(3)]
-        report(f"powerlaw {n} {mode} C32 s512 split {frac[0]:.2f}/{frac[1]:.2f}/{frac[2]:.2f} (build {tb:.1f} s)", sec, nb, 2.0 * nnz)
+        report(f"powerlaw {n} {mode} C32 s{SIG} split {frac[0]:.2f}/{frac[1]:.2f}/{frac[2]:.2f} (build {tb:.1f} s)", sec, nb, 2.0 * nnz)
         del coos, P
 
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)

@@ -11,6 +11,7 @@
 // half*float), accumulates those products in fp64 and rounds y to fp32 (interface.hpp:1620-1645).
 // One launch reads all parts: the parts share C, n_chunks and the row permutation of the first part.
 #include "common.cuh"
+#include "scs_stream.cuh"
 
 #include <cub/device/device_scan.cuh>
 
@@ -164,6 +165,29 @@ k_ap_spmv(long n_pad, int C, PartArgs dp, PartArgs sp, PartArgs hp, const void *
     }
 }
 
+template <int MODE>
+void launch_ap_stream(long n_chunks, const int *order, const stream::ApPart &a, const stream::ApPart &b, const stream::ApPart &c, const void *x,
+                      void *y, cudaStream_t st) {
+    constexpr int LMAX = 8, D = 2, WARPS = 8;
+    using R = stream::WarpRing<double, LMAX, D>;
+    auto kern = stream::k_scs32_stream_ap<MODE, LMAX, D, WARPS>;
+    constexpr int smem = WARPS * R::BYTES_ALIGNED;
+    static bool configured = false;
+    static int bps = 1;
+    if (!configured) {
+        USPMV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        USPMV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, WARPS * 32, smem));
+        if (bps < 1) bps = 1;
+        configured = true;
+    }
+    int dev = 0;
+    USPMV_CUDA(cudaGetDevice(&dev));
+    long grid = (long)sm_count(dev) * bps;
+    const long need = (n_chunks + WARPS - 1) / WARPS;
+    if (grid > need) grid = need;
+    kern<<<(unsigned)grid, WARPS * 32, smem, st>>>(n_chunks, order, a, b, c, x, y);
+}
+
 void exclusive_scan_i32(const int *in, int *out, long n) {
     size_t bytes = 0;
     USPMV_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, (int)n));
@@ -284,6 +308,18 @@ int uspmv_ap_spmv(int ap_mode, const uspmv_scs *dp, const uspmv_scs *sp, const u
         };
         const PartArgs a = args(use_dp ? dp : nullptr), b = args(use_sp ? sp : nullptr), c = args(use_hp ? hp : nullptr);
         cudaStream_t st = as_stream(stream);
+        if (first->C == 32 && options().scs_stream) {  // streamed one-pass kernel
+            const stream::ApPart sa{a.cp, a.cl, a.ci, a.v}, sb{b.cp, b.cl, b.ci, b.v}, sc{c.cp, c.cl, c.ci, c.v};
+            const int *order = first->balanced_order.p;
+            switch (ap_mode) {
+            case USPMV_AP_DP_SP: launch_ap_stream<USPMV_AP_DP_SP>(first->n_chunks, order, sa, sb, sc, x, y, st); break;
+            case USPMV_AP_DP_HP: launch_ap_stream<USPMV_AP_DP_HP>(first->n_chunks, order, sa, sb, sc, x, y, st); break;
+            case USPMV_AP_SP_HP: launch_ap_stream<USPMV_AP_SP_HP>(first->n_chunks, order, sa, sb, sc, x, y, st); break;
+            default: launch_ap_stream<USPMV_AP_DP_SP_HP>(first->n_chunks, order, sa, sb, sc, x, y, st);
+            }
+            USPMV_LAUNCH_CHECK();
+            return;
+        }
         const unsigned g = blocks_for(n_pad);
         const int C = (int)first->C;
         switch (ap_mode) {

@@ -147,6 +147,9 @@ struct uspmv_scs {
     uspmv::DevBuf<int> new_to_old;  // n_rows_padded, -1 where no real row lands
     uspmv::DevBuf<int> row_lengths; // n_rows_padded: stored elements of the row at each (permuted) position
     uspmv::DevBuf<unsigned char> h2d_stage_x, d2h_stage_y;  // device staging for the host-buffer call
+    // chunk ids sorted by length (longest first, ties in chunk order); only built when lengths are very uneven, so that
+    // one-warp-per-chunk kernels stay load balanced (longest-processing-time-first over the persistent warps)
+    uspmv::DevBuf<int> balanced_order;
     bool chunks_split = false;
     uspmv::DevBuf<int> interior_chunks, boundary_chunks;  // chunk ids without / with halo columns (order kept)
     bool interior_contig = false, boundary_contig = false;

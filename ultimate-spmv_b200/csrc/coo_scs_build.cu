@@ -19,6 +19,7 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
+#include <algorithm>
 #include <vector>
 
 using namespace uspmv;
@@ -382,6 +383,30 @@ void dispatch_fill_vt(const uspmv_coo *coo, uspmv_scs *s, const RC *rc, const in
     }
 }
 
+// Longest-first chunk order for matrices with very uneven chunk lengths (power-law rows): the kernels give one warp a whole
+// chunk (that keeps the per-row summation order of the reference), so a few 4096-slot chunks at the end of an interleaved
+// assignment would leave the GPU idle behind them.
+void build_balanced_order(uspmv_scs *s) {
+    const long nc = s->n_chunks;
+    if (nc < 4096 || s->n_elements == 0) return;
+    std::vector<int> len(nc);
+    USPMV_CUDA(cudaMemcpy(len.data(), s->chunk_lengths.p, nc * sizeof(int), cudaMemcpyDeviceToHost));
+    int mx = 0;
+    for (int v : len) mx = std::max(mx, v);
+    const double mean = (double)s->n_elements / (double)(nc * s->C);
+    if (mx <= 64 || mx < 8.0 * mean) return;
+    DevBuf<int> iota(nc), keys_out(nc);
+    s->balanced_order.alloc(nc);
+    k_iota<<<blocks_for(nc), TPB>>>(iota.p, nc);
+    USPMV_LAUNCH_CHECK();
+    size_t bytes = 0;
+    USPMV_CUDA(cub::DeviceRadixSort::SortPairsDescending(nullptr, bytes, s->chunk_lengths.p, keys_out.p, iota.p, s->balanced_order.p, (int)nc));
+    DevBuf<unsigned char> tmp(bytes);
+    USPMV_CUDA(cub::DeviceRadixSort::SortPairsDescending(tmp.p, bytes, s->chunk_lengths.p, keys_out.p, iota.p, s->balanced_order.p, (int)nc));
+    g_launches.fetch_add(8);
+    USPMV_CUDA(cudaDeviceSynchronize());
+}
+
 void check_flags(DevBuf<int> &flags, int out[2]) {
     USPMV_CUDA(cudaMemcpy(out, flags.p, 2 * sizeof(int), cudaMemcpyDeviceToHost));
 }
@@ -610,6 +635,7 @@ int uspmv_scs_build(uspmv_ctx *ctx, const uspmv_coo *coo, long C, long sigma, in
                 }
             }
             USPMV_CUDA(cudaDeviceSynchronize());
+            build_balanced_order(s);
         } catch (...) { delete s; throw; }
         *out = s;
     });

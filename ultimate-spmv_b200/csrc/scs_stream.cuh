@@ -529,5 +529,169 @@ k_scs32_stream_mmv(long n_items, const int *__restrict__ chunk_ptrs, const int *
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Adaptive precision, C = 32: ONE pass over the dp / sp / hp parts of every chunk through the same per-warp ring.
+// The parts share C, n_chunks and the row permutation; each has its own chunk_ptrs / chunk_lengths / col_idxs / values.
+// For a chunk the producer emits the pieces of the dp part, then sp, then hp; the header's `pad` field carries the part.
+// Arithmetic = the reference's library kernels (interface.hpp:1434-1733): one fp64 accumulator per part, the narrower value
+// widened before the FMA, y = dp + sp + hp; MODE 2 (sp_hp): fp32 products against the fp32 x, fp64 accumulators, fp32 y.
+// ---------------------------------------------------------------------------------------------------------------------
+struct ApPart {
+    const int *cp, *cl, *ci;
+    const void *v;
+};
+
+template <int MODE, int LMAX, int D, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+k_scs32_stream_ap(long n_items, const int *__restrict__ order, ApPart p0, ApPart p1, ApPart p2, const void *__restrict__ xv_, void *__restrict__ yv_) {
+    using R = WarpRing<double, LMAX, D>;  // stages sized for the widest part
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char *base = smem_raw + (size_t)warp * R::BYTES_ALIGNED;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(base + D * R::STAGE_BYTES);
+    PieceHdr *hdrs = reinterpret_cast<PieceHdr *>(base + D * R::STAGE_BYTES + D * 8);
+    const long W = (long)gridDim.x * WARPS;
+    const long gw = (long)blockIdx.x * WARPS + warp;
+    constexpr bool USE0 = MODE != 2, USE1 = MODE != 1, USE2 = MODE != 0;  // dp, sp, hp parts in use
+    const ApPart parts[3] = {p0, p1, p2};
+
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < D; ++s) mbar_init(&bars[s], 1);
+        fence_barrier_init();
+    }
+    __syncwarp();
+    const uint64_t pol = policy_evict_first();
+
+    // ---- producer (lane 0): items gw, gw + W, ...; per item the parts in order dp, sp, hp ------------------------------
+    long pc = gw;
+    int pchunk = 0, nchunk = 0;
+    int plen[3] = {0, 0, 0}, pcs[3] = {0, 0, 0}, nlen[3] = {0, 0, 0}, ncs[3] = {0, 0, 0};
+    int pp = 0, pj = 0;        // current part and slot inside it
+    bool pfirst = true;        // no piece of the current chunk emitted yet
+    auto load_meta = [&](int chunk, int *len, int *cs) {
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            const bool use = q == 0 ? USE0 : (q == 1 ? USE1 : USE2);
+            len[q] = use ? parts[q].cl[chunk] : 0;
+            cs[q] = use ? parts[q].cp[chunk] : 0;
+        }
+    };
+    if (lane == 0) {
+        if (pc < n_items) { pchunk = order ? order[pc] : (int)pc; load_meta(pchunk, plen, pcs); }
+        if (pc + W < n_items) { nchunk = order ? order[pc + W] : (int)(pc + W); load_meta(nchunk, nlen, ncs); }
+    }
+    auto issue = [&](int s) {
+        PieceHdr h;
+        h.ns = 0; h.flags = 0; h.chunk = 0; h.pad = 0;
+        if (pc >= n_items) { hdrs[s] = h; return; }
+        while (pp < 3 && pj >= plen[pp]) { ++pp; pj = 0; }  // skip exhausted / empty parts
+        int ns = 0;
+        if (pp < 3) {
+            ns = min(LMAX, plen[pp] - pj);
+            const long e0 = (long)pcs[pp] + (long)pj * 32;
+            const uint32_t vsz = pp == 0 ? 8u : (pp == 1 ? 4u : 2u);
+            const uint32_t vb = (uint32_t)ns * 32u * vsz, cb = (uint32_t)ns * 128u;
+            unsigned char *st = base + s * R::STAGE_BYTES;
+            mbar_expect_tx(&bars[s], vb + cb);
+            bulk_g2s(st, static_cast<const unsigned char *>(parts[pp].v) + e0 * vsz, vb, &bars[s], pol);
+            bulk_g2s(st + R::VAL_BYTES, parts[pp].ci + e0, cb, &bars[s], pol);
+            h.pad = pp;
+            pj += ns;
+        }
+        // is anything left in this chunk after this piece?
+        bool more = false;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) more |= (q > pp && plen[q] > 0) || (q == pp && pj < plen[q]);
+        h.ns = ns;
+        h.flags = 4 | (pfirst ? 1 : 0) | (more ? 0 : 2);
+        h.chunk = pchunk;
+        hdrs[s] = h;
+        pfirst = false;
+        if (!more) {  // next chunk
+            pc += W;
+            pp = 0; pj = 0; pfirst = true;
+            pchunk = nchunk;
+#pragma unroll
+            for (int q = 0; q < 3; ++q) { plen[q] = nlen[q]; pcs[q] = ncs[q]; }
+            if (pc + W < n_items) { nchunk = order ? order[pc + W] : (int)(pc + W); load_meta(nchunk, nlen, ncs); }
+        }
+    };
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < D; ++s) issue(s);
+    }
+    __syncwarp();
+
+    // ---- consumer --------------------------------------------------------------------------------------------------------
+    uint32_t phase_bits = 0;
+    double acc[3] = {0.0, 0.0, 0.0};
+    for (int s = 0;; s = (s + 1 == D) ? 0 : s + 1) {
+        const PieceHdr h = hdrs[s];
+        if (h.flags == 0) break;
+        if (h.flags & 1) { acc[0] = 0.0; acc[1] = 0.0; acc[2] = 0.0; }
+        if (h.ns > 0) {
+            mbar_wait(&bars[s], (phase_bits >> s) & 1u);
+            phase_bits ^= (1u << s);
+            const unsigned char *sv = base + s * R::STAGE_BYTES;
+            const int *sc = reinterpret_cast<const int *>(base + s * R::STAGE_BYTES + R::VAL_BYTES) + lane;
+            int col[LMAX];
+#pragma unroll
+            for (int j = 0; j < LMAX; ++j)
+                if (j < h.ns) col[j] = sc[j * 32];
+            if constexpr (MODE == 2) {
+                const float *x = static_cast<const float *>(xv_);
+                float xf[LMAX];
+#pragma unroll
+                for (int j = 0; j < LMAX; ++j)
+                    if (j < h.ns) xf[j] = __ldg(x + col[j]);
+                if (h.pad == 1) {
+                    const float *v = reinterpret_cast<const float *>(sv) + lane;
+#pragma unroll
+                    for (int j = 0; j < LMAX; ++j)
+                        if (j < h.ns) acc[1] += (double)__fmul_rn(v[j * 32], xf[j]);
+                } else {
+                    const __half *v = reinterpret_cast<const __half *>(sv) + lane;
+#pragma unroll
+                    for (int j = 0; j < LMAX; ++j)
+                        if (j < h.ns) acc[2] += (double)__fmul_rn(__half2float(v[j * 32]), xf[j]);
+                }
+            } else {
+                const double *x = static_cast<const double *>(xv_);
+                double xd[LMAX];
+#pragma unroll
+                for (int j = 0; j < LMAX; ++j)
+                    if (j < h.ns) xd[j] = __ldg(x + col[j]);
+                if (h.pad == 0) {
+                    const double *v = reinterpret_cast<const double *>(sv) + lane;
+#pragma unroll
+                    for (int j = 0; j < LMAX; ++j)
+                        if (j < h.ns) acc[0] = fma(v[j * 32], xd[j], acc[0]);
+                } else if (h.pad == 1) {
+                    const float *v = reinterpret_cast<const float *>(sv) + lane;
+#pragma unroll
+                    for (int j = 0; j < LMAX; ++j)
+                        if (j < h.ns) acc[1] = fma((double)v[j * 32], xd[j], acc[1]);
+                } else {
+                    const __half *v = reinterpret_cast<const __half *>(sv) + lane;
+#pragma unroll
+                    for (int j = 0; j < LMAX; ++j)
+                        if (j < h.ns) acc[2] = fma((double)__half2float(v[j * 32]), xd[j], acc[2]);
+                }
+            }
+        }
+        if (h.flags & 2) {
+            const long row = (long)h.chunk * 32 + lane;
+            if constexpr (MODE == 2) static_cast<float *>(yv_)[row] = (float)(acc[1] + acc[2]);
+            else if constexpr (MODE == 0) static_cast<double *>(yv_)[row] = acc[0] + acc[1];
+            else if constexpr (MODE == 1) static_cast<double *>(yv_)[row] = acc[0] + acc[2];
+            else static_cast<double *>(yv_)[row] = acc[0] + acc[1] + acc[2];
+        }
+        __syncwarp();
+        if (lane == 0) issue(s);
+        __syncwarp();
+    }
+}
+
 }  // namespace stream
 }  // namespace uspmv

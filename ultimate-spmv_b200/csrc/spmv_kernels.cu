@@ -110,25 +110,35 @@ k_scs_spmv(long n_pad, int Crt, const int *__restrict__ chunk_list, int chunk_of
 // memory so the value/column streams stay coalesced; partial sums are combined by a shuffle tree.
 // (Summation order differs from the sequential CPU loop => compared within tolerance, not bit-exact.)
 // ---------------------------------------------------------------------------------------------
-template <typename VT, int T>
+template <typename VT, int T, int R>
 __global__ void __launch_bounds__(TPB)
 k_csr_spmv(long n_rows, const int *__restrict__ row_ptrs, const int *__restrict__ col_idxs, const VT *__restrict__ values,
            const VT *__restrict__ x, VT *__restrict__ y) {
+    // a group of T lanes handles R ADJACENT rows (their elements are contiguous); the loads of all R rows are issued
+    // before any reduction so that R*ceil(len/T) independent load chains are in flight per lane
     using A = Arith<VT>;
     const long gt = blockIdx.x * (long)TPB + threadIdx.x;
-    const long row = gt / T;
+    const long row0 = (gt / T) * R;
     const int t = (int)(gt % T);
-    typename A::acc_t acc = A::zero();
-    if (row < n_rows) {
-        const int beg = row_ptrs[row], end = row_ptrs[row + 1];
-        for (int j = beg + t; j < end; j += T) acc = A::mad(ld_stream(values + j), ld_x(x + ld_stream(col_idxs + j)), acc);
+    typename A::acc_t acc[R];
+    int beg[R + 1];
+#pragma unroll
+    for (int r = 0; r <= R; ++r) beg[r] = row0 + r <= n_rows ? row_ptrs[row0 + r] : (row0 < n_rows ? row_ptrs[n_rows] : 0);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        acc[r] = A::zero();
+        if (row0 + r < n_rows)
+            for (int j = beg[r] + t; j < beg[r + 1]; j += T) acc[r] = A::mad(ld_stream(values + j), ld_x(x + ld_stream(col_idxs + j)), acc[r]);
     }
 #pragma unroll
-    for (int off = T / 2; off > 0; off >>= 1) {
-        typename A::acc_t other = __shfl_down_sync(0xffffffffu, acc, off, T);
-        acc = A::add(acc, other);
+    for (int r = 0; r < R; ++r) {
+#pragma unroll
+        for (int off = T / 2; off > 0; off >>= 1) {
+            typename A::acc_t other = __shfl_down_sync(0xffffffffu, acc[r], off, T);
+            acc[r] = A::add(acc[r], other);
+        }
+        if (row0 + r < n_rows && t == 0) y[row0 + r] = A::out(acc[r]);
     }
-    if (row < n_rows && t == 0) y[row] = A::out(acc);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -375,13 +385,14 @@ void launch_csr(long n_rows, long nnz_hint, const int *rp, const int *ci, const 
     const double avg = nnz_hint >= 0 ? (double)nnz_hint / (double)n_rows : 8.0;
     int T = 2;
     while (T < 32 && T < avg) T *= 2;
-    const unsigned g = blocks_for(n_rows * T);
+    constexpr int R = 4;
+    const unsigned g = blocks_for((n_rows + R - 1) / R * T);
     switch (T) {
-    case 2: k_csr_spmv<VT, 2><<<g, TPB, 0, st>>>(n_rows, rp, ci, v, xx, yy); break;
-    case 4: k_csr_spmv<VT, 4><<<g, TPB, 0, st>>>(n_rows, rp, ci, v, xx, yy); break;
-    case 8: k_csr_spmv<VT, 8><<<g, TPB, 0, st>>>(n_rows, rp, ci, v, xx, yy); break;
-    case 16: k_csr_spmv<VT, 16><<<g, TPB, 0, st>>>(n_rows, rp, ci, v, xx, yy); break;
-    default: k_csr_spmv<VT, 32><<<g, TPB, 0, st>>>(n_rows, rp, ci, v, xx, yy); break;
+    case 2: k_csr_spmv<VT, 2, R><<<g, TPB, 0, st>>>(n_rows, rp, ci, v, xx, yy); break;
+    case 4: k_csr_spmv<VT, 4, R><<<g, TPB, 0, st>>>(n_rows, rp, ci, v, xx, yy); break;
+    case 8: k_csr_spmv<VT, 8, R><<<g, TPB, 0, st>>>(n_rows, rp, ci, v, xx, yy); break;
+    case 16: k_csr_spmv<VT, 16, R><<<g, TPB, 0, st>>>(n_rows, rp, ci, v, xx, yy); break;
+    default: k_csr_spmv<VT, 32, R><<<g, TPB, 0, st>>>(n_rows, rp, ci, v, xx, yy); break;
     }
     USPMV_LAUNCH_CHECK();
 }
@@ -530,15 +541,15 @@ int uspmv_spmv(const uspmv_scs *s, const void *x, void *y, void *stream) {
         switch (s->vt) {
         case USPMV_F64:
             if (crs) launch_csr<double>(s->n_rows, s->nnz, s->chunk_ptrs.p, s->col_idxs.p, s->values.p, x, y, st);
-            else launch_scs<double, false>(s->C, s->n_chunks, s->chunk_ptrs.p, s->chunk_lengths.p, s->col_idxs.p, s->values.p, x, y, nullptr, st);
+            else launch_scs<double, false>(s->C, s->n_chunks, s->chunk_ptrs.p, s->chunk_lengths.p, s->col_idxs.p, s->values.p, x, y, nullptr, st, s->balanced_order.p);
             break;
         case USPMV_F32:
             if (crs) launch_csr<float>(s->n_rows, s->nnz, s->chunk_ptrs.p, s->col_idxs.p, s->values.p, x, y, st);
-            else launch_scs<float, false>(s->C, s->n_chunks, s->chunk_ptrs.p, s->chunk_lengths.p, s->col_idxs.p, s->values.p, x, y, nullptr, st);
+            else launch_scs<float, false>(s->C, s->n_chunks, s->chunk_ptrs.p, s->chunk_lengths.p, s->col_idxs.p, s->values.p, x, y, nullptr, st, s->balanced_order.p);
             break;
         default:
             if (crs) launch_csr<__half>(s->n_rows, s->nnz, s->chunk_ptrs.p, s->col_idxs.p, s->values.p, x, y, st);
-            else launch_scs<__half, false>(s->C, s->n_chunks, s->chunk_ptrs.p, s->chunk_lengths.p, s->col_idxs.p, s->values.p, x, y, nullptr, st);
+            else launch_scs<__half, false>(s->C, s->n_chunks, s->chunk_ptrs.p, s->chunk_lengths.p, s->col_idxs.p, s->values.p, x, y, nullptr, st, s->balanced_order.p);
         }
     });
 }
@@ -601,9 +612,9 @@ int uspmv_spmv_unpermuted(const uspmv_scs *s, const void *x, void *y, void *stre
         if (s->cols_permuted) fail("uspmv_spmv_unpermuted: columns were already permuted (permute_scs_cols); use uspmv_spmv");
         cudaStream_t st = as_stream(stream);
         switch (s->vt) {
-        case USPMV_F64: launch_scs<double, true>(s->C, s->n_chunks, s->chunk_ptrs.p, s->chunk_lengths.p, s->col_idxs.p, s->values.p, x, y, s->new_to_old.p, st); break;
-        case USPMV_F32: launch_scs<float, true>(s->C, s->n_chunks, s->chunk_ptrs.p, s->chunk_lengths.p, s->col_idxs.p, s->values.p, x, y, s->new_to_old.p, st); break;
-        default: launch_scs<__half, true>(s->C, s->n_chunks, s->chunk_ptrs.p, s->chunk_lengths.p, s->col_idxs.p, s->values.p, x, y, s->new_to_old.p, st);
+        case USPMV_F64: launch_scs<double, true>(s->C, s->n_chunks, s->chunk_ptrs.p, s->chunk_lengths.p, s->col_idxs.p, s->values.p, x, y, s->new_to_old.p, st, s->balanced_order.p); break;
+        case USPMV_F32: launch_scs<float, true>(s->C, s->n_chunks, s->chunk_ptrs.p, s->chunk_lengths.p, s->col_idxs.p, s->values.p, x, y, s->new_to_old.p, st, s->balanced_order.p); break;
+        default: launch_scs<__half, true>(s->C, s->n_chunks, s->chunk_ptrs.p, s->chunk_lengths.p, s->col_idxs.p, s->values.p, x, y, s->new_to_old.p, st, s->balanced_order.p);
         }
     });
 }

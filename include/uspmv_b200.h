@@ -137,6 +137,12 @@ int uspmv_spmmv(const uspmv_scs *scs, const void *X_d, void *Y_d, int bvs, long 
 /* Host-buffer call (the reference-facing path measured as "e2e"): copies x to the device, runs the
  * kernel, copies y (n_rows_padded entries) back, synchronises. */
 int uspmv_spmv_host(const uspmv_scs *scs, const void *x_h, long x_len, void *y_h, long y_len);
+/* Pipelined form of the same call for back-to-back SpMVs with different host vectors (up to 3 slots in flight): submit
+ * enqueues H2D(x) -> kernel -> D2H(y) on three streams and returns; wait blocks until y_h of that slot is complete.
+ * The transfers of one SpMV overlap the kernel and the opposite-direction transfer of its neighbours (PCIe is full duplex).
+ * x_h / y_h must stay valid until wait; pin them with uspmv_host_alloc. */
+int uspmv_spmv_host_submit(const uspmv_scs *scs, const void *x_h, long x_len, void *y_h, long y_len, int slot);
+int uspmv_spmv_host_wait(const uspmv_scs *scs, int slot);
 
 /* ---- adaptive precision --------------------------------------------------------------------------- */
 /* partition_precisions (interface.hpp:690-978; utilities.hpp:2810-3123): order-preserving split of a

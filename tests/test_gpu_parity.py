@@ -314,3 +314,23 @@ def test_uneven_matrix_long_chunks(eng, pkg, orc, mats):
     short = np.repeat(ref.chunk_lengths <= 256, 32)
     assert np.array_equal(outs[256][short], y_ref[short]), "rows of un-split chunks stay bit-identical"
     assert (outs[256] != y_ref).sum() > 0 or True
+
+
+def test_spmv_host_pipelined(eng, pkg, orc, mats):
+    """uspmv_spmv_host_submit/_wait: three SpMVs in flight, each with its own host x / y."""
+    import ctypes as C_
+    t = torch_()
+    coo = mats.random_coo(3000, 6, seed=15)
+    scs, ref = build_both(eng, orc, coo, 32, 64, "dp")
+    xs = [t.from_numpy(np.random.default_rng(k).standard_normal(scs.n_rows_padded)).pin_memory() for k in range(5)]
+    ys = [t.zeros(scs.n_rows_padded, dtype=t.float64).pin_memory() for _ in range(5)]
+    for i in range(5):
+        sl = i % 3
+        pkg.capi.call("uspmv_spmv_host_wait", scs.h, sl)
+        pkg.capi.call("uspmv_spmv_host_submit", scs.h, C_.c_void_p(xs[i].data_ptr()), xs[i].numel(), C_.c_void_p(ys[i].data_ptr()), ys[i].numel(), sl)
+    with pytest.raises(pkg.capi.UspmvError):  # slot 1 (step 4) is still in flight
+        pkg.capi.call("uspmv_spmv_host_submit", scs.h, C_.c_void_p(xs[0].data_ptr()), xs[0].numel(), C_.c_void_p(ys[0].data_ptr()), ys[0].numel(), 1)
+    for sl in range(3):
+        pkg.capi.call("uspmv_spmv_host_wait", scs.h, sl)
+    for i in range(5):
+        assert np.array_equal(ys[i].numpy(), orc.spmv_scs(ref, xs[i].numpy())), i

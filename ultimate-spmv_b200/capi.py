@@ -61,6 +61,8 @@ _sigs = {
     "uspmv_spmv_unpermuted": [vp, vp, vp, vp],
     "uspmv_spmmv": [vp, vp, vp, C.c_int, C.c_long, C.c_int, vp],
     "uspmv_spmv_host": [vp, vp, C.c_long, vp, C.c_long],
+    "uspmv_spmv_host_submit": [vp, vp, C.c_long, vp, C.c_long, C.c_int],
+    "uspmv_spmv_host_wait": [vp, C.c_int],
     "uspmv_partition_precisions": [vp, vp, C.c_int, C.c_double, C.c_double, vp, vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)],
     "uspmv_ap_spmv": [C.c_int, vp, vp, vp, vp, vp, vp],
     "uspmv_seg_work_sharing_arr": [C.c_int, C.c_long, C.c_long, vp, C.c_int, vp],

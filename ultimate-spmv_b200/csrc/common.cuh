@@ -148,6 +148,12 @@ struct uspmv_scs {
     uspmv::DevBuf<int> new_to_old;  // n_rows_padded, -1 where no real row lands
     uspmv::DevBuf<int> row_lengths; // n_rows_padded: stored elements of the row at each (permuted) position
     uspmv::DevBuf<unsigned char> h2d_stage_x, d2h_stage_y;  // device staging for the host-buffer call
+    // pipelined host-buffer calls: per slot a device x / y pair, three streams and events
+    static constexpr int HOST_SLOTS = 3;
+    uspmv::DevBuf<unsigned char> slot_x[HOST_SLOTS], slot_y[HOST_SLOTS];
+    cudaStream_t s_h2d = nullptr, s_run = nullptr, s_d2h = nullptr;
+    cudaEvent_t ev_x[HOST_SLOTS] = {}, ev_y[HOST_SLOTS] = {}, ev_done[HOST_SLOTS] = {};
+    bool slot_busy[HOST_SLOTS] = {};
     // chunk ids sorted by length (longest first, ties in chunk order); only built when lengths are very uneven, so that
     // one-warp-per-chunk kernels stay load balanced (longest-processing-time-first over the persistent warps)
     uspmv::DevBuf<int> balanced_order;

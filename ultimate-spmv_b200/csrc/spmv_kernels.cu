@@ -689,6 +689,53 @@ int uspmv_spmv_host(const uspmv_scs *s_, const void *x_h, long x_len, void *y_h,
     });
 }
 
+// Pipelined host-buffer SpMV: submit() enqueues H2D(x) on a copy stream, the kernel on a compute stream and D2H(y) on a
+// second copy stream; up to HOST_SLOTS calls are in flight, so the PCIe transfers of one SpMV overlap the kernel and the
+// opposite-direction transfer of its neighbours.  x_h / y_h should be pinned (uspmv_host_alloc) for the copies to be async.
+int uspmv_spmv_host_submit(const uspmv_scs *s_, const void *x_h, long x_len, void *y_h, long y_len, int slot) {
+    return guarded([&] {
+        uspmv_scs *s = const_cast<uspmv_scs *>(s_);
+        if (!s || !x_h || !y_h) fail("uspmv_spmv_host_submit: NULL argument");
+        if (slot < 0 || slot >= uspmv_scs::HOST_SLOTS) fail("uspmv_spmv_host_submit: slot must be in [0,%d)", uspmv_scs::HOST_SLOTS);
+        if (y_len < s->n_rows_padded) fail("uspmv_spmv_host_submit: y_len %ld < n_rows_padded %ld", y_len, s->n_rows_padded);
+        if (s->slot_busy[slot]) fail("uspmv_spmv_host_submit: slot %d is still in flight (call uspmv_spmv_host_wait)", slot);
+        USPMV_CUDA(cudaSetDevice(s->ctx->device));
+        const size_t es = vt_size(s->vt);
+        if (!s->s_run) {
+            USPMV_CUDA(cudaStreamCreateWithFlags(&s->s_h2d, cudaStreamNonBlocking));
+            USPMV_CUDA(cudaStreamCreateWithFlags(&s->s_run, cudaStreamNonBlocking));
+            USPMV_CUDA(cudaStreamCreateWithFlags(&s->s_d2h, cudaStreamNonBlocking));
+            for (int k = 0; k < uspmv_scs::HOST_SLOTS; ++k) {
+                USPMV_CUDA(cudaEventCreateWithFlags(&s->ev_x[k], cudaEventDisableTiming));
+                USPMV_CUDA(cudaEventCreateWithFlags(&s->ev_y[k], cudaEventDisableTiming));
+                USPMV_CUDA(cudaEventCreateWithFlags(&s->ev_done[k], cudaEventDisableTiming));
+            }
+        }
+        if (s->slot_x[slot].n < (size_t)x_len * es) s->slot_x[slot].alloc((size_t)x_len * es);
+        if (s->slot_y[slot].n < (size_t)s->n_rows_padded * es) s->slot_y[slot].alloc((size_t)s->n_rows_padded * es);
+        USPMV_CUDA(cudaMemcpyAsync(s->slot_x[slot].p, x_h, (size_t)x_len * es, cudaMemcpyHostToDevice, s->s_h2d));
+        USPMV_CUDA(cudaEventRecord(s->ev_x[slot], s->s_h2d));
+        USPMV_CUDA(cudaStreamWaitEvent(s->s_run, s->ev_x[slot], 0));
+        if (uspmv_spmv(s, s->slot_x[slot].p, s->slot_y[slot].p, s->s_run)) throw Error(uspmv_last_error());
+        USPMV_CUDA(cudaEventRecord(s->ev_y[slot], s->s_run));
+        USPMV_CUDA(cudaStreamWaitEvent(s->s_d2h, s->ev_y[slot], 0));
+        USPMV_CUDA(cudaMemcpyAsync(y_h, s->slot_y[slot].p, (size_t)s->n_rows_padded * es, cudaMemcpyDeviceToHost, s->s_d2h));
+        USPMV_CUDA(cudaEventRecord(s->ev_done[slot], s->s_d2h));
+        s->slot_busy[slot] = true;
+    });
+}
+
+int uspmv_spmv_host_wait(const uspmv_scs *s_, int slot) {
+    return guarded([&] {
+        uspmv_scs *s = const_cast<uspmv_scs *>(s_);
+        if (!s) fail("uspmv_spmv_host_wait: NULL argument");
+        if (slot < 0 || slot >= uspmv_scs::HOST_SLOTS) fail("uspmv_spmv_host_wait: slot must be in [0,%d)", uspmv_scs::HOST_SLOTS);
+        if (!s->slot_busy[slot]) return;
+        USPMV_CUDA(cudaEventSynchronize(s->ev_done[slot]));
+        s->slot_busy[slot] = false;
+    });
+}
+
 int uspmv_apply_permutation(uspmv_ctx *ctx, void *out, const void *in, const int *perm, long n, int vt, void *stream) {
     return guarded([&] {
         if (!ctx) fail("uspmv_apply_permutation: ctx is NULL");

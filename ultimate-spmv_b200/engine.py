@@ -340,19 +340,31 @@ class SingleGpuSpmv:
         t.cuda.synchronize()
         return e0.elapsed_time(e1) / steps
 
-    def time_e2e(self, steps: int, barrier) -> float:
-        """Seconds per step through the host-buffer C-ABI call with pinned host x / y."""
+    def time_e2e(self, steps: int, barrier, pipelined: bool = True) -> float:
+        """Seconds per step through the host-buffer C-ABI call with pinned host x / y.  pipelined: up to three SpMVs in
+        flight (uspmv_spmv_host_submit / _wait), each still copying its own x in and its own y out."""
         import time
         t = _torch()
-        xh = t.full((self.x.numel(),), 5.0, dtype=self.x.dtype).pin_memory()
-        yh = t.zeros(self.y.numel(), dtype=self.y.dtype).pin_memory()
-        for _ in range(2):
-            spmv_host_ptr(self.scs, xh.data_ptr(), xh.numel(), yh.data_ptr(), yh.numel())
+        nslots = 3 if pipelined else 1
+        xh = [t.full((self.x.numel(),), 5.0, dtype=self.x.dtype).pin_memory() for _ in range(nslots)]
+        yh = [t.zeros(self.y.numel(), dtype=self.y.dtype).pin_memory() for _ in range(nslots)]
+
+        def run(k):
+            if not pipelined:
+                for _ in range(k):
+                    spmv_host_ptr(self.scs, xh[0].data_ptr(), xh[0].numel(), yh[0].data_ptr(), yh[0].numel())
+                return
+            for i in range(k):
+                sl = i % nslots
+                call("uspmv_spmv_host_wait", self.scs.h, sl)
+                call("uspmv_spmv_host_submit", self.scs.h, vp(xh[sl].data_ptr()), xh[sl].numel(), vp(yh[sl].data_ptr()), yh[sl].numel(), sl)
+            for sl in range(nslots):
+                call("uspmv_spmv_host_wait", self.scs.h, sl)
+        run(3)
         barrier()
         t0 = time.perf_counter()
-        for _ in range(steps):
-            spmv_host_ptr(self.scs, xh.data_ptr(), xh.numel(), yh.data_ptr(), yh.numel())
+        run(steps)
         barrier()
         dt = (time.perf_counter() - t0) / steps
-        self.e2e_checksum = float(yh[: self.n_rows].double().sum())
+        self.e2e_checksum = float(yh[0][: self.n_rows].double().sum())
         return dt

@@ -156,14 +156,18 @@ class DistributedSpmv:
 
     kernel_name = "k_scs32_stream"
 
-    def __init__(self, ctx, points, n, C_, sigma, vt, rank, world, overlap=True, group=None, halo="p2p"):
+    def __init__(self, ctx, points, n, C_, sigma, vt, rank, world, overlap=True, group=None, halo="p2p", strong=False):
+        """strong=False: weak scaling, an n^3 slab per rank (grid n x n x n*world); strong=True: ONE n^3 grid cut into
+        `world` z-slabs (BASELINE.json config 5: 512^3 27-point over 2/4/8 GPUs)."""
         import torch
         import torch.distributed as dist
         from . import engine as eng
         self.ctx, self.rank, self.world, self.overlap = ctx, rank, world, overlap
-        rows_per = n * n * n
-        wsa = seg_rows_equal(rows_per * world, world)
-        mtx = eng.MtxData.stencil(points, n, n, n * world, int(wsa[rank]), int(wsa[rank + 1]), ctx=ctx)
+        nz_total = n if strong else n * world
+        if strong and n % world:
+            raise ValueError("strong scaling needs n divisible by the number of ranks")
+        wsa = seg_rows_equal(n * n * nz_total, world)
+        mtx = eng.MtxData.stencil(points, n, n, nz_total, int(wsa[rank]), int(wsa[rank + 1]), ctx=ctx)
         self.scs = eng.convert_to_scs(mtx, C_, sigma, vt)
         del mtx
         self.plan = HaloPlan(self.scs, wsa, rank, world)

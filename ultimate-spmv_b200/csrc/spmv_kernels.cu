@@ -259,10 +259,14 @@ __global__ void k_flag_boundary_chunks(long n_chunks, int C, int n_local, const 
     if (lane == 0) flag[w] = hit;
 }
 
-// measured best SpMMV variant (scripts/tune_mmv.py on B200); 1 = lane per row, 2 = T lanes per row ("wide")
+// measured best SpMMV variant (scripts/tune_mmv.py on B200, 256^3 7-pt): 1 = lane per row / 8 warps, 2 = T lanes per row ("wide") /
+// 8 warps, 6 = wide / 24 warps per CTA, 8 = lane per row / 24 warps per CTA
 inline int mmv_default_variant(size_t vsize, int bvs, bool rowwise) {
     if (!rowwise) return 1;
-    return (long)vsize * bvs >= 64 ? 2 : 1;
+    const long row_bytes = (long)vsize * bvs;
+    if (row_bytes >= 64) return 6;
+    if (row_bytes == 32) return vsize == 8 ? 8 : 2;
+    return 1;
 }
 
 // ---- launch helpers ----------------------------------------------------------------------------
@@ -462,6 +466,10 @@ void launch_spmmv_stream(const uspmv_scs *s, const VT *X, VT *Y, long ld, cudaSt
     case 2: launch_spmmv_stream_v<VT, BVS, ROWWISE, 8, 8, true>(s, X, Y, ld, st); break;
     case 3: launch_spmmv_stream_v<VT, BVS, ROWWISE, 4, 8, false>(s, X, Y, ld, st); break;
     case 4: launch_spmmv_stream_v<VT, BVS, ROWWISE, 4, 8, true>(s, X, Y, ld, st); break;
+    case 5: launch_spmmv_stream_v<VT, BVS, ROWWISE, 8, 16, true>(s, X, Y, ld, st); break;
+    case 6: launch_spmmv_stream_v<VT, BVS, ROWWISE, 8, 24, true>(s, X, Y, ld, st); break;
+    case 7: launch_spmmv_stream_v<VT, BVS, ROWWISE, 8, 16, false>(s, X, Y, ld, st); break;
+    case 8: launch_spmmv_stream_v<VT, BVS, ROWWISE, 8, 24, false>(s, X, Y, ld, st); break;
     default: launch_spmmv_stream_v<VT, BVS, ROWWISE, 8, 8, false>(s, X, Y, ld, st); break;
     }
 }

@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _run_rank(rank, world, port, out_dir):
+def _run_rank(rank, world, port, out_dir, C=32):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
@@ -23,7 +23,7 @@ def _run_rank(rank, world, port, out_dir):
         n = 48
         results = {}
         for halo, mode in (("p2p", 2), ("p2p", 1), ("p2p", 0), ("nccl", True), ("nccl", False)):
-            r = d.DistributedSpmv(eng.default_context(rank), 27, n, 32, 64, "dp", rank, world, overlap=mode, halo=halo)
+            r = d.DistributedSpmv(eng.default_context(rank), 27, n, C, 64, "dp", rank, world, overlap=mode, halo=halo)
             # x = global row index pattern so that halo values are distinguishable
             rows = torch.arange(rank * n ** 3, (rank + 1) * n ** 3, device="cuda", dtype=torch.float64)
             xs = torch.sin(rows * 0.37) + 1.5
@@ -59,17 +59,20 @@ def _check(out_dir, world, mats):
     assert np.all(np.abs(y - y_ref) <= 1e-12 * scale)
 
 
-def test_world_size_1_fused_kernel(eng, mats, tmp_path):
-    port = 29700 + os.getpid() % 200
-    _run_rank(0, 1, port, str(tmp_path))
+@pytest.mark.parametrize("C", [32, 16])
+def test_world_size_1_fused_kernel(eng, mats, tmp_path, C):
+    """C = 32: fused kernel; C = 16: the P2P step falls back to the push / wait / ack kernels around the direct SpMV kernel."""
+    port = 29700 + os.getpid() % 200 + C
+    _run_rank(0, 1, port, str(tmp_path), C)
     _check(str(tmp_path), 1, mats)
 
 
-def test_two_ranks_over_nvlink(eng, mats, tmp_path):
+@pytest.mark.parametrize("C", [32, 16])
+def test_two_ranks_over_nvlink(eng, mats, tmp_path, C):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
-    port = 29900 + os.getpid() % 100
-    mp.spawn(_run_rank, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    port = 29900 + os.getpid() % 100 + C
+    mp.spawn(_run_rank, args=(2, port, str(tmp_path), C), nprocs=2, join=True)
     _check(str(tmp_path), 2, mats)

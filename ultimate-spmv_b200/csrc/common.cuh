@@ -154,6 +154,16 @@ struct uspmv_scs {
     cudaStream_t s_h2d = nullptr, s_run = nullptr, s_d2h = nullptr;
     cudaEvent_t ev_x[HOST_SLOTS] = {}, ev_y[HOST_SLOTS] = {}, ev_done[HOST_SLOTS] = {};
     bool slot_busy[HOST_SLOTS] = {};
+    ~uspmv_scs() {
+        for (int k = 0; k < HOST_SLOTS; ++k) {
+            if (ev_x[k]) cudaEventDestroy(ev_x[k]);
+            if (ev_y[k]) cudaEventDestroy(ev_y[k]);
+            if (ev_done[k]) cudaEventDestroy(ev_done[k]);
+        }
+        if (s_h2d) cudaStreamDestroy(s_h2d);
+        if (s_run) cudaStreamDestroy(s_run);
+        if (s_d2h) cudaStreamDestroy(s_d2h);
+    }
     // chunk ids sorted by length (longest first, ties in chunk order); only built when lengths are very uneven, so that
     // one-warp-per-chunk kernels stay load balanced (longest-processing-time-first over the persistent warps)
     uspmv::DevBuf<int> balanced_order;

@@ -194,6 +194,16 @@ def test_spmv_crs(eng, orc, mats, vt):
     xp, y = run_spmv(eng, scs, ref, x, vt)
     y_ref = orc.spmv_csr(ref.n_rows, ref.chunk_ptrs, ref.col_idxs, ref.values, xp[:ref.n_cols])
     assert rel_err(y, y_ref) <= TOL[vt]
+    # library-built CRS matrices run the streamed kernel: sequential per row => bit-identical to the reference loop
+    assert np.array_equal(y.view(np.uint8), y_ref.view(np.uint8))
+    # the split-row vector kernel (raw-array entry point / scs_stream = 0) stays within tolerance
+    eng_capi = __import__("importlib").import_module("ultimate-spmv_b200").capi
+    eng_capi.set_option("scs_stream", 0)
+    try:
+        _, y2 = run_spmv(eng, scs, ref, x, vt)
+    finally:
+        eng_capi.set_option("scs_stream", 1)
+    assert rel_err(y2, y_ref) <= TOL[vt]
 
 
 def test_spmv_raw_array_entry_points(eng, orc, mats):

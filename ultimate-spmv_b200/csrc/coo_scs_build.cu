@@ -653,8 +653,11 @@ int uspmv_scs_build(uspmv_ctx *ctx, const uspmv_coo *coo, long C, long sigma, in
                 k_perms<<<blocks_for(n_pad), TPB>>>(rc.p, n_rows, n_pad, fixed_perm_h != nullptr, s->old_to_new.p, s->new_to_old.p, s->row_lengths.p);
                 USPMV_LAUNCH_CHECK();
             }
-            s->col_idxs.alloc(s->n_elements);
-            s->values.alloc(s->n_elements * vt_size(vt));
+            // 8 elements of slack: the streamed CRS kernel rounds its bulk copies up to 16-byte multiples
+            s->col_idxs.alloc(s->n_elements + 8);
+            s->values.alloc((s->n_elements + 8) * vt_size(vt));
+            USPMV_CUDA(cudaMemset(s->col_idxs.p + s->n_elements, 0, 8 * sizeof(int)));
+            USPMV_CUDA(cudaMemset(s->values.p + s->n_elements * vt_size(vt), 0, 8 * vt_size(vt)));
             if (n_pad && s->n_elements) {
                 switch (coo->mt) {
                 case USPMV_F64: dispatch_fill_vt<double>(coo, s, rc.p, row_ptr.p, ord); break;

@@ -603,6 +603,130 @@ __global__ void k_reduce_partials(long n_split, const int *__restrict__ split_ch
     y[(long)split_chunk[w] * 32 + lane] = A::out(acc);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// CRS (C = 1, sigma = 1) through the same per-warp ring.  A warp takes blocks of 32 consecutive rows; their elements are
+// one contiguous range [row_ptrs[r0], row_ptrs[r0+32]) which is streamed in tiles of LMAX*32 elements (tile starts aligned to
+// 8 elements so that every bulk copy is 16-byte aligned for fp64 / fp32 / fp16; the arrays carry 8 elements of slack).
+// Lane l walks the part of ITS row that lies inside the current tile sequentially, so the per-row summation order is the
+// reference's (kernels.hpp:46-57): bit-identical to the sequential loop, unlike the split-row vector kernel.
+// ---------------------------------------------------------------------------------------------------------------------
+template <typename VT, typename A, int LMAX, int D, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, (1024 / (WARPS * 32)) > 0 ? (1024 / (WARPS * 32)) : 1)
+k_csr_stream(long n_rows, const int *__restrict__ row_ptrs, const int *__restrict__ col_idxs, const VT *__restrict__ values,
+             const VT *__restrict__ x, VT *__restrict__ y) {
+    using R = WarpRing<VT, LMAX, D>;
+    constexpr int TILE = LMAX * 32;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char *base = smem_raw + (size_t)warp * R::BYTES_ALIGNED;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(base + D * R::STAGE_BYTES);
+    PieceHdr *hdrs = reinterpret_cast<PieceHdr *>(base + D * R::STAGE_BYTES + D * 8);
+    const long W = (long)gridDim.x * WARPS;
+    const long gw = (long)blockIdx.x * WARPS + warp;
+    const long n_blocks = (n_rows + 31) / 32;
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < D; ++s) mbar_init(&bars[s], 1);
+        fence_barrier_init();
+    }
+    __syncwarp();
+    const uint64_t pol = policy_evict_first();
+
+    auto block_range = [&](long rb, int &b0, int &b1) {
+        const long r0 = rb * 32, r1 = min(r0 + 32, n_rows);
+        b0 = row_ptrs[r0];
+        b1 = row_ptrs[r1];
+    };
+    // ---- producer (lane 0): tiles of the blocks gw, gw + W, ... -------------------------------------------------------
+    long pb = gw;
+    int pb0 = 0, pb1 = 0, nb0 = 0, nb1 = 0, pt = 0;  // current block's element range, next block's, next tile start
+    if (lane == 0) {
+        if (pb < n_blocks) { block_range(pb, pb0, pb1); pt = pb0 & ~7; }
+        if (pb + W < n_blocks) block_range(pb + W, nb0, nb1);
+    }
+    auto issue = [&](int s) {
+        PieceHdr h;
+        if (pb >= n_blocks) {
+            h.ns = 0; h.flags = 0; h.chunk = 0; h.pad = 0;
+            hdrs[s] = h;
+            return;
+        }
+        int n = 0;
+        if (pt < pb1) {
+            const int end8 = (pb1 + 7) & ~7;
+            n = min(TILE, end8 - pt);
+            unsigned char *st = base + s * R::STAGE_BYTES;
+            const uint32_t vb = (uint32_t)n * (uint32_t)sizeof(VT), cb = (uint32_t)n * 4u;
+            mbar_expect_tx(&bars[s], vb + cb);
+            bulk_g2s(st, values + pt, vb, &bars[s], pol);
+            bulk_g2s(st + R::VAL_BYTES, col_idxs + pt, cb, &bars[s], pol);
+        }
+        const bool first = pt == (pb0 & ~7);
+        const bool last = pt + n >= pb1;
+        h.ns = n;                 // elements in this tile (0: the block has no elements at all)
+        h.flags = 4 | (first ? 1 : 0) | (last ? 2 : 0);
+        h.chunk = (int)pb;        // row block
+        h.pad = pt;               // first element of the tile
+        hdrs[s] = h;
+        pt += n;
+        if (last) {
+            pb += W;
+            pb0 = nb0; pb1 = nb1; pt = pb0 & ~7;
+            if (pb + W < n_blocks) block_range(pb + W, nb0, nb1);
+        }
+    };
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < D; ++s) issue(s);
+    }
+    __syncwarp();
+
+    // ---- consumer -----------------------------------------------------------------------------------------------------
+    uint32_t phase_bits = 0;
+    typename A::acc_t acc = A::zero();
+    int beg = 0, end = 0;
+    for (int s = 0;; s = (s + 1 == D) ? 0 : s + 1) {
+        const PieceHdr h = hdrs[s];
+        if (h.flags == 0) break;
+        if (h.flags & 1) {
+            acc = A::zero();
+            const long r = (long)h.chunk * 32 + lane;
+            beg = row_ptrs[min(r, n_rows)];
+            end = row_ptrs[min(r + 1, n_rows)];
+        }
+        if (h.ns > 0) {
+            mbar_wait(&bars[s], (phase_bits >> s) & 1u);
+            phase_bits ^= (1u << s);
+            const VT *sv = reinterpret_cast<const VT *>(base + s * R::STAGE_BYTES);
+            const int *sc = reinterpret_cast<const int *>(base + s * R::STAGE_BYTES + R::VAL_BYTES);
+            const int lo = max(beg, h.pad) - h.pad, hi = min(end, h.pad + h.ns) - h.pad;
+            for (int j = lo; j < hi; j += 4) {
+                int col[4];
+                VT v[4], xv[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (j + u < hi) col[u] = sc[j + u];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (j + u < hi) xv[u] = __ldg(x + col[u]);
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (j + u < hi) v[u] = sv[j + u];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (j + u < hi) acc = A::mad(v[u], xv[u], acc);
+            }
+        }
+        if (h.flags & 2) {
+            const long r = (long)h.chunk * 32 + lane;
+            if (r < n_rows) y[r] = A::out(acc);
+        }
+        __syncwarp();
+        if (lane == 0) issue(s);
+        __syncwarp();
+    }
+}
+
 // SELL-32 SpMMV through the same per-warp bulk-copy ring (smaller stages: the block vectors want the L1 capacity).
 template <typename VT, typename A, int LMAX, int D, int WARPS, int BVS, bool ROWWISE, bool WIDE>
 __global__ void __launch_bounds__(WARPS * 32)  // ~80 registers, 24 warps/SM: capping at 64 spills and is 30-50 % slower (measured)

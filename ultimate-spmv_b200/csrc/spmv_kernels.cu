@@ -432,6 +432,28 @@ void launch_csr(long n_rows, long nnz_hint, const int *rp, const int *ci, const 
     USPMV_LAUNCH_CHECK();
 }
 
+// CRS of a library-built matrix (arrays carry the 8-element slack): streamed, sequential per row => bit-identical
+template <typename VT>
+void launch_csr_stream(long n_rows, const int *rp, const int *ci, const void *vals, const void *x, void *y, cudaStream_t st) {
+    if (n_rows == 0) return;
+    constexpr int LMAX = 8, D = 2, WARPS = 16;
+    using R = stream::WarpRing<VT, LMAX, D>;
+    auto kern = stream::k_csr_stream<VT, Arith<VT>, LMAX, D, WARPS>;
+    constexpr int smem = WARPS * R::BYTES_ALIGNED;
+    static bool configured = false;
+    if (!configured) {
+        USPMV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    int dev = 0;
+    USPMV_CUDA(cudaGetDevice(&dev));
+    long grid = (long)sm_count(dev) * 2;
+    const long need = ((n_rows + 31) / 32 + WARPS - 1) / WARPS;
+    if (grid > need) grid = need;
+    kern<<<(unsigned)grid, WARPS * 32, smem, st>>>(n_rows, rp, ci, static_cast<const VT *>(vals), static_cast<const VT *>(x), static_cast<VT *>(y));
+    USPMV_LAUNCH_CHECK();
+}
+
 // C = 32 and bvs in {2,4,8,16}: streamed kernel
 template <typename VT, int BVS, bool ROWWISE, int LMAX, int WARPS, bool WIDE>
 void launch_spmmv_stream_v(const uspmv_scs *s, const VT *X, VT *Y, long ld, cudaStream_t st) {
@@ -587,15 +609,18 @@ int uspmv_spmv(const uspmv_scs *s, const void *x, void *y, void *stream) {
         }
         switch (s->vt) {
         case USPMV_F64:
-            if (crs) launch_csr<double>(s->n_rows, s->nnz, s->chunk_ptrs.p, s->col_idxs.p, s->values.p, x, y, st);
+            if (crs && options().scs_stream) launch_csr_stream<double>(s->n_rows, s->chunk_ptrs.p, s->col_idxs.p, s->values.p, x, y, st);
+            else if (crs) launch_csr<double>(s->n_rows, s->nnz, s->chunk_ptrs.p, s->col_idxs.p, s->values.p, x, y, st);
             else launch_scs<double, false>(s->C, s->n_chunks, s->chunk_ptrs.p, s->chunk_lengths.p, s->col_idxs.p, s->values.p, x, y, nullptr, st, s->balanced_order.p);
             break;
         case USPMV_F32:
-            if (crs) launch_csr<float>(s->n_rows, s->nnz, s->chunk_ptrs.p, s->col_idxs.p, s->values.p, x, y, st);
+            if (crs && options().scs_stream) launch_csr_stream<float>(s->n_rows, s->chunk_ptrs.p, s->col_idxs.p, s->values.p, x, y, st);
+            else if (crs) launch_csr<float>(s->n_rows, s->nnz, s->chunk_ptrs.p, s->col_idxs.p, s->values.p, x, y, st);
             else launch_scs<float, false>(s->C, s->n_chunks, s->chunk_ptrs.p, s->chunk_lengths.p, s->col_idxs.p, s->values.p, x, y, nullptr, st, s->balanced_order.p);
             break;
         default:
-            if (crs) launch_csr<__half>(s->n_rows, s->nnz, s->chunk_ptrs.p, s->col_idxs.p, s->values.p, x, y, st);
+            if (crs && options().scs_stream) launch_csr_stream<__half>(s->n_rows, s->chunk_ptrs.p, s->col_idxs.p, s->values.p, x, y, st);
+            else if (crs) launch_csr<__half>(s->n_rows, s->nnz, s->chunk_ptrs.p, s->col_idxs.p, s->values.p, x, y, st);
             else launch_scs<__half, false>(s->C, s->n_chunks, s->chunk_ptrs.p, s->chunk_lengths.p, s->col_idxs.p, s->values.p, x, y, nullptr, st, s->balanced_order.p);
         }
     });

@@ -31,8 +31,8 @@ UNIT = "GFLOP/s"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="laplace7_256", help="laplace7_<n> | stencil27_<n> (n^3 grid per GPU)")
     ap.add_argument("--C", type=int, default=32)

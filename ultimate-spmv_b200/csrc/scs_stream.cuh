@@ -313,20 +313,20 @@ struct SpmmvBodyRowWide {
 
 // The streaming loop of one warp over work items first, first + W, ... < n_items (item k -> chunk list[k] or k + off).
 template <typename VT, int LMAX, int D, typename Body>
-__device__ __forceinline__ void stream_items(unsigned char *base, uint64_t *bars, PieceHdr *hdrs, uint32_t &phase_bits, const long W,
-                                             const long first, const int lane, const long n_items, const int *__restrict__ chunk_list,
+__device__ __forceinline__ void stream_items(unsigned char *base, uint64_t *bars, PieceHdr *hdrs, uint32_t &phase_bits, const int W,
+                                             const int first, const int lane, const int n_items, const int *__restrict__ chunk_list,
                                              const int chunk_offset, const int *__restrict__ chunk_ptrs,
                                              const int *__restrict__ chunk_lengths, const int *__restrict__ col_idxs,
                                              const VT *__restrict__ values, Body &body, const uint64_t pol) {
     using R = WarpRing<VT, LMAX, D>;
-    auto item_chunk = [&](long k) -> int { return chunk_list ? chunk_list[k] : (int)k + chunk_offset; };
+    auto item_chunk = [&](int k) -> int { return chunk_list ? chunk_list[k] : k + chunk_offset; };  // 32-bit index math throughout
 
     // ---- producer state (meaningful in lane 0 only) --------------------------------------------------
     // Three-deep metadata lookahead so that no load issued by lane 0 is consumed in the same piece:
     //   cur  = (pchunk, plen, pcs)  item being cut into pieces
     //   nxt  = (nchunk, nlen, ncs)  item pc + W, loaded when cur became current
     //   n2chunk                     chunk id of item pc + 2W (only needed with a chunk list)
-    long pc = first;  // work item of the next piece
+    int pc = first;  // work item of the next piece (n_items + 2W < 2^31: one item per 32 rows)
     int pj = 0, plen = 0, pcs = 0, pchunk = 0, nlen = 0, ncs = 0, nchunk = 0, n2chunk = 0;
     if (lane == 0) {
         if (pc < n_items) {
@@ -355,7 +355,7 @@ __device__ __forceinline__ void stream_items(unsigned char *base, uint64_t *bars
         h.pad = 0;
         hdrs[s] = h;
         if (ns > 0) {
-            const long e0 = (long)pcs + (long)pj * 32;
+            const int e0 = pcs + pj * 32;  // < n_elements < 2^31
             const uint32_t vb = (uint32_t)ns * 32u * (uint32_t)sizeof(VT), cb = (uint32_t)ns * 128u;
             unsigned char *st = base + s * R::STAGE_BYTES;
             mbar_expect_tx(&bars[s], vb + cb);
@@ -427,7 +427,7 @@ k_scs32_stream(long n_items, const int *__restrict__ chunk_list, int chunk_offse
 
     if constexpr (!FUSED) {
         SpmvBody<VT, A, LMAX, UNPERM, false> body{x, y, new_to_old, lane, A::zero()};
-        stream_items<VT, LMAX, D>(base, bars, hdrs, phase_bits, W, gw, lane, n_items, chunk_list, chunk_offset,
+        stream_items<VT, LMAX, D>(base, bars, hdrs, phase_bits, (int)W, (int)gw, lane, (int)n_items, chunk_list, chunk_offset,
                                   chunk_ptrs, chunk_lengths, col_idxs, values, body, pol);
     } else {
         // (a) push: warp pw handles send elements [32 pw, 32 pw + 32)
@@ -459,14 +459,14 @@ k_scs32_stream(long n_items, const int *__restrict__ chunk_list, int chunk_offse
         // (b) interior chunks: no halo column, identical code path to the single-GPU kernel
         {
             SpmvBody<VT, A, LMAX, UNPERM, false> body{x, y, new_to_old, lane, A::zero()};
-            stream_items<VT, LMAX, D>(base, bars, hdrs, phase_bits, W, gw, lane, fa.n_int, fa.int_list, fa.int_off,
+            stream_items<VT, LMAX, D>(base, bars, hdrs, phase_bits, (int)W, (int)gw, lane, (int)fa.n_int, fa.int_list, fa.int_off,
                                       chunk_ptrs, chunk_lengths, col_idxs, values, body, pol);
         }
         // (c) boundary chunks once the neighbours' elements for this step have landed in our x tail
         if (gw < fa.n_bnd) {
             warp_wait_flags(fa.arrived, fa.is_sender, fa.P, epoch_e, lane, fa.error);
             SpmvBody<VT, A, LMAX, UNPERM, true> body{x, y, new_to_old, lane, A::zero()};
-            stream_items<VT, LMAX, D>(base, bars, hdrs, phase_bits, W, gw, lane, fa.n_bnd, fa.bnd_list, fa.bnd_off, chunk_ptrs,
+            stream_items<VT, LMAX, D>(base, bars, hdrs, phase_bits, (int)W, (int)gw, lane, (int)fa.n_bnd, fa.bnd_list, fa.bnd_off, chunk_ptrs,
                                       chunk_lengths, col_idxs, values, body, pol);
         }
         // (d) the last warp of the grid acknowledges consumption to the senders and closes the epoch
@@ -491,6 +491,137 @@ k_scs32_stream(long n_items, const int *__restrict__ chunk_list, int chunk_offse
                 __threadfence();
             }
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Variant with SOFTWARE-PIPELINED x gathers (D >= 3).  ncu on k_scs32_stream (profiles/r01i_*): 46 % of the stall samples
+// sit on the first FMA of a piece, i.e. warps wait for the x gathers they have just issued.  Here the gathers of piece p+1
+// are issued BEFORE the FMAs of piece p, so a piece's gathers have one whole piece-time to come back:
+//   stage s   : piece p    (gathered x already in registers)  -> FMAs now
+//   stage s+1 : piece p+1  (data landed)                       -> read columns, issue gathers now
+//   stage s+2 : piece p+2                                      -> bulk copy in flight
+// Same producer, same per-row FMA order (bit-identical); costs a second set of x registers (~80 regs, 24 warps/SM).
+// ---------------------------------------------------------------------------------------------------------------------
+template <typename VT, typename A, int LMAX, int D, int WARPS, bool UNPERM>
+__global__ void __launch_bounds__(WARPS * 32, 768 / (WARPS * 32))
+k_scs32_stream_pf(int n_items, const int *__restrict__ chunk_list, int chunk_offset, const int *__restrict__ chunk_ptrs,
+                  const int *__restrict__ chunk_lengths, const int *__restrict__ col_idxs, const VT *__restrict__ values,
+                  const VT *__restrict__ x, VT *__restrict__ y, const int *__restrict__ new_to_old) {
+    static_assert(D >= 3, "the prefetching consumer needs three stages");
+    using R = WarpRing<VT, LMAX, D>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char *base = smem_raw + (size_t)warp * R::BYTES_ALIGNED;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(base + D * R::STAGE_BYTES);
+    PieceHdr *hdrs = reinterpret_cast<PieceHdr *>(base + D * R::STAGE_BYTES + D * 8);
+    const int W = (int)gridDim.x * WARPS;
+    const int first = (int)blockIdx.x * WARPS + warp;
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < D; ++s) mbar_init(&bars[s], 1);
+        fence_barrier_init();
+    }
+    __syncwarp();
+    const uint64_t pol = policy_evict_first();
+    auto item_chunk = [&](int k) -> int { return chunk_list ? chunk_list[k] : k + chunk_offset; };
+
+    int pc = first;
+    int pj = 0, plen = 0, pcs = 0, pchunk = 0, nlen = 0, ncs = 0, nchunk = 0, n2chunk = 0;
+    if (lane == 0) {
+        if (pc < n_items) { pchunk = item_chunk(pc); plen = chunk_lengths[pchunk]; pcs = chunk_ptrs[pchunk]; }
+        if (pc + W < n_items) { nchunk = item_chunk(pc + W); nlen = chunk_lengths[nchunk]; ncs = chunk_ptrs[nchunk]; }
+        if (pc + 2 * W < n_items) n2chunk = item_chunk(pc + 2 * W);
+    }
+    auto issue = [&](int s) {
+        PieceHdr h;
+        if (pc >= n_items) {
+            h.ns = 0; h.flags = 0; h.chunk = 0; h.pad = 0;
+            hdrs[s] = h;
+            return;
+        }
+        const int ns = min(LMAX, plen - pj);
+        h.ns = ns;
+        h.flags = 4 | (pj == 0 ? 1 : 0) | (pj + ns >= plen ? 2 : 0);
+        h.chunk = pchunk;
+        h.pad = 0;
+        hdrs[s] = h;
+        if (ns > 0) {
+            const int e0 = pcs + pj * 32;
+            const uint32_t vb = (uint32_t)ns * 32u * (uint32_t)sizeof(VT), cb = (uint32_t)ns * 128u;
+            unsigned char *st = base + s * R::STAGE_BYTES;
+            mbar_expect_tx(&bars[s], vb + cb);
+            bulk_g2s(st, values + e0, vb, &bars[s], pol);
+            bulk_g2s(st + R::VAL_BYTES, col_idxs + e0, cb, &bars[s], pol);
+        }
+        pj += ns;
+        if (pj >= plen) {
+            pc += W;
+            pj = 0;
+            pchunk = nchunk; plen = nlen; pcs = ncs;
+            nchunk = n2chunk;
+            if (pc + W < n_items) { nlen = chunk_lengths[nchunk]; ncs = chunk_ptrs[nchunk]; }
+            if (pc + 2 * W < n_items) n2chunk = item_chunk(pc + 2 * W);
+        }
+    };
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < D; ++s) issue(s);
+    }
+    __syncwarp();
+
+    uint32_t phase_bits = 0;
+    auto gather = [&](int s, int ns, VT *xo) {  // wait for stage s, read its columns, issue the x gathers
+        mbar_wait(&bars[s], (phase_bits >> s) & 1u);
+        phase_bits ^= (1u << s);
+        const int *sc = reinterpret_cast<const int *>(base + s * R::STAGE_BYTES + R::VAL_BYTES) + lane;
+        int col[LMAX];
+#pragma unroll
+        for (int j = 0; j < LMAX; ++j)
+            if (j < ns) col[j] = sc[j * 32];
+#pragma unroll
+        for (int j = 0; j < LMAX; ++j)
+            if (j < ns) xo[j] = __ldg(x + col[j]);
+    };
+
+    typename A::acc_t acc = A::zero();
+    int s = 0;
+    PieceHdr hc = hdrs[0];
+    if (hc.flags == 0) return;
+    VT xv[LMAX];
+    if (hc.ns > 0) gather(0, hc.ns, xv);
+    for (;;) {
+        const int sn = (s + 1 == D) ? 0 : s + 1;
+        const PieceHdr hn = hdrs[sn];
+        VT xn[LMAX];
+        if (hn.flags != 0 && hn.ns > 0) gather(sn, hn.ns, xn);
+        if (hc.flags & 1) acc = A::zero();
+        if (hc.ns > 0) {
+            const VT *sv = reinterpret_cast<const VT *>(base + s * R::STAGE_BYTES) + lane;
+            VT v[LMAX];
+#pragma unroll
+            for (int j = 0; j < LMAX; ++j)
+                if (j < hc.ns) v[j] = sv[j * 32];
+#pragma unroll
+            for (int j = 0; j < LMAX; ++j)
+                if (j < hc.ns) acc = A::mad(v[j], xv[j], acc);
+        }
+        if (hc.flags & 2) {
+            const long row = (long)hc.chunk * 32 + lane;
+            if (UNPERM) {
+                const int o = new_to_old[row];
+                if (o >= 0) y[o] = A::out(acc);
+            } else
+                y[row] = A::out(acc);
+        }
+        __syncwarp();
+        if (lane == 0) issue(s);
+        __syncwarp();
+        if (hn.flags == 0) break;
+        hc = hn;
+#pragma unroll
+        for (int j = 0; j < LMAX; ++j) xv[j] = xn[j];
+        s = sn;
     }
 }
 
@@ -752,12 +883,12 @@ k_scs32_stream_mmv(long n_items, const int *__restrict__ chunk_ptrs, const int *
     if constexpr (WIDE && ROWWISE && ROW_BYTES >= 32 && ROW_BYTES <= 128 && (ROW_BYTES & (ROW_BYTES - 1)) == 0) {
         SpmmvBodyRowWide<VT, A, LMAX, BVS> body;
         body.X = X; body.Y = Y; body.lane = lane;
-        stream_items<VT, LMAX, D>(base, bars, hdrs, phase_bits, W, gw, lane, n_items, nullptr, 0, chunk_ptrs,
+        stream_items<VT, LMAX, D>(base, bars, hdrs, phase_bits, (int)W, (int)gw, lane, (int)n_items, nullptr, 0, chunk_ptrs,
                                   chunk_lengths, col_idxs, values, body, pol);
     } else {
         SpmmvBody<VT, A, LMAX, BVS, ROWWISE> body;
         body.X = X; body.Y = Y; body.ld = ld; body.lane = lane;
-        stream_items<VT, LMAX, D>(base, bars, hdrs, phase_bits, W, gw, lane, n_items, nullptr, 0, chunk_ptrs,
+        stream_items<VT, LMAX, D>(base, bars, hdrs, phase_bits, (int)W, (int)gw, lane, (int)n_items, nullptr, 0, chunk_ptrs,
                                   chunk_lengths, col_idxs, values, body, pol);
     }
 }

@@ -292,6 +292,28 @@ void launch_stream_v(long n_chunks, const int *list, int off, const int *cp, con
     kern<<<(unsigned)grid, WARPS * 32, smem, st>>>(n_chunks, list, off, cp, cl, ci, v, x, y, n2o, stream::FusedArgs{});
 }
 
+template <typename VT, bool UNPERM, int LMAX, int D, int WARPS>
+void launch_stream_pf(long n_chunks, const int *list, int off, const int *cp, const int *cl, const int *ci, const VT *v, const VT *x, VT *y,
+                      const int *n2o, cudaStream_t st, int bps_req) {
+    using R = stream::WarpRing<VT, LMAX, D>;
+    auto kern = stream::k_scs32_stream_pf<VT, Arith<VT>, LMAX, D, WARPS, UNPERM>;
+    constexpr int smem = WARPS * R::BYTES_ALIGNED;
+    static bool configured = false;
+    static int bps_max = 1;
+    if (!configured) {
+        USPMV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        USPMV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps_max, kern, WARPS * 32, smem));
+        if (bps_max < 1) bps_max = 1;
+        configured = true;
+    }
+    int dev = 0;
+    USPMV_CUDA(cudaGetDevice(&dev));
+    long grid = (long)sm_count(dev) * std::min(bps_req > 0 ? bps_req : bps_max, bps_max);
+    const long need = (n_chunks + WARPS - 1) / WARPS;
+    if (grid > need) grid = need;
+    kern<<<(unsigned)grid, WARPS * 32, smem, st>>>((int)n_chunks, list, off, cp, cl, ci, v, x, y, n2o);
+}
+
 template <typename VT, bool UNPERM>
 void launch_stream(long n_chunks, const int *list, int off, const int *cp, const int *cl, const int *ci, const VT *v, const VT *x, VT *y,
                    const int *n2o, cudaStream_t st) {
@@ -306,6 +328,9 @@ void launch_stream(long n_chunks, const int *list, int off, const int *cp, const
     case 7: launch_stream_v<VT, UNPERM, 16, 2, 8>(n_chunks, list, off, cp, cl, ci, v, x, y, n2o, st, c.stream_blocks_per_sm); break;
     case 8: launch_stream_v<VT, UNPERM, 8, 2, 32>(n_chunks, list, off, cp, cl, ci, v, x, y, n2o, st, c.stream_blocks_per_sm); break;
     case 9: launch_stream_v<VT, UNPERM, 2, 4, 16>(n_chunks, list, off, cp, cl, ci, v, x, y, n2o, st, c.stream_blocks_per_sm); break;
+    case 10: launch_stream_pf<VT, UNPERM, 8, 3, 8>(n_chunks, list, off, cp, cl, ci, v, x, y, n2o, st, c.stream_blocks_per_sm); break;
+    case 11: launch_stream_pf<VT, UNPERM, 8, 4, 8>(n_chunks, list, off, cp, cl, ci, v, x, y, n2o, st, c.stream_blocks_per_sm); break;
+    case 12: launch_stream_pf<VT, UNPERM, 4, 4, 8>(n_chunks, list, off, cp, cl, ci, v, x, y, n2o, st, c.stream_blocks_per_sm); break;
     default: launch_stream_v<VT, UNPERM, 8, 2, 16>(n_chunks, list, off, cp, cl, ci, v, x, y, n2o, st, c.stream_blocks_per_sm); break;
     }
 }
@@ -436,7 +461,9 @@ void launch_csr(long n_rows, long nnz_hint, const int *rp, const int *ci, const 
 template <typename VT>
 void launch_csr_stream(long n_rows, const int *rp, const int *ci, const void *vals, const void *x, void *y, cudaStream_t st) {
     if (n_rows == 0) return;
-    constexpr int LMAX = 8, D = 2, WARPS = 16;
+    // tiles of 256 (fp64) / 384 (fp32) / 512 (fp16) elements = 3 KB per stage for every type (2 CTAs x 16 warps stay resident):
+    // the bulk-copy engine serves roughly one copy per 46 cycles per SM, so narrow types want more elements per copy
+    constexpr int LMAX = sizeof(VT) == 8 ? 8 : (sizeof(VT) == 4 ? 12 : 16), D = 2, WARPS = 16;
     using R = stream::WarpRing<VT, LMAX, D>;
     auto kern = stream::k_csr_stream<VT, Arith<VT>, LMAX, D, WARPS>;
     constexpr int smem = WARPS * R::BYTES_ALIGNED;

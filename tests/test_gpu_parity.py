@@ -344,3 +344,16 @@ def test_spmv_host_pipelined(eng, pkg, orc, mats):
         pkg.capi.call("uspmv_spmv_host_wait", scs.h, sl)
     for i in range(5):
         assert np.array_equal(ys[i].numpy(), orc.spmv_scs(ref, xs[i].numpy())), i
+
+
+def test_fixed_permutation_must_be_injective(eng, pkg, mats):
+    n, nc, I, J, V = mats.random_coo(100, 4, seed=3, empty_rows=False)
+    mtx = eng.MtxData.from_host(n, nc, I, J, V)
+    perm = np.arange(n, dtype=np.int32)
+    perm[5] = 6
+    with pytest.raises(pkg.capi.UspmvError, match="not injective"):
+        eng.convert_to_scs(mtx, 4, 8, "dp", fixed_permutation=perm)
+    perm = np.arange(n, dtype=np.int32)
+    perm[7] = 10 ** 6
+    with pytest.raises(pkg.capi.UspmvError, match="outside"):
+        eng.convert_to_scs(mtx, 4, 8, "dp", fixed_permutation=perm)

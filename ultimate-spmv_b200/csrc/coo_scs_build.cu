@@ -81,10 +81,8 @@ __global__ void k_scatter_fixed(const int *__restrict__ row_ptr, const int *__re
     if (i >= n_rows) return;
     int p = fixed_perm[i];
     if (p < 0 || p >= n_pad) { atomicOr(&flags[1], 1); return; }
-    RC v;
-    v.idx = (int)i;
-    v.cnt = row_ptr[i + 1] - row_ptr[i];
-    rc[p] = v;
+    if (atomicExch(&rc[p].idx, (int)i) != -1) { atomicOr(&flags[1], 2); return; }  // two rows mapped to one position
+    rc[p].cnt = row_ptr[i + 1] - row_ptr[i];
 }
 
 __global__ void k_fill_rc_empty(long n_pad, RC *rc) {
@@ -614,6 +612,7 @@ int uspmv_scs_build(uspmv_ctx *ctx, const uspmv_coo *coo, long C, long sigma, in
                 k_scatter_fixed<<<blocks_for(n_rows), TPB>>>(row_ptr.p, fixed_perm_d.p, n_rows, n_pad, rc.p, flags.p);
                 USPMV_LAUNCH_CHECK();
                 check_flags(flags, hflags);
+                if (hflags[1] & 2) fail("uspmv_scs_build: fixed_permutation is not injective (two rows map to the same position)");
                 if (hflags[1]) fail("uspmv_scs_build: fixed_permutation entry outside [0, n_rows_padded)");
             }
         } else if (n_pad) {

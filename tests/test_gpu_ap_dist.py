@@ -96,6 +96,66 @@ def test_ap_spmv_fused(eng, orc, mats, mode, C, sigma):
     assert np.array_equal(y.view(np.uint8), y_ref.view(np.uint8)), "fused AP kernel is expected to be bit-identical to the oracle"
 
 
+@pytest.mark.parametrize("mode", MODES)
+def test_ap_spmv_uneven_long_chunks(eng, pkg, orc, mode):
+    """Power-law-like rows: chunks whose parts hold more than `split_long_chunks` slots are summed in per-part segments
+    (deterministic, within tolerance); un-split chunks and the option-off run stay bit-identical to the oracle."""
+    t = torch_()
+    rng = np.random.default_rng(11)
+    n = 140000
+    cnt = rng.integers(1, 8, n)
+    long_rows = rng.choice(n, 40, replace=False)
+    cnt[long_rows] = rng.integers(600, 3000, 40)
+    I = np.repeat(np.arange(n), cnt).astype(np.int32)
+    J = rng.integers(0, n, len(I)).astype(np.int32)
+    V = np.sign(rng.standard_normal(len(I))) * 10.0 ** rng.uniform(-3, 1, len(I))
+    C, sigma = 32, 128
+    part, _ = orc.partition_precisions(mode, I, J, V, 0.5, 0.01)
+    used = USED[mode]
+    ref_parts = [None] * 3
+    sel = part == used[0]
+    ref_parts[used[0]] = orc.convert_to_scs(n, n, I[sel], J[sel], V[sel], C, sigma, VTS[used[0]])
+    perm = ref_parts[used[0]].old_to_new
+    for p in used[1:]:
+        sel = part == p
+        ref_parts[p] = orc.convert_to_scs(n, n, I[sel], J[sel], V[sel], C, sigma, VTS[p], fixed_perm=perm)
+    x = rng.uniform(-1, 1, n)
+    y_ref = orc.ap_scs(mode, ref_parts[0], ref_parts[1], ref_parts[2], x, x.astype(np.float32))
+    n_pad = ref_parts[used[0]].n_rows_padded
+    tot = sum(ref_parts[p].chunk_lengths[: n_pad // 32].astype(np.int64) for p in used)
+    assert tot.max() > 256
+    scale = np.zeros(n)
+    np.add.at(scale, I, np.abs(V * x[J]))
+    sp_ = np.zeros(n_pad)
+    sp_[perm] = scale
+    tol = 1e-5 if mode == "ap[sp_hp]" else 1e-12
+    mtx = eng.MtxData.from_host(n, n, I, J, V)
+    coos = eng.partition_precisions(mtx, mode, 0.5, 0.01)
+    dev_parts = [None] * 3
+    dev_parts[used[0]] = eng.convert_to_scs(coos[used[0]], C, sigma, VTS[used[0]])
+    for p in used[1:]:
+        dev_parts[p] = eng.convert_to_scs(coos[p], C, sigma, VTS[p], fixed_permutation=perm)
+    outs = {}
+    try:
+        for split in (256, 0, 64):
+            pkg.capi.set_option("split_long_chunks", split)
+            if mode == "ap[sp_hp]":
+                xd, yd = dev(x.astype(np.float32)), t.zeros(n_pad, dtype=t.float32, device="cuda")
+            else:
+                xd, yd = dev(x), t.zeros(n_pad, dtype=t.float64, device="cuda")
+            for _ in range(2):  # second call re-uses the cached plan
+                eng.ap_spmv(mode, dev_parts[0], dev_parts[1], dev_parts[2], xd, yd)
+            t.cuda.synchronize()
+            outs[split] = yd.cpu().numpy()
+    finally:
+        pkg.capi.set_option("split_long_chunks", 256)
+    assert np.array_equal(outs[0].view(np.uint8), y_ref.view(np.uint8)), "without segments: bit-identical to the oracle"
+    for split in (256, 64):
+        assert np.all(np.abs(outs[split].astype(np.float64) - y_ref.astype(np.float64)) <= tol * np.maximum(sp_, 1e-300)), split
+        short = np.repeat(tot <= split, 32)
+        assert np.array_equal(outs[split][short].view(np.uint8), y_ref[short].view(np.uint8)), "rows of un-split chunks stay bit-identical"
+
+
 def test_ap_golden_fixtures(eng):
     """y of the reference's interface.hpp AP kernels (tests/golden/ref_ap.npz, generated from the real reference)."""
     import os

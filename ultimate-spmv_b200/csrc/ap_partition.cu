@@ -15,6 +15,9 @@
 
 #include <cub/device/device_scan.cuh>
 
+#include <algorithm>
+#include <vector>
+
 using namespace uspmv;
 
 namespace {
@@ -165,12 +168,78 @@ k_ap_spmv(long n_pad, int C, PartArgs dp, PartArgs sp, PartArgs hp, const void *
     }
 }
 
-template <int MODE>
-void launch_ap_stream(long n_chunks, const int *order, const stream::ApPart &a, const stream::ApPart &b, const stream::ApPart &c, const void *x,
-                      void *y, cudaStream_t st) {
-    constexpr int LMAX = 8, D = 2, WARPS = 8;
+// Work items for very uneven matrices (power-law rows): a chunk whose parts together hold more than L slots is cut, part by
+// part, into segments of <= L slots; every segment is its own work item (k_scs32_stream_ap writes its sum to a partial buffer,
+// k_reduce_partials_ap adds a part's segments in slot order).  All items longest first.  Without this one warp walks a 4096-slot
+// chunk alone (~0.4 ms) while the rest of the GPU idles (ncu r01j: L1 busy 53 % of active but 27 % of elapsed cycles).
+const uspmv_scs::ApPlan *ap_plan_for(int mode, const uspmv_scs *first, const uspmv_scs *o1, const uspmv_scs *o2) {
+    const int L = options().split_long_chunks;
+    uspmv_scs::ApPlan *pl = first->ap_plan.get();
+    const long ne1 = o1 ? o1->n_elements : -1, ne2 = o2 ? o2->n_elements : -1;
+    if (pl && pl->mode == mode && pl->other[0] == o1 && pl->other[1] == o2 && pl->other_ne[0] == ne1 && pl->other_ne[1] == ne2 && pl->seg_slots == L)
+        return pl;
+    first->ap_plan.reset(new uspmv_scs::ApPlan());
+    pl = first->ap_plan.get();
+    pl->mode = mode; pl->other[0] = o1; pl->other[1] = o2; pl->other_ne[0] = ne1; pl->other_ne[1] = ne2; pl->seg_slots = L;
+    const long nc = first->n_chunks;
+    if (L <= 0 || nc < 4096) return pl;
+    // parts in dp, sp, hp order; `first` is the dp part (or sp for sp_hp)
+    const uspmv_scs *part[3] = {nullptr, nullptr, nullptr};
+    if (mode == USPMV_AP_SP_HP) { part[1] = first; part[2] = o2; }
+    else { part[0] = first; part[1] = o1; part[2] = o2; }
+    std::vector<int> len[3];
+    std::vector<long> tot(nc, 0);
+    long slots_all = 0;
+    for (int q = 0; q < 3; ++q) {
+        if (!part[q]) continue;
+        len[q].resize(nc);
+        USPMV_CUDA(cudaMemcpy(len[q].data(), part[q]->chunk_lengths.p, nc * sizeof(int), cudaMemcpyDeviceToHost));
+        for (long c = 0; c < nc; ++c) { tot[c] += len[q][c]; slots_all += len[q][c]; }
+    }
+    long mx = 0;
+    for (long c = 0; c < nc; ++c) mx = std::max(mx, tot[c]);
+    const double mean = (double)slots_all / (double)nc;
+    if (mx <= L || mx < 8.0 * mean) return pl;
+    std::vector<int4> items;
+    std::vector<int> split_chunk, split_ptr{0};
+    std::vector<unsigned char> seg_part;
+    items.reserve(nc + nc / 8);
+    for (long c = 0; c < nc; ++c) {
+        if (tot[c] <= L) { items.push_back(make_int4((int)c, 0, (int)tot[c], -1)); continue; }
+        for (int q = 0; q < 3; ++q) {
+            if (!part[q]) continue;
+            for (int j0 = 0; j0 < len[q][c]; j0 += L) {
+                const int pslot = (int)seg_part.size();
+                if (pslot >= (1 << 28)) fail("uspmv_ap_spmv: too many chunk segments");
+                items.push_back(make_int4((int)c, j0, std::min(L, len[q][c] - j0), (pslot << 2) | q));
+                seg_part.push_back((unsigned char)q);
+            }
+        }
+        split_chunk.push_back((int)c);
+        split_ptr.push_back((int)seg_part.size());
+    }
+    std::stable_sort(items.begin(), items.end(), [](const int4 &a, const int4 &b) { return a.z > b.z; });
+    pl->n_items = (long)items.size();
+    pl->n_split = (long)split_chunk.size();
+    pl->items.alloc(items.size());
+    pl->split_chunk.alloc(split_chunk.size());
+    pl->split_ptr.alloc(split_ptr.size());
+    pl->seg_part.alloc(seg_part.size());
+    pl->partials.alloc(seg_part.size() * 32);
+    USPMV_CUDA(cudaMemcpy(pl->items.p, items.data(), items.size() * sizeof(int4), cudaMemcpyHostToDevice));
+    USPMV_CUDA(cudaMemcpy(pl->split_chunk.p, split_chunk.data(), split_chunk.size() * sizeof(int), cudaMemcpyHostToDevice));
+    USPMV_CUDA(cudaMemcpy(pl->split_ptr.p, split_ptr.data(), split_ptr.size() * sizeof(int), cudaMemcpyHostToDevice));
+    USPMV_CUDA(cudaMemcpy(pl->seg_part.p, seg_part.data(), seg_part.size(), cudaMemcpyHostToDevice));
+    pl->use = true;
+    return pl;
+}
+
+template <int MODE, int D, int MINB>
+void launch_ap_stream_v(long n_chunks, const int *order, const uspmv_scs::ApPlan *pl, const stream::ApPart &a, const stream::ApPart &b,
+                        const stream::ApPart &c, const void *x, void *y, cudaStream_t st) {
+    constexpr int LMAX = 8, WARPS = 8;
     using R = stream::WarpRing<double, LMAX, D>;
-    auto kern = stream::k_scs32_stream_ap<MODE, LMAX, D, WARPS>;
+    auto kern = stream::k_scs32_stream_ap<MODE, LMAX, D, WARPS, MINB>;
     constexpr int smem = WARPS * R::BYTES_ALIGNED;
     static bool configured = false;
     static int bps = 1;
@@ -182,10 +251,29 @@ void launch_ap_stream(long n_chunks, const int *order, const stream::ApPart &a, 
     }
     int dev = 0;
     USPMV_CUDA(cudaGetDevice(&dev));
+    const bool split = pl && pl->use;
+    const long n_items = split ? pl->n_items : n_chunks;
     long grid = (long)sm_count(dev) * bps;
-    const long need = (n_chunks + WARPS - 1) / WARPS;
+    const long need = (n_items + WARPS - 1) / WARPS;
     if (grid > need) grid = need;
-    kern<<<(unsigned)grid, WARPS * 32, smem, st>>>(n_chunks, order, a, b, c, x, y);
+    kern<<<(unsigned)grid, WARPS * 32, smem, st>>>(n_items, order, split ? pl->items.p : nullptr, a, b, c, x, y, split ? pl->partials.p : nullptr);
+    if (split && pl->n_split) {
+        USPMV_LAUNCH_CHECK();
+        stream::k_reduce_partials_ap<MODE><<<(unsigned)((pl->n_split * 32 + 255) / 256), 256, 0, st>>>(pl->n_split, pl->split_chunk.p, pl->split_ptr.p,
+                                                                                                     pl->seg_part.p, pl->partials.p, y);
+    }
+}
+
+// ap_variant: ring depth x register cap (1 = uncapped ~80 registers / 24 warps per SM, 4 = 64 registers / 32 warps per SM)
+template <int MODE>
+void launch_ap_stream(long n_chunks, const int *order, const uspmv_scs::ApPlan *pl, const stream::ApPart &a, const stream::ApPart &b,
+                      const stream::ApPart &c, const void *x, void *y, cudaStream_t st) {
+    switch (options().ap_variant) {
+    case 1: launch_ap_stream_v<MODE, 4, 1>(n_chunks, order, pl, a, b, c, x, y, st); break;
+    case 2: launch_ap_stream_v<MODE, 2, 4>(n_chunks, order, pl, a, b, c, x, y, st); break;
+    case 3: launch_ap_stream_v<MODE, 3, 3>(n_chunks, order, pl, a, b, c, x, y, st); break;
+    default: launch_ap_stream_v<MODE, 2, 1>(n_chunks, order, pl, a, b, c, x, y, st); break;
+    }
 }
 
 void exclusive_scan_i32(const int *in, int *out, long n) {
@@ -311,11 +399,12 @@ int uspmv_ap_spmv(int ap_mode, const uspmv_scs *dp, const uspmv_scs *sp, const u
         if (first->C == 32 && options().scs_stream) {  // streamed one-pass kernel
             const stream::ApPart sa{a.cp, a.cl, a.ci, a.v}, sb{b.cp, b.cl, b.ci, b.v}, sc{c.cp, c.cl, c.ci, c.v};
             const int *order = first->balanced_order.p;
+            const uspmv_scs::ApPlan *pl = ap_plan_for(ap_mode, first, use_dp && use_sp ? sp : nullptr, use_hp ? hp : nullptr);
             switch (ap_mode) {
-            case USPMV_AP_DP_SP: launch_ap_stream<USPMV_AP_DP_SP>(first->n_chunks, order, sa, sb, sc, x, y, st); break;
-            case USPMV_AP_DP_HP: launch_ap_stream<USPMV_AP_DP_HP>(first->n_chunks, order, sa, sb, sc, x, y, st); break;
-            case USPMV_AP_SP_HP: launch_ap_stream<USPMV_AP_SP_HP>(first->n_chunks, order, sa, sb, sc, x, y, st); break;
-            default: launch_ap_stream<USPMV_AP_DP_SP_HP>(first->n_chunks, order, sa, sb, sc, x, y, st);
+            case USPMV_AP_DP_SP: launch_ap_stream<USPMV_AP_DP_SP>(first->n_chunks, order, pl, sa, sb, sc, x, y, st); break;
+            case USPMV_AP_DP_HP: launch_ap_stream<USPMV_AP_DP_HP>(first->n_chunks, order, pl, sa, sb, sc, x, y, st); break;
+            case USPMV_AP_SP_HP: launch_ap_stream<USPMV_AP_SP_HP>(first->n_chunks, order, pl, sa, sb, sc, x, y, st); break;
+            default: launch_ap_stream<USPMV_AP_DP_SP_HP>(first->n_chunks, order, pl, sa, sb, sc, x, y, st);
             }
             USPMV_LAUNCH_CHECK();
             return;

@@ -8,6 +8,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <stdexcept>
+#include <memory>
 #include <string>
 
 #include "../../include/uspmv_b200.h"
@@ -105,6 +106,8 @@ struct Options {
     int stream_blocks_per_sm = 2;
     int mmv_variant = 0;         // SpMMV streamed kernel: 0 = tuned default, 1..4 force a variant (see spmv_kernels.cu)
     int mmv_blocks_per_sm = 0;   // SpMMV streamed kernel: CTAs (8 warps) per SM, 0 = as many as fit
+    int ap_variant = 0;          // fused adaptive-precision streamed kernel: ring depth / register cap instantiation
+    int mmv_far_rows = 0;        // row-major SpMMV: X rows further than this from the chunk are loaded with L1::no_allocate (0 = off)
     int split_long_chunks = 256; // C = 32, uneven matrices: chunks longer than this many slots are summed in segments (0 = never)
     bool strict_reference_halo = false;  // true: padding slots (column 0) become a halo element on ranks > 0, like the reference
 };
@@ -173,6 +176,20 @@ struct uspmv_scs {
     uspmv::DevBuf<unsigned char> partials;
     long n_vitems = 0, n_split = 0;
     bool chunks_split = false;
+    // adaptive precision, C = 32, very uneven matrices: work items of the fused kernel (built lazily by the first uspmv_ap_spmv
+    // call on this part as the FIRST part, keyed on the other parts), see k_scs32_stream_ap
+    struct ApPlan {
+        const uspmv_scs *other[2] = {nullptr, nullptr};
+        long other_ne[2] = {-1, -1};
+        int mode = -1, seg_slots = 0;
+        bool use = false;
+        long n_items = 0, n_split = 0;
+        uspmv::DevBuf<int4> items;
+        uspmv::DevBuf<int> split_chunk, split_ptr;
+        uspmv::DevBuf<unsigned char> seg_part;
+        uspmv::DevBuf<double> partials;
+    };
+    mutable std::unique_ptr<ApPlan> ap_plan;
     uspmv::DevBuf<int> interior_chunks, boundary_chunks;  // chunk ids without / with halo columns (order kept)
     bool interior_contig = false, boundary_contig = false;
     int interior_off = 0, boundary_off = 0;

@@ -62,6 +62,13 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
         : "memory");
 }
 
+// read-only 128-bit load that does not allocate a line in L1 (streaming gathers must not evict the reusable lines)
+__device__ __forceinline__ int4 ldg_no_allocate(const int4 *p) {
+    int4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
 struct PieceHdr {
     int ns;     // slots in this piece (0 with flags != 0: empty chunk; flags == 0 && ns == 0: end of stream)
     int flags;  // bit0 first piece of the chunk, bit1 last piece, bit2 valid
@@ -136,7 +143,7 @@ struct SpmvBody {
     const int *__restrict__ new_to_old;
     int lane;
     typename A::acc_t acc;
-    __device__ __forceinline__ void begin_chunk() { acc = A::zero(); }
+    __device__ __forceinline__ void begin_chunk(int = 0) { acc = A::zero(); }
     __device__ __forceinline__ void piece(const int ns, const VT *sv, const int *sc) {
         VT v[LMAX], xv[LMAX];
         int col[LMAX];
@@ -172,8 +179,10 @@ struct SpmmvBody {
     VT *__restrict__ Y;
     long ld;
     int lane;
+    int far_rows = 0, row_base = 0;  // far_rows > 0: rows gathered from further than that from the chunk bypass L1 allocation
     typename A::acc_t acc[BVS];
-    __device__ __forceinline__ void begin_chunk() {
+    __device__ __forceinline__ void begin_chunk(int chunk = 0) {
+        row_base = chunk * 32;
 #pragma unroll
         for (int v = 0; v < BVS; ++v) acc[v] = A::zero();
     }
@@ -182,8 +191,9 @@ struct SpmmvBody {
             constexpr int BYTES = BVS * (int)sizeof(VT);
             if constexpr (BYTES % 16 == 0) {
                 const int4 *p = reinterpret_cast<const int4 *>(X + col * BVS);
+                const bool far = far_rows > 0 && abs((int)col - row_base) > far_rows;
 #pragma unroll
-                for (int k = 0; k < BYTES / 16; ++k) reinterpret_cast<int4 *>(xv)[k] = __ldg(p + k);
+                for (int k = 0; k < BYTES / 16; ++k) reinterpret_cast<int4 *>(xv)[k] = far ? ldg_no_allocate(p + k) : __ldg(p + k);
             } else if constexpr (BYTES % 8 == 0) {
                 const int2 *p = reinterpret_cast<const int2 *>(X + col * BVS);
 #pragma unroll
@@ -255,8 +265,10 @@ struct SpmmvBodyRowWide {
     const VT *__restrict__ X;
     VT *__restrict__ Y;
     int lane;
+    int far_rows = 0, row_base = 0;  // see SpmmvBody
     typename A::acc_t acc[T][PER];
-    __device__ __forceinline__ void begin_chunk() {
+    __device__ __forceinline__ void begin_chunk(int chunk = 0) {
+        row_base = chunk * 32;
 #pragma unroll
         for (int k = 0; k < T; ++k)
 #pragma unroll
@@ -277,8 +289,10 @@ struct SpmmvBodyRowWide {
                     if (j0 + u < ns) {
 #pragma unroll
                         for (int k = 0; k < T; ++k) {
-                            const long col = c0[(j0 + u) * 32 + r0 + RPI * k];
-                            *reinterpret_cast<int4 *>(xv[u][k]) = __ldg(reinterpret_cast<const int4 *>(X + col * BVS) + part);
+                            const int col = c0[(j0 + u) * 32 + r0 + RPI * k];
+                            const int4 *p = reinterpret_cast<const int4 *>(X + (long)col * BVS) + part;
+                            const bool far = far_rows > 0 && abs(col - row_base) > far_rows;
+                            *reinterpret_cast<int4 *>(xv[u][k]) = far ? ldg_no_allocate(p) : __ldg(p);
                         }
                     }
 #pragma unroll
@@ -387,7 +401,7 @@ __device__ __forceinline__ void stream_items(unsigned char *base, uint64_t *bars
     for (int s = 0;; s = (s + 1 == D) ? 0 : s + 1) {
         const PieceHdr h = hdrs[s];
         if (h.flags == 0) break;
-        if (h.flags & 1) body.begin_chunk();
+        if (h.flags & 1) body.begin_chunk(h.chunk);
         if (h.ns > 0) {
             mbar_wait(&bars[s], (phase_bits >> s) & 1u);
             phase_bits ^= (1u << s);
@@ -862,7 +876,7 @@ k_csr_stream(long n_rows, const int *__restrict__ row_ptrs, const int *__restric
 template <typename VT, typename A, int LMAX, int D, int WARPS, int BVS, bool ROWWISE, bool WIDE>
 __global__ void __launch_bounds__(WARPS * 32)  // ~80 registers, 24 warps/SM: capping at 64 spills and is 30-50 % slower (measured)
 k_scs32_stream_mmv(long n_items, const int *__restrict__ chunk_ptrs, const int *__restrict__ chunk_lengths, const int *__restrict__ col_idxs,
-                   const VT *__restrict__ values, const VT *__restrict__ X, VT *__restrict__ Y, long ld) {
+                   const VT *__restrict__ values, const VT *__restrict__ X, VT *__restrict__ Y, long ld, int far_rows) {
     using R = WarpRing<VT, LMAX, D>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -882,12 +896,12 @@ k_scs32_stream_mmv(long n_items, const int *__restrict__ chunk_ptrs, const int *
     constexpr int ROW_BYTES = BVS * (int)sizeof(VT);
     if constexpr (WIDE && ROWWISE && ROW_BYTES >= 32 && ROW_BYTES <= 128 && (ROW_BYTES & (ROW_BYTES - 1)) == 0) {
         SpmmvBodyRowWide<VT, A, LMAX, BVS> body;
-        body.X = X; body.Y = Y; body.lane = lane;
+        body.X = X; body.Y = Y; body.lane = lane; body.far_rows = far_rows;
         stream_items<VT, LMAX, D>(base, bars, hdrs, phase_bits, (int)W, (int)gw, lane, (int)n_items, nullptr, 0, chunk_ptrs,
                                   chunk_lengths, col_idxs, values, body, pol);
     } else {
         SpmmvBody<VT, A, LMAX, BVS, ROWWISE> body;
-        body.X = X; body.Y = Y; body.ld = ld; body.lane = lane;
+        body.X = X; body.Y = Y; body.ld = ld; body.lane = lane; body.far_rows = far_rows;
         stream_items<VT, LMAX, D>(base, bars, hdrs, phase_bits, (int)W, (int)gw, lane, (int)n_items, nullptr, 0, chunk_ptrs,
                                   chunk_lengths, col_idxs, values, body, pol);
     }
@@ -905,9 +919,10 @@ struct ApPart {
     const void *v;
 };
 
-template <int MODE, int LMAX, int D, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32)
-k_scs32_stream_ap(long n_items, const int *__restrict__ order, ApPart p0, ApPart p1, ApPart p2, const void *__restrict__ xv_, void *__restrict__ yv_) {
+template <int MODE, int LMAX, int D, int WARPS, int MINB = 1>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
+k_scs32_stream_ap(long n_items, const int *__restrict__ order, const int4 *__restrict__ items, ApPart p0, ApPart p1, ApPart p2,
+                  const void *__restrict__ xv_, void *__restrict__ yv_, double *__restrict__ partial) {
     using R = WarpRing<double, LMAX, D>;  // stages sized for the widest part
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -941,9 +956,33 @@ k_scs32_stream_ap(long n_items, const int *__restrict__ order, ApPart p0, ApPart
             cs[q] = use ? parts[q].cp[chunk] : 0;
         }
     };
+    // With `items` (very uneven matrices) a work item is either a whole chunk (code < 0) or ONE slot segment of ONE part of a long
+    // chunk, {chunk, first slot, slots, code = partial slot << 2 | part}; its sum goes to partial[] and k_reduce_partials_ap adds the
+    // segments of a part in slot order.  A segment looks to the producer like a chunk whose other parts are empty.
+    int pcode = -1, ncode = -1;
+    auto load_item = [&](long k, int &chunk, int *len, int *cs, int &code) {
+        if (items) {
+            const int4 it = items[k];
+            chunk = it.x;
+            code = it.w;
+            if (code < 0) load_meta(chunk, len, cs);
+            else {
+                const int part = code & 3;
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    len[q] = q == part ? it.z : 0;
+                    cs[q] = q == part ? parts[q].cp[chunk] + it.y * 32 : 0;
+                }
+            }
+        } else {
+            chunk = order ? order[k] : (int)k;
+            code = -1;
+            load_meta(chunk, len, cs);
+        }
+    };
     if (lane == 0) {
-        if (pc < n_items) { pchunk = order ? order[pc] : (int)pc; load_meta(pchunk, plen, pcs); }
-        if (pc + W < n_items) { nchunk = order ? order[pc + W] : (int)(pc + W); load_meta(nchunk, nlen, ncs); }
+        if (pc < n_items) load_item(pc, pchunk, plen, pcs, pcode);
+        if (pc + W < n_items) load_item(pc + W, nchunk, nlen, ncs, ncode);
     }
     auto issue = [&](int s) {
         PieceHdr h;
@@ -960,7 +999,7 @@ k_scs32_stream_ap(long n_items, const int *__restrict__ order, ApPart p0, ApPart
             mbar_expect_tx(&bars[s], vb + cb);
             bulk_g2s(st, static_cast<const unsigned char *>(parts[pp].v) + e0 * vsz, vb, &bars[s], pol);
             bulk_g2s(st + R::VAL_BYTES, parts[pp].ci + e0, cb, &bars[s], pol);
-            h.pad = pp;
+            h.pad = pp | (pcode < 0 ? 0 : ((pcode >> 2) + 1) << 2);
             pj += ns;
         }
         // is anything left in this chunk after this piece?
@@ -976,9 +1015,10 @@ k_scs32_stream_ap(long n_items, const int *__restrict__ order, ApPart p0, ApPart
             pc += W;
             pp = 0; pj = 0; pfirst = true;
             pchunk = nchunk;
+            pcode = ncode;
 #pragma unroll
             for (int q = 0; q < 3; ++q) { plen[q] = nlen[q]; pcs[q] = ncs[q]; }
-            if (pc + W < n_items) { nchunk = order ? order[pc + W] : (int)(pc + W); load_meta(nchunk, nlen, ncs); }
+            if (pc + W < n_items) load_item(pc + W, nchunk, nlen, ncs, ncode);
         }
     };
     if (lane == 0) {
@@ -994,6 +1034,7 @@ k_scs32_stream_ap(long n_items, const int *__restrict__ order, ApPart p0, ApPart
         const PieceHdr h = hdrs[s];
         if (h.flags == 0) break;
         if (h.flags & 1) { acc[0] = 0.0; acc[1] = 0.0; acc[2] = 0.0; }
+        const int part = h.pad & 3, pslot1 = h.pad >> 2;  // pslot1 > 0: segment of a split chunk -> partial[pslot1 - 1]
         if (h.ns > 0) {
             mbar_wait(&bars[s], (phase_bits >> s) & 1u);
             phase_bits ^= (1u << s);
@@ -1009,7 +1050,7 @@ k_scs32_stream_ap(long n_items, const int *__restrict__ order, ApPart p0, ApPart
 #pragma unroll
                 for (int j = 0; j < LMAX; ++j)
                     if (j < h.ns) xf[j] = __ldg(x + col[j]);
-                if (h.pad == 1) {
+                if (part == 1) {
                     const float *v = reinterpret_cast<const float *>(sv) + lane;
 #pragma unroll
                     for (int j = 0; j < LMAX; ++j)
@@ -1026,12 +1067,12 @@ k_scs32_stream_ap(long n_items, const int *__restrict__ order, ApPart p0, ApPart
 #pragma unroll
                 for (int j = 0; j < LMAX; ++j)
                     if (j < h.ns) xd[j] = __ldg(x + col[j]);
-                if (h.pad == 0) {
+                if (part == 0) {
                     const double *v = reinterpret_cast<const double *>(sv) + lane;
 #pragma unroll
                     for (int j = 0; j < LMAX; ++j)
                         if (j < h.ns) acc[0] = fma(v[j * 32], xd[j], acc[0]);
-                } else if (h.pad == 1) {
+                } else if (part == 1) {
                     const float *v = reinterpret_cast<const float *>(sv) + lane;
 #pragma unroll
                     for (int j = 0; j < LMAX; ++j)
@@ -1044,7 +1085,9 @@ k_scs32_stream_ap(long n_items, const int *__restrict__ order, ApPart p0, ApPart
                 }
             }
         }
-        if (h.flags & 2) {
+        if ((h.flags & 2) && pslot1 > 0) {
+            partial[(long)(pslot1 - 1) * 32 + lane] = part == 0 ? acc[0] : (part == 1 ? acc[1] : acc[2]);
+        } else if (h.flags & 2) {
             const long row = (long)h.chunk * 32 + lane;
             if constexpr (MODE == 2) static_cast<float *>(yv_)[row] = (float)(acc[1] + acc[2]);
             else if constexpr (MODE == 0) static_cast<double *>(yv_)[row] = acc[0] + acc[1];
@@ -1055,6 +1098,30 @@ k_scs32_stream_ap(long n_items, const int *__restrict__ order, ApPart p0, ApPart
         if (lane == 0) issue(s);
         __syncwarp();
     }
+}
+
+// y[rows of a split chunk] from its segment sums: per part the segments are added in slot order, then dp + sp + hp as in the
+// un-split path; one warp per split chunk
+template <int MODE>
+__global__ void k_reduce_partials_ap(long n_split, const int *__restrict__ split_chunk, const int *__restrict__ split_ptr,
+                                     const unsigned char *__restrict__ seg_part, const double *__restrict__ partial, void *__restrict__ yv_) {
+    const long w = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= n_split) return;
+    double acc[3] = {0.0, 0.0, 0.0};
+    bool any[3] = {false, false, false};
+    for (int s = split_ptr[w]; s < split_ptr[w + 1]; ++s) {
+        const int q = seg_part[s];
+        const double v = partial[(long)s * 32 + lane];
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            if (q == k) { acc[k] = any[k] ? acc[k] + v : v; any[k] = true; }
+    }
+    const long row = (long)split_chunk[w] * 32 + lane;
+    if constexpr (MODE == 2) static_cast<float *>(yv_)[row] = (float)(acc[1] + acc[2]);
+    else if constexpr (MODE == 0) static_cast<double *>(yv_)[row] = acc[0] + acc[1];
+    else if constexpr (MODE == 1) static_cast<double *>(yv_)[row] = acc[0] + acc[2];
+    else static_cast<double *>(yv_)[row] = acc[0] + acc[1] + acc[2];
 }
 
 }  // namespace stream

@@ -482,9 +482,8 @@ void launch_csr_stream(long n_rows, const int *rp, const int *ci, const void *va
 }
 
 // C = 32 and bvs in {2,4,8,16}: streamed kernel
-template <typename VT, int BVS, bool ROWWISE, int LMAX, int WARPS, bool WIDE>
+template <typename VT, int BVS, bool ROWWISE, int LMAX, int WARPS, bool WIDE, int D = 2>
 void launch_spmmv_stream_v(const uspmv_scs *s, const VT *X, VT *Y, long ld, cudaStream_t st) {
-    constexpr int D = 2;
     using R = stream::WarpRing<VT, LMAX, D>;
     auto kern = stream::k_scs32_stream_mmv<VT, Arith<VT>, LMAX, D, WARPS, BVS, ROWWISE, WIDE>;
     constexpr int smem = WARPS * R::BYTES_ALIGNED;
@@ -503,7 +502,8 @@ void launch_spmmv_stream_v(const uspmv_scs *s, const VT *X, VT *Y, long ld, cuda
     const long need = (s->n_chunks + WARPS - 1) / WARPS;
     if (grid > need) grid = need;
     kern<<<(unsigned)grid, WARPS * 32, smem, st>>>(s->n_chunks, s->chunk_ptrs.p, s->chunk_lengths.p, s->col_idxs.p,
-                                                  reinterpret_cast<const VT *>(s->values.p), X, Y, ld);
+                                                  reinterpret_cast<const VT *>(s->values.p), X, Y, ld,
+                                                  ROWWISE ? options().mmv_far_rows : 0);
 }
 
 // variant: 0 = tuned default per (precision, bvs, layout); 1..4 force (wide body?, slots per stage)
@@ -519,6 +519,12 @@ void launch_spmmv_stream(const uspmv_scs *s, const VT *X, VT *Y, long ld, cudaSt
     case 6: launch_spmmv_stream_v<VT, BVS, ROWWISE, 8, 24, true>(s, X, Y, ld, st); break;
     case 7: launch_spmmv_stream_v<VT, BVS, ROWWISE, 8, 16, false>(s, X, Y, ld, st); break;
     case 8: launch_spmmv_stream_v<VT, BVS, ROWWISE, 8, 24, false>(s, X, Y, ld, st); break;
+    case 9: launch_spmmv_stream_v<VT, BVS, ROWWISE, 4, 24, true>(s, X, Y, ld, st); break;    // half-size stages: twice the L1 left for X
+    case 10: launch_spmmv_stream_v<VT, BVS, ROWWISE, 4, 24, false>(s, X, Y, ld, st); break;
+    case 11: launch_spmmv_stream_v<VT, BVS, ROWWISE, 4, 24, true, 3>(s, X, Y, ld, st); break;
+    case 12: launch_spmmv_stream_v<VT, BVS, ROWWISE, 4, 16, true, 3>(s, X, Y, ld, st); break;
+    case 13: launch_spmmv_stream_v<VT, BVS, ROWWISE, 4, 32, true>(s, X, Y, ld, st); break;
+    case 14: launch_spmmv_stream_v<VT, BVS, ROWWISE, 4, 32, false>(s, X, Y, ld, st); break;
     default: launch_spmmv_stream_v<VT, BVS, ROWWISE, 8, 8, false>(s, X, Y, ld, st); break;
     }
 }

@@ -178,6 +178,10 @@ int uspmv_scs_split_chunks(uspmv_scs *scs, long *n_interior, long *n_boundary);
 int uspmv_spmv_part(const uspmv_scs *scs, int which, const void *x_d, void *y_d, void *stream);
 /* pack_send_buf / pack_d_send_buf (classes_structs.hpp:786-831; kernels.hpp:554-577) for ALL peers in one
  * launch: buf[send_ptr[p] + i] = x[perm[send_idx[p][i]]] (block vectors: bvs values per index). */
+/* SpMMV over the interior (1) / boundary (2) chunks only (0 = all); subsets need the streamed kernel — ask first. */
+int uspmv_spmmv_part_supported(const uspmv_scs *scs, int block_vec_size);
+int uspmv_spmmv_part(const uspmv_scs *scs, int which, const void *X_d, void *Y_d, int block_vec_size, long vec_length, int layout,
+                     void *stream);
 int uspmv_halo_pack(const uspmv_halo *plan, const void *x_d, void *sendbuf_d, int vt, int bvs, long vec_length, int layout,
                     void *stream);
 void uspmv_halo_destroy(uspmv_halo *plan);
@@ -197,6 +201,21 @@ int uspmv_p2p_spmv(uspmv_p2p *p2p, const uspmv_scs *scs, void *y_d, void *stream
  * chunks, acknowledge; mode 1: separate push/wait kernels on comm_stream next to the interior kernel; mode 0: exchange,
  * then one full SpMV (the reference's begin -> finish -> execute order, main.cpp:464-468) */
 int uspmv_p2p_set_overlap(uspmv_p2p *p2p, int overlap);
+/* Generalised arena: n_buf (1 or 2) buffers, each holding block_vec_size vectors of vec_length elements in `layout`.
+ * x_d receives the n_buf buffer addresses.  peer_vec_length[q] (connect) is q's vec_length, needed for column-major block
+ * vectors.  Replaces the per-vector / strided-datatype messages of the reference's multivec / bulkvec modes
+ * (classes_structs.hpp:909-970, mpi_funcs.hpp:1003-1059) with ONE push per neighbour. */
+int uspmv_p2p_create_ex(uspmv_halo *plan, int vt, long vec_length, int block_vec_size, int layout, int n_buf, uspmv_p2p **out,
+                        void *ipc_handle64, void **x_d);
+int uspmv_p2p_connect_ex(uspmv_p2p *p2p, const void *all_handles, const long *peer_x_bytes, const long *peer_halo_base,
+                         const long *peer_vec_length);
+/* SpMV that reads x from buffer x_buf and writes y to y_d, or (y_d NULL) into buffer y_buf — rows < n_rows only, the tail of
+ * that buffer receives the next step's halo.  With two buffers `rev` x { SpMV ; swap } (solve mode, main.cpp:528-631;
+ * SpmvKernel::swap_local_vectors, classes_structs.hpp:1130-1165) stays on the device with no copy. */
+int uspmv_p2p_spmv_buf(uspmv_p2p *p2p, const uspmv_scs *scs, int x_buf, int y_buf, void *y_d, void *stream, void *comm_stream);
+/* SpMMV over the arena's block vector (buffer x_buf) incl. the exchange of all block_vec_size vectors of the halo rows,
+ * overlapped with the interior chunks when the streamed kernel applies. */
+int uspmv_p2p_spmmv(uspmv_p2p *p2p, const uspmv_scs *scs, int x_buf, void *Y_d, void *stream, void *comm_stream);
 int uspmv_p2p_status(uspmv_p2p *p2p, int *error_flag, long *epoch);
 void uspmv_p2p_destroy(uspmv_p2p *p2p);
 

@@ -42,6 +42,53 @@ def _run_rank(rank, world, port, out_dir, C=32):
         for k, v in results.items():
             assert np.array_equal(v, base), k
         np.save(os.path.join(out_dir, f"y{rank}.npy"), base)
+
+        # ---- block vectors (bulkvec exchange): all bvs vectors of the halo rows in one push, both layouts, with / without overlap
+        rows = torch.arange(rank * n ** 3, (rank + 1) * n ** 3, device="cuda", dtype=torch.float64)
+        for layout in ("rowwise", "colwise"):
+            for bvs, mode in ((4, 1), (4, 0), (3, 1)):
+                r = d.DistributedSpmv(eng.default_context(rank), 27, n, C, 64, "dp", rank, world, overlap=mode, halo="p2p", bvs=bvs, layout=layout)
+                perm = torch.from_numpy(r.scs.export().old_to_new.astype(np.int64)).cuda()
+                nl, ld = r.scs.n_rows, r.vec_length
+                r.x.zero_()
+                for v in range(bvs):
+                    xs = torch.sin(rows * (0.37 + 0.11 * v)) + 1.5
+                    if layout == "rowwise":
+                        r.x[:nl * bvs].view(nl, bvs)[perm, v] = xs
+                    else:
+                        r.x[v * ld: v * ld + nl][perm] = xs
+                torch.cuda.synchronize()
+                dist.barrier()  # a fast neighbour must not push its halo into x before the zero_() above has run
+                for _ in range(3):
+                    r.y.zero_()
+                    r.step()
+                torch.cuda.synchronize()
+                err, ep = r.p2p.status()
+                assert err == 0 and ep == 3
+                out = np.zeros((bvs, nl))
+                for v in range(bvs):
+                    if layout == "rowwise":
+                        out[v] = r.y[: r.scs.n_rows_padded * bvs].view(-1, bvs)[perm, v].cpu().numpy()
+                    else:
+                        out[v] = r.y[v * ld: v * ld + r.scs.n_rows_padded][perm].cpu().numpy()
+                np.save(os.path.join(out_dir, f"Y{rank}_{layout}_{bvs}_{mode}.npy"), out)
+                del r
+
+        # ---- device-resident solve loop: 3 x { exchange ; SpMV ; swap } over the two arena buffers, every overlap mode
+        for mode in (2, 1, 0):
+            r = d.DistributedSpmv(eng.default_context(rank), 27, n, C, 64, "dp", rank, world, overlap=mode, halo="p2p", n_buf=2)
+            perm = torch.from_numpy(r.scs.export().old_to_new.astype(np.int64)).cuda()
+            for b in r.p2p.bufs:
+                b.zero_()
+            r.p2p.bufs[0][: r.scs.n_rows][perm] = (torch.sin(rows * 0.37) + 1.5) / 64.0
+            torch.cuda.synchronize()
+            dist.barrier()
+            xf = r.solve(3)
+            torch.cuda.synchronize()
+            err, ep = r.p2p.status()
+            assert err == 0 and ep == 3
+            np.save(os.path.join(out_dir, f"solve{rank}_{mode}.npy"), xf[: r.scs.n_rows][perm].cpu().numpy())
+            del r
         dist.barrier()
     finally:
         dist.destroy_process_group()
@@ -57,6 +104,26 @@ def _check(out_dir, world, mats):
     scale = np.zeros(nr)
     np.add.at(scale, I, np.abs(V * x[J]))
     assert np.all(np.abs(y - y_ref) <= 1e-12 * scale)
+    # block vectors
+    for layout in ("rowwise", "colwise"):
+        for bvs, mode in ((4, 1), (4, 0), (3, 1)):
+            Y = np.concatenate([np.load(os.path.join(out_dir, f"Y{r}_{layout}_{bvs}_{mode}.npy")) for r in range(world)], axis=1)
+            for v in range(bvs):
+                xv = np.sin(np.arange(nr) * (0.37 + 0.11 * v)) + 1.5
+                ref = np.zeros(nr)
+                np.add.at(ref, I, V * xv[J])
+                sc = np.zeros(nr)
+                np.add.at(sc, I, np.abs(V * xv[J]))
+                assert np.all(np.abs(Y[v] - ref) <= 1e-12 * sc), (layout, bvs, mode, v)
+    # solve loop: x3 = A^3 x0
+    import scipy.sparse as sp
+    A = sp.csr_matrix((V, (I, J)), shape=(nr, nr))
+    x3 = (np.sin(np.arange(nr) * 0.37) + 1.5) / 64.0
+    for _ in range(3):
+        x3 = A @ x3
+    for mode in (2, 1, 0):
+        got = np.concatenate([np.load(os.path.join(out_dir, f"solve{r}_{mode}.npy")) for r in range(world)])
+        assert np.max(np.abs(got - x3)) <= 1e-11 * np.max(np.abs(x3)), mode
 
 
 @pytest.mark.parametrize("C", [32, 16])

@@ -76,6 +76,12 @@ _sigs = {
     "uspmv_p2p_connect": [vp, vp, vp, vp],
     "uspmv_p2p_spmv": [vp, vp, vp, vp, vp],
     "uspmv_p2p_set_overlap": [vp, C.c_int],
+    "uspmv_p2p_create_ex": [vp, C.c_int, C.c_long, C.c_int, C.c_int, C.c_int, C.POINTER(vp), vp, C.POINTER(vp)],
+    "uspmv_p2p_connect_ex": [vp, vp, vp, vp, vp],
+    "uspmv_p2p_spmv_buf": [vp, vp, C.c_int, C.c_int, vp, vp, vp],
+    "uspmv_p2p_spmmv": [vp, vp, C.c_int, vp, vp, vp],
+    "uspmv_spmmv_part": [vp, C.c_int, vp, vp, C.c_int, C.c_long, C.c_int, vp],
+    "uspmv_spmmv_part_supported": [vp, C.c_int],
     "uspmv_p2p_status": [vp, C.POINTER(C.c_int), C.POINTER(C.c_long)],
     "uspmv_halo_pack": [vp, vp, vp, C.c_int, C.c_int, C.c_long, C.c_int, vp],
 }

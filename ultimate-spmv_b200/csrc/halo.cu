@@ -309,20 +309,26 @@ void uspmv_halo_destroy(uspmv_halo *h) { delete h; }
 struct uspmv_p2p {
     uspmv_halo *plan = nullptr;
     int vt = USPMV_F64;
-    long x_len = 0;
+    int n_buf = 1, bvs = 1, layout = USPMV_COLWISE;
+    long vec_length = 0;             // elements per vector: n_local + max(padding, halo)
+    long x_len = 0;                  // elements per buffer = bvs * vec_length
     size_t x_bytes = 0, arena_bytes = 0;
-    unsigned char *arena = nullptr;  // local
+    unsigned char *arena = nullptr;  // local: [ buffer 0 | ... | buffer n_buf-1 | arrived[P] | acked[P] | epoch | error ]
     unsigned int *arrived = nullptr, *acked = nullptr, *epoch = nullptr, *error = nullptr;
     std::vector<unsigned char *> peer_arena;  // P entries (NULL for self / unused)
-    DevBuf<unsigned long long> peer_x_dst;    // per peer q: device address where OUR elements for q start
+    DevBuf<unsigned long long> peer_x_dst;    // [buffer][peer q]: device address where OUR elements for q start (bvs = 1)
+    DevBuf<unsigned long long> peer_x0;       // [buffer][peer q]: start of q's buffer
+    DevBuf<long> peer_base, peer_ld;          // per peer q: element offset of our elements in q's vectors; q's vec_length
     DevBuf<unsigned long long> peer_arrived;  // per peer q: address of q.arrived[rank]
     DevBuf<unsigned long long> peer_acked;    // per peer p: address of p.acked[rank]
     DevBuf<int> send_ptr_d, is_sender_d, is_receiver_d;
     DevBuf<unsigned int> block_counter;
+    DevBuf<unsigned char> scratch_y;          // solve loop on the multi-kernel paths: y is staged here, n_rows are copied
     cudaEvent_t ev_main = nullptr, ev_comm = nullptr;
     bool connected = false;
     int mode = 2;  // 0: exchange, then one full SpMV; 1: push/wait kernels next to the interior kernel; 2: ONE fused kernel (C = 32)
     DevBuf<unsigned int> fused_counters;
+    unsigned char *buffer(int b) const { return arena + (size_t)b * x_bytes; }
 };
 
 namespace {
@@ -351,10 +357,14 @@ __device__ bool spin_until_ge(const unsigned int *flag, unsigned int target, uns
     return true;
 }
 
+// Gathers x[perm[send_idx]] (all bvs vectors of a block vector) and stores it straight into the neighbours' vectors over NVLink.
+// Row-major block vectors: element (i, v) of peer q lands at q.X[(base_q + i) * bvs + v]; column-major: q.X[base_q + i + v * ld_q]
+// (the reference sends one strided / per-vector message per neighbour instead, classes_structs.hpp:909-970).
 template <typename VT>
 __global__ void __launch_bounds__(256)
 k_p2p_push(int P, int my_rank, const int *__restrict__ send_ptr, const int *__restrict__ is_receiver, const int *__restrict__ send_idx,
-           const int *__restrict__ perm, const VT *__restrict__ x, const unsigned long long *__restrict__ peer_x_dst,
+           const int *__restrict__ perm, const VT *__restrict__ x, const unsigned long long *__restrict__ peer_x0,
+           const long *__restrict__ peer_base, const long *__restrict__ peer_ld, int bvs, int layout, long ld,
            const unsigned long long *__restrict__ peer_arrived, const unsigned int *acked, const unsigned int *epoch, unsigned int *error,
            unsigned int *block_counter) {
     __shared__ unsigned int s_last;
@@ -364,11 +374,18 @@ k_p2p_push(int P, int my_rank, const int *__restrict__ send_ptr, const int *__re
     __syncthreads();
     // (2) gather + store over NVLink
     const long n_send = send_ptr[P];
-    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n_send; i += (long)gridDim.x * blockDim.x) {
+    const long total = n_send * bvs;
+    for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+        long i, v;
+        if (layout == USPMV_ROWWISE) { i = t / bvs; v = t - i * bvs; }
+        else { v = t / n_send; i = t - v * n_send; }
         int q = 0;
         while (i >= send_ptr[q + 1]) ++q;
-        VT *dst = reinterpret_cast<VT *>(peer_x_dst[q]);
-        dst[i - send_ptr[q]] = x[perm[send_idx[i]]];
+        const long src = perm[send_idx[i]];
+        const long k = peer_base[q] + (i - send_ptr[q]);
+        VT *dst = reinterpret_cast<VT *>(peer_x0[q]);
+        if (layout == USPMV_ROWWISE) dst[k * bvs + v] = x[src * bvs + v];
+        else dst[k + v * peer_ld[q]] = x[src + v * ld];
     }
     // (3) publish: all stores of all CTAs are system-visible before the flag
     __threadfence_system();
@@ -404,27 +421,57 @@ __global__ void k_p2p_ack(int P, const int *__restrict__ is_sender, const unsign
     if (threadIdx.x == 0) *epoch = e;
 }
 
+void launch_push(uspmv_p2p *p, const void *x, int buf, cudaStream_t comm) {
+    uspmv_halo *h = p->plan;
+    const int P = h->P;
+    const long total = h->n_send * p->bvs;
+    long g = (total + 2047) / 2048;
+    if (g < 1) g = 1;
+    if (g > 64) g = 64;
+    const unsigned long long *x0 = p->peer_x0.p + (size_t)buf * P;
+#define USPMV_PUSH(T)                                                                                                                     \
+    k_p2p_push<T><<<(unsigned)g, 256, 0, comm>>>(P, h->rank, p->send_ptr_d.p, p->is_receiver_d.p, h->send_idx.p, h->perm_d, (const T *)x, x0, \
+                                                 p->peer_base.p, p->peer_ld.p, p->bvs, p->layout, p->vec_length, p->peer_arrived.p, p->acked,  \
+                                                 p->epoch, p->error, p->block_counter.p)
+    switch (p->vt) {
+    case USPMV_F64: USPMV_PUSH(double); break;
+    case USPMV_F32: USPMV_PUSH(float); break;
+    default: USPMV_PUSH(__half);
+    }
+#undef USPMV_PUSH
+    USPMV_LAUNCH_CHECK();
+}
+
 }  // namespace
 
 extern "C" {
 
-int uspmv_p2p_create(uspmv_halo *plan, int vt, long x_len, uspmv_p2p **out, void *ipc_handle64, void **x_d) {
+/* Arena with n_buf buffers of bvs vectors of vec_length elements each (bvs = 1, n_buf = 1: uspmv_p2p_create).
+ * x_d receives the n_buf buffer addresses.  Two buffers make the solve loop's swap a pointer swap (SpmvKernel::swap_local_vectors,
+ * classes_structs.hpp:1130-1165): step k reads buffer k & 1 and writes y into the other one. */
+int uspmv_p2p_create_ex(uspmv_halo *plan, int vt, long vec_length, int bvs, int layout, int n_buf, uspmv_p2p **out, void *ipc_handle64,
+                        void **x_d) {
     return guarded([&] {
         if (!plan || !out || !ipc_handle64 || !x_d) fail("uspmv_p2p_create: NULL argument");
         if (plan->P > 256) fail("uspmv_p2p_create: at most 256 ranks");
-        if (x_len < plan->n_local + plan->n_halo) fail("uspmv_p2p_create: x_len %ld < n_local + n_halo = %ld", x_len, plan->n_local + plan->n_halo);
+        if (bvs < 1 || bvs > 16) fail("uspmv_p2p_create: block_vec_size must be in [1,16] (got %d)", bvs);
+        if (n_buf < 1 || n_buf > 2) fail("uspmv_p2p_create: 1 or 2 buffers");
+        if (layout != USPMV_COLWISE && layout != USPMV_ROWWISE) fail("uspmv_p2p_create: invalid layout %d", layout);
+        if (vec_length < plan->n_local + plan->n_halo)
+            fail("uspmv_p2p_create: vec_length %ld < n_local + n_halo = %ld", vec_length, plan->n_local + plan->n_halo);
         USPMV_CUDA(cudaSetDevice(plan->ctx->device));
         static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
         auto p = new uspmv_p2p();
         try {
-            p->plan = plan; p->vt = vt; p->x_len = x_len;
+            p->plan = plan; p->vt = vt; p->vec_length = vec_length; p->bvs = bvs; p->layout = layout; p->n_buf = n_buf;
+            p->x_len = vec_length * bvs;
             const size_t es = vt_size(vt);
-            p->x_bytes = ((size_t)x_len * es + 255) / 256 * 256;
+            p->x_bytes = ((size_t)p->x_len * es + 255) / 256 * 256;
             const int P = plan->P;
-            p->arena_bytes = p->x_bytes + (2 * (size_t)P + 2) * sizeof(unsigned int) + 256;
+            p->arena_bytes = (size_t)n_buf * p->x_bytes + (2 * (size_t)P + 2) * sizeof(unsigned int) + 256;
             USPMV_CUDA(cudaMalloc(&p->arena, p->arena_bytes));
             USPMV_CUDA(cudaMemset(p->arena, 0, p->arena_bytes));
-            p->arrived = reinterpret_cast<unsigned int *>(p->arena + p->x_bytes);
+            p->arrived = reinterpret_cast<unsigned int *>(p->arena + (size_t)n_buf * p->x_bytes);
             p->acked = p->arrived + P;
             p->epoch = p->acked + P;
             p->error = p->epoch + 1;
@@ -439,22 +486,30 @@ int uspmv_p2p_create(uspmv_halo *plan, int vt, long x_len, uspmv_p2p **out, void
             USPMV_CUDA(cudaEventCreateWithFlags(&p->ev_comm, cudaEventDisableTiming));
             USPMV_CUDA(cudaDeviceSynchronize());
         } catch (...) { if (p->arena) cudaFree(p->arena); delete p; throw; }
-        *x_d = p->arena;
+        for (int b = 0; b < n_buf; ++b) x_d[b] = p->buffer(b);
         *out = p;
     });
 }
 
-/* all_handles: P x 64 bytes (IPC handle of every rank's arena); peer_x_bytes[q]: size of q's x region in bytes;
- * peer_halo_base[q]: element offset in q's x where this rank's elements start (q.n_local + q.recv_cumsum[rank]). */
-int uspmv_p2p_connect(uspmv_p2p *p, const void *all_handles, const long *peer_x_bytes, const long *peer_halo_base) {
+int uspmv_p2p_create(uspmv_halo *plan, int vt, long x_len, uspmv_p2p **out, void *ipc_handle64, void **x_d) {
+    return uspmv_p2p_create_ex(plan, vt, x_len, 1, USPMV_COLWISE, 1, out, ipc_handle64, x_d);
+}
+
+/* all_handles: P x 64 bytes (IPC handle of every rank's arena); peer_x_bytes[q]: size of ONE buffer of q in bytes (every rank uses
+ * the same number of buffers); peer_halo_base[q]: element offset in q's vectors where this rank's elements start
+ * (q.n_local + q.recv_cumsum[rank]); peer_vec_length[q]: q's vec_length (column-major block vectors; may be NULL for bvs = 1). */
+int uspmv_p2p_connect_ex(uspmv_p2p *p, const void *all_handles, const long *peer_x_bytes, const long *peer_halo_base,
+                         const long *peer_vec_length) {
     return guarded([&] {
         if (!p || !all_handles || !peer_x_bytes || !peer_halo_base) fail("uspmv_p2p_connect: NULL argument");
+        if (!peer_vec_length && p->bvs > 1 && p->layout == USPMV_COLWISE) fail("uspmv_p2p_connect: column-major block vectors need peer_vec_length");
         uspmv_halo *h = p->plan;
         USPMV_CUDA(cudaSetDevice(h->ctx->device));
-        const int P = h->P, me = h->rank;
+        const int P = h->P, me = h->rank, nb = p->n_buf;
         const size_t es = vt_size(p->vt);
         p->peer_arena.assign(P, nullptr);
-        std::vector<unsigned long long> dst(P, 0), arr(P, 0), ack(P, 0);
+        std::vector<unsigned long long> dst((size_t)nb * P, 0), x0((size_t)nb * P, 0), arr(P, 0), ack(P, 0);
+        std::vector<long> base(P, 0), pld(P, 0);
         std::vector<int> is_s(P, 0), is_r(P, 0);
         for (int q = 0; q < P; ++q) {
             is_s[q] = h->recv_cumsum[q + 1] > h->recv_cumsum[q];
@@ -465,15 +520,25 @@ int uspmv_p2p_connect(uspmv_p2p *p, const void *all_handles, const long *peer_x_
             void *ptr = nullptr;
             USPMV_CUDA(cudaIpcOpenMemHandle(&ptr, ih, cudaIpcMemLazyEnablePeerAccess));
             p->peer_arena[q] = static_cast<unsigned char *>(ptr);
-            unsigned int *q_arrived = reinterpret_cast<unsigned int *>(p->peer_arena[q] + peer_x_bytes[q]);
+            unsigned int *q_arrived = reinterpret_cast<unsigned int *>(p->peer_arena[q] + (size_t)nb * peer_x_bytes[q]);
             unsigned int *q_acked = q_arrived + P;
-            dst[q] = reinterpret_cast<unsigned long long>(p->peer_arena[q] + (size_t)peer_halo_base[q] * es);
+            for (int b = 0; b < nb; ++b) {
+                unsigned char *qb = p->peer_arena[q] + (size_t)b * peer_x_bytes[q];
+                x0[(size_t)b * P + q] = reinterpret_cast<unsigned long long>(qb);
+                dst[(size_t)b * P + q] = reinterpret_cast<unsigned long long>(qb + (size_t)peer_halo_base[q] * es);
+            }
+            base[q] = peer_halo_base[q];
+            pld[q] = peer_vec_length ? peer_vec_length[q] : 0;
             arr[q] = reinterpret_cast<unsigned long long>(q_arrived + me);
             ack[q] = reinterpret_cast<unsigned long long>(q_acked + me);
         }
-        p->peer_x_dst.alloc(P); p->peer_arrived.alloc(P); p->peer_acked.alloc(P);
+        p->peer_x_dst.alloc((size_t)nb * P); p->peer_x0.alloc((size_t)nb * P); p->peer_base.alloc(P); p->peer_ld.alloc(P);
+        p->peer_arrived.alloc(P); p->peer_acked.alloc(P);
         p->send_ptr_d.alloc(P + 1); p->is_sender_d.alloc(P); p->is_receiver_d.alloc(P);
-        USPMV_CUDA(cudaMemcpy(p->peer_x_dst.p, dst.data(), P * 8, cudaMemcpyHostToDevice));
+        USPMV_CUDA(cudaMemcpy(p->peer_x_dst.p, dst.data(), dst.size() * 8, cudaMemcpyHostToDevice));
+        USPMV_CUDA(cudaMemcpy(p->peer_x0.p, x0.data(), x0.size() * 8, cudaMemcpyHostToDevice));
+        USPMV_CUDA(cudaMemcpy(p->peer_base.p, base.data(), P * sizeof(long), cudaMemcpyHostToDevice));
+        USPMV_CUDA(cudaMemcpy(p->peer_ld.p, pld.data(), P * sizeof(long), cudaMemcpyHostToDevice));
         USPMV_CUDA(cudaMemcpy(p->peer_arrived.p, arr.data(), P * 8, cudaMemcpyHostToDevice));
         USPMV_CUDA(cudaMemcpy(p->peer_acked.p, ack.data(), P * 8, cudaMemcpyHostToDevice));
         USPMV_CUDA(cudaMemcpy(p->send_ptr_d.p, h->send_ptr.data(), (P + 1) * sizeof(int), cudaMemcpyHostToDevice));
@@ -483,17 +548,27 @@ int uspmv_p2p_connect(uspmv_p2p *p, const void *all_handles, const long *peer_x_
     });
 }
 
-/* One distributed SpMV step (comm_halos = 1) with overlap: push/wait on `comm_stream`, interior chunks on `stream`,
- * then boundary chunks and the ack.  x must be the arena's x (uspmv_p2p_create). */
-int uspmv_p2p_spmv(uspmv_p2p *p, const uspmv_scs *scs, void *y_d, void *stream, void *comm_stream) {
+int uspmv_p2p_connect(uspmv_p2p *p, const void *all_handles, const long *peer_x_bytes, const long *peer_halo_base) {
+    return uspmv_p2p_connect_ex(p, all_handles, peer_x_bytes, peer_halo_base, nullptr);
+}
+
+/* One distributed SpMV step (comm_halos = 1): x = buffer x_buf of the arena.  y goes to y_d, or — y_d NULL, y_buf >= 0 — into
+ * buffer y_buf (rows < n_rows only, the tail of that buffer is the next step's halo), which makes `rev` x { SpMV ; swap } a
+ * device-resident loop with no copy (solve mode, main.cpp:528-631).  Overlap modes as set by uspmv_p2p_set_overlap. */
+int uspmv_p2p_spmv_buf(uspmv_p2p *p, const uspmv_scs *scs, int x_buf, int y_buf, void *y_d, void *stream, void *comm_stream) {
     return guarded([&] {
         if (!p || !scs) fail("uspmv_p2p_spmv: NULL argument");
         if (!p->connected) fail("uspmv_p2p_spmv: call uspmv_p2p_connect first");
         if (!scs->chunks_split) fail("uspmv_p2p_spmv: call uspmv_scs_split_chunks first");
+        if (p->bvs != 1) fail("uspmv_p2p_spmv: the arena was created for block vectors; use uspmv_p2p_spmmv");
+        if (x_buf < 0 || x_buf >= p->n_buf) fail("uspmv_p2p_spmv: x buffer %d out of range", x_buf);
+        const bool to_buf = y_d == nullptr;
+        if (to_buf && (y_buf < 0 || y_buf >= p->n_buf || y_buf == x_buf)) fail("uspmv_p2p_spmv: y needs a device pointer or another buffer of the arena");
+        if (to_buf && scs->n_rows_padded > p->x_len) fail("uspmv_p2p_spmv: buffer shorter than n_rows_padded");
         uspmv_halo *h = p->plan;
         cudaStream_t main = as_stream(stream), comm = as_stream(comm_stream);
         const int P = h->P;
-        const void *x = p->arena;
+        const void *x = p->buffer(x_buf);
         if (p->mode == 2 && scs->C == 32 && P <= 32) {
             stream::FusedArgs fa{};
             fa.n_int = (long)scs->interior_chunks.n;
@@ -505,37 +580,71 @@ int uspmv_p2p_spmv(uspmv_p2p *p, const uspmv_scs *scs, void *y_d, void *stream, 
             fa.P = P; fa.my_rank = h->rank; fa.n_send = h->n_send;
             fa.send_ptr = p->send_ptr_d.p; fa.is_receiver = p->is_receiver_d.p; fa.is_sender = p->is_sender_d.p;
             fa.send_idx = h->send_idx.p; fa.perm = h->perm_d;
-            fa.peer_x_dst = p->peer_x_dst.p; fa.peer_arrived = p->peer_arrived.p; fa.peer_acked = p->peer_acked.p;
+            fa.peer_x_dst = p->peer_x_dst.p + (size_t)x_buf * P; fa.peer_arrived = p->peer_arrived.p; fa.peer_acked = p->peer_acked.p;
             fa.acked = p->acked; fa.arrived = p->arrived; fa.epoch = p->epoch; fa.error = p->error; fa.counters = p->fused_counters.p;
-            launch_scs32_fused(scs, x, y_d, fa, main);
+            fa.y_rows = (int)(to_buf ? scs->n_rows : scs->n_rows_padded);
+            launch_scs32_fused(scs, x, to_buf ? (void *)p->buffer(y_buf) : y_d, fa, main);
             return;
+        }
+        void *y = y_d;
+        if (to_buf) {  // the multi-kernel paths store every padded row: stage y, then copy the real rows
+            const size_t need = (size_t)scs->n_rows_padded * vt_size(p->vt);
+            if (p->scratch_y.n < need) p->scratch_y.alloc(need);
+            y = p->scratch_y.p;
         }
         const bool overlap = p->mode != 0;
         USPMV_CUDA(cudaEventRecord(p->ev_main, main));
         // the persistent interior kernel is launched FIRST so that its CTAs get their SM slots; the (small) push /
         // wait kernels then run next to it in the leftover registers instead of delaying some of its CTAs
-        if (overlap && uspmv_spmv_part(scs, 1, x, y_d, stream)) throw Error(uspmv_last_error());
+        if (overlap && uspmv_spmv_part(scs, 1, x, y, stream)) throw Error(uspmv_last_error());
         USPMV_CUDA(cudaStreamWaitEvent(comm, p->ev_main, 0));
-        const long n_send = h->n_send;
-        long g = (n_send + 2047) / 2048;
-        if (g < 1) g = 1;
-        if (g > 64) g = 64;
-        const int tpb = 256;
-        switch (p->vt) {
-        case USPMV_F64: k_p2p_push<double><<<(unsigned)g, tpb, 0, comm>>>(P, h->rank, p->send_ptr_d.p, p->is_receiver_d.p, h->send_idx.p, h->perm_d, (const double *)x, p->peer_x_dst.p, p->peer_arrived.p, p->acked, p->epoch, p->error, p->block_counter.p); break;
-        case USPMV_F32: k_p2p_push<float><<<(unsigned)g, tpb, 0, comm>>>(P, h->rank, p->send_ptr_d.p, p->is_receiver_d.p, h->send_idx.p, h->perm_d, (const float *)x, p->peer_x_dst.p, p->peer_arrived.p, p->acked, p->epoch, p->error, p->block_counter.p); break;
-        default: k_p2p_push<__half><<<(unsigned)g, tpb, 0, comm>>>(P, h->rank, p->send_ptr_d.p, p->is_receiver_d.p, h->send_idx.p, h->perm_d, (const __half *)x, p->peer_x_dst.p, p->peer_arrived.p, p->acked, p->epoch, p->error, p->block_counter.p);
-        }
-        USPMV_LAUNCH_CHECK();
+        launch_push(p, x, x_buf, comm);
         k_p2p_wait<<<1, 256, 0, comm>>>(P, p->is_sender_d.p, p->arrived, p->epoch, p->error);
         USPMV_LAUNCH_CHECK();
         USPMV_CUDA(cudaEventRecord(p->ev_comm, comm));
         USPMV_CUDA(cudaStreamWaitEvent(main, p->ev_comm, 0));
         if (overlap) {
-            if (uspmv_spmv_part(scs, 2, x, y_d, stream)) throw Error(uspmv_last_error());
+            if (uspmv_spmv_part(scs, 2, x, y, stream)) throw Error(uspmv_last_error());
         } else {
-            if (uspmv_spmv(scs, x, y_d, stream)) throw Error(uspmv_last_error());
+            if (uspmv_spmv(scs, x, y, stream)) throw Error(uspmv_last_error());
         }
+        k_p2p_ack<<<1, 256, 0, main>>>(P, p->is_sender_d.p, p->peer_acked.p, p->epoch);
+        USPMV_LAUNCH_CHECK();
+        if (to_buf) USPMV_CUDA(cudaMemcpyAsync(p->buffer(y_buf), y, (size_t)scs->n_rows * vt_size(p->vt), cudaMemcpyDeviceToDevice, main));
+    });
+}
+
+int uspmv_p2p_spmv(uspmv_p2p *p, const uspmv_scs *scs, void *y_d, void *stream, void *comm_stream) {
+    if (!y_d) {
+        set_error("uspmv_p2p_spmv: y is NULL");
+        return 1;
+    }
+    return uspmv_p2p_spmv_buf(p, scs, 0, -1, y_d, stream, comm_stream);
+}
+
+/* One distributed SpMMV step over the arena's block vector (buffer x_buf): every neighbour receives all block_vec_size vectors
+ * of its halo rows in ONE push (the reference's bulkvec mode, classes_structs.hpp:909-923,962-970), overlapped with the interior
+ * chunks when the streamed kernel applies (C = 32, block_vec_size 2/4/8/16); otherwise exchange first, then one full SpMMV. */
+int uspmv_p2p_spmmv(uspmv_p2p *p, const uspmv_scs *scs, int x_buf, void *Y_d, void *stream, void *comm_stream) {
+    return guarded([&] {
+        if (!p || !scs || !Y_d) fail("uspmv_p2p_spmmv: NULL argument");
+        if (!p->connected) fail("uspmv_p2p_spmmv: call uspmv_p2p_connect first");
+        if (!scs->chunks_split) fail("uspmv_p2p_spmmv: call uspmv_scs_split_chunks first");
+        if (x_buf < 0 || x_buf >= p->n_buf) fail("uspmv_p2p_spmmv: x buffer %d out of range", x_buf);
+        uspmv_halo *h = p->plan;
+        cudaStream_t main = as_stream(stream), comm = as_stream(comm_stream);
+        const int P = h->P;
+        const void *X = p->buffer(x_buf);
+        const bool overlap = p->mode != 0 && uspmv_spmmv_part_supported(scs, p->bvs);
+        USPMV_CUDA(cudaEventRecord(p->ev_main, main));
+        if (overlap && uspmv_spmmv_part(scs, 1, X, Y_d, p->bvs, p->vec_length, p->layout, stream)) throw Error(uspmv_last_error());
+        USPMV_CUDA(cudaStreamWaitEvent(comm, p->ev_main, 0));
+        launch_push(p, X, x_buf, comm);
+        k_p2p_wait<<<1, 256, 0, comm>>>(P, p->is_sender_d.p, p->arrived, p->epoch, p->error);
+        USPMV_LAUNCH_CHECK();
+        USPMV_CUDA(cudaEventRecord(p->ev_comm, comm));
+        USPMV_CUDA(cudaStreamWaitEvent(main, p->ev_comm, 0));
+        if (uspmv_spmmv_part(scs, overlap ? 2 : 0, X, Y_d, p->bvs, p->vec_length, p->layout, stream)) throw Error(uspmv_last_error());
         k_p2p_ack<<<1, 256, 0, main>>>(P, p->is_sender_d.p, p->peer_acked.p, p->epoch);
         USPMV_LAUNCH_CHECK();
     });

@@ -101,6 +101,7 @@ struct FusedArgs {
     const int *send_ptr, *is_receiver, *is_sender, *send_idx, *perm;
     const unsigned long long *peer_x_dst, *peer_arrived, *peer_acked;
     unsigned int *acked, *arrived, *epoch, *error, *counters;  // counters[0] push warps done, [1] warps finished
+    int y_rows;                   // rows >= y_rows are not stored (solve loop: y is the other x buffer, see uspmv_p2p_spmv_buf)
 };
 
 __device__ __forceinline__ unsigned int ld_flag(const unsigned int *p) {
@@ -136,13 +137,14 @@ template <typename T> __device__ __forceinline__ T ld_x_coherent(const T *p) { r
 //   piece(ns, sv, sc)                   consume ns slots: sv/sc point at this lane's value / column of slot 0 (stride 32)
 //   end_chunk(chunk)                    write the rows of `chunk`
 // SpMV: y = A x.  COHERENT: x through L2 only (ld.global.cg) because a peer GPU wrote part of it during this kernel.
-template <typename VT, typename A, int LMAX, bool UNPERM, bool COHERENT>
+template <typename VT, typename A, int LMAX, bool UNPERM, bool COHERENT, bool BOUNDED = false>
 struct SpmvBody {
     const VT *__restrict__ x;
     VT *__restrict__ y;
     const int *__restrict__ new_to_old;
     int lane;
     typename A::acc_t acc;
+    int y_rows = 0;  // BOUNDED: positions >= y_rows are not stored (y aliases the next x, whose tail holds the halo)
     __device__ __forceinline__ void begin_chunk(int = 0) { acc = A::zero(); }
     __device__ __forceinline__ void piece(const int ns, const VT *sv, const int *sc) {
         VT v[LMAX], xv[LMAX];
@@ -165,7 +167,7 @@ struct SpmvBody {
         if (UNPERM) {
             const int o = new_to_old[row];
             if (o >= 0) y[o] = A::out(acc);
-        } else
+        } else if (!BOUNDED || chunk * 32 + lane < y_rows)
             y[row] = A::out(acc);
     }
 };
@@ -472,14 +474,14 @@ k_scs32_stream(long n_items, const int *__restrict__ chunk_list, int chunk_offse
         }
         // (b) interior chunks: no halo column, identical code path to the single-GPU kernel
         {
-            SpmvBody<VT, A, LMAX, UNPERM, false> body{x, y, new_to_old, lane, A::zero()};
+            SpmvBody<VT, A, LMAX, UNPERM, false, true> body{x, y, new_to_old, lane, A::zero(), fa.y_rows};
             stream_items<VT, LMAX, D>(base, bars, hdrs, phase_bits, (int)W, (int)gw, lane, (int)fa.n_int, fa.int_list, fa.int_off,
                                       chunk_ptrs, chunk_lengths, col_idxs, values, body, pol);
         }
         // (c) boundary chunks once the neighbours' elements for this step have landed in our x tail
         if (gw < fa.n_bnd) {
             warp_wait_flags(fa.arrived, fa.is_sender, fa.P, epoch_e, lane, fa.error);
-            SpmvBody<VT, A, LMAX, UNPERM, true> body{x, y, new_to_old, lane, A::zero()};
+            SpmvBody<VT, A, LMAX, UNPERM, true, true> body{x, y, new_to_old, lane, A::zero(), fa.y_rows};
             stream_items<VT, LMAX, D>(base, bars, hdrs, phase_bits, (int)W, (int)gw, lane, (int)fa.n_bnd, fa.bnd_list, fa.bnd_off, chunk_ptrs,
                                       chunk_lengths, col_idxs, values, body, pol);
         }
@@ -875,8 +877,9 @@ k_csr_stream(long n_rows, const int *__restrict__ row_ptrs, const int *__restric
 // SELL-32 SpMMV through the same per-warp bulk-copy ring (smaller stages: the block vectors want the L1 capacity).
 template <typename VT, typename A, int LMAX, int D, int WARPS, int BVS, bool ROWWISE, bool WIDE>
 __global__ void __launch_bounds__(WARPS * 32)  // ~80 registers, 24 warps/SM: capping at 64 spills and is 30-50 % slower (measured)
-k_scs32_stream_mmv(long n_items, const int *__restrict__ chunk_ptrs, const int *__restrict__ chunk_lengths, const int *__restrict__ col_idxs,
-                   const VT *__restrict__ values, const VT *__restrict__ X, VT *__restrict__ Y, long ld, int far_rows) {
+k_scs32_stream_mmv(long n_items, const int *__restrict__ chunk_list, int chunk_offset, const int *__restrict__ chunk_ptrs,
+                   const int *__restrict__ chunk_lengths, const int *__restrict__ col_idxs, const VT *__restrict__ values,
+                   const VT *__restrict__ X, VT *__restrict__ Y, long ld, int far_rows) {
     using R = WarpRing<VT, LMAX, D>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -897,12 +900,12 @@ k_scs32_stream_mmv(long n_items, const int *__restrict__ chunk_ptrs, const int *
     if constexpr (WIDE && ROWWISE && ROW_BYTES >= 32 && ROW_BYTES <= 128 && (ROW_BYTES & (ROW_BYTES - 1)) == 0) {
         SpmmvBodyRowWide<VT, A, LMAX, BVS> body;
         body.X = X; body.Y = Y; body.lane = lane; body.far_rows = far_rows;
-        stream_items<VT, LMAX, D>(base, bars, hdrs, phase_bits, (int)W, (int)gw, lane, (int)n_items, nullptr, 0, chunk_ptrs,
+        stream_items<VT, LMAX, D>(base, bars, hdrs, phase_bits, (int)W, (int)gw, lane, (int)n_items, chunk_list, chunk_offset, chunk_ptrs,
                                   chunk_lengths, col_idxs, values, body, pol);
     } else {
         SpmmvBody<VT, A, LMAX, BVS, ROWWISE> body;
         body.X = X; body.Y = Y; body.ld = ld; body.lane = lane; body.far_rows = far_rows;
-        stream_items<VT, LMAX, D>(base, bars, hdrs, phase_bits, (int)W, (int)gw, lane, (int)n_items, nullptr, 0, chunk_ptrs,
+        stream_items<VT, LMAX, D>(base, bars, hdrs, phase_bits, (int)W, (int)gw, lane, (int)n_items, chunk_list, chunk_offset, chunk_ptrs,
                                   chunk_lengths, col_idxs, values, body, pol);
     }
 }

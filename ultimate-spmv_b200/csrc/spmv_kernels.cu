@@ -482,8 +482,15 @@ void launch_csr_stream(long n_rows, const int *rp, const int *ci, const void *va
 }
 
 // C = 32 and bvs in {2,4,8,16}: streamed kernel
+// chunk subset of a launch: n items, item k -> chunk list[k] (list != NULL) or k + off
+struct ChunkSel {
+    long n;
+    const int *list;
+    int off;
+};
+
 template <typename VT, int BVS, bool ROWWISE, int LMAX, int WARPS, bool WIDE, int D = 2>
-void launch_spmmv_stream_v(const uspmv_scs *s, const VT *X, VT *Y, long ld, cudaStream_t st) {
+void launch_spmmv_stream_v(const uspmv_scs *s, const VT *X, VT *Y, long ld, cudaStream_t st, const ChunkSel &sel) {
     using R = stream::WarpRing<VT, LMAX, D>;
     auto kern = stream::k_scs32_stream_mmv<VT, Arith<VT>, LMAX, D, WARPS, BVS, ROWWISE, WIDE>;
     constexpr int smem = WARPS * R::BYTES_ALIGNED;
@@ -499,50 +506,57 @@ void launch_spmmv_stream_v(const uspmv_scs *s, const VT *X, VT *Y, long ld, cuda
     USPMV_CUDA(cudaGetDevice(&dev));
     const int bps = options().mmv_blocks_per_sm > 0 ? std::min(options().mmv_blocks_per_sm, blocks_per_sm) : blocks_per_sm;
     long grid = (long)sm_count(dev) * bps;
-    const long need = (s->n_chunks + WARPS - 1) / WARPS;
+    const long need = (sel.n + WARPS - 1) / WARPS;
     if (grid > need) grid = need;
-    kern<<<(unsigned)grid, WARPS * 32, smem, st>>>(s->n_chunks, s->chunk_ptrs.p, s->chunk_lengths.p, s->col_idxs.p,
+    if (grid < 1) return;
+    kern<<<(unsigned)grid, WARPS * 32, smem, st>>>(sel.n, sel.list, sel.off, s->chunk_ptrs.p, s->chunk_lengths.p, s->col_idxs.p,
                                                   reinterpret_cast<const VT *>(s->values.p), X, Y, ld,
                                                   ROWWISE ? options().mmv_far_rows : 0);
 }
 
 // variant: 0 = tuned default per (precision, bvs, layout); 1..4 force (wide body?, slots per stage)
 template <typename VT, int BVS, bool ROWWISE>
-void launch_spmmv_stream(const uspmv_scs *s, const VT *X, VT *Y, long ld, cudaStream_t st) {
+void launch_spmmv_stream(const uspmv_scs *s, const VT *X, VT *Y, long ld, cudaStream_t st, const ChunkSel &sel) {
     int v = options().mmv_variant;
     if (v == 0) v = mmv_default_variant(sizeof(VT), BVS, ROWWISE);
     switch (v) {
-    case 2: launch_spmmv_stream_v<VT, BVS, ROWWISE, 8, 8, true>(s, X, Y, ld, st); break;
-    case 3: launch_spmmv_stream_v<VT, BVS, ROWWISE, 4, 8, false>(s, X, Y, ld, st); break;
-    case 4: launch_spmmv_stream_v<VT, BVS, ROWWISE, 4, 8, true>(s, X, Y, ld, st); break;
-    case 5: launch_spmmv_stream_v<VT, BVS, ROWWISE, 8, 16, true>(s, X, Y, ld, st); break;
-    case 6: launch_spmmv_stream_v<VT, BVS, ROWWISE, 8, 24, true>(s, X, Y, ld, st); break;
-    case 7: launch_spmmv_stream_v<VT, BVS, ROWWISE, 8, 16, false>(s, X, Y, ld, st); break;
-    case 8: launch_spmmv_stream_v<VT, BVS, ROWWISE, 8, 24, false>(s, X, Y, ld, st); break;
-    case 9: launch_spmmv_stream_v<VT, BVS, ROWWISE, 4, 24, true>(s, X, Y, ld, st); break;    // half-size stages: twice the L1 left for X
-    case 10: launch_spmmv_stream_v<VT, BVS, ROWWISE, 4, 24, false>(s, X, Y, ld, st); break;
-    case 11: launch_spmmv_stream_v<VT, BVS, ROWWISE, 4, 24, true, 3>(s, X, Y, ld, st); break;
-    case 12: launch_spmmv_stream_v<VT, BVS, ROWWISE, 4, 16, true, 3>(s, X, Y, ld, st); break;
-    case 13: launch_spmmv_stream_v<VT, BVS, ROWWISE, 4, 32, true>(s, X, Y, ld, st); break;
-    case 14: launch_spmmv_stream_v<VT, BVS, ROWWISE, 4, 32, false>(s, X, Y, ld, st); break;
-    default: launch_spmmv_stream_v<VT, BVS, ROWWISE, 8, 8, false>(s, X, Y, ld, st); break;
+    case 2: launch_spmmv_stream_v<VT, BVS, ROWWISE, 8, 8, true>(s, X, Y, ld, st, sel); break;
+    case 3: launch_spmmv_stream_v<VT, BVS, ROWWISE, 4, 8, false>(s, X, Y, ld, st, sel); break;
+    case 4: launch_spmmv_stream_v<VT, BVS, ROWWISE, 4, 8, true>(s, X, Y, ld, st, sel); break;
+    case 5: launch_spmmv_stream_v<VT, BVS, ROWWISE, 8, 16, true>(s, X, Y, ld, st, sel); break;
+    case 6: launch_spmmv_stream_v<VT, BVS, ROWWISE, 8, 24, true>(s, X, Y, ld, st, sel); break;
+    case 7: launch_spmmv_stream_v<VT, BVS, ROWWISE, 8, 16, false>(s, X, Y, ld, st, sel); break;
+    case 8: launch_spmmv_stream_v<VT, BVS, ROWWISE, 8, 24, false>(s, X, Y, ld, st, sel); break;
+    case 9: launch_spmmv_stream_v<VT, BVS, ROWWISE, 4, 24, true>(s, X, Y, ld, st, sel); break;    // half-size stages: twice the L1 left for X
+    case 10: launch_spmmv_stream_v<VT, BVS, ROWWISE, 4, 24, false>(s, X, Y, ld, st, sel); break;
+    case 11: launch_spmmv_stream_v<VT, BVS, ROWWISE, 4, 24, true, 3>(s, X, Y, ld, st, sel); break;
+    case 12: launch_spmmv_stream_v<VT, BVS, ROWWISE, 4, 16, true, 3>(s, X, Y, ld, st, sel); break;
+    case 13: launch_spmmv_stream_v<VT, BVS, ROWWISE, 4, 32, true>(s, X, Y, ld, st, sel); break;
+    case 14: launch_spmmv_stream_v<VT, BVS, ROWWISE, 4, 32, false>(s, X, Y, ld, st, sel); break;
+    default: launch_spmmv_stream_v<VT, BVS, ROWWISE, 8, 8, false>(s, X, Y, ld, st, sel); break;
     }
 }
 
+inline bool spmmv_streamed(const uspmv_scs *s, int bvs) {
+    return s->C == 32 && options().scs_stream && (bvs == 2 || bvs == 4 || bvs == 8 || bvs == 16);
+}
+
 template <typename VT, int LAYOUT>
-void launch_spmmv_l(const uspmv_scs *s, const void *X, void *Y, int bvs, long ld, cudaStream_t st) {
+void launch_spmmv_l(const uspmv_scs *s, const void *X, void *Y, int bvs, long ld, cudaStream_t st, const ChunkSel *subset = nullptr) {
     const long n_pad = s->n_rows_padded;
     if (n_pad == 0) return;
+    if (subset && !spmmv_streamed(s, bvs)) fail("uspmv_spmmv_part: chunk subsets need the streamed kernel (C = 32, block_vec_size 2/4/8/16)");
+    const ChunkSel sel = subset ? *subset : ChunkSel{s->n_chunks, nullptr, 0};
     const VT *v = reinterpret_cast<const VT *>(s->values.p);
     const VT *xx = static_cast<const VT *>(X);
     VT *yy = static_cast<VT *>(Y);
-    if (s->C == 32 && options().scs_stream && (bvs == 2 || bvs == 4 || bvs == 8 || bvs == 16)) {
+    if (spmmv_streamed(s, bvs)) {
         constexpr bool RW = LAYOUT == USPMV_ROWWISE;
         switch (bvs) {
-        case 2: launch_spmmv_stream<VT, 2, RW>(s, xx, yy, ld, st); break;
-        case 4: launch_spmmv_stream<VT, 4, RW>(s, xx, yy, ld, st); break;
-        case 8: launch_spmmv_stream<VT, 8, RW>(s, xx, yy, ld, st); break;
-        default: launch_spmmv_stream<VT, 16, RW>(s, xx, yy, ld, st);
+        case 2: launch_spmmv_stream<VT, 2, RW>(s, xx, yy, ld, st, sel); break;
+        case 4: launch_spmmv_stream<VT, 4, RW>(s, xx, yy, ld, st, sel); break;
+        case 8: launch_spmmv_stream<VT, 8, RW>(s, xx, yy, ld, st, sel); break;
+        default: launch_spmmv_stream<VT, 16, RW>(s, xx, yy, ld, st, sel);
         }
         USPMV_LAUNCH_CHECK();
         return;
@@ -564,9 +578,9 @@ void launch_spmmv_l(const uspmv_scs *s, const void *X, void *Y, int bvs, long ld
 }
 
 template <typename VT>
-void launch_spmmv(const uspmv_scs *s, const void *X, void *Y, int bvs, long ld, int layout, cudaStream_t st) {
-    if (layout == USPMV_ROWWISE) launch_spmmv_l<VT, USPMV_ROWWISE>(s, X, Y, bvs, ld, st);
-    else launch_spmmv_l<VT, USPMV_COLWISE>(s, X, Y, bvs, ld, st);
+void launch_spmmv(const uspmv_scs *s, const void *X, void *Y, int bvs, long ld, int layout, cudaStream_t st, const ChunkSel *subset = nullptr) {
+    if (layout == USPMV_ROWWISE) launch_spmmv_l<VT, USPMV_ROWWISE>(s, X, Y, bvs, ld, st, subset);
+    else launch_spmmv_l<VT, USPMV_COLWISE>(s, X, Y, bvs, ld, st, subset);
 }
 
 // ---- permutation kernels -----------------------------------------------------------------------
@@ -735,6 +749,35 @@ int uspmv_spmmv(const uspmv_scs *s, const void *X, void *Y, int bvs, long vec_le
         case USPMV_F64: launch_spmmv<double>(s, X, Y, bvs, vec_length, layout, st); break;
         case USPMV_F32: launch_spmmv<float>(s, X, Y, bvs, vec_length, layout, st); break;
         default: launch_spmmv<__half>(s, X, Y, bvs, vec_length, layout, st);
+        }
+    });
+}
+
+/* SpMMV over the interior (1) or boundary (2) chunks only (uspmv_scs_split_chunks); 0 = all.  Subsets need the streamed
+ * kernel; uspmv_spmmv_part_supported tells the caller whether to overlap or to run one full SpMMV after the exchange. */
+int uspmv_spmmv_part_supported(const uspmv_scs *s, int bvs) { return s && s->chunks_split && spmmv_streamed(s, bvs) ? 1 : 0; }
+
+int uspmv_spmmv_part(const uspmv_scs *s, int which, const void *X, void *Y, int bvs, long vec_length, int layout, void *stream) {
+    return guarded([&] {
+        if (!s) fail("uspmv_spmmv_part: scs is NULL");
+        if (which == 0) {
+            if (uspmv_spmmv(s, X, Y, bvs, vec_length, layout, stream)) throw Error(uspmv_last_error());
+            return;
+        }
+        if (which != 1 && which != 2) fail("uspmv_spmmv_part: which must be 0 (all), 1 (interior) or 2 (boundary)");
+        if (!s->chunks_split) fail("uspmv_spmmv_part: call uspmv_scs_split_chunks first");
+        if (bvs < 1 || bvs > 16) fail("uspmv_spmmv_part: block_vec_size must be in [1,16] (got %d)", bvs);
+        if (layout != USPMV_COLWISE && layout != USPMV_ROWWISE) fail("uspmv_spmmv_part: invalid layout %d", layout);
+        if (layout == USPMV_COLWISE && vec_length < s->n_rows_padded) fail("uspmv_spmmv_part: vec_length %ld < n_rows_padded %ld", vec_length, s->n_rows_padded);
+        const DevBuf<int> &l = which == 1 ? s->interior_chunks : s->boundary_chunks;
+        if (l.n == 0) return;
+        const bool contig = which == 1 ? s->interior_contig : s->boundary_contig;
+        const ChunkSel sel{(long)l.n, contig ? nullptr : l.p, contig ? (which == 1 ? s->interior_off : s->boundary_off) : 0};
+        cudaStream_t st = as_stream(stream);
+        switch (s->vt) {
+        case USPMV_F64: launch_spmmv<double>(s, X, Y, bvs, vec_length, layout, st, &sel); break;
+        case USPMV_F32: launch_spmmv<float>(s, X, Y, bvs, vec_length, layout, st, &sel); break;
+        default: launch_spmmv<__half>(s, X, Y, bvs, vec_length, layout, st, &sel);
         }
     });
 }

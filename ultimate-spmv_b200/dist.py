@@ -112,32 +112,48 @@ class _DevArray:
 
 
 class P2PHalo:
-    """NVLink peer-to-peer exchange (uspmv_p2p_*): arena with x + epoch flags, IPC handles all-gathered over
-    torch.distributed at setup; no collective call inside the SpMV loop."""
+    """NVLink peer-to-peer exchange (uspmv_p2p_*): arena with n_buf buffers (each bvs vectors of vec_length elements) + epoch
+    flags, IPC handles all-gathered over torch.distributed at setup; no collective call inside the SpMV loop."""
 
-    def __init__(self, plan: HaloPlan, vt: int, x_len: int, rank: int, world: int, group=None):
+    def __init__(self, plan: HaloPlan, vt: int, vec_length: int, rank: int, world: int, group=None, bvs: int = 1,
+                 layout: int = capi.COLWISE, n_buf: int = 1):
         import torch
         import torch.distributed as dist
         from .engine import NP_OF
-        self.plan = plan
-        h, xptr = vp(), vp()
+        self.plan, self.bvs, self.layout, self.n_buf, self.vec_length = plan, int(bvs), int(layout), int(n_buf), int(vec_length)
+        h = vp()
+        xptr = (vp * n_buf)()
         handle = (C.c_ubyte * 64)()
-        call("uspmv_p2p_create", plan.h, int(vt), int(x_len), C.byref(h), handle, C.byref(xptr))
+        call("uspmv_p2p_create_ex", plan.h, int(vt), int(vec_length), int(bvs), int(layout), int(n_buf), C.byref(h), handle, xptr)
         self.h = h
         es = {capi.F64: 8, capi.F32: 4, capi.F16: 2}[vt]
+        x_len = vec_length * bvs
         x_bytes = (x_len * es + 255) // 256 * 256
-        info = {"handle": bytes(handle), "x_bytes": x_bytes, "n_local": plan.scs.n_rows, "recv_cumsum": [int(v) for v in plan.recv_cumsum]}
+        info = {"handle": bytes(handle), "x_bytes": x_bytes, "n_local": plan.scs.n_rows, "recv_cumsum": [int(v) for v in plan.recv_cumsum],
+                "vec_length": int(vec_length), "n_buf": int(n_buf), "bvs": int(bvs), "layout": int(layout)}
         infos = [None] * world
         dist.all_gather_object(infos, info, group=group)
+        if any((i["n_buf"], i["bvs"], i["layout"]) != (n_buf, bvs, layout) for i in infos):
+            raise ValueError("every rank must create the P2P arena with the same n_buf / block_vec_size / layout")
         handles = b"".join(i["handle"] for i in infos)
         peer_x_bytes = (C.c_long * world)(*[i["x_bytes"] for i in infos])
         peer_base = (C.c_long * world)(*[i["n_local"] + i["recv_cumsum"][rank] for i in infos])
-        call("uspmv_p2p_connect", self.h, handles, peer_x_bytes, peer_base)
-        self.x = torch.as_tensor(_DevArray(xptr.value, x_len, NP_OF[vt]), device=f"cuda:{plan.scs.ctx.device}")
+        peer_ld = (C.c_long * world)(*[i["vec_length"] for i in infos])
+        call("uspmv_p2p_connect_ex", self.h, handles, peer_x_bytes, peer_base, peer_ld)
+        dev = f"cuda:{plan.scs.ctx.device}"
+        self.bufs = [torch.as_tensor(_DevArray(xptr[b], x_len, NP_OF[vt]), device=dev) for b in range(n_buf)]
+        self.x = self.bufs[0]
         dist.barrier(group=group)
 
     def spmv(self, scs, y, main_stream, comm_stream):
         call("uspmv_p2p_spmv", self.h, scs.h, vp(y.data_ptr()), vp(main_stream.cuda_stream), vp(comm_stream.cuda_stream))
+
+    def spmv_buf(self, scs, x_buf, y_buf, main_stream, comm_stream):
+        """x = buffer x_buf, y -> buffer y_buf (rows < n_rows): one step of the device-resident solve loop."""
+        call("uspmv_p2p_spmv_buf", self.h, scs.h, int(x_buf), int(y_buf), None, vp(main_stream.cuda_stream), vp(comm_stream.cuda_stream))
+
+    def spmmv(self, scs, Y, main_stream, comm_stream, x_buf=0):
+        call("uspmv_p2p_spmmv", self.h, scs.h, int(x_buf), vp(Y.data_ptr()), vp(main_stream.cuda_stream), vp(comm_stream.cuda_stream))
 
     def status(self):
         err, ep = C.c_int(0), C.c_long(0)
@@ -156,13 +172,21 @@ class DistributedSpmv:
 
     kernel_name = "k_scs32_stream"
 
-    def __init__(self, ctx, points, n, C_, sigma, vt, rank, world, overlap=True, group=None, halo="p2p", strong=False):
+    def __init__(self, ctx, points, n, C_, sigma, vt, rank, world, overlap=True, group=None, halo="p2p", strong=False, bvs=1,
+                 layout="colwise", n_buf=1):
         """strong=False: weak scaling, an n^3 slab per rank (grid n x n x n*world); strong=True: ONE n^3 grid cut into
-        `world` z-slabs (BASELINE.json config 5: 512^3 27-point over 2/4/8 GPUs)."""
+        `world` z-slabs (BASELINE.json config 5: 512^3 27-point over 2/4/8 GPUs).
+        bvs > 1: SpMMV over a block vector of bvs right-hand sides in `layout`, all vectors of a neighbour's halo rows exchanged in
+        one push (the reference's bulkvec mode).  n_buf = 2: two x buffers for the device-resident solve loop (solve())."""
         import torch
         import torch.distributed as dist
         from . import engine as eng
         self.ctx, self.rank, self.world, self.overlap = ctx, rank, world, overlap
+        self.bvs, self.layout = int(bvs), eng.LAYOUT[layout] if isinstance(layout, str) else int(layout)
+        if self.bvs > 1 and halo != "p2p":
+            raise ValueError("block vectors are exchanged over the P2P arena only")
+        if self.bvs > 1 and n_buf != 1:
+            raise ValueError("the two-buffer solve loop is SpMV only")
         nz_total = n if strong else n * world
         if strong and n % world:
             raise ValueError("strong scaling needs n divisible by the number of ranks")
@@ -183,27 +207,36 @@ class DistributedSpmv:
         dev = f"cuda:{ctx.device}"
         # vector length n_local + max(scs_padding, halo_count) (main.cpp:1405-1420)
         x_len = s.n_rows + max(s.n_rows_padded - s.n_rows, self.n_halo)
+        self.vec_length = x_len
         self.halo = halo
         self.p2p = None
         if halo == "p2p":
-            self.p2p = P2PHalo(self.plan, s.vt, x_len, rank, world, group)
-            call("uspmv_p2p_set_overlap", self.p2p.h, {True: 2, False: 0}.get(overlap, overlap))
+            self.p2p = P2PHalo(self.plan, s.vt, x_len, rank, world, group, bvs=self.bvs, layout=self.layout, n_buf=n_buf)
+            # True / False: fused one-launch step / exchange first; 0, 1, 2: the library's modes (uspmv_p2p_set_overlap)
+            call("uspmv_p2p_set_overlap", self.p2p.h, 2 if overlap is True else (0 if overlap is False else int(overlap)))
             self.x = self.p2p.x
             self.x.fill_(5.0)
         else:
             self.x = torch.full((x_len,), 5.0, dtype=dt, device=dev)
-        self.y = torch.zeros(s.n_rows_padded, dtype=dt, device=dev)
+        # column-major Y uses the same leading dimension as X (one vec_length for both, like the harness)
+        self.y = torch.zeros((x_len if self.layout == capi.COLWISE else s.n_rows_padded) * self.bvs if self.bvs > 1 else s.n_rows_padded,
+                             dtype=dt, device=dev)
         self.sendbuf = torch.zeros(max(self.plan.n_send, 1), dtype=dt, device=dev)
         self.ex = HaloExchange(rank, world, s.n_rows, self.plan.recv_cumsum, self.plan.send_ptr, group)
         self.comm_stream = torch.cuda.Stream(device=dev)
-        self.e2e_h2d_bytes = s.n_rows * self.x.element_size()
-        self.e2e_d2h_bytes = s.n_rows_padded * self.y.element_size()
+        self.e2e_h2d_bytes = s.n_rows * self.x.element_size() * self.bvs
+        self.e2e_d2h_bytes = self.y.numel() * self.y.element_size()
         self._torch, self._eng = torch, eng
+        if self.bvs > 1:
+            self.kernel_name = "k_scs32_stream_mmv"
         dist.barrier()
 
     def step(self):
         torch, eng = self._torch, self._eng
         main = torch.cuda.current_stream()
+        if self.bvs > 1:
+            self.p2p.spmmv(self.scs, self.y, main, self.comm_stream)
+            return
         if self.p2p is not None:
             self.p2p.spmv(self.scs, self.y, main, self.comm_stream)
             return
@@ -222,13 +255,29 @@ class DistributedSpmv:
         main.wait_stream(self.comm_stream)
         call("uspmv_spmv_part", self.scs.h, 2, vp(self.x.data_ptr()), vp(self.y.data_ptr()), vp(main.cuda_stream))
 
+    def solve(self, revisions: int, first_buf: int = 0):
+        """Solve mode (main.cpp:528-631): `revisions` x { halo exchange ; SpMV ; swap }, device resident: step k reads buffer
+        k & 1 of the arena and writes its y (the next x, already in permuted order) into the other buffer, so the swap is free.
+        Returns the tensor that holds the final vector (first n_rows entries, permuted order)."""
+        if self.p2p is None or self.p2p.n_buf != 2:
+            raise ValueError("solve() needs halo='p2p' and n_buf=2")
+        main = self._torch.cuda.current_stream()
+        b = first_buf
+        for _ in range(revisions):
+            self.p2p.spmv_buf(self.scs, b, b ^ 1, main, self.comm_stream)
+            b ^= 1
+        return self.p2p.bufs[b]
+
     def time_kernel(self, steps):
         torch, eng = self._torch, self._eng
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         e0.record()
         for _ in range(steps):
-            eng.spmv(self.scs, self.x, self.y)
+            if self.bvs > 1:
+                eng.spmmv(self.scs, self.x, self.y, self.bvs, self.vec_length, self.layout)
+            else:
+                eng.spmv(self.scs, self.x, self.y)
         e1.record()
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / steps
@@ -238,11 +287,17 @@ class DistributedSpmv:
         import time
         torch = self._torch
         n = self.scs.n_rows
-        xh = torch.full((n,), 5.0, dtype=self.x.dtype).pin_memory()
+        rowwise = self.bvs > 1 and self.layout == capi.ROWWISE
+        n_in = n * self.bvs if (self.bvs == 1 or rowwise) else n  # column-major: the local part of every vector
+        xh = torch.full((n_in,), 5.0, dtype=self.x.dtype).pin_memory()
         yh = torch.zeros(self.y.numel(), dtype=self.y.dtype).pin_memory()
 
         def one():
-            self.x[:n].copy_(xh, non_blocking=True)
+            if self.bvs > 1 and not rowwise:
+                for v in range(self.bvs):
+                    self.x[v * self.vec_length: v * self.vec_length + n].copy_(xh, non_blocking=True)
+            else:
+                self.x[:n_in].copy_(xh, non_blocking=True)
             self.step()
             yh.copy_(self.y, non_blocking=True)
             torch.cuda.current_stream().synchronize()

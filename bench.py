@@ -44,6 +44,9 @@ def parse_args():
     ap.add_argument("--strong", action="store_true", help="N>1: ONE n^3 grid cut into N z-slabs (config 5) instead of n^3 per GPU")
     ap.add_argument("--no-overlap", action="store_true", help="N>1: exchange first, then one full SpMV (the reference's order)")
     ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"], help="N>1: NVLink peer stores + epoch flags, or NCCL send/recv")
+    ap.add_argument("--bvs", type=int, default=1, help="block_vec_size > 1: SpMMV (config 3), block-vector halo exchange when N>1")
+    ap.add_argument("--layout", default="rowwise", choices=["rowwise", "colwise"], help="block vector layout for --bvs > 1")
+    ap.add_argument("--solve", action="store_true", help="solve mode: a step is { halo exchange ; SpMV ; swap } on two device buffers")
     return ap.parse_args()
 
 
@@ -196,9 +199,13 @@ def run_ours(args):
         if world == 1 and args.gpus > 1:
             raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N > 1")
     torch.cuda.set_device(local_rank)
+    block_or_solve = args.bvs > 1 or args.solve
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    elif block_or_solve:  # the distributed runner also serves N = 1 for these modes (an arena with no peers)
+        dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{29400 + os.getpid() % 500}", rank=0, world_size=1,
+                                device_id=torch.device("cuda", local_rank))
 
     pkg = importlib.import_module("ultimate-spmv_b200")
     eng, capi = pkg.engine, pkg.capi
@@ -208,12 +215,25 @@ def run_ours(args):
     tdt = {"dp": torch.float64, "sp": torch.float32, "hp": torch.float16}[vt]
     ctx = eng.default_context(local_rank)
 
-    if world == 1:
+    if world == 1 and not block_or_solve:
         runner = pkg.engine.SingleGpuSpmv(ctx, pts, n, args.C, args.sigma, vt)
     else:
-        runner = pkg.dist.DistributedSpmv(ctx, pts, n, args.C, args.sigma, vt, rank, world, halo=args.halo, overlap=not args.no_overlap, strong=args.strong)
-    nnz_local = runner.nnz
-    bytes_local = algorithmic_bytes(runner.n_elements, runner.n_chunks, runner.n_cols_local + runner.n_halo, runner.n_rows_padded, vsize)
+        runner = pkg.dist.DistributedSpmv(ctx, pts, n, args.C, args.sigma, vt, rank, world, halo=args.halo, overlap=not args.no_overlap,
+                                          strong=args.strong, bvs=args.bvs, layout=args.layout, n_buf=2 if args.solve else 1)
+        if args.solve:
+            state = {"buf": 0}
+
+            def solve_step():
+                runner.p2p.spmv_buf(runner.scs, state["buf"], state["buf"] ^ 1, torch.cuda.current_stream(), runner.comm_stream)
+                state["buf"] ^= 1
+            runner.step = solve_step
+            for b in runner.p2p.bufs:
+                b.fill_(0.0)  # x stays finite over thousands of revisions of the stencil operator
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+    nnz_local = runner.nnz * args.bvs
+    bytes_local = algorithmic_bytes(runner.n_elements, runner.n_chunks, runner.n_cols_local + runner.n_halo, runner.n_rows_padded, vsize, args.bvs)
 
     def barrier():
         if world > 1:
@@ -259,7 +279,7 @@ def run_ours(args):
 
     # end-to-end through the host-buffer C-ABI call (pinned host x / y, copies inside the timed region)
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and not args.solve:
         e2e_steps = max(3, min(args.steps, 20))
         sec = runner.time_e2e(e2e_steps, barrier)
         te = torch.tensor([sec], dtype=torch.float64, device="cuda")
@@ -268,9 +288,9 @@ def run_ours(args):
         e2e = {"value": 2.0 * nnz_total / float(te.item()) / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(runner.e2e_h2d_bytes),
                "d2h_bytes_per_step": int(runner.e2e_d2h_bytes), "steps": e2e_steps,
                "api": ("uspmv_spmv_host_submit/_wait (C ABI, pinned host x/y; every step copies its own x in and its own y out, "
-                       "3 steps in flight so H2D / kernel / D2H of neighbouring steps overlap)") if world == 1 else
+                       "3 steps in flight so H2D / kernel / D2H of neighbouring steps overlap)") if (world == 1 and not block_or_solve) else
                       "host x slab -> device, halo exchange + SpMV, y -> host, sync, per step"}
-        if world == 1:
+        if world == 1 and not block_or_solve:
             sec1 = runner.time_e2e(max(3, e2e_steps // 2), barrier, pipelined=False)
             e2e["single_call_value"] = 2.0 * nnz_total / sec1 / 1e9
             e2e["single_call_api"] = "uspmv_spmv_host: H2D(x) + SpMV + D2H(y) + sync, one step at a time"
@@ -291,7 +311,9 @@ def run_ours(args):
             "ms_per_step": sec_per_step * 1e3, "higher_is_better": True, "scaling": "strong" if (args.strong and world > 1) else "weak", "vs_baseline": None,
             "dtype": {"dp": "f64", "sp": "f32", "hp": "f16"}[vt], "data": "synthetic",
             "config": {"workload": (f"{args.workload}: {pts}-point stencil on ONE {n}^3 grid cut into {world} z-slabs" if (args.strong and world > 1) else
-                                    f"{args.workload}: {pts}-point stencil on a {n}^3 grid per GPU") + f", scs C={args.C} sigma={args.sigma} {vt} SpMV",
+                                    f"{args.workload}: {pts}-point stencil on a {n}^3 grid per GPU") + f", scs C={args.C} sigma={args.sigma} {vt} " +
+                                   (f"SpMMV block_vec_size={args.bvs} {args.layout}" if args.bvs > 1 else "SpMV") +
+                                   (", solve mode: each step = halo exchange + SpMV + swap on two device buffers" if args.solve else ""),
                        "rows_per_gpu": runner.n_rows, "nnz_per_gpu": int(nnz_local), "n_elements_per_gpu": int(runner.n_elements),
                        "partition": "none" if world == 1 else f"seg_rows z-slabs x{world}, halo exchange every step (comm_halos=1) via {args.halo}",
                        "l2": "inputs (>= 1.4 GB per GPU) are larger than the 126 MB L2; no explicit flush",
@@ -302,7 +324,7 @@ def run_ours(args):
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
-    if world > 1:
+    if dist.is_initialized():
         dist.destroy_process_group()
 
 

@@ -79,6 +79,13 @@ int uspmv_coo_from_device(uspmv_ctx *ctx, long n_rows, long n_cols, long nnz, co
  * points-1, off-diagonals -1; dp values.  I is made slab-local (I - row0), J stays global
  * (localize_row_idx, mpi_funcs.hpp:862-877). */
 int uspmv_coo_stencil(uspmv_ctx *ctx, int points, long nx, long ny, long nz, long row0, long row1, uspmv_coo **out);
+/* read_mtx's post-processing (utilities.hpp:2214-2290) on the device: entries in file order (0-based), symmetric != 0 expands
+ * (i,j) into (i,j),(j,i) for i != j, then a stable sort by row.  Text parsing stays with the caller. */
+int uspmv_coo_from_entries(uspmv_ctx *ctx, long n_rows, long n_cols, long nz, const int *I_h, const int *J_h, const double *values_h,
+                           int symmetric, uspmv_coo **out);
+/* equilibrate_matrix (utilities.hpp:2605-2684), in place on a dp COO; rowmax_h / colmax_h (optional) receive the row maxima and
+ * the column maxima of the row-scaled matrix (-equilibrate; main.cpp:1118-1153). */
+int uspmv_coo_equilibrate(uspmv_coo *coo, double *rowmax_h, double *colmax_h);
 int uspmv_coo_dims(const uspmv_coo *coo, long out3[3]); /* n_rows, n_cols, nnz */
 int uspmv_coo_export(const uspmv_coo *coo, int *I_h, int *J_h, void *values_h);
 void uspmv_coo_destroy(uspmv_coo *coo);

@@ -56,6 +56,7 @@ class Oracle:
         L.orc_scs_structure.restype = C.c_long
         L.orc_collect_halo.restype = C.c_long
         L.orc_stencil_coo.restype = C.c_long
+        L.orc_ingest_entries.restype = C.c_long
 
     def stencil_coo(self, points, nx, ny, nz, row0=0, row1=None):
         row1 = nx * ny * nz if row1 is None else row1
@@ -164,6 +165,23 @@ class Oracle:
         rm, cm = np.zeros(n_rows), np.zeros(n_cols)
         self.lib.orc_largest_elems(C.c_long(len(I)), _p(I), _p(J), _p(vals), _p(rm), _p(cm))
         return rm, cm
+
+    def equilibrate(self, n_rows, n_cols, I, J, vals):
+        """equilibrate_matrix (utilities.hpp:2668-2684).  Returns (scaled values, rowmax, colmax)."""
+        I, J = _i32(I), _i32(J)
+        v = np.ascontiguousarray(vals, np.float64).copy()
+        rm, cm = np.zeros(n_rows), np.zeros(n_cols)
+        self.lib.orc_equilibrate(C.c_long(len(I)), _p(I), _p(J), _p(v), _p(rm), _p(cm))
+        return v, rm, cm
+
+    def ingest_entries(self, n_rows, I, J, vals, symmetric):
+        """read_mtx post-processing: symmetric expansion + stable row sort of the file-order entries."""
+        I, J = _i32(I), _i32(J)
+        vals = np.ascontiguousarray(vals, np.float64)
+        nz = len(I)
+        Io, Jo, Vo = np.zeros(2 * nz + 1, np.int32), np.zeros(2 * nz + 1, np.int32), np.zeros(2 * nz + 1)
+        n = self.lib.orc_ingest_entries(C.c_long(nz), _p(I), _p(J), _p(vals), C.c_int(1 if symmetric else 0), C.c_int(n_rows), _p(Io), _p(Jo), _p(Vo))
+        return Io[:n].copy(), Jo[:n].copy(), Vo[:n].copy()
 
     def seg_work_sharing_arr(self, method, n_rows, I, P):
         I = _i32(I)
@@ -299,6 +317,12 @@ class Ref:
                                          _p(dI), _p(dJ), _p(dV), _p(sI), _p(sJ), _p(sV), C.byref(nsp))
         ns = nsp.value
         return (dI[:nd], dJ[:nd], dV[:nd]), (sI[:ns], sJ[:ns], sV[:ns])
+
+    def equilibrate(self, n_rows, n_cols, I, J, vals):
+        I, J = _i32(I), _i32(J)
+        v = np.ascontiguousarray(vals, np.float64).copy()
+        self.lib.ref_equilibrate(C.c_long(n_rows), C.c_long(n_cols), C.c_long(len(I)), _p(I), _p(J), _p(v))
+        return v
 
     def read_mtx(self, path):
         nr, nc = C.c_long(0), C.c_long(0)

@@ -12,6 +12,7 @@ Outputs (committed; /root/reference does not exist on the GPU box):
                                  pins libstdc++ 13.3's std::sort tie order (introsort + heapsort fallback)
   tests/golden/ref_dist.npz      seg_work_sharing_arr and collect_local_needed_heri results (P = 2, 3, 4)
   tests/golden/ref_ap.npz        adaptive-precision y (interface.hpp kernels) for dp_sp / dp_hp / sp_hp / dp_sp_hp
+  tests/golden/ref_ingest.npz    raw file-order entries of the ten matrices + values after the reference's equilibrate_matrix
 """
 from __future__ import annotations
 
@@ -50,7 +51,28 @@ def killer(n):
     return np.array(a)
 
 
+def ingest_fixtures(ref):
+    """tests/golden/ref_ingest.npz: per matrix the raw file-order entries (what the device ingest receives; parsed with the
+    product's text parser) and the values after the reference's equilibrate_matrix applied to its own read_mtx result."""
+    import importlib
+    mats = importlib.import_module("ultimate-spmv_b200.matrices")
+    g = {}
+    for name in NAMES:
+        path = os.path.join(REF_MAT, name + ".mtx")
+        n, nc, I, J, V, sym = mats.read_mtx_entries(path)
+        g[f"{name}__n"] = np.int64(n)
+        g[f"{name}__sym"] = np.int64(1 if sym else 0)
+        g[f"{name}__I"], g[f"{name}__J"], g[f"{name}__V"] = I, J, V
+        rn, rc, rI, rJ, rV = ref.read_mtx(path)
+        g[f"{name}__equil"] = ref.equilibrate(rn, rc, rI, rJ, rV)
+    np.savez_compressed(os.path.join(OUT, "ref_ingest.npz"), **g)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "ingest":  # only the ingest / equilibrate fixtures
+        build("all")
+        ingest_fixtures(Ref("col"))
+        return
     build("all")
     os.makedirs(OUT, exist_ok=True)
     ref = Ref("col")
@@ -194,6 +216,7 @@ def main():
                 a[key + "|y"] = yp[s_first.old_to_new]
     a["cases"] = np.array(acases)
     np.savez_compressed(os.path.join(OUT, "ref_ap.npz"), **a)
+    ingest_fixtures(ref)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -24,6 +24,7 @@
  *   partition_precisions      utilities.hpp:2810-3123 (2-way dp/sp only: the harness
  *                             version exits on any hp element, utilities.hpp:2941-2944)
  *   read_mtx                  utilities.hpp:2148-2309
+ *   equilibrate_matrix        utilities.hpp:2668-2684
  *   seg_work_sharing_arr      mpi_funcs.hpp:424-622
  *   seg_mtx_struct            mpi_funcs.hpp:636-674
  *   localize_row_idx          mpi_funcs.hpp:862-877
@@ -293,6 +294,17 @@ long ref_read_mtx(const char *path, long *n_rows, long *n_cols, int *I, int *J, 
     if (J) std::memcpy(J, cache.J.data(), sizeof(int) * cache.nnz);
     if (vals) std::memcpy(vals, cache.values.data(), sizeof(double) * cache.nnz);
     return cache.nnz;
+}
+
+/* equilibrate_matrix (utilities.hpp:2668-2684) on a square dp COO, values scaled in place */
+void ref_equilibrate(long n_rows, long n_cols, long nnz, const int *I, const int *J, double *vals) {
+    MtxData<double, int> m;
+    m.n_rows = n_rows; m.n_cols = n_cols; m.nnz = nnz;
+    m.I.assign(I, I + nnz);
+    m.J.assign(J, J + nnz);
+    m.values.assign(vals, vals + nnz);
+    equilibrate_matrix<double, int>(&m);
+    std::memcpy(vals, m.values.data(), sizeof(double) * nnz);
 }
 
 /* seg_method: 0 = seg-rows, 1 = seg-nnz.  wsa has P+1 entries. */

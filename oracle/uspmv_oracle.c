@@ -454,6 +454,43 @@ void orc_largest_elems(long nnz, const int *I, const int *J, const double *vals,
     }
 }
 
+/* equilibrate_matrix (utilities.hpp:2668-2684): rows scaled by their largest |value| (:2646-2654), then columns by the largest
+ * |row-scaled value| (:2657-2665).  rowmax / colmax (n_rows / n_cols, zero-initialised) return the two sets of maxima. */
+void orc_equilibrate(long nnz, const int *I, const int *J, double *vals, double *rowmax, double *colmax) {
+    for (long i = 0; i < nnz; ++i) {
+        double a = fabs(vals[i]);
+        if (a > rowmax[I[i]]) rowmax[I[i]] = a;
+    }
+    for (long i = 0; i < nnz; ++i) vals[i] = vals[i] / rowmax[I[i]];
+    for (long i = 0; i < nnz; ++i) {
+        double a = fabs(vals[i]);
+        if (a > colmax[J[i]]) colmax[J[i]] = a;
+    }
+    for (long i = 0; i < nnz; ++i) vals[i] = vals[i] / colmax[J[i]];
+}
+
+/* read_mtx post-processing (utilities.hpp:2214-2290): entries in file order; symmetric files are expanded (i,j) -> (i,j),(j,i) for
+ * i != j (:2237-2251), then a stable sort by row (:2278, sort_perm :2139-2146).  Outputs need 2*nz capacity; returns nnz. */
+long orc_ingest_entries(long nz, const int *I, const int *J, const double *V, int symmetric, int n_rows, int *Io, int *Jo, double *Vo) {
+    long nnz = 0;
+    int *ti = (int *)malloc(sizeof(int) * (size_t)(2 * nz + 1)), *tj = (int *)malloc(sizeof(int) * (size_t)(2 * nz + 1));
+    double *tv = (double *)malloc(sizeof(double) * (size_t)(2 * nz + 1));
+    for (long k = 0; k < nz; ++k) {
+        ti[nnz] = I[k]; tj[nnz] = J[k]; tv[nnz] = V[k]; ++nnz;
+        if (symmetric && I[k] != J[k]) { ti[nnz] = J[k]; tj[nnz] = I[k]; tv[nnz] = V[k]; ++nnz; }
+    }
+    /* stable counting sort by row == std::stable_sort with the row comparator */
+    long *start = (long *)calloc((size_t)n_rows + 1, sizeof(long));
+    for (long k = 0; k < nnz; ++k) start[ti[k] + 1]++;
+    for (int r = 0; r < n_rows; ++r) start[r + 1] += start[r];
+    for (long k = 0; k < nnz; ++k) {
+        long p = start[ti[k]]++;
+        Io[p] = ti[k]; Jo[p] = tj[k]; Vo[p] = tv[k];
+    }
+    free(ti); free(tj); free(tv); free(start);
+    return nnz;
+}
+
 /* ---------------------------------------------------------------------------------------------
  * Row partitioning + halo bookkeeping
  * --------------------------------------------------------------------------------------------- */

@@ -83,3 +83,31 @@ def test_cli_rejections(eng, tmp_path):
                       (["scs", "-bogus"], "unknown argument")):
         r = run([m] + args, str(tmp_path))
         assert r.returncode != 0 and msg in r.stderr, (args, r.stderr)
+
+
+def test_cli_symmetric_file_equilibrate_and_dropout(eng, tmp_path):
+    """A `symmetric` Matrix Market file goes through the device-side ingest (expansion + stable row sort), -equilibrate scales
+    rows then columns on the device (one precision and AP, where the maxima also scale the thresholds), -dropout filters."""
+    import os
+    from conftest import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "ref_ingest.npz"))
+    name = "bcsstk13"
+    assert int(z[f"{name}__sym"]) == 1
+    path = str(tmp_path / "sym.mtx")
+    with open(path, "w") as f:
+        f.write("%%MatrixMarket matrix coordinate real symmetric\n")
+        n = int(z[f"{name}__n"])
+        f.write(f"{n} {n} {len(z[f'{name}__I'])}\n")
+        for i, j, v in zip(z[f"{name}__I"], z[f"{name}__J"], z[f"{name}__V"]):
+            f.write(f"{i + 1} {j + 1} {float(v)!r}\n")
+    r = run([path, "scs", "-c", "32", "-s", "512", "-dp", "-mode", "s", "-rand_x", "1"], str(tmp_path))
+    assert r.returncode == 0 and "-> OK" in r.stdout, r.stdout + r.stderr
+    assert "2003 rows, 83883 nnz" in r.stdout, r.stdout  # SURVEY.md section 8: nnz after symmetric expansion
+    r = run([path, "scs", "-c", "32", "-s", "512", "-dp", "-mode", "s", "-rand_x", "1", "-equilibrate", "1"], str(tmp_path))
+    assert r.returncode == 0 and "-> OK" in r.stdout, r.stdout + r.stderr
+    r = run([path, "scs", "-c", "32", "-s", "64", "-ap[dp_sp]", "-apt1", "0.1", "-mode", "s", "-rand_x", "1", "-equilibrate", "1"], str(tmp_path))
+    assert r.returncode == 0 and ("-> OK" in r.stdout or "-> WARNING" in r.stdout), r.stdout + r.stderr
+    r = run([path, "scs", "-c", "32", "-s", "64", "-dp", "-mode", "s", "-rand_x", "1", "-dropout", "1", "-dropout_threshold", "1000"], str(tmp_path))
+    assert r.returncode == 0 and "-> OK" in r.stdout, r.stdout + r.stderr
+    m = re.search(r"2003 rows, (\d+) nnz", r.stdout)
+    assert m and int(m.group(1)) < 83883, r.stdout

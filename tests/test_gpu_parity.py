@@ -357,3 +357,32 @@ def test_fixed_permutation_must_be_injective(eng, pkg, mats):
     perm[7] = 10 ** 6
     with pytest.raises(pkg.capi.UspmvError, match="outside"):
         eng.convert_to_scs(mtx, 4, 8, "dp", fixed_permutation=perm)
+
+
+# ------------------------------------------------------------------------------------------------
+# matrix ingest (device-side read_mtx post-processing) and equilibration
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", MATRIX_NAMES)
+def test_device_ingest_and_equilibrate(eng, orc, name):
+    """uspmv_coo_from_entries == the reference's read_mtx result (symmetric expansion order + stable row sort), then
+    uspmv_coo_equilibrate == the reference's equilibrate_matrix output, both bit-exact (tests/golden/ref_ingest.npz)."""
+    import os
+    from conftest import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "ref_ingest.npz"))
+    n, nc, I, J, V = load_matrix(name)
+    mtx = eng.MtxData.from_entries(int(z[f"{name}__n"]), int(z[f"{name}__n"]), z[f"{name}__I"], z[f"{name}__J"], z[f"{name}__V"],
+                                   bool(z[f"{name}__sym"]))
+    gI, gJ, gV = mtx.to_host()
+    assert mtx.nnz == len(I)
+    assert np.array_equal(gI, I) and np.array_equal(gJ, J)
+    assert np.array_equal(gV.view(np.uint8), V.view(np.uint8))
+    rm, cm = mtx.equilibrate()
+    _, _, eV = mtx.to_host()
+    assert np.array_equal(eV.view(np.uint8), z[f"{name}__equil"].view(np.uint8))
+    v_o, rm_o, cm_o = orc.equilibrate(n, nc, I, J, V)
+    assert np.array_equal(rm, rm_o) and np.array_equal(cm, cm_o)
+
+
+def test_device_ingest_rejects_out_of_range(eng, pkg):
+    with pytest.raises(pkg.capi.UspmvError, match="outside"):
+        eng.MtxData.from_entries(4, 4, [0, 5], [0, 1], [1.0, 2.0], False)

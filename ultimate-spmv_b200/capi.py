@@ -46,6 +46,8 @@ _sigs = {
     "uspmv_coo_from_host": [vp, C.c_long, C.c_long, C.c_long, vp, vp, vp, C.c_int, C.POINTER(vp)],
     "uspmv_coo_from_device": [vp, C.c_long, C.c_long, C.c_long, vp, vp, vp, C.c_int, C.POINTER(vp)],
     "uspmv_coo_stencil": [vp, C.c_int, C.c_long, C.c_long, C.c_long, C.c_long, C.c_long, C.POINTER(vp)],
+    "uspmv_coo_from_entries": [vp, C.c_long, C.c_long, C.c_long, vp, vp, vp, C.c_int, C.POINTER(vp)],
+    "uspmv_coo_equilibrate": [vp, vp, vp],
     "uspmv_coo_dims": [vp, C.POINTER(C.c_long)],
     "uspmv_coo_export": [vp, vp, vp, vp],
     "uspmv_scs_build": [vp, vp, C.c_long, C.c_long, C.c_int, vp, C.POINTER(vp)],

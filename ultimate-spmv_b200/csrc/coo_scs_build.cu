@@ -433,6 +433,43 @@ void build_balanced_order(uspmv_scs *s) {
     USPMV_CUDA(cudaMemcpy(s->split_ptr.p, split_ptr.data(), split_ptr.size() * sizeof(int), cudaMemcpyHostToDevice));
 }
 
+// ---- matrix ingest (read_mtx, utilities.hpp:2148-2309): symmetric expansion and the stable sort by row, on the device ----
+__global__ void k_sym_count(const int *__restrict__ I, const int *__restrict__ J, long nz, int *__restrict__ cnt) {
+    long k = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (k < nz) cnt[k] = 1 + (I[k] != J[k]);
+    else if (k == nz) cnt[k] = 0;
+}
+// entry k -> (i, j, v) at pos[k], immediately followed by (j, i, v) when off-diagonal (utilities.hpp:2237-2251)
+__global__ void k_sym_expand(const int *__restrict__ I, const int *__restrict__ J, const double *__restrict__ V, long nz,
+                             const int *__restrict__ pos, int *__restrict__ Io, int *__restrict__ Jo, double *__restrict__ Vo) {
+    long k = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (k >= nz) return;
+    const int i = I[k], j = J[k], p = pos[k];
+    const double v = V[k];
+    Io[p] = i; Jo[p] = j; Vo[p] = v;
+    if (i != j) { Io[p + 1] = j; Jo[p + 1] = i; Vo[p + 1] = v; }
+}
+__global__ void k_gather_coo(const int *__restrict__ order, const int *__restrict__ J, const double *__restrict__ V, long nnz,
+                             int *__restrict__ Jo, double *__restrict__ Vo) {
+    long k = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (k >= nnz) return;
+    const int o = order[k];
+    Jo[k] = J[o];
+    Vo[k] = V[o];
+}
+
+// ---- equilibration (equilibrate_matrix, utilities.hpp:2605-2684): |v| >= 0, so its IEEE bit pattern orders like an integer ----
+__global__ void k_absmax_by(const int *__restrict__ idx, const double *__restrict__ V, long nnz, unsigned long long *__restrict__ mx) {
+    long k = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (k >= nnz) return;
+    const double a = fabs(V[k]);
+    if (a == a) atomicMax(&mx[idx[k]], (unsigned long long)__double_as_longlong(a));
+}
+__global__ void k_scale_by(const int *__restrict__ idx, double *__restrict__ V, long nnz, const double *__restrict__ mx) {
+    long k = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (k < nnz) V[k] = V[k] / mx[idx[k]];
+}
+
 void check_flags(DevBuf<int> &flags, int out[2]) {
     USPMV_CUDA(cudaMemcpy(out, flags.p, 2 * sizeof(int), cudaMemcpyDeviceToHost));
 }
@@ -532,6 +569,100 @@ int uspmv_coo_dims(const uspmv_coo *coo, long out3[3]) {
     return guarded([&] {
         if (!coo || !out3) fail("uspmv_coo_dims: NULL argument");
         out3[0] = coo->n_rows; out3[1] = coo->n_cols; out3[2] = coo->nnz;
+    });
+}
+
+/* read_mtx's post-processing on the device (utilities.hpp:2214-2290): the nz (row, col, value) entries of a Matrix Market file in
+ * file order, 0-based; symmetric != 0 expands every off-diagonal entry (i,j) into (i,j),(j,i); then a STABLE sort by row. */
+int uspmv_coo_from_entries(uspmv_ctx *ctx, long n_rows, long n_cols, long nz, const int *I_h, const int *J_h, const double *V_h,
+                           int symmetric, uspmv_coo **out) {
+    return guarded([&] {
+        if (!out) fail("uspmv_coo_from_entries: out is NULL");
+        if (nz > 0 && (!I_h || !J_h || !V_h)) fail("uspmv_coo_from_entries: NULL array");
+        if (!ctx) fail("uspmv_coo_from_entries: ctx is NULL");
+        if (n_rows < 0 || n_cols < 0 || nz < 0 || nz > INT32_MAX / 2) fail("uspmv_coo_from_entries: bad dimensions");
+        USPMV_CUDA(cudaSetDevice(ctx->device));
+        for (long k = 0; k < nz; ++k)
+            if (I_h[k] < 0 || I_h[k] >= n_rows || J_h[k] < 0 || J_h[k] >= n_cols || (symmetric && (J_h[k] >= n_rows || I_h[k] >= n_cols)))
+                fail("uspmv_coo_from_entries: entry %ld (%d, %d) outside the %ld x %ld matrix", k, I_h[k], J_h[k], n_rows, n_cols);
+        DevBuf<int> I0(nz), J0(nz);
+        DevBuf<double> V0(nz);
+        if (nz) {
+            USPMV_CUDA(cudaMemcpy(I0.p, I_h, nz * sizeof(int), cudaMemcpyHostToDevice));
+            USPMV_CUDA(cudaMemcpy(J0.p, J_h, nz * sizeof(int), cudaMemcpyHostToDevice));
+            USPMV_CUDA(cudaMemcpy(V0.p, V_h, nz * sizeof(double), cudaMemcpyHostToDevice));
+        }
+        long nnz = nz;
+        DevBuf<int> I1, J1;
+        DevBuf<double> V1;
+        const int *Iu = I0.p, *Ju = J0.p;
+        const double *Vu = V0.p;
+        if (symmetric && nz) {
+            DevBuf<int> cnt(nz + 1), pos(nz + 1);
+            k_sym_count<<<blocks_for(nz + 1), TPB>>>(I0.p, J0.p, nz, cnt.p);
+            USPMV_LAUNCH_CHECK();
+            size_t bytes = 0;
+            USPMV_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, cnt.p, pos.p, (int)(nz + 1)));
+            DevBuf<unsigned char> tmp(bytes);
+            USPMV_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, bytes, cnt.p, pos.p, (int)(nz + 1)));
+            g_launches.fetch_add(2);
+            int tot = 0;
+            USPMV_CUDA(cudaMemcpy(&tot, pos.p + nz, sizeof(int), cudaMemcpyDeviceToHost));
+            nnz = tot;
+            I1.alloc(nnz); J1.alloc(nnz); V1.alloc(nnz);
+            k_sym_expand<<<blocks_for(nz), TPB>>>(I0.p, J0.p, V0.p, nz, pos.p, I1.p, J1.p, V1.p);
+            USPMV_LAUNCH_CHECK();
+            Iu = I1.p; Ju = J1.p; Vu = V1.p;
+        }
+        auto c = new uspmv_coo();
+        try {
+            coo_common(ctx, n_rows, n_cols, nnz, USPMV_F64, c);
+            if (nnz) {
+                DevBuf<int> iota(nnz), order(nnz);
+                k_iota<<<blocks_for(nnz), TPB>>>(iota.p, nnz);
+                USPMV_LAUNCH_CHECK();
+                int end_bit = 1;
+                while (end_bit < 31 && (1L << end_bit) < n_rows) ++end_bit;
+                size_t bytes = 0;  // LSD radix sort: stable, i.e. std::stable_sort by row (sort_perm, utilities.hpp:2139-2146)
+                USPMV_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, Iu, c->I.p, iota.p, order.p, (int)nnz, 0, end_bit));
+                DevBuf<unsigned char> tmp(bytes);
+                USPMV_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, Iu, c->I.p, iota.p, order.p, (int)nnz, 0, end_bit));
+                g_launches.fetch_add(8);
+                k_gather_coo<<<blocks_for(nnz), TPB>>>(order.p, Ju, Vu, nnz, c->J.p, reinterpret_cast<double *>(c->values.p));
+                USPMV_LAUNCH_CHECK();
+                USPMV_CUDA(cudaDeviceSynchronize());
+            }
+        } catch (...) { delete c; throw; }
+        *out = c;
+    });
+}
+
+/* equilibrate_matrix (utilities.hpp:2668-2684) in place on a dp COO: every value divided by the largest |value| of its row, then
+ * by the largest |scaled value| of its column.  rowmax_h / colmax_h (optional, n_rows / n_cols doubles) receive the two maxima —
+ * what the harness hands to partition_precisions in AP mode (main.cpp:1143-1153). */
+int uspmv_coo_equilibrate(uspmv_coo *coo, double *rowmax_h, double *colmax_h) {
+    return guarded([&] {
+        if (!coo) fail("uspmv_coo_equilibrate: coo is NULL");
+        if (coo->mt != USPMV_F64) fail("uspmv_coo_equilibrate: the COO matrix must hold doubles");
+        USPMV_CUDA(cudaSetDevice(coo->ctx->device));
+        const long nnz = coo->nnz;
+        DevBuf<unsigned long long> rm(coo->n_rows > 0 ? coo->n_rows : 1), cm(coo->n_cols > 0 ? coo->n_cols : 1);
+        USPMV_CUDA(cudaMemset(rm.p, 0, rm.n * 8));
+        USPMV_CUDA(cudaMemset(cm.p, 0, cm.n * 8));
+        double *V = reinterpret_cast<double *>(coo->values.p);
+        if (nnz) {
+            k_absmax_by<<<blocks_for(nnz), TPB>>>(coo->I.p, V, nnz, rm.p);
+            USPMV_LAUNCH_CHECK();
+            k_scale_by<<<blocks_for(nnz), TPB>>>(coo->I.p, V, nnz, reinterpret_cast<const double *>(rm.p));
+            USPMV_LAUNCH_CHECK();
+            k_absmax_by<<<blocks_for(nnz), TPB>>>(coo->J.p, V, nnz, cm.p);
+            USPMV_LAUNCH_CHECK();
+            k_scale_by<<<blocks_for(nnz), TPB>>>(coo->J.p, V, nnz, reinterpret_cast<const double *>(cm.p));
+            USPMV_LAUNCH_CHECK();
+        }
+        if (rowmax_h && coo->n_rows) USPMV_CUDA(cudaMemcpy(rowmax_h, rm.p, coo->n_rows * 8, cudaMemcpyDeviceToHost));
+        if (colmax_h && coo->n_cols) USPMV_CUDA(cudaMemcpy(colmax_h, cm.p, coo->n_cols * 8, cudaMemcpyDeviceToHost));
+        USPMV_CUDA(cudaDeviceSynchronize());
     });
 }
 

@@ -105,6 +105,24 @@ class MtxData:
         return cls(h, ctx)
 
     @classmethod
+    def from_entries(cls, n_rows, n_cols, I, J, values, symmetric, ctx: Context | None = None):
+        """read_mtx's post-processing on the device (utilities.hpp:2214-2290): file-order entries -> symmetric expansion -> stable
+        sort by row.  See matrices.read_mtx_entries for the text parser."""
+        ctx = ctx or default_context()
+        I = np.ascontiguousarray(I, np.int32)
+        J = np.ascontiguousarray(J, np.int32)
+        values = np.ascontiguousarray(values, np.float64)
+        h = vp()
+        call("uspmv_coo_from_entries", ctx.h, int(n_rows), int(n_cols), len(I), _hp(I), _hp(J), _hp(values), 1 if symmetric else 0, C.byref(h))
+        return cls(h, ctx)
+
+    def equilibrate(self):
+        """equilibrate_matrix (utilities.hpp:2668-2684) in place; returns (rowmax, colmax) for partition_precisions."""
+        rm, cm = np.zeros(self.n_rows), np.zeros(self.n_cols)
+        call("uspmv_coo_equilibrate", self.h, _hp(rm), _hp(cm))
+        return rm, cm
+
+    @classmethod
     def stencil(cls, points, nx, ny, nz, row0=0, row1=None, ctx: Context | None = None):
         ctx = ctx or default_context()
         if row1 is None:

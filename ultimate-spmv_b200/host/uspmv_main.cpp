@@ -153,9 +153,14 @@ struct Coo {
     std::vector<double> V;
 };
 
-// read_mtx (utilities.hpp:2148-2309 + mmio.h:138-263): real/integer/pattern, general/symmetric; symmetric entries expanded as
-// (i,j) immediately followed by (j,i); stable sort by row.
-Coo read_mtx(const std::string &path) {
+// read_mtx (utilities.hpp:2148-2309 + mmio.h:138-263): real/integer/pattern, general/symmetric.  Only the text is parsed here;
+// the symmetric expansion ((i,j) immediately followed by (j,i)) and the stable sort by row run on the device
+// (uspmv_coo_from_entries).
+struct MtxFile {
+    Coo entries;  // file order, 0-based
+    bool symmetric = false;
+};
+MtxFile read_mtx(const std::string &path) {
     std::ifstream f(path);
     if (!f) die("Unable to open file");
     std::string line;
@@ -173,25 +178,18 @@ Coo read_mtx(const std::string &path) {
     long M, N, nz;
     { std::istringstream s(line); if (!(s >> M >> N >> nz)) die("read_unsymmetric_sparse(): could not parse matrix size."); }
     if (M != N) die("Matrix not square. Currently only square matrices are supported");
-    std::vector<int> I, J;
-    std::vector<double> V;
-    I.reserve(nz * 2); J.reserve(nz * 2); V.reserve(nz * 2);
-    const bool pattern = field == "pattern", sym = symm == "symmetric";
+    MtxFile m;
+    m.symmetric = symm == "symmetric";
+    m.entries.n_rows = M; m.entries.n_cols = N;
+    m.entries.I.reserve(nz); m.entries.J.reserve(nz); m.entries.V.reserve(nz);
+    const bool pattern = field == "pattern";
     for (long k = 0; k < nz; ++k) {
         long i, j;
         double v = 0.01;  // pattern matrices: mmio.h:195-203
         if (!(f >> i >> j)) die("Error in file reading");
         if (!pattern && !(f >> v)) die("Error in file reading");
-        I.push_back((int)i - 1); J.push_back((int)j - 1); V.push_back(v);
-        if (sym && i != j) { I.push_back((int)j - 1); J.push_back((int)i - 1); V.push_back(v); }
+        m.entries.I.push_back((int)i - 1); m.entries.J.push_back((int)j - 1); m.entries.V.push_back(v);
     }
-    std::vector<int> perm(I.size());
-    std::iota(perm.begin(), perm.end(), 0);
-    std::stable_sort(perm.begin(), perm.end(), [&](int a, int c) { return I[a] < I[c]; });
-    Coo m;
-    m.n_rows = M; m.n_cols = N;
-    m.I.resize(I.size()); m.J.resize(I.size()); m.V.resize(I.size());
-    for (size_t k = 0; k < perm.size(); ++k) { m.I[k] = I[perm[k]]; m.J[k] = J[perm[k]]; m.V[k] = V[perm[k]]; }
     return m;
 }
 
@@ -271,19 +269,37 @@ int main(int argc, char **argv) {
         ck(uspmv_coo_stencil(ctx, pts, n, n, n, 0, n * n * n, &coo));
         cfg.matrix_min = -1.0; cfg.matrix_max = pts - 1.0; cfg.matrix_mean = 0.0;
     } else {
-        host = read_mtx(cfg.matrix_file_name);
-        have_host = true;
-        if (host.V.empty()) die("ERROR: empty matrix");
-        if (cfg.dropout) {  // -dropout: remove elements below the threshold (utilities.hpp, -dt)
-            Coo k; k.n_rows = host.n_rows; k.n_cols = host.n_cols;
-            for (size_t i = 0; i < host.V.size(); ++i)
-                if (std::fabs(host.V[i]) >= cfg.dropout_threshold) { k.I.push_back(host.I[i]); k.J.push_back(host.J[i]); k.V.push_back(host.V[i]); }
-            host = k;
+        MtxFile file = read_mtx(cfg.matrix_file_name);
+        if (file.entries.V.empty()) die("ERROR: empty matrix");
+        if (cfg.dropout) {  // -dropout: remove elements below the threshold (utilities.hpp, -dt); (i,j) and (j,i) share the value
+            Coo k; k.n_rows = file.entries.n_rows; k.n_cols = file.entries.n_cols;
+            for (size_t i = 0; i < file.entries.V.size(); ++i)
+                if (std::fabs(file.entries.V[i]) >= cfg.dropout_threshold) {
+                    k.I.push_back(file.entries.I[i]); k.J.push_back(file.entries.J[i]); k.V.push_back(file.entries.V[i]);
+                }
+            file.entries = k;
+            if (file.entries.V.empty()) die("ERROR: dropout removed every element");
         }
+        ck(uspmv_coo_from_entries(ctx, file.entries.n_rows, file.entries.n_cols, (long)file.entries.V.size(), file.entries.I.data(),
+                                  file.entries.J.data(), file.entries.V.data(), file.symmetric ? 1 : 0, &coo));
+        long d3[3];
+        ck(uspmv_coo_dims(coo, d3));
+        host.n_rows = d3[0]; host.n_cols = d3[1];
+        host.I.resize(d3[2]); host.J.resize(d3[2]); host.V.resize(d3[2]);
+        ck(uspmv_coo_export(coo, host.I.data(), host.J.data(), host.V.data()));
+        have_host = true;
         cfg.matrix_min = *std::min_element(host.V.begin(), host.V.end());
         cfg.matrix_max = *std::max_element(host.V.begin(), host.V.end());
         cfg.matrix_mean = std::accumulate(host.V.begin(), host.V.end(), 0.0) / host.V.size();
-        ck(uspmv_coo_from_host(ctx, host.n_rows, host.n_cols, (long)host.V.size(), host.I.data(), host.J.data(), host.V.data(), USPMV_F64, &coo));
+    }
+    // -equilibrate (main.cpp:1118-1153): scale rows, then columns; AP also hands the maxima to partition_precisions
+    std::vector<double> rowmax, colmax;
+    if (cfg.equilibrate) {
+        long d3[3];
+        ck(uspmv_coo_dims(coo, d3));
+        rowmax.resize(d3[0]); colmax.resize(d3[1]);
+        ck(uspmv_coo_equilibrate(coo, rowmax.data(), colmax.data()));
+        if (have_host) ck(uspmv_coo_export(coo, nullptr, nullptr, host.V.data()));  // validation uses the scaled matrix (main.cpp:1753)
     }
     long cd[3];
     ck(uspmv_coo_dims(coo, cd));
@@ -304,7 +320,8 @@ int main(int argc, char **argv) {
         ck(uspmv_scs_dims(scs, dims));
     } else {
         uspmv_coo *pc[3] = {nullptr, nullptr, nullptr};
-        ck(uspmv_partition_precisions(ctx, coo, ap_mode, cfg.ap_threshold_1, cfg.ap_threshold_2, nullptr, nullptr, &pc[0], &pc[1], &pc[2]));
+        ck(uspmv_partition_precisions(ctx, coo, ap_mode, cfg.ap_threshold_1, cfg.ap_threshold_2, cfg.equilibrate ? rowmax.data() : nullptr,
+                                      cfg.equilibrate ? colmax.data() : nullptr, &pc[0], &pc[1], &pc[2]));
         const int first = ap_mode == USPMV_AP_SP_HP ? 1 : 0;
         const int vts[3] = {USPMV_F64, USPMV_F32, USPMV_F16};
         ck(uspmv_scs_build(ctx, pc[first], cfg.chunk_size, cfg.sigma, vts[first], nullptr, &part[first]));

@@ -13,6 +13,35 @@ from __future__ import annotations
 import numpy as np
 
 
+def read_mtx_entries(path: str):
+    """Text parsing only: (n_rows, n_cols, I, J, values, symmetric) in FILE order, 0-based — the input of the device-side ingest
+    (engine.MtxData.from_entries -> uspmv_coo_from_entries), which does the symmetric expansion and the stable row sort."""
+    with open(path, "r") as f:
+        banner = f.readline().strip().split()
+        if len(banner) < 5 or banner[0] != "%%MatrixMarket":
+            raise ValueError("mm_read_unsymetric: Could not process Matrix Market banner")
+        obj, fmt, field, symm = (s.lower() for s in banner[1:5])
+        if obj != "matrix" or fmt != "coordinate":
+            raise ValueError("The matrix market file provided is not supported: matrix has to be sparse")
+        if field not in ("real", "integer", "pattern"):
+            raise ValueError("The matrix market file provided is not supported: matrix has to be real or pattern")
+        if symm not in ("general", "symmetric"):
+            raise ValueError("The matrix market file provided is not supported: matrix has to be either general or symmetric")
+        line = f.readline()
+        while line.startswith("%") or not line.strip():
+            line = f.readline()
+        M, N, nz = (int(t) for t in line.split()[:3])
+        if M != N:
+            raise ValueError("Matrix not square. Currently only square matrices are supported")
+        data = np.loadtxt(f, ndmin=2, dtype=np.float64) if nz else np.zeros((0, 3))
+    if data.shape[0] != nz:
+        raise ValueError("premature EOF in matrix market file")
+    I = np.ascontiguousarray(data[:, 0].astype(np.int32) - 1)
+    J = np.ascontiguousarray(data[:, 1].astype(np.int32) - 1)
+    V = np.full(nz, 0.01) if field == "pattern" else np.ascontiguousarray(data[:, 2].astype(np.float64))
+    return M, N, I, J, V, symm == "symmetric"
+
+
 def read_mtx(path: str):
     """Returns (n_rows, n_cols, I, J, values) with int32 indices and float64 values."""
     with open(path, "r") as f:

@@ -90,5 +90,26 @@ if "ap" in which:
         report(f"powerlaw {n} {mode} C32 s{SIG} split {frac[0]:.2f}/{frac[1]:.2f}/{frac[2]:.2f} (build {tb:.1f} s)", sec, nb, 2.0 * nnz)
         del coos, P
 
+if "cusparse" in which:
+    # second GPU baseline (the reference's cuSPARSE comparison mode, utilities.hpp:3380-3550): cusparseSpMV on the same matrix in
+    # CSR, reached through torch's sparse CSR tensor (library code, not part of the product path)
+    for vt in ("dp", "sp"):
+        mtx = eng.MtxData.stencil(7, N, N, N)
+        I, J, V = mtx.to_host()
+        n = mtx.n_rows
+        crow = np.zeros(n + 1, np.int64); np.add.at(crow, I.astype(np.int64) + 1, 1); crow = np.cumsum(crow)
+        A = torch.sparse_csr_tensor(torch.from_numpy(crow.astype(np.int32)).cuda(), torch.from_numpy(J).cuda(),
+                                    torch.from_numpy(V.astype({"dp": np.float64, "sp": np.float32}[vt])).cuda(), size=(n, n))
+        x = torch.full((n,), 5.0, dtype=TD[vt], device="cuda")
+        sec = timeit(lambda: torch.mv(A, x), 30)
+        nb = len(I) * (VS[vt] + 4) + 4 * (n + 1) + 2 * VS[vt] * n
+        report(f"cuSPARSE CSR SpMV (torch.mv) 7pt{N} {vt}", sec, nb, 2.0 * len(I))
+        scs = eng.convert_to_scs(mtx, 32, 1, vt); eng.permute_scs_cols(scs); del mtx
+        xs = torch.full((scs.n_rows_padded,), 5.0, dtype=TD[vt], device="cuda"); ys = torch.zeros_like(xs)
+        sec = timeit(lambda: eng.spmv(scs, xs, ys), 30)
+        nb = scs.n_elements * (VS[vt] + 4) + 8 * scs.n_chunks + 2 * VS[vt] * scs.n_rows_padded
+        report(f"this library SELL-32 SpMV 7pt{N} {vt}", sec, nb, 2.0 * scs.nnz)
+        del A, x, scs, xs, ys, I, J, V
+
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 json.dump(res, open(os.path.join(ROOT, "gpurun_out", "configs_" + "_".join(which) + ".json"), "w"), indent=1)

@@ -1,4 +1,5 @@
-"""Row-major SpMMV sweep: stage size / warps per CTA variants x far-row L1 bypass threshold (run under gpurun)."""
+"""Row-major SpMMV sweep over the stage size / ring depth / warps per CTA variants (run under gpurun).
+A far-row L1::no_allocate gather policy was also measured here (round 1): slower in every case, removed."""
 import importlib, json, os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
@@ -23,24 +24,11 @@ for vt, bvs in cases:
     X = torch.full((ld * bvs,), 1.0, dtype=TD[vt], device="cuda"); Y = torch.zeros_like(X)
     line = f"spmmv {vt} b{bvs} rowwise: "
     for var in (1, 2, 6, 8, 9, 10, 11, 12, 13, 14):
-        for far in (0, 1024):
-            capi.set_option("mmv_variant", var); capi.set_option("mmv_far_rows", far)
-            us = timeit(lambda: eng.spmmv(scs, X, Y, bvs, ld, "rowwise"))
-            res[f"{vt}|b{bvs}|v{var}|far{far}"] = us
-            line += f"v{var}/f{far}={us:.0f} "
-    print(line, flush=True); del X, Y
-    best = min((v, k) for k, v in res.items() if k.startswith(f"{vt}|b{bvs}|"))
-    print("   best:", best, flush=True)
-    # far threshold sweep on the best variant
-    var = int(best[1].split("|")[2][1:])
-    X = torch.full((ld * bvs,), 1.0, dtype=TD[vt], device="cuda"); Y = torch.zeros_like(X)
-    capi.set_option("mmv_variant", var)
-    line = f"   v{var} far sweep: "
-    for far in (256, 512, 768, 2048, 8192, 32768):
-        capi.set_option("mmv_far_rows", far)
+        capi.set_option("mmv_variant", var)
         us = timeit(lambda: eng.spmmv(scs, X, Y, bvs, ld, "rowwise"))
-        res[f"{vt}|b{bvs}|v{var}|far{far}"] = us
-        line += f"f{far}={us:.0f} "
+        res[f"{vt}|b{bvs}|v{var}"] = us
+        line += f"v{var}={us:.0f} "
     print(line, flush=True); del X, Y
+    print("   best:", min((v, k) for k, v in res.items() if k.startswith(f"{vt}|b{bvs}|")), flush=True)
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 json.dump(res, open(os.path.join(ROOT, "gpurun_out", "tune_mmv2.json"), "w"), indent=1)

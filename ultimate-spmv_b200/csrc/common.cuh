@@ -107,7 +107,6 @@ struct Options {
     int mmv_variant = 0;         // SpMMV streamed kernel: 0 = tuned default, 1..4 force a variant (see spmv_kernels.cu)
     int mmv_blocks_per_sm = 0;   // SpMMV streamed kernel: CTAs (8 warps) per SM, 0 = as many as fit
     int ap_variant = 0;          // fused adaptive-precision streamed kernel: ring depth / register cap instantiation
-    int mmv_far_rows = 0;        // row-major SpMMV: X rows further than this from the chunk are loaded with L1::no_allocate (0 = off)
     int split_long_chunks = 256; // C = 32, uneven matrices: chunks longer than this many slots are summed in segments (0 = never)
     bool strict_reference_halo = false;  // true: padding slots (column 0) become a halo element on ranks > 0, like the reference
 };

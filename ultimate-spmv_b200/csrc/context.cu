@@ -40,7 +40,6 @@ int uspmv_set_option(const char *name, long value) {
         else if (!std::strcmp(name, "mmv_variant")) c.mmv_variant = (int)std::max(0L, value);
         else if (!std::strcmp(name, "mmv_blocks_per_sm")) c.mmv_blocks_per_sm = (int)std::max(0L, value);
         else if (!std::strcmp(name, "ap_variant")) c.ap_variant = (int)std::max(0L, value);
-        else if (!std::strcmp(name, "mmv_far_rows")) c.mmv_far_rows = (int)std::max(0L, value);
         else if (!std::strcmp(name, "split_long_chunks")) c.split_long_chunks = (int)std::max(0L, value);
         else if (!std::strcmp(name, "strict_reference_halo")) c.strict_reference_halo = value != 0;
         else fail("uspmv_set_option: unknown option '%s'", name);

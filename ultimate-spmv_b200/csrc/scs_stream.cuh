@@ -62,13 +62,6 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
         : "memory");
 }
 
-// read-only 128-bit load that does not allocate a line in L1 (streaming gathers must not evict the reusable lines)
-__device__ __forceinline__ int4 ldg_no_allocate(const int4 *p) {
-    int4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
-    return r;
-}
-
 struct PieceHdr {
     int ns;     // slots in this piece (0 with flags != 0: empty chunk; flags == 0 && ns == 0: end of stream)
     int flags;  // bit0 first piece of the chunk, bit1 last piece, bit2 valid
@@ -181,10 +174,8 @@ struct SpmmvBody {
     VT *__restrict__ Y;
     long ld;
     int lane;
-    int far_rows = 0, row_base = 0;  // far_rows > 0: rows gathered from further than that from the chunk bypass L1 allocation
     typename A::acc_t acc[BVS];
-    __device__ __forceinline__ void begin_chunk(int chunk = 0) {
-        row_base = chunk * 32;
+    __device__ __forceinline__ void begin_chunk(int = 0) {
 #pragma unroll
         for (int v = 0; v < BVS; ++v) acc[v] = A::zero();
     }
@@ -193,9 +184,8 @@ struct SpmmvBody {
             constexpr int BYTES = BVS * (int)sizeof(VT);
             if constexpr (BYTES % 16 == 0) {
                 const int4 *p = reinterpret_cast<const int4 *>(X + col * BVS);
-                const bool far = far_rows > 0 && abs((int)col - row_base) > far_rows;
 #pragma unroll
-                for (int k = 0; k < BYTES / 16; ++k) reinterpret_cast<int4 *>(xv)[k] = far ? ldg_no_allocate(p + k) : __ldg(p + k);
+                for (int k = 0; k < BYTES / 16; ++k) reinterpret_cast<int4 *>(xv)[k] = __ldg(p + k);
             } else if constexpr (BYTES % 8 == 0) {
                 const int2 *p = reinterpret_cast<const int2 *>(X + col * BVS);
 #pragma unroll
@@ -267,10 +257,8 @@ struct SpmmvBodyRowWide {
     const VT *__restrict__ X;
     VT *__restrict__ Y;
     int lane;
-    int far_rows = 0, row_base = 0;  // see SpmmvBody
     typename A::acc_t acc[T][PER];
-    __device__ __forceinline__ void begin_chunk(int chunk = 0) {
-        row_base = chunk * 32;
+    __device__ __forceinline__ void begin_chunk(int = 0) {
 #pragma unroll
         for (int k = 0; k < T; ++k)
 #pragma unroll
@@ -291,10 +279,8 @@ struct SpmmvBodyRowWide {
                     if (j0 + u < ns) {
 #pragma unroll
                         for (int k = 0; k < T; ++k) {
-                            const int col = c0[(j0 + u) * 32 + r0 + RPI * k];
-                            const int4 *p = reinterpret_cast<const int4 *>(X + (long)col * BVS) + part;
-                            const bool far = far_rows > 0 && abs(col - row_base) > far_rows;
-                            *reinterpret_cast<int4 *>(xv[u][k]) = far ? ldg_no_allocate(p) : __ldg(p);
+                            const long col = c0[(j0 + u) * 32 + r0 + RPI * k];
+                            *reinterpret_cast<int4 *>(xv[u][k]) = __ldg(reinterpret_cast<const int4 *>(X + col * BVS) + part);
                         }
                     }
 #pragma unroll
@@ -879,7 +865,7 @@ template <typename VT, typename A, int LMAX, int D, int WARPS, int BVS, bool ROW
 __global__ void __launch_bounds__(WARPS * 32)  // ~80 registers, 24 warps/SM: capping at 64 spills and is 30-50 % slower (measured)
 k_scs32_stream_mmv(long n_items, const int *__restrict__ chunk_list, int chunk_offset, const int *__restrict__ chunk_ptrs,
                    const int *__restrict__ chunk_lengths, const int *__restrict__ col_idxs, const VT *__restrict__ values,
-                   const VT *__restrict__ X, VT *__restrict__ Y, long ld, int far_rows) {
+                   const VT *__restrict__ X, VT *__restrict__ Y, long ld) {
     using R = WarpRing<VT, LMAX, D>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -899,12 +885,12 @@ k_scs32_stream_mmv(long n_items, const int *__restrict__ chunk_list, int chunk_o
     constexpr int ROW_BYTES = BVS * (int)sizeof(VT);
     if constexpr (WIDE && ROWWISE && ROW_BYTES >= 32 && ROW_BYTES <= 128 && (ROW_BYTES & (ROW_BYTES - 1)) == 0) {
         SpmmvBodyRowWide<VT, A, LMAX, BVS> body;
-        body.X = X; body.Y = Y; body.lane = lane; body.far_rows = far_rows;
+        body.X = X; body.Y = Y; body.lane = lane;
         stream_items<VT, LMAX, D>(base, bars, hdrs, phase_bits, (int)W, (int)gw, lane, (int)n_items, chunk_list, chunk_offset, chunk_ptrs,
                                   chunk_lengths, col_idxs, values, body, pol);
     } else {
         SpmmvBody<VT, A, LMAX, BVS, ROWWISE> body;
-        body.X = X; body.Y = Y; body.ld = ld; body.lane = lane; body.far_rows = far_rows;
+        body.X = X; body.Y = Y; body.ld = ld; body.lane = lane;
         stream_items<VT, LMAX, D>(base, bars, hdrs, phase_bits, (int)W, (int)gw, lane, (int)n_items, chunk_list, chunk_offset, chunk_ptrs,
                                   chunk_lengths, col_idxs, values, body, pol);
     }

@@ -510,8 +510,7 @@ void launch_spmmv_stream_v(const uspmv_scs *s, const VT *X, VT *Y, long ld, cuda
     if (grid > need) grid = need;
     if (grid < 1) return;
     kern<<<(unsigned)grid, WARPS * 32, smem, st>>>(sel.n, sel.list, sel.off, s->chunk_ptrs.p, s->chunk_lengths.p, s->col_idxs.p,
-                                                  reinterpret_cast<const VT *>(s->values.p), X, Y, ld,
-                                                  ROWWISE ? options().mmv_far_rows : 0);
+                                                  reinterpret_cast<const VT *>(s->values.p), X, Y, ld);
 }
 
 // variant: 0 = tuned default per (precision, bvs, layout); 1..4 force (wide body?, slots per stage)

@@ -199,7 +199,31 @@ struct SpmmvBody {
             for (int v = 0; v < BVS; ++v) xv[v] = __ldg(X + col + v * ld);
         }
     }
-    __device__ __forceinline__ void piece(const int ns, const VT *sv, const int *sc) {
+    // The slot count is a template constant: with a run-time count every gather became a predicated load into a scratch register
+    // followed by a predicated move (ncu r01e: 40 % of the stall samples sat on those moves), which serialises the loads.
+    template <int NS>
+    __device__ __forceinline__ void piece_n(const VT *sv, const int *sc) {
+#pragma unroll
+        for (int j0 = 0; j0 < NS; j0 += SB) {
+            alignas(16) VT xv[SB][BVS];
+            VT v[SB];
+#pragma unroll
+            for (int u = 0; u < SB; ++u)
+                if (j0 + u < NS) load_row((long)sc[(j0 + u) * 32], xv[u]);
+#pragma unroll
+            for (int u = 0; u < SB; ++u)
+                if (j0 + u < NS) v[u] = sv[(j0 + u) * 32];
+#pragma unroll
+            for (int u = 0; u < SB; ++u)
+                if (j0 + u < NS) {
+#pragma unroll
+                    for (int w = 0; w < BVS; ++w) acc[w] = A::mad(v[u], xv[u][w], acc[w]);
+                }
+        }
+    }
+    // run-time slot count: kept for column-major block vectors (scalar gathers per vector; the templated form raised the register
+    // count there and was 35-75 % slower, measured)
+    __device__ __forceinline__ void piece_rt(const int ns, const VT *sv, const int *sc) {
 #pragma unroll
         for (int j0 = 0; j0 < LMAX; j0 += SB) {
             if (j0 < ns) {
@@ -218,6 +242,23 @@ struct SpmmvBody {
                         for (int w = 0; w < BVS; ++w) acc[w] = A::mad(v[u], xv[u][w], acc[w]);
                     }
             }
+        }
+    }
+    __device__ __forceinline__ void piece(const int ns, const VT *sv, const int *sc) {
+        static_assert(LMAX <= 8, "piece() dispatches on up to 8 slots");
+        if constexpr (!ROWWISE) {
+            piece_rt(ns, sv, sc);
+            return;
+        }
+        switch (ns) {
+        case 1: piece_n<1>(sv, sc); break;
+        case 2: piece_n<(LMAX >= 2 ? 2 : 1)>(sv, sc); break;
+        case 3: piece_n<(LMAX >= 3 ? 3 : 1)>(sv, sc); break;
+        case 4: piece_n<(LMAX >= 4 ? 4 : 1)>(sv, sc); break;
+        case 5: piece_n<(LMAX >= 5 ? 5 : 1)>(sv, sc); break;
+        case 6: piece_n<(LMAX >= 6 ? 6 : 1)>(sv, sc); break;
+        case 7: piece_n<(LMAX >= 7 ? 7 : 1)>(sv, sc); break;
+        default: piece_n<LMAX>(sv, sc); break;
         }
     }
     __device__ __forceinline__ void end_chunk(const int chunk) {
@@ -265,39 +306,51 @@ struct SpmmvBodyRowWide {
             for (int m = 0; m < PER; ++m) acc[k][m] = A::zero();
     }
     // sv / sc arrive offset by `lane`; rebase to the chunk's lane 0
+    template <int NS>  // slot count as a template constant, see SpmmvBody::piece_n
+    __device__ __forceinline__ void piece_n(const VT *v0, const int *c0, const int r0, const int part) {
+#pragma unroll
+        for (int j0 = 0; j0 < NS; j0 += SB) {
+            alignas(16) VT xv[SB][T][PER];
+            VT v[SB][T];
+#pragma unroll
+            for (int u = 0; u < SB; ++u)
+                if (j0 + u < NS) {
+#pragma unroll
+                    for (int k = 0; k < T; ++k) {
+                        const long col = c0[(j0 + u) * 32 + r0 + RPI * k];
+                        *reinterpret_cast<int4 *>(xv[u][k]) = __ldg(reinterpret_cast<const int4 *>(X + col * BVS) + part);
+                    }
+                }
+#pragma unroll
+            for (int u = 0; u < SB; ++u)
+                if (j0 + u < NS) {
+#pragma unroll
+                    for (int k = 0; k < T; ++k) v[u][k] = v0[(j0 + u) * 32 + r0 + RPI * k];
+                }
+#pragma unroll
+            for (int u = 0; u < SB; ++u)
+                if (j0 + u < NS) {
+#pragma unroll
+                    for (int k = 0; k < T; ++k)
+#pragma unroll
+                        for (int m = 0; m < PER; ++m) acc[k][m] = A::mad(v[u][k], xv[u][k][m], acc[k][m]);
+                }
+        }
+    }
     __device__ __forceinline__ void piece(const int ns, const VT *sv, const int *sc) {
+        static_assert(LMAX <= 8, "piece() dispatches on up to 8 slots");
         const VT *v0 = sv - lane;
         const int *c0 = sc - lane;
         const int r0 = lane / T, part = lane % T;
-#pragma unroll
-        for (int j0 = 0; j0 < LMAX; j0 += SB) {
-            if (j0 < ns) {
-                alignas(16) VT xv[SB][T][PER];
-                VT v[SB][T];
-#pragma unroll
-                for (int u = 0; u < SB; ++u)
-                    if (j0 + u < ns) {
-#pragma unroll
-                        for (int k = 0; k < T; ++k) {
-                            const long col = c0[(j0 + u) * 32 + r0 + RPI * k];
-                            *reinterpret_cast<int4 *>(xv[u][k]) = __ldg(reinterpret_cast<const int4 *>(X + col * BVS) + part);
-                        }
-                    }
-#pragma unroll
-                for (int u = 0; u < SB; ++u)
-                    if (j0 + u < ns) {
-#pragma unroll
-                        for (int k = 0; k < T; ++k) v[u][k] = v0[(j0 + u) * 32 + r0 + RPI * k];
-                    }
-#pragma unroll
-                for (int u = 0; u < SB; ++u)
-                    if (j0 + u < ns) {
-#pragma unroll
-                        for (int k = 0; k < T; ++k)
-#pragma unroll
-                            for (int m = 0; m < PER; ++m) acc[k][m] = A::mad(v[u][k], xv[u][k][m], acc[k][m]);
-                    }
-            }
+        switch (ns) {
+        case 1: piece_n<1>(v0, c0, r0, part); break;
+        case 2: piece_n<(LMAX >= 2 ? 2 : 1)>(v0, c0, r0, part); break;
+        case 3: piece_n<(LMAX >= 3 ? 3 : 1)>(v0, c0, r0, part); break;
+        case 4: piece_n<(LMAX >= 4 ? 4 : 1)>(v0, c0, r0, part); break;
+        case 5: piece_n<(LMAX >= 5 ? 5 : 1)>(v0, c0, r0, part); break;
+        case 6: piece_n<(LMAX >= 6 ? 6 : 1)>(v0, c0, r0, part); break;
+        case 7: piece_n<(LMAX >= 7 ? 7 : 1)>(v0, c0, r0, part); break;
+        default: piece_n<LMAX>(v0, c0, r0, part); break;
         }
     }
     __device__ __forceinline__ void end_chunk(const int chunk) {

@@ -259,14 +259,14 @@ __global__ void k_flag_boundary_chunks(long n_chunks, int C, int n_local, const 
     if (lane == 0) flag[w] = hit;
 }
 
-// measured best SpMMV variant (scripts/tune_mmv.py on B200, 256^3 7-pt): 1 = lane per row / 8 warps, 2 = T lanes per row ("wide") /
-// 8 warps, 6 = wide / 24 warps per CTA, 8 = lane per row / 24 warps per CTA
+// measured best SpMMV variant (scripts/tune_mmv2.py on B200, 256^3 7-pt, profiles/r01m_tune_spmmv_variants.json): 1 = lane per row /
+// 8 warps, 2 = T lanes per row ("wide") / 8 warps, 6 = wide / 24 warps per CTA
 inline int mmv_default_variant(size_t vsize, int bvs, bool rowwise) {
     if (!rowwise) return 1;
     const long row_bytes = (long)vsize * bvs;
-    if (row_bytes >= 64) return 6;
-    if (row_bytes == 32) return vsize == 8 ? 8 : 2;
-    return 1;
+    if (row_bytes < 32) return 1;                  // one 128-bit load per row: nothing to widen
+    if (row_bytes == 64 && vsize == 8) return 6;   // dp bvs 8: 579 vs 593 us
+    return 2;
 }
 
 // ---- launch helpers ----------------------------------------------------------------------------

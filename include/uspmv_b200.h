@@ -173,6 +173,9 @@ int uspmv_seg_work_sharing_arr(int seg_method, long n_rows, long nnz, const int 
  * columns to local/halo numbering (first-seen order, grouped by owner) and records the need lists. */
 int uspmv_halo_plan_create(uspmv_scs *scs, const int *wsa_h, int rank, int P, uspmv_halo **out);
 /* recv_counts_cumsum (P+1 ints) and the per-owner need lists, flattened; need_ptr has P+1 entries. */
+/* the same over the dp / sp / hp parts of an adaptive-precision matrix (one shared numbering of the remote columns);
+ * x_permuted = 0: x stays in the original row order, as the AP kernels expect (main.cpp:1308-1332) */
+int uspmv_halo_plan_create_multi(uspmv_scs **parts, int n_parts, const int *wsa_h, int rank, int P, int x_permuted, uspmv_halo **out);
 int uspmv_halo_plan_counts(const uspmv_halo *plan, int *recv_counts_cumsum_h, long *n_halo);
 int uspmv_halo_plan_need(const uspmv_halo *plan, int *need_flat_h, int *need_ptr_h);
 /* collect_comm_idxs (mpi_funcs.hpp:117-172): install what every peer needs from this rank
@@ -207,6 +210,11 @@ int uspmv_p2p_spmv(uspmv_p2p *p2p, const uspmv_scs *scs, void *y_d, void *stream
 /* mode 2 (default, C = 32): ONE fused kernel per SpMV — push to the peers, interior chunks, wait for the own halo, boundary
  * chunks, acknowledge; mode 1: separate push/wait kernels on comm_stream next to the interior kernel; mode 0: exchange,
  * then one full SpMV (the reference's begin -> finish -> execute order, main.cpp:464-468) */
+/* distributed adaptive-precision SpMV: halo push + wait, one fused pass over the parts, acknowledge (x = the arena's buffer 0,
+ * original row order; plan from uspmv_halo_plan_create_multi).  New behaviour: the reference refuses AP with MPI
+ * (utilities.hpp:1445-1451); BASELINE config 4 defines it as seg_nnz partitioning + per-rank partition_precisions. */
+int uspmv_p2p_ap_spmv(uspmv_p2p *p2p, int ap_mode, const uspmv_scs *dp, const uspmv_scs *sp, const uspmv_scs *hp, void *y_d,
+                      void *stream, void *comm_stream);
 int uspmv_p2p_set_overlap(uspmv_p2p *p2p, int overlap);
 /* Generalised arena: n_buf (1 or 2) buffers, each holding block_vec_size vectors of vec_length elements in `layout`.
  * x_d receives the n_buf buffer addresses.  peer_vec_length[q] (connect) is q's vec_length, needed for column-major block

@@ -76,3 +76,23 @@ def test_two_rank_gloo_halo_exchange(tmp_path, method, C, sigma):
     np.add.at(scale, I, np.abs(V * x_glob[J]))
     assert len(y) == n
     assert np.all(np.abs(y - y_coo) <= 1e-12 * np.maximum(scale, 1e-300))
+
+
+def test_seg_nnz_from_row_counts_matches_the_oracle():
+    """dist.seg_nnz_from_row_counts (used when no rank holds the whole COO) == seg_work_sharing_arr on the row array."""
+    sys.path.insert(0, ROOT)
+    pkg = importlib.import_module("ultimate-spmv_b200")
+    from oracle.bindings import Oracle
+    orc = Oracle()
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        n = int(rng.integers(5, 400))
+        P = int(rng.integers(1, min(n, 9)))
+        cnt = rng.integers(0, 9, n)
+        cnt[rng.integers(0, n)] += int(rng.integers(1, 50))
+        I = np.repeat(np.arange(n), cnt).astype(np.int32)
+        assert np.array_equal(pkg.dist.seg_nnz_from_row_counts(cnt, P), orc.seg_work_sharing_arr("seg-nnz", n, I, P)), (n, P)
+    # the reference's own probe (SURVEY.md section 8 a'-11): bcsstk13, P = 4 -> 0 724 1183 1600 2003
+    z = np.load(os.path.join(ROOT, "tests", "golden", "matrices.npz"))
+    cnt = np.bincount(z["bcsstk13__I"], minlength=int(z["bcsstk13__n"]))
+    assert pkg.dist.seg_nnz_from_row_counts(cnt, 4).tolist() == [0, 724, 1183, 1600, 2003]

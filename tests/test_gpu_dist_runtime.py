@@ -143,3 +143,89 @@ def test_two_ranks_over_nvlink(eng, mats, tmp_path, C):
     port = 29900 + os.getpid() % 100 + C
     mp.spawn(_run_rank, args=(2, port, str(tmp_path), C), nprocs=2, join=True)
     _check(str(tmp_path), 2, mats)
+
+
+# ---- adaptive precision, row-partitioned with seg-nnz (BASELINE config 4) --------------------------------------------------------
+def _ap_matrix(n=6000, seed=5):
+    rng = np.random.default_rng(seed)
+    cnt = rng.integers(1, 12, n)
+    cnt[rng.choice(n, 12, replace=False)] = rng.integers(200, 700, 12)       # a few long rows: uneven nnz per rank
+    I = np.repeat(np.arange(n), cnt).astype(np.int32)
+    J = rng.integers(0, n, len(I)).astype(np.int32)
+    V = np.sign(rng.standard_normal(len(I))) * 10.0 ** rng.uniform(-3, 1, len(I))
+    return n, I, J, V, cnt
+
+
+def _run_ap_rank(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        pkg = importlib.import_module("ultimate-spmv_b200")
+        eng, d = pkg.engine, pkg.dist
+        n, I, J, V, cnt = _ap_matrix()
+        wsa = d.seg_nnz_from_row_counts(cnt, world)
+        sel = (I >= wsa[rank]) & (I < wsa[rank + 1])
+        n_loc = int(wsa[rank + 1] - wsa[rank])
+        x_glob = np.sin(np.arange(n) * 0.37) + 1.5
+        for mode in ("ap[dp_sp_hp]", "ap[dp_sp]", "ap[sp_hp]"):
+            r = d.DistributedApSpmv(eng.default_context(rank), wsa, (n_loc, n, (I[sel] - wsa[rank]).astype(np.int32), J[sel], V[sel]), mode, 0.5, 0.01,
+                                    32, 64, rank, world)
+            r.x.zero_()
+            r.x[:n_loc] = torch.from_numpy(x_glob[wsa[rank]:wsa[rank + 1]]).to(r.x.dtype).cuda()   # original local row order
+            torch.cuda.synchronize()
+            dist.barrier()
+            for _ in range(3):
+                r.y.zero_()
+                r.step()
+            torch.cuda.synchronize()
+            err, ep = r.p2p.status()
+            assert err == 0 and ep == 3
+            y = r.y.cpu().numpy()[r.old_to_new]
+            np.save(os.path.join(out_dir, f"ap{rank}_{mode}.npy"), y.astype(np.float64))
+            del r
+        np.save(os.path.join(out_dir, f"apwsa{rank}.npy"), wsa)
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def _check_ap(out_dir, world):
+    n, I, J, V, cnt = _ap_matrix()
+    x = np.sin(np.arange(n) * 0.37) + 1.5
+    a = np.abs(V)
+    for mode in ("ap[dp_sp_hp]", "ap[dp_sp]", "ap[sp_hp]"):
+        # values as stored by partition_precisions (interface.hpp:938-964): dp / sp / hp by abs(v) against t1 = 0.5, t2 = 0.01
+        if mode == "ap[dp_sp_hp]":
+            Vs = np.where(a >= 0.5, V, np.where(a >= 0.01, V.astype(np.float32).astype(np.float64), V.astype(np.float16).astype(np.float64)))
+            xs, tol = x, 1e-12
+        elif mode == "ap[dp_sp]":
+            Vs = np.where(a >= 0.5, V, V.astype(np.float32).astype(np.float64))
+            xs, tol = x, 1e-12
+        else:
+            Vs = np.where(a >= 0.5, V.astype(np.float32).astype(np.float64), V.astype(np.float16).astype(np.float64))
+            xs, tol = x.astype(np.float32).astype(np.float64), 1e-5
+        y = np.concatenate([np.load(os.path.join(out_dir, f"ap{r}_{mode}.npy")) for r in range(world)])
+        ref = np.zeros(n)
+        np.add.at(ref, I, Vs * xs[J])
+        sc = np.zeros(n)
+        np.add.at(sc, I, np.abs(Vs * xs[J]))
+        assert len(y) == n and np.all(np.abs(y - ref) <= tol * sc), mode
+    wsa = np.load(os.path.join(out_dir, "apwsa0.npy"))
+    assert wsa[0] == 0 and wsa[-1] == n and np.all(np.diff(wsa) > 0)
+
+
+def test_ap_world_size_1(eng, tmp_path):
+    _run_ap_rank(0, 1, 29300 + os.getpid() % 200, str(tmp_path))
+    _check_ap(str(tmp_path), 1)
+
+
+def test_ap_two_ranks_seg_nnz(eng, tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    mp.spawn(_run_ap_rank, args=(2, 29350 + os.getpid() % 100, str(tmp_path)), nprocs=2, join=True)
+    _check_ap(str(tmp_path), 2)

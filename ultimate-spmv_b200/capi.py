@@ -69,6 +69,8 @@ _sigs = {
     "uspmv_ap_spmv": [C.c_int, vp, vp, vp, vp, vp, vp],
     "uspmv_seg_work_sharing_arr": [C.c_int, C.c_long, C.c_long, vp, C.c_int, vp],
     "uspmv_halo_plan_create": [vp, vp, C.c_int, C.c_int, C.POINTER(vp)],
+    "uspmv_halo_plan_create_multi": [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.POINTER(vp)],
+    "uspmv_p2p_ap_spmv": [vp, C.c_int, vp, vp, vp, vp, vp, vp],
     "uspmv_halo_plan_counts": [vp, vp, C.POINTER(C.c_long)],
     "uspmv_halo_plan_need": [vp, vp, vp],
     "uspmv_halo_plan_set_send": [vp, vp, vp],

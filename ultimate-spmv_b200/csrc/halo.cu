@@ -51,7 +51,7 @@ __global__ void k_fill_int(int *p, long n, int v) {
 // one thread per (permuted) row position: slot j of the row is padding iff j >= row_lengths[p]
 __global__ void k_mark_remote(const int *__restrict__ chunk_ptrs, const int *__restrict__ chunk_lengths, const int *__restrict__ row_lengths,
                               const int *__restrict__ col_idxs, long n_pad, int C, int lo, int hi, int n_glob, bool strict,
-                              int *__restrict__ first) {
+                              int slot_base, int *__restrict__ first) {
     long p = blockIdx.x * (long)blockDim.x + threadIdx.x;
     if (p >= n_pad) return;
     const long c = p / C;
@@ -62,7 +62,7 @@ __global__ void k_mark_remote(const int *__restrict__ chunk_ptrs, const int *__r
         const int col = col_idxs[e];
         if (col >= lo && col < hi) continue;
         if (col < 0 || col >= n_glob) continue;  // no owner: the reference leaves such a column untouched
-        atomicMin(&first[col], (int)e);
+        atomicMin(&first[col], slot_base + (int)e);  // slot_base: storage order continues over the parts of an AP matrix
     }
 }
 
@@ -119,7 +119,7 @@ __global__ void k_pack(const int *__restrict__ send_idx, const int *__restrict__
     long i, v;
     if (layout == USPMV_ROWWISE) { i = t / bvs; v = t % bvs; }
     else { v = t / n_send; i = t % n_send; }
-    const long src = perm[send_idx[i]];
+    const long src = perm ? perm[send_idx[i]] : send_idx[i];
     // buffer layout: rowwise -> [i][v]; colwise -> [v][i] (one contiguous run per vector, like bulkvec messages)
     if (layout == USPMV_ROWWISE) buf[i * bvs + v] = x[src * bvs + v];
     else buf[v * n_send + i] = x[src + v * ld];
@@ -162,22 +162,34 @@ int uspmv_seg_work_sharing_arr(int seg_method, long n_rows, long nnz, const int 
     });
 }
 
-int uspmv_halo_plan_create(uspmv_scs *s, const int *wsa_h, int rank, int P, uspmv_halo **out) {
+/* Halo discovery over n_parts matrices that share the rows of one rank (the dp / sp / hp parts of an adaptive-precision matrix; one
+ * part = collect_local_needed_heri, mpi_funcs.hpp:242-415): ONE numbering of the remote columns for all parts, first-seen order of a
+ * scan that walks part 0's storage, then part 1's, ...  x_permuted = 0: the x vector stays in the original row order (AP structs keep
+ * the original column numbering, main.cpp:1308-1332), so the elements sent to the neighbours are x[send_idx], not x[perm[send_idx]]. */
+int uspmv_halo_plan_create_multi(uspmv_scs **parts, int n_parts, const int *wsa_h, int rank, int P, int x_permuted, uspmv_halo **out) {
     return guarded([&] {
-        if (!s || !wsa_h || !out) fail("uspmv_halo_plan_create: NULL argument");
+        if (!parts || !wsa_h || !out || n_parts < 1 || n_parts > 3) fail("uspmv_halo_plan_create: NULL argument or bad part count");
         if (P < 1 || rank < 0 || rank >= P) fail("uspmv_halo_plan_create: bad rank/comm_size");
-        if (s->cols_permuted) fail("uspmv_halo_plan_create: call before permute_scs_cols (main.cpp:1271-1308 order)");
-        USPMV_CUDA(cudaSetDevice(s->ctx->device));
+        uspmv_scs *s0 = parts[0];
+        long slots_total = 0;
+        for (int q = 0; q < n_parts; ++q) {
+            if (!parts[q]) fail("uspmv_halo_plan_create: part %d is NULL", q);
+            if (parts[q]->cols_permuted) fail("uspmv_halo_plan_create: call before permute_scs_cols (main.cpp:1271-1308 order)");
+            if (parts[q]->n_rows != s0->n_rows || parts[q]->C != s0->C || parts[q]->n_rows_padded != s0->n_rows_padded)
+                fail("uspmv_halo_plan_create: the parts do not share n_rows / C");
+            slots_total += parts[q]->n_elements;
+        }
+        if (slots_total > INT32_MAX - 1024) fail("uspmv_halo_plan_create: more than 2^31 stored elements on one rank");
+        USPMV_CUDA(cudaSetDevice(s0->ctx->device));
         const int lo = wsa_h[rank], hi = wsa_h[rank + 1], n_glob = wsa_h[P];
         const long n_local = hi - lo;
-        if (n_local != s->n_rows) fail("uspmv_halo_plan_create: work_sharing_arr gives %ld local rows but the matrix has %ld", n_local, s->n_rows);
+        if (n_local != s0->n_rows) fail("uspmv_halo_plan_create: work_sharing_arr gives %ld local rows but the matrix has %ld", n_local, s0->n_rows);
         auto h = new uspmv_halo();
         try {
-            h->ctx = s->ctx; h->rank = rank; h->P = P; h->n_local = n_local;
+            h->ctx = s0->ctx; h->rank = rank; h->P = P; h->n_local = n_local;
             h->recv_cumsum.assign(P + 1, 0);
             h->send_ptr.assign(P + 1, 0);
-            h->perm_d = s->old_to_new.p;
-            const long ne = s->n_elements;
+            h->perm_d = x_permuted ? s0->old_to_new.p : nullptr;
             DevBuf<int> wsa_d(P + 1), first(n_glob > 0 ? n_glob : 1), flag(n_glob + 1), pos(n_glob + 1);
             USPMV_CUDA(cudaMemcpy(wsa_d.p, wsa_h, (P + 1) * sizeof(int), cudaMemcpyHostToDevice));
             if (n_glob) {
@@ -185,11 +197,16 @@ int uspmv_halo_plan_create(uspmv_scs *s, const int *wsa_h, int rank, int P, uspm
                 USPMV_LAUNCH_CHECK();
             }
             const bool strict = options().strict_reference_halo;
-            const long n_pad = s->n_rows_padded;
-            if (ne) {
-                k_mark_remote<<<blocks_for(n_pad), TPB>>>(s->chunk_ptrs.p, s->chunk_lengths.p, s->row_lengths.p, s->col_idxs.p, n_pad, (int)s->C, lo,
-                                                         hi, n_glob, strict, first.p);
-                USPMV_LAUNCH_CHECK();
+            const long n_pad = s0->n_rows_padded;
+            long slot_base = 0;
+            for (int q = 0; q < n_parts; ++q) {
+                uspmv_scs *s = parts[q];
+                if (s->n_elements) {
+                    k_mark_remote<<<blocks_for(n_pad), TPB>>>(s->chunk_ptrs.p, s->chunk_lengths.p, s->row_lengths.p, s->col_idxs.p, n_pad, (int)s->C,
+                                                             lo, hi, n_glob, strict, (int)slot_base, first.p);
+                    USPMV_LAUNCH_CHECK();
+                }
+                slot_base += s->n_elements;
             }
             long n_halo = 0;
             if (n_glob) {
@@ -226,7 +243,9 @@ int uspmv_halo_plan_create(uspmv_scs *s, const int *wsa_h, int rank, int P, uspm
                 for (long k = 0; k < n_halo; ++k) h->recv_cumsum[owner_h[k] + 1]++;
                 for (int p = 0; p < P; ++p) h->recv_cumsum[p + 1] += h->recv_cumsum[p];
             }
-            if (ne) {
+            for (int q = 0; q < n_parts; ++q) {
+                uspmv_scs *s = parts[q];
+                if (!s->n_elements) continue;
                 k_rewrite_cols<<<blocks_for(n_pad), TPB>>>(s->chunk_ptrs.p, s->chunk_lengths.p, s->row_lengths.p, s->col_idxs.p, n_pad, (int)s->C,
                                                           lo, hi, n_glob, strict, first.p);
                 USPMV_LAUNCH_CHECK();
@@ -235,6 +254,14 @@ int uspmv_halo_plan_create(uspmv_scs *s, const int *wsa_h, int rank, int P, uspm
         } catch (...) { delete h; throw; }
         *out = h;
     });
+}
+
+int uspmv_halo_plan_create(uspmv_scs *s, const int *wsa_h, int rank, int P, uspmv_halo **out) {
+    if (!s) {
+        set_error("uspmv_halo_plan_create: NULL argument");
+        return 1;
+    }
+    return uspmv_halo_plan_create_multi(&s, 1, wsa_h, rank, P, 1, out);
 }
 
 int uspmv_halo_plan_counts(const uspmv_halo *h, int *recv_counts_cumsum_h, long *n_halo) {
@@ -381,7 +408,7 @@ k_p2p_push(int P, int my_rank, const int *__restrict__ send_ptr, const int *__re
         else { v = t / n_send; i = t - v * n_send; }
         int q = 0;
         while (i >= send_ptr[q + 1]) ++q;
-        const long src = perm[send_idx[i]];
+        const long src = perm ? perm[send_idx[i]] : send_idx[i];  // AP: x stays in the original row order
         const long k = peer_base[q] + (i - send_ptr[q]);
         VT *dst = reinterpret_cast<VT *>(peer_x0[q]);
         if (layout == USPMV_ROWWISE) dst[k * bvs + v] = x[src * bvs + v];
@@ -561,6 +588,7 @@ int uspmv_p2p_spmv_buf(uspmv_p2p *p, const uspmv_scs *scs, int x_buf, int y_buf,
         if (!p->connected) fail("uspmv_p2p_spmv: call uspmv_p2p_connect first");
         if (!scs->chunks_split) fail("uspmv_p2p_spmv: call uspmv_scs_split_chunks first");
         if (p->bvs != 1) fail("uspmv_p2p_spmv: the arena was created for block vectors; use uspmv_p2p_spmmv");
+        if (!p->plan->perm_d) fail("uspmv_p2p_spmv: the halo plan was built for an un-permuted x (adaptive precision); use uspmv_p2p_ap_spmv");
         if (x_buf < 0 || x_buf >= p->n_buf) fail("uspmv_p2p_spmv: x buffer %d out of range", x_buf);
         const bool to_buf = y_d == nullptr;
         if (to_buf && (y_buf < 0 || y_buf >= p->n_buf || y_buf == x_buf)) fail("uspmv_p2p_spmv: y needs a device pointer or another buffer of the arena");
@@ -645,6 +673,34 @@ int uspmv_p2p_spmmv(uspmv_p2p *p, const uspmv_scs *scs, int x_buf, void *Y_d, vo
         USPMV_CUDA(cudaEventRecord(p->ev_comm, comm));
         USPMV_CUDA(cudaStreamWaitEvent(main, p->ev_comm, 0));
         if (uspmv_spmmv_part(scs, overlap ? 2 : 0, X, Y_d, p->bvs, p->vec_length, p->layout, stream)) throw Error(uspmv_last_error());
+        k_p2p_ack<<<1, 256, 0, main>>>(P, p->is_sender_d.p, p->peer_acked.p, p->epoch);
+        USPMV_LAUNCH_CHECK();
+    });
+}
+
+/* One distributed adaptive-precision SpMV (BASELINE config 4 with seg_nnz partitioning; the reference has no AP + MPI path,
+ * utilities.hpp:1445-1451): push the halo of x (original row order) to the neighbours, wait for the own halo, one fused pass over
+ * the dp / sp / hp parts, acknowledge.  The plan must come from uspmv_halo_plan_create_multi over the same parts. */
+int uspmv_p2p_ap_spmv(uspmv_p2p *p, int ap_mode, const uspmv_scs *dp, const uspmv_scs *sp, const uspmv_scs *hp, void *y_d, void *stream,
+                      void *comm_stream) {
+    return guarded([&] {
+        if (!p || !y_d) fail("uspmv_p2p_ap_spmv: NULL argument");
+        if (!p->connected) fail("uspmv_p2p_ap_spmv: call uspmv_p2p_connect first");
+        if (p->bvs != 1) fail("uspmv_p2p_ap_spmv: the arena was created for block vectors");
+        if (p->plan->perm_d) fail("uspmv_p2p_ap_spmv: the halo plan was built for a permuted x (use uspmv_halo_plan_create_multi with x_permuted = 0)");
+        if (p->vt != (ap_mode == USPMV_AP_SP_HP ? USPMV_F32 : USPMV_F64)) fail("uspmv_p2p_ap_spmv: arena value type does not match the AP mode's x");
+        uspmv_halo *h = p->plan;
+        cudaStream_t main = as_stream(stream), comm = as_stream(comm_stream);
+        const int P = h->P;
+        const void *x = p->buffer(0);
+        USPMV_CUDA(cudaEventRecord(p->ev_main, main));
+        USPMV_CUDA(cudaStreamWaitEvent(comm, p->ev_main, 0));
+        launch_push(p, x, 0, comm);
+        k_p2p_wait<<<1, 256, 0, comm>>>(P, p->is_sender_d.p, p->arrived, p->epoch, p->error);
+        USPMV_LAUNCH_CHECK();
+        USPMV_CUDA(cudaEventRecord(p->ev_comm, comm));
+        USPMV_CUDA(cudaStreamWaitEvent(main, p->ev_comm, 0));
+        if (uspmv_ap_spmv(ap_mode, dp, sp, hp, x, y_d, stream)) throw Error(uspmv_last_error());
         k_p2p_ack<<<1, 256, 0, main>>>(P, p->is_sender_d.p, p->peer_acked.p, p->epoch);
         USPMV_LAUNCH_CHECK();
     });

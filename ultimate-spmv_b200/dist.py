@@ -27,6 +27,35 @@ def seg_rows_equal(n_rows_total: int, world: int) -> np.ndarray:
     return wsa.astype(np.int32)
 
 
+def seg_nnz_from_row_counts(counts, world: int) -> np.ndarray:
+    """seg-nnz work_sharing_arr (mpi_funcs.hpp:466-493,602-606) from the per-row element counts of a row-sorted COO instead of
+    its row array — the same walk (count nnz // world elements, close the segment after the row holding the NEXT element, restart
+    counting after that element), done on row boundaries so that no rank needs the whole COO."""
+    counts = np.asarray(counts, np.int64)
+    n_rows, nnz = len(counts), int(counts.sum())
+    if n_rows < world:
+        raise ValueError("seg_work_sharing_arr ERROR: total_mtx->n_rows < comm_size.")
+    ptr = np.concatenate(([0], np.cumsum(counts)))
+    last_row = int(np.max(np.nonzero(counts)[0]))
+    per = nnz // world
+    wsa = np.zeros(world + 1, np.int64)
+    g, seg = 0, 1
+    while True:
+        g += per              # element index at which local == per
+        if g >= nnz:
+            break
+        if seg <= world:
+            wsa[seg] = int(np.searchsorted(ptr, g, side="right") - 1) + 1  # row of element g, + 1
+        seg += 1
+        g += 1                # that element is skipped by the `continue`
+    wsa[world] = last_row + 1
+    if wsa[world - 1] == wsa[world]:
+        wsa[1:world] -= 1
+    if np.any(np.diff(wsa) < 0):
+        raise ValueError("seg_work_sharing_arr ERROR: flaw in work_sharing_arr, work_sharing_arr[i] < work_sharing_arr[i-1].")
+    return wsa.astype(np.int32)
+
+
 def comm_schedule(need_lists, rank: int, world: int, group=None):
     """collect_comm_idxs (mpi_funcs.hpp:117-172): every rank tells every owner which owner-local x indices it needs.
     need_lists[p] = indices this rank needs from owner p.  Returns send_lists[q] = indices rank q needs from us."""
@@ -308,3 +337,90 @@ class DistributedSpmv:
             one()
         barrier()
         return (time.perf_counter() - t0) / steps
+
+
+class DistributedApSpmv:
+    """Row-partitioned adaptive-precision SpMV (BASELINE.json config 4: ap[...] with seg_nnz partitioning).  The reference refuses
+    AP under MPI (utilities.hpp:1445-1451); defined here as: contiguous row blocks from work_sharing_arr, per-rank
+    partition_precisions, the first part sigma-sorted and the others built on its permutation, ONE halo numbering over all parts
+    (uspmv_halo_plan_create_multi), x in the original local row order with the halo at its tail, y in the first part's row order.
+
+    local_coo = (n_local, n_global_cols, I_local, J_global, V) of this rank's rows [wsa[rank], wsa[rank+1])."""
+
+    kernel_name = "k_scs32_stream_ap"
+
+    def __init__(self, ctx, wsa, local_coo, mode, t1, t2, C_, sigma, rank, world, group=None):
+        import torch
+        import torch.distributed as dist
+        from . import engine as eng
+        self.ctx, self.rank, self.world, self.mode = ctx, rank, world, mode
+        n_loc, n_glob, I, J, V = local_coo
+        mtx = eng.MtxData.from_host(n_loc, n_glob, I, J, V, ctx=ctx)
+        self.nnz = mtx.nnz
+        coos = eng.partition_precisions(mtx, mode, t1, t2)
+        del mtx
+        self.used = [k for k in range(3) if coos[k] is not None]
+        vts = ("dp", "sp", "hp")
+        self.parts = [None] * 3
+        first = self.used[0]
+        self.parts[first] = eng.convert_to_scs(coos[first], C_, sigma, vts[first])
+        self.old_to_new = self.parts[first].export().old_to_new
+        for k in self.used[1:]:
+            self.parts[k] = eng.convert_to_scs(coos[k], C_, sigma, vts[k], fixed_permutation=self.old_to_new)
+        del coos
+        # one halo plan over all parts; x is NOT permuted for AP
+        arr = (vp * len(self.used))(*[self.parts[k].h for k in self.used])
+        from .engine import _hp
+        wsa = np.ascontiguousarray(wsa, np.int32)
+        h = vp()
+        call("uspmv_halo_plan_create_multi", arr, len(self.used), _hp(wsa), int(rank), int(world), 0, C.byref(h))
+        plan = HaloPlan.__new__(HaloPlan)
+        plan.scs, plan.rank, plan.world, plan.h = self.parts[first], rank, world, h
+        cum = np.zeros(world + 1, np.int32)
+        nh = C.c_long(0)
+        call("uspmv_halo_plan_counts", h, _hp(cum), C.byref(nh))
+        plan.recv_cumsum, plan.n_halo = cum, int(nh.value)
+        flat = np.zeros(max(plan.n_halo, 1), np.int32)
+        ptr = np.zeros(world + 1, np.int32)
+        call("uspmv_halo_plan_need", h, _hp(flat), _hp(ptr))
+        plan.need_lists = [flat[ptr[p]:ptr[p + 1]].copy() for p in range(world)]
+        plan.send_lists = plan.send_ptr = None
+        self.plan = plan
+        plan.set_send(comm_schedule(plan.need_lists, rank, world, group))
+        s0 = self.parts[first]
+        self.n_rows, self.n_rows_padded, self.n_halo = s0.n_rows, s0.n_rows_padded, plan.n_halo
+        self.n_elements = [self.parts[k].n_elements if self.parts[k] is not None else 0 for k in range(3)]
+        self.n_chunks = s0.n_chunks
+        xvt = capi.F32 if mode == "ap[sp_hp]" else capi.F64
+        self.vec_length = s0.n_rows + max(s0.n_rows_padded - s0.n_rows, plan.n_halo)
+        self.p2p = P2PHalo(plan, xvt, self.vec_length, rank, world, group)
+        self.x = self.p2p.x
+        self.x.fill_(1.0)
+        self.y = torch.zeros(s0.n_rows_padded, dtype=self.x.dtype, device=f"cuda:{ctx.device}")
+        self.comm_stream = torch.cuda.Stream(device=f"cuda:{ctx.device}")
+        self._torch, self._eng = torch, eng
+        dist.barrier(group=group)
+
+    def algorithmic_bytes(self):
+        vs = (8, 4, 2)
+        xs = self.x.element_size()
+        return (sum(self.n_elements[k] * (vs[k] + 4) + 8 * self.n_chunks for k in self.used) + xs * (self.n_rows + self.n_halo)
+                + xs * self.n_rows_padded)
+
+    def step(self):
+        main = self._torch.cuda.current_stream()
+        P = self.parts
+        h = lambda q: q.h if q is not None else None
+        call("uspmv_p2p_ap_spmv", self.p2p.h, self._eng.AP_MODE[self.mode], h(P[0]), h(P[1]), h(P[2]), vp(self.y.data_ptr()),
+             vp(main.cuda_stream), vp(self.comm_stream.cuda_stream))
+
+    def time_kernel(self, steps):
+        torch, eng = self._torch, self._eng
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(steps):
+            eng.ap_spmv(self.mode, self.parts[0], self.parts[1], self.parts[2], self.x, self.y)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps

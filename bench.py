@@ -34,7 +34,9 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="laplace7_256", help="laplace7_<n> | stencil27_<n> (n^3 grid per GPU)")
+    ap.add_argument("--workload", default="laplace7_256", help="laplace7_<n> | stencil27_<n> (n^3 grid per GPU) | powerlaw_<log2 rows> (config 4, needs --ap)")
+    ap.add_argument("--ap", default=None, choices=["ap[dp_sp]", "ap[dp_hp]", "ap[sp_hp]", "ap[dp_sp_hp]"],
+                    help="adaptive precision on the power-law matrix: thresholds 1.0 / 1e-2, rows split over the ranks by seg-nnz")
     ap.add_argument("--C", type=int, default=32)
     ap.add_argument("--sigma", type=int, default=1)
     ap.add_argument("--vt", default="dp", choices=["dp", "sp", "hp"])
@@ -53,8 +55,42 @@ def parse_args():
 def workload_dims(name):
     kind, n = name.rsplit("_", 1)
     n = int(n)
-    pts = {"laplace7": 7, "stencil27": 27}[kind]
+    pts = {"laplace7": 7, "stencil27": 27, "powerlaw": 0}[kind]
     return pts, n
+
+
+def build_powerlaw_ap(pkg, ctx, log2_rows, mode, C, sigma, rank, world):
+    """BASELINE config 4: power-law matrix with 2^log2_rows rows, rows split by seg-nnz, per-rank
+    partition_precisions with t1 = 1.0, t2 = 1e-2.  Every rank generates only its own rows (twice: once on an equal-rows split to
+    count the elements per row for the seg-nnz walk, once on the final split)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    mats, d = pkg.matrices, pkg.dist
+    n = 1 << log2_rows
+    target = n * 15
+    slab = 1 << 20
+
+    def gen(r0, r1):
+        parts = [mats.powerlaw_coo(n, target, row0=a, row1=min(r1, a + slab)) for a in range(r0, r1, slab)]
+        I = np.concatenate([p[2].astype(np.int64) + (a - r0) for p, a in zip(parts, range(r0, r1, slab))]).astype(np.int32)
+        return I, np.concatenate([p[3] for p in parts]), np.concatenate([p[4] for p in parts])
+    if world > 1:
+        eq = np.arange(world + 1, dtype=np.int64) * (n // world)
+        eq[world] = n
+        I, J, V = gen(int(eq[rank]), int(eq[rank + 1]))
+        cnt = torch.from_numpy(np.bincount(I, minlength=int(eq[rank + 1] - eq[rank])).astype(np.int32)).cuda()
+        sizes = [int(eq[r + 1] - eq[r]) for r in range(world)]
+        bufs = [torch.empty(sz, dtype=torch.int32, device="cuda") for sz in sizes]
+        dist.all_gather(bufs, cnt)
+        wsa = d.seg_nnz_from_row_counts(torch.cat(bufs).cpu().numpy(), world)
+        if (int(wsa[rank]), int(wsa[rank + 1])) != (int(eq[rank]), int(eq[rank + 1])):
+            I, J, V = gen(int(wsa[rank]), int(wsa[rank + 1]))
+    else:
+        wsa = np.array([0, n], np.int32)
+        I, J, V = gen(0, n)
+    n_loc = int(wsa[rank + 1] - wsa[rank])
+    return d.DistributedApSpmv(ctx, wsa, (n_loc, n, I, J, V), mode, 1.0, 1e-2, C, sigma, rank, world), wsa
 
 
 def measured_peak():
@@ -199,7 +235,10 @@ def run_ours(args):
         if world == 1 and args.gpus > 1:
             raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N > 1")
     torch.cuda.set_device(local_rank)
-    block_or_solve = args.bvs > 1 or args.solve
+    is_ap = args.workload.startswith("powerlaw")
+    if is_ap and not args.ap:
+        raise SystemExit("--workload powerlaw_<log2 rows> needs --ap")
+    block_or_solve = args.bvs > 1 or args.solve or is_ap
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -215,7 +254,11 @@ def run_ours(args):
     tdt = {"dp": torch.float64, "sp": torch.float32, "hp": torch.float16}[vt]
     ctx = eng.default_context(local_rank)
 
-    if world == 1 and not block_or_solve:
+    wsa = None
+    if is_ap:
+        runner, wsa = build_powerlaw_ap(pkg, ctx, n, args.ap, args.C, args.sigma, rank, world)
+        vt = "sp" if args.ap == "ap[sp_hp]" else "dp"
+    elif world == 1 and not block_or_solve:
         runner = pkg.engine.SingleGpuSpmv(ctx, pts, n, args.C, args.sigma, vt)
     else:
         runner = pkg.dist.DistributedSpmv(ctx, pts, n, args.C, args.sigma, vt, rank, world, halo=args.halo, overlap=not args.no_overlap,
@@ -233,7 +276,10 @@ def run_ours(args):
             if world > 1:
                 dist.barrier()
     nnz_local = runner.nnz * args.bvs
-    bytes_local = algorithmic_bytes(runner.n_elements, runner.n_chunks, runner.n_cols_local + runner.n_halo, runner.n_rows_padded, vsize, args.bvs)
+    if is_ap:
+        bytes_local = runner.algorithmic_bytes()
+    else:
+        bytes_local = algorithmic_bytes(runner.n_elements, runner.n_chunks, runner.n_cols_local + runner.n_halo, runner.n_rows_padded, vsize, args.bvs)
 
     def barrier():
         if world > 1:
@@ -279,7 +325,7 @@ def run_ours(args):
 
     # end-to-end through the host-buffer C-ABI call (pinned host x / y, copies inside the timed region)
     e2e = None
-    if not args.no_e2e and not args.solve:
+    if not args.no_e2e and not args.solve and not is_ap:
         e2e_steps = max(3, min(args.steps, 20))
         sec = runner.time_e2e(e2e_steps, barrier)
         te = torch.tensor([sec], dtype=torch.float64, device="cuda")
@@ -296,7 +342,7 @@ def run_ours(args):
             e2e["single_call_api"] = "uspmv_spmv_host: H2D(x) + SpMV + D2H(y) + sync, one step at a time"
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not is_ap:
         try:
             dt, done, nnz_c, threads, build_s = cpu_reference_run(pts, n, args.C, args.sigma, vt, 10 ** 9, 10, time_box=args.cpu_seconds)
             cpu = {"value": 2.0 * nnz_c / dt / 1e9, "unit": UNIT, "cores": threads, "kind": "reference",
@@ -310,7 +356,12 @@ def run_ours(args):
             "metric": METRIC, "value": gflops, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": sec_per_step * 1e3, "higher_is_better": True, "scaling": "strong" if (args.strong and world > 1) else "weak", "vs_baseline": None,
             "dtype": {"dp": "f64", "sp": "f32", "hp": "f16"}[vt], "data": "synthetic",
-            "config": {"workload": (f"{args.workload}: {pts}-point stencil on ONE {n}^3 grid cut into {world} z-slabs" if (args.strong and world > 1) else
+            "config": {"workload": f"{args.workload}: power-law matrix with 2^{n} rows (config 4), {args.ap} t1=1.0 t2=1e-2, scs C={args.C} sigma={args.sigma}"} |
+                      {"rows_per_gpu": runner.n_rows, "nnz_per_gpu": int(nnz_local), "n_elements_per_gpu": [int(v) for v in runner.n_elements],
+                       "partition": "none" if world == 1 else f"seg_nnz over {world} ranks (work_sharing_arr {[int(v) for v in wsa]}), halo exchange every step via p2p",
+                       "halo_elements_per_gpu": int(runner.n_halo), "x": "constant 1.0",
+                       "l2": "matrix parts larger than the 126 MB L2; no explicit flush"} if is_ap else
+                      {"workload": (f"{args.workload}: {pts}-point stencil on ONE {n}^3 grid cut into {world} z-slabs" if (args.strong and world > 1) else
                                     f"{args.workload}: {pts}-point stencil on a {n}^3 grid per GPU") + f", scs C={args.C} sigma={args.sigma} {vt} " +
                                    (f"SpMMV block_vec_size={args.bvs} {args.layout}" if args.bvs > 1 else "SpMV") +
                                    (", solve mode: each step = halo exchange + SpMV + swap on two device buffers" if args.solve else ""),

@@ -452,9 +452,12 @@ void launch_push(uspmv_p2p *p, const void *x, int buf, cudaStream_t comm) {
     uspmv_halo *h = p->plan;
     const int P = h->P;
     const long total = h->n_send * p->bvs;
+    // small halos (stencil faces): a few CTAs next to the interior kernel; large ones (power-law matrices exchange ~100 MB per
+    // SpMV) need the whole GPU's worth of stores in flight to fill the NVLink ports
     long g = (total + 2047) / 2048;
     if (g < 1) g = 1;
-    if (g > 64) g = 64;
+    const long cap = total >= (1L << 20) ? 4L * sm_count(h->ctx->device) : 64;
+    if (g > cap) g = cap;
     const unsigned long long *x0 = p->peer_x0.p + (size_t)buf * P;
 #define USPMV_PUSH(T)                                                                                                                     \
     k_p2p_push<T><<<(unsigned)g, 256, 0, comm>>>(P, h->rank, p->send_ptr_d.p, p->is_receiver_d.p, h->send_idx.p, h->perm_d, (const T *)x, x0, \

@@ -29,7 +29,7 @@ for mode in ("ap[dp_sp_hp]", "ap[dp_sp]"):
     n_pad = P[used[0]].n_rows_padded
     x = torch.full((max(n_pad, n),), 1.0, dtype=torch.float64, device="cuda"); y = torch.zeros(n_pad, dtype=torch.float64, device="cuda")
     print(mode, "n_elements", [p.n_elements if p is not None else 0 for p in P], "nnz", nnz, flush=True)
-    for var in (0, 1, 2, 3):
+    for var in (0, 1, 3, 4):
         line = f"  variant {var}: "
         for split in (0, 64, 128, 256, 512):
             capi.set_option("ap_variant", var); capi.set_option("split_long_chunks", split)

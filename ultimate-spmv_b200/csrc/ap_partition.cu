@@ -272,7 +272,8 @@ void launch_ap_stream(long n_chunks, const int *order, const uspmv_scs::ApPlan *
     case 1: launch_ap_stream_v<MODE, 4, 1>(n_chunks, order, pl, a, b, c, x, y, st); break;
     case 2: launch_ap_stream_v<MODE, 2, 4>(n_chunks, order, pl, a, b, c, x, y, st); break;
     case 3: launch_ap_stream_v<MODE, 3, 3>(n_chunks, order, pl, a, b, c, x, y, st); break;
-    default: launch_ap_stream_v<MODE, 2, 1>(n_chunks, order, pl, a, b, c, x, y, st); break;
+    case 4: launch_ap_stream_v<MODE, 2, 1>(n_chunks, order, pl, a, b, c, x, y, st); break;
+    default: launch_ap_stream_v<MODE, 2, 3>(n_chunks, order, pl, a, b, c, x, y, st); break;  // <= 80 registers: 24 warps per SM
     }
 }
 

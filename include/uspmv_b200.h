@@ -231,6 +231,9 @@ int uspmv_p2p_spmv_buf(uspmv_p2p *p2p, const uspmv_scs *scs, int x_buf, int y_bu
 /* SpMMV over the arena's block vector (buffer x_buf) incl. the exchange of all block_vec_size vectors of the halo rows,
  * overlapped with the interior chunks when the streamed kernel applies. */
 int uspmv_p2p_spmmv(uspmv_p2p *p2p, const uspmv_scs *scs, int x_buf, void *Y_d, void *stream, void *comm_stream);
+/* The halo exchange alone — init_halo_exchange + finalize_halo_exchange (classes_structs.hpp:857-995): push the halo rows of
+ * buffer x_buf into the neighbours' vectors over NVLink, wait for the own halo, acknowledge. */
+int uspmv_p2p_exchange(uspmv_p2p *p2p, int x_buf, void *stream, void *comm_stream);
 int uspmv_p2p_status(uspmv_p2p *p2p, int *error_flag, long *epoch);
 void uspmv_p2p_destroy(uspmv_p2p *p2p);
 

@@ -183,6 +183,22 @@ def _run_ap_rank(rank, world, port, out_dir):
             torch.cuda.synchronize()
             err, ep = r.p2p.status()
             assert err == 0 and ep == 3
+            # the large-halo push kernels (tiled direct stores / shared memory + bulk copy over NVLink), forced onto this small halo
+            y0 = r.y.clone()
+            for variant in (0, 1, 2):
+                pkg.capi.set_option("push_variant", variant)
+                pkg.capi.set_option("push_min_elements", 0)
+                r.x[n_loc:] = 0
+                r.y.zero_()
+                torch.cuda.synchronize()
+                dist.barrier()
+                r.step()
+                torch.cuda.synchronize()
+                assert torch.equal(r.y, y0), (mode, variant)
+            pkg.capi.set_option("push_variant", -1)
+            pkg.capi.set_option("push_min_elements", 1 << 20)
+            err, ep = r.p2p.status()
+            assert err == 0 and ep == 6
             y = r.y.cpu().numpy()[r.old_to_new]
             np.save(os.path.join(out_dir, f"ap{rank}_{mode}.npy"), y.astype(np.float64))
             del r

@@ -109,6 +109,11 @@ struct Options {
     int ap_variant = 0;          // fused adaptive-precision streamed kernel: ring depth / register cap instantiation
     int split_long_chunks = 256; // C = 32, uneven matrices: chunks longer than this many slots are summed in segments (0 = never)
     bool strict_reference_halo = false;  // true: padding slots (column 0) become a halo element on ranks > 0, like the reference
+    int push_variant = -1;       // large single-vector halos: -1 = tuned default, 0 = one store per thread, 1 = tiles of 2048 elements,
+                                 // direct peer stores, 2 = tiles gathered into shared memory and written to the peer by the bulk-copy
+                                 // engine, 3 = like 1 with tiles of 4096 elements
+    int push_ctas_per_sm = 0;    // CTAs per SM of the large-halo push kernels (0 = default)
+    long push_min_elements = 1L << 20;  // halos with at least this many elements to send use the tiled push kernels
 };
 Options &options();
 

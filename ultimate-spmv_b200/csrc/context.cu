@@ -16,6 +16,8 @@ Options &options() {
         if (const char *e = std::getenv("USPMV_STREAM_VARIANT")) c.stream_variant = std::atoi(e);
         if (const char *e = std::getenv("USPMV_STREAM_BPS")) c.stream_blocks_per_sm = std::max(1, std::atoi(e));
         if (const char *e = std::getenv("USPMV_STRICT_REFERENCE_HALO")) c.strict_reference_halo = std::atoi(e) != 0;
+        if (const char *e = std::getenv("USPMV_PUSH_VARIANT")) c.push_variant = std::atoi(e);
+        if (const char *e = std::getenv("USPMV_PUSH_CTAS_PER_SM")) c.push_ctas_per_sm = std::max(0, std::atoi(e));
         return c;
     }();
     return o;
@@ -42,6 +44,9 @@ int uspmv_set_option(const char *name, long value) {
         else if (!std::strcmp(name, "ap_variant")) c.ap_variant = (int)std::max(0L, value);
         else if (!std::strcmp(name, "split_long_chunks")) c.split_long_chunks = (int)std::max(0L, value);
         else if (!std::strcmp(name, "strict_reference_halo")) c.strict_reference_halo = value != 0;
+        else if (!std::strcmp(name, "push_variant")) c.push_variant = (int)value;
+        else if (!std::strcmp(name, "push_ctas_per_sm")) c.push_ctas_per_sm = (int)std::max(0L, value);
+        else if (!std::strcmp(name, "push_min_elements")) c.push_min_elements = std::max(0L, value);
         else fail("uspmv_set_option: unknown option '%s'", name);
     });
 }

@@ -17,6 +17,7 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
+#include <algorithm>
 #include <cstring>
 #include <vector>
 
@@ -355,10 +356,13 @@ struct uspmv_p2p {
     bool connected = false;
     int mode = 2;  // 0: exchange, then one full SpMV; 1: push/wait kernels next to the interior kernel; 2: ONE fused kernel (C = 32)
     DevBuf<unsigned int> fused_counters;
+    long n_push_tiles = 0, n_push_tiles_4k = 0;  // tiles (2048 / 4096 elements) of the large-halo push kernels (k_p2p_push_tiles)
     unsigned char *buffer(int b) const { return arena + (size_t)b * x_bytes; }
 };
 
 namespace {
+
+constexpr int USPMV_PUSH_DEFAULT_VARIANT = 1;
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
     unsigned long long t;
@@ -430,6 +434,120 @@ k_p2p_push(int P, int my_rank, const int *__restrict__ send_ptr, const int *__re
     }
 }
 
+// ---- large single-vector halos ------------------------------------------------------------------------------------------------
+// Power-law matrices exchange ~100 MB per rank and SpMV (BASELINE config 4 at 8 GPUs: 14.7 M elements per rank); one dependent
+// idx -> x -> peer-store chain per thread leaves NVLink mostly idle.  Here the send list is cut into tiles of PUSH_TILE elements
+// that never cross a peer and start, in the PEER's vector, at multiples of PUSH_TILE (so every tile but the edges of a peer's
+// range is 16-byte aligned at the destination); a CTA gathers a tile with PUSH_TILE/256 independent loads per thread and
+//   MODE 1: stores it straight to the peer (8 or 16 stores in flight per thread; the default — measured fastest at 2, 4 and 8 GPUs);
+//   MODE 2: lands it in shared memory and lets the bulk-copy engine write the 16-byte-aligned middle of the tile over NVLink
+//           (cp.async.bulk.global.shared::cta, double-buffered), the unaligned edge elements go by plain stores.
+inline long push_tile_count(const std::vector<int> &send_ptr, const std::vector<long> &peer_base, int P, long PUSH_TILE) {
+    long t = 0;
+    for (int q = 0; q < P; ++q) {
+        const long nq = send_ptr[q + 1] - send_ptr[q];
+        if (nq > 0) t += (peer_base[q] + nq - 1) / PUSH_TILE - peer_base[q] / PUSH_TILE + 1;
+    }
+    return t;
+}
+
+template <typename VT, int MODE, int PUSH_TILE>
+__global__ void __launch_bounds__(256)
+k_p2p_push_tiles(int P, const int *__restrict__ send_ptr, const int *__restrict__ is_receiver, const int *__restrict__ send_idx,
+                 const int *__restrict__ perm, const VT *__restrict__ x, const unsigned long long *__restrict__ peer_x0,
+                 const long *__restrict__ peer_base, const unsigned long long *__restrict__ peer_arrived, const unsigned int *acked,
+                 const unsigned int *epoch, unsigned int *error, unsigned int *block_counter) {
+    constexpr int U = PUSH_TILE / 256;
+    constexpr long A = 16 / (long)sizeof(VT);  // elements per 16 bytes
+    extern __shared__ __align__(128) unsigned char push_smem[];  // MODE 2: two tiles
+    __shared__ int s_tile_ptr[257];
+    __shared__ unsigned int s_last;
+    const int tid = threadIdx.x;
+    const unsigned int e = *epoch + 1u;
+    if (tid == 0) {
+        int t = 0;
+        s_tile_ptr[0] = 0;
+        for (int q = 0; q < P; ++q) {
+            const long nq = send_ptr[q + 1] - send_ptr[q], b = peer_base[q];
+            if (nq > 0) t += (int)((b + nq - 1) / PUSH_TILE - b / PUSH_TILE + 1);
+            s_tile_ptr[q + 1] = t;
+        }
+    }
+    if (tid < P && is_receiver[tid]) spin_until_ge(acked + tid, e - 1u, error);
+    __syncthreads();
+    const int total_tiles = s_tile_ptr[P];
+    int q = 0, it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+        while (t >= s_tile_ptr[q + 1]) ++q;
+        const long base = peer_base[q];
+        const int s0 = send_ptr[q], nq = send_ptr[q + 1] - s0;
+        const long k0 = (base / PUSH_TILE + (t - s_tile_ptr[q])) * PUSH_TILE;  // destination index of the tile's first slot
+        const long k_lo = k0 > base ? k0 : base;
+        const long k_hi = k0 + PUSH_TILE < base + nq ? k0 + PUSH_TILE : base + nq;
+        VT *dst = reinterpret_cast<VT *>(peer_x0[q]);
+        VT *buf = reinterpret_cast<VT *>(push_smem) + (size_t)(it & 1) * PUSH_TILE;
+        long ka = (k_lo + A - 1) / A * A, kb = k_hi / A * A;
+        if (kb < ka) kb = ka;
+        if (MODE == 2) {
+            // the bulk copy issued two tiles ago has finished READING this buffer
+            if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            __syncthreads();
+        }
+        int src[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long k = k0 + tid + u * 256;
+            src[u] = (k >= k_lo && k < k_hi) ? send_idx[s0 + (k - base)] : -1;
+        }
+        if (perm) {
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (src[u] >= 0) src[u] = perm[src[u]];
+        }
+        VT v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (src[u] >= 0) v[u] = x[src[u]];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long k = k0 + tid + u * 256;
+            if (src[u] < 0) continue;
+            if (MODE == 2 && k >= ka && k < kb) buf[k - k0] = v[u];
+            else dst[k] = v[u];
+        }
+        if (MODE == 2) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the bulk-copy engine
+            __syncthreads();
+            if (tid == 0) {
+                if (kb > ka) {
+                    const unsigned int s_addr = (unsigned int)__cvta_generic_to_shared(buf + (ka - k0));
+                    const unsigned int bytes = (unsigned int)((kb - ka) * (long)sizeof(VT));
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + ka), "r"(s_addr), "r"(bytes)
+                                 : "memory");
+                }
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        }
+    }
+    if (MODE == 2 && tid == 0) {
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // every bulk write of this CTA has been performed
+        asm volatile("fence.proxy.async;" ::: "memory");
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(block_counter, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (s_last) {
+        __threadfence_system();
+        if (tid < P && is_receiver[tid]) {
+            volatile unsigned int *f = reinterpret_cast<volatile unsigned int *>(peer_arrived[tid]);
+            *f = e;
+        }
+        if (tid == 0) *block_counter = 0;
+        __threadfence_system();
+    }
+}
+
 __global__ void k_p2p_wait(int P, const int *__restrict__ is_sender, const unsigned int *arrived, const unsigned int *epoch, unsigned int *error) {
     const unsigned int e = *epoch + 1u;
     if (threadIdx.x < P && is_sender[threadIdx.x]) spin_until_ge(arrived + threadIdx.x, e, error);
@@ -452,13 +570,39 @@ void launch_push(uspmv_p2p *p, const void *x, int buf, cudaStream_t comm) {
     uspmv_halo *h = p->plan;
     const int P = h->P;
     const long total = h->n_send * p->bvs;
-    // small halos (stencil faces): a few CTAs next to the interior kernel; large ones (power-law matrices exchange ~100 MB per
-    // SpMV) need the whole GPU's worth of stores in flight to fill the NVLink ports
+    const unsigned long long *x0 = p->peer_x0.p + (size_t)buf * P;
+    // large single-vector halos: tiled gather with many loads in flight per thread (see k_p2p_push_tiles)
+    int variant = options().push_variant;
+    if (variant < 0) variant = USPMV_PUSH_DEFAULT_VARIANT;
+    if (p->bvs == 1 && total >= options().push_min_elements && variant != 0 && p->n_push_tiles > 0) {
+        const int per_sm = options().push_ctas_per_sm > 0 ? options().push_ctas_per_sm : 8;
+        const long tiles = variant == 3 ? p->n_push_tiles_4k : p->n_push_tiles;
+        long g = std::min<long>(tiles, (long)per_sm * sm_count(h->ctx->device));
+#define USPMV_PUSH_T(T, M, TILE, SH)                                                                                                     \
+    k_p2p_push_tiles<T, M, TILE><<<(unsigned)g, 256, SH, comm>>>(P, p->send_ptr_d.p, p->is_receiver_d.p, h->send_idx.p, h->perm_d,        \
+                                                                 (const T *)x, x0, p->peer_base.p, p->peer_arrived.p, p->acked, p->epoch, \
+                                                                 p->error, p->block_counter.p)
+#define USPMV_PUSH_TV(T)                                                        \
+    do {                                                                        \
+        if (variant == 2) USPMV_PUSH_T(T, 2, 2048, 2 * 2048 * sizeof(T));       \
+        else if (variant == 3) USPMV_PUSH_T(T, 1, 4096, 0);                     \
+        else USPMV_PUSH_T(T, 1, 2048, 0);                                       \
+    } while (0)
+        switch (p->vt) {
+        case USPMV_F64: USPMV_PUSH_TV(double); break;
+        case USPMV_F32: USPMV_PUSH_TV(float); break;
+        default: USPMV_PUSH_TV(__half);
+        }
+#undef USPMV_PUSH_TV
+#undef USPMV_PUSH_T
+        USPMV_LAUNCH_CHECK();
+        return;
+    }
+    // small halos (stencil faces): a few CTAs next to the interior kernel
     long g = (total + 2047) / 2048;
     if (g < 1) g = 1;
     const long cap = total >= (1L << 20) ? 4L * sm_count(h->ctx->device) : 64;
     if (g > cap) g = cap;
-    const unsigned long long *x0 = p->peer_x0.p + (size_t)buf * P;
 #define USPMV_PUSH(T)                                                                                                                     \
     k_p2p_push<T><<<(unsigned)g, 256, 0, comm>>>(P, h->rank, p->send_ptr_d.p, p->is_receiver_d.p, h->send_idx.p, h->perm_d, (const T *)x, x0, \
                                                  p->peer_base.p, p->peer_ld.p, p->bvs, p->layout, p->vec_length, p->peer_arrived.p, p->acked,  \
@@ -574,6 +718,8 @@ int uspmv_p2p_connect_ex(uspmv_p2p *p, const void *all_handles, const long *peer
         USPMV_CUDA(cudaMemcpy(p->send_ptr_d.p, h->send_ptr.data(), (P + 1) * sizeof(int), cudaMemcpyHostToDevice));
         USPMV_CUDA(cudaMemcpy(p->is_sender_d.p, is_s.data(), P * sizeof(int), cudaMemcpyHostToDevice));
         USPMV_CUDA(cudaMemcpy(p->is_receiver_d.p, is_r.data(), P * sizeof(int), cudaMemcpyHostToDevice));
+        p->n_push_tiles = push_tile_count(h->send_ptr, base, P, 2048);
+        p->n_push_tiles_4k = push_tile_count(h->send_ptr, base, P, 4096);
         p->connected = true;
     });
 }
@@ -705,6 +851,27 @@ int uspmv_p2p_ap_spmv(uspmv_p2p *p, int ap_mode, const uspmv_scs *dp, const uspm
         USPMV_CUDA(cudaStreamWaitEvent(main, p->ev_comm, 0));
         if (uspmv_ap_spmv(ap_mode, dp, sp, hp, x, y_d, stream)) throw Error(uspmv_last_error());
         k_p2p_ack<<<1, 256, 0, main>>>(P, p->is_sender_d.p, p->peer_acked.p, p->epoch);
+        USPMV_LAUNCH_CHECK();
+    });
+}
+
+/* The halo exchange alone (init_halo_exchange + finalize_halo_exchange, classes_structs.hpp:857-995): push the halo rows of
+ * buffer x_buf into the neighbours' vectors, wait for the own halo, acknowledge.  After it x_buf holds local rows + halo. */
+int uspmv_p2p_exchange(uspmv_p2p *p, int x_buf, void *stream, void *comm_stream) {
+    return guarded([&] {
+        if (!p) fail("uspmv_p2p_exchange: NULL argument");
+        if (!p->connected) fail("uspmv_p2p_exchange: call uspmv_p2p_connect first");
+        if (x_buf < 0 || x_buf >= p->n_buf) fail("uspmv_p2p_exchange: x buffer %d out of range", x_buf);
+        uspmv_halo *h = p->plan;
+        cudaStream_t main = as_stream(stream), comm = as_stream(comm_stream);
+        USPMV_CUDA(cudaEventRecord(p->ev_main, main));
+        USPMV_CUDA(cudaStreamWaitEvent(comm, p->ev_main, 0));
+        launch_push(p, p->buffer(x_buf), x_buf, comm);
+        k_p2p_wait<<<1, 256, 0, comm>>>(h->P, p->is_sender_d.p, p->arrived, p->epoch, p->error);
+        USPMV_LAUNCH_CHECK();
+        USPMV_CUDA(cudaEventRecord(p->ev_comm, comm));
+        USPMV_CUDA(cudaStreamWaitEvent(main, p->ev_comm, 0));
+        k_p2p_ack<<<1, 256, 0, main>>>(h->P, p->is_sender_d.p, p->peer_acked.p, p->epoch);
         USPMV_LAUNCH_CHECK();
     });
 }

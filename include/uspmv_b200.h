@@ -56,6 +56,9 @@ int uspmv_set_option(const char *name, long value);
 int uspmv_ctx_create(int device, uspmv_ctx **out);
 void uspmv_ctx_destroy(uspmv_ctx *ctx);
 int uspmv_ctx_sync(uspmv_ctx *ctx);
+/* a second stream for the halo exchange (cudaStream_t as void *; the harness' per-peer cudaStreams, classes_structs.hpp:857-995) */
+int uspmv_stream_create(uspmv_ctx *ctx, void **out_stream);
+int uspmv_stream_destroy(uspmv_ctx *ctx, void *stream);
 /* cudaMalloc/cudaMemcpy staging of assign_spmv_kernel_gpu_data (utilities.hpp:3302-3815, 3720-3811) */
 int uspmv_malloc(uspmv_ctx *ctx, size_t bytes, void **out_d);
 int uspmv_free(uspmv_ctx *ctx, void *ptr_d);

@@ -17,7 +17,7 @@ def timeit(fn, k=20):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / k * 1e3
 res = {}
-for mode in ("ap[dp_sp_hp]", "ap[dp_sp]"):
+for mode in os.environ.get("PL_MODES", "ap[dp_sp_hp],ap[dp_sp]").split(","):
     coos = eng.partition_precisions(mtx, mode, 1.0, 1e-2)
     used = [k for k in range(3) if coos[k] is not None]
     vts = ("dp", "sp", "hp")
@@ -29,9 +29,9 @@ for mode in ("ap[dp_sp_hp]", "ap[dp_sp]"):
     n_pad = P[used[0]].n_rows_padded
     x = torch.full((max(n_pad, n),), 1.0, dtype=torch.float64, device="cuda"); y = torch.zeros(n_pad, dtype=torch.float64, device="cuda")
     print(mode, "n_elements", [p.n_elements if p is not None else 0 for p in P], "nnz", nnz, flush=True)
-    for var in (0, 1, 3, 4):
+    for var in (0, 1, 2, 3, 4):
         line = f"  variant {var}: "
-        for split in (0, 64, 128, 256, 512):
+        for split in [int(v) for v in os.environ.get("PL_SPLITS", "0,64,128,256,512").split(",")]:
             capi.set_option("ap_variant", var); capi.set_option("split_long_chunks", split)
             us = timeit(lambda: eng.ap_spmv(mode, P[0], P[1], P[2], x, y))
             res[f"{mode}|v{var}|split{split}"] = us

@@ -111,3 +111,42 @@ def test_cli_symmetric_file_equilibrate_and_dropout(eng, tmp_path):
     assert r.returncode == 0 and "-> OK" in r.stdout, r.stdout + r.stderr
     m = re.search(r"2003 rows, (\d+) nnz", r.stdout)
     assert m and int(m.group(1)) < 83883, r.stdout
+
+
+def _two_gpus():
+    import torch
+    return torch.cuda.device_count() >= 2
+
+
+@pytest.mark.parametrize("seg", ["-seg_rows", "-seg_nnz"])
+@pytest.mark.parametrize("fmt_args", [["scs", "-c", "32", "-s", "128"], ["scs", "-c", "16", "-s", "64"], ["crs"]])
+def test_cli_multi_gpu_solve_validates(eng, tmp_path, seg, fmt_args):
+    """`uspmv ... -gpus 2` = the reference's `mpirun -n 2 ./uspmv ...`: forked ranks, row partition, device halo discovery, need
+    lists / IPC handles through shared memory, NVLink exchange inside every SpMV; validated against the host COO product."""
+    if not _two_gpus():
+        pytest.skip("needs 2 GPUs")
+    m = write_mtx(str(tmp_path / "bcsstk13.mtx"), "bcsstk13")
+    r = run([m] + fmt_args + ["-dp", "-mode", "s", "-rev", "2", "-rand_x", "1", "-gpus", "2", seg], str(tmp_path))
+    assert r.returncode == 0, r.stdout + r.stderr
+    m_ = re.search(r"max relative difference ([0-9.e+-]+) -> (\w+)", r.stdout)
+    assert m_ and m_.group(2) == "OK" and float(m_.group(1)) < 1e-10, r.stdout + r.stderr
+    w = re.search(r"work_sharing_arr \(seg-(rows|nnz)\): 0 (\d+) 2003", r.stdout)
+    assert w, r.stdout
+    # seg_work_sharing_arr on bcsstk13 (SURVEY.md section 8a' item 11): seg-rows floor(n/P), seg-nnz closes after the row holding element nnz/P + 1
+    assert int(w.group(2)) == (1001 if seg == "-seg_rows" else 1183), r.stdout
+
+
+def test_cli_multi_gpu_bench_spmmv_ap(eng, tmp_path):
+    if not _two_gpus():
+        pytest.skip("needs 2 GPUs")
+    r = run(["gen:laplace7:64", "scs", "-c", "32", "-s", "1", "-dp", "-mode", "b", "-bench_time", "0.1", "-gpus", "2"], str(tmp_path))
+    assert r.returncode == 0 and "Total Gflops" in r.stdout and "ranks: 2" in r.stdout, r.stdout + r.stderr
+    rep = open(tmp_path / "spmv_bench.txt").read()
+    assert re.search(r"gen:laplace7:64 with 2 MPI processes, and \d+ block\(s\), and 256 thread\(s\) per block", rep), rep
+    m = write_mtx(str(tmp_path / "impcol_e.mtx"), "impcol_e")
+    for extra in (["-block_vec_size", "4", "-block_vec_layout", "rowwise"], ["-block_vec_size", "3"]):
+        r = run([m, "scs", "-c", "32", "-s", "16", "-dp", "-mode", "s", "-rand_x", "1", "-gpus", "2"] + extra, str(tmp_path))
+        assert r.returncode == 0 and "-> OK" in r.stdout, r.stdout + r.stderr
+    r = run([m, "scs", "-c", "32", "-s", "16", "-ap[dp_sp_hp]", "-apt1", "10", "-apt2", "0.1", "-mode", "s", "-rand_x", "1", "-gpus", "2", "-seg_nnz"],
+            str(tmp_path))
+    assert r.returncode == 0 and ("-> OK" in r.stdout or "-> WARNING" in r.stdout), r.stdout + r.stderr

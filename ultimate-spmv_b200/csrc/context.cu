@@ -51,6 +51,23 @@ int uspmv_set_option(const char *name, long value) {
     });
 }
 
+/* a second CUDA stream for the halo exchange next to the SpMV stream (host code without CUDA headers: the `uspmv` harness) */
+int uspmv_stream_create(uspmv_ctx *ctx, void **out) {
+    return guarded([&] {
+        if (!ctx || !out) fail("uspmv_stream_create: NULL argument");
+        USPMV_CUDA(cudaSetDevice(ctx->device));
+        cudaStream_t st;
+        USPMV_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        *out = st;
+    });
+}
+int uspmv_stream_destroy(uspmv_ctx *ctx, void *stream) {
+    return guarded([&] {
+        if (!ctx) fail("uspmv_stream_destroy: NULL argument");
+        if (stream) USPMV_CUDA(cudaStreamDestroy(static_cast<cudaStream_t>(stream)));
+    });
+}
+
 int uspmv_ctx_create(int device, uspmv_ctx **out) {
     return guarded([&] {
         if (!out) fail("uspmv_ctx_create: out is NULL");

@@ -9,7 +9,11 @@
 // then n_iter = 2,4,8,... until one loop takes >= bench_time; Gflops = 2*nnz*block_vec_size / (t / n_iter) / 1e9.
 // Solve mode (main.cpp:528-631): `rev` x { SpMV ; y becomes the next x }, result un-permuted and compared with a
 // host-side COO product (the reference needs MKL for this step, write_results.hpp:442-556).
-// Single process = single GPU here; the multi-GPU path is launched with torchrun (bench.py / dist.py).
+// Multi-GPU: `-gpus N` (or USPMV_NUM_GPUS=N) stands in for `mpirun -n N ./uspmv ...`: the process forks one rank per GPU; the ranks
+// partition the rows (-seg_rows / -seg_nnz, identical work_sharing_arr), build their slab's SELL-C-sigma, discover the halo on the
+// device, trade need lists and CUDA-IPC handles through a shared-memory segment (what the reference does with MPI_Alltoallv /
+// MPI_Bcast at setup, mpi_funcs.hpp:117-232,1061-1124) and then run the SpMV loop with the NVLink peer-to-peer exchange
+// (uspmv_p2p_*): no MPI, no NCCL, no Python.
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -19,11 +23,18 @@
 #include <fstream>
 #include <iomanip>
 #include <iostream>
+#include <new>
 #include <numeric>
 #include <random>
 #include <sstream>
 #include <string>
 #include <vector>
+
+#include <pthread.h>
+#include <signal.h>
+#include <sys/mman.h>
+#include <sys/wait.h>
+#include <unistd.h>
 
 #include "../../include/uspmv_b200.h"
 
@@ -36,7 +47,7 @@ struct Config {  // classes_structs.hpp:47-153
     char random_init_x = '0';
     unsigned long n_repetitions = 1;
     int validate_result = 1, verbose = 0, block_vec_size = 1, comm_halos = 1, ba_synch = 1, par_pack = 0, no_pack = 0, print_comm_vol = 0,
-        equilibrate = 0;
+        equilibrate = 0, n_gpus = 1;
     char mode = 'b';
     double bench_time = 5.0, ap_threshold_1 = 0.0, ap_threshold_2 = 0.0, dropout = 0, dropout_threshold = 0.0;
     double matrix_min = 1.0, matrix_mean = 1.0, matrix_max = 1.0;
@@ -66,7 +77,8 @@ void usage(const char *argv0, const Config &c) {
             "-rev [%li] (int: number of back-to-back revisions to perform) \n"
             "-rand_x [%c] (0/1: random x vector option) \n"
             "-dp / sp / hp / ap[dp_sp] / ap[dp_hp] / ap[sp_hp] / ap[dp_sp_hp] [%s] (numerical precision of matrix data) \n"
-            "-seg_metis / seg_nnz / seg_rows [%s] (global matrix partitioning; multi-GPU runs use torchrun + bench.py) \n"
+            "-gpus [1] (ranks = GPUs of this node, replaces `mpirun -n`; env USPMV_NUM_GPUS) \n"
+            "-seg_metis / seg_nnz / seg_rows [%s] (global matrix partitioning over the ranks) \n"
             "-validate [%i] (0/1: check result against a host COO product in solve mode) \n"
             "-verbose [%i] (0/1: verbose validation of results) \n"
             "-mode [%c] ('s'/'b': either in solve mode or bench mode) \n"
@@ -89,6 +101,7 @@ void parse_cli(int argc, char **argv, Config &c) {  // utilities.hpp:1047-1545
     if (argc < 3) { usage(argv[0], c); exit(1); }
     c.matrix_file_name = argv[1];
     c.kernel_format = argv[2];
+    if (const char *e = getenv("USPMV_NUM_GPUS")) c.n_gpus = std::max(1, std::min(16, atoi(e)));
     auto need = [&](int &i) -> const char * {
         if (i + 1 >= argc) { fprintf(stderr, "ERROR: missing value for %s\n", argv[i]); usage(argv[0], c); exit(1); }
         return argv[++i];
@@ -122,6 +135,7 @@ void parse_cli(int argc, char **argv, Config &c) {  // utilities.hpp:1047-1545
         else if (a == "-seg_rows") c.seg_method = "seg-rows";
         else if (a == "-seg_nnz") c.seg_method = "seg-nnz";
         else if (a == "-seg_metis") c.seg_method = "seg-metis";
+        else if (a == "-gpus") { c.n_gpus = atoi(need(i)); if (c.n_gpus < 1 || c.n_gpus > 16) bad("ERROR: -gpus must be in [1,16]."); }
         else { fprintf(stderr, "ERROR: unknown argument: %s\n", argv[i]); usage(argv[0], c); exit(1); }
     }
     // sanity checks, utilities.hpp:1371-1545
@@ -143,8 +157,13 @@ void parse_cli(int argc, char **argv, Config &c) {  // utilities.hpp:1047-1545
     if (c.dropout && c.dropout_threshold == 0.0) fprintf(stderr, "WARNING: Dropout selected, but dropout_threshold is 0.\n");
     if (c.kernel_format != "crs" && c.kernel_format != "csr" && c.kernel_format != "scs") die("ERROR: kernel format not recognized.");
     if (c.kernel_format != "scs") { c.chunk_size = 1; c.sigma = 1; }  // CRS is the C = 1, sigma = 1 instance
-    printf("Single process: forcing comm_halos = 0.\n");
-    c.comm_halos = 0;
+    if (c.n_gpus == 1) {
+        printf("Single process: forcing comm_halos = 0.\n");
+        c.comm_halos = 0;
+    } else {
+        if (c.comm_halos != 1) die("ERROR: -gpus N > 1 always exchanges the halo (comm_halos = 1): the kernels read remote x elements.");
+        if (c.equilibrate && is_ap(c.value_type)) die("ERROR: -equilibrate with adaptive precision is single-GPU only.");
+    }
 }
 
 struct Coo {
@@ -248,11 +267,444 @@ std::vector<double> download(uspmv_ctx *ctx, const void *src, size_t n, int vt) 
     return out;
 }
 
+
+// =====================================================================================================================
+// Multi-GPU harness: one forked rank per GPU (stands in for the reference's MPI build, main.cpp:1035-1560).
+// =====================================================================================================================
+constexpr int MAXP = 16;
+struct RankInfo {
+    long n_local, n_halo, x_bytes, vec_length, nnz, n_elements, n_chunks, n_pad, part_nnz[3];
+    double runtime;
+    int recv_cumsum[MAXP + 1], need_ptr[MAXP + 1];
+    unsigned char ipc[64];
+};
+struct Shared {
+    pthread_barrier_t bar;
+    RankInfo info[MAXP];
+    long cap;        // ints per rank in the need-list area
+    long y_len;      // doubles in the result area
+};
+inline int *need_area(Shared *sh, int q) { return reinterpret_cast<int *>(reinterpret_cast<unsigned char *>(sh) + 65536) + (size_t)q * sh->cap; }
+inline double *y_area(Shared *sh, int P) { return reinterpret_cast<double *>(need_area(sh, P)); }
+
+// global problem size without touching CUDA (the parent must not create a context before fork)
+long peek_rows(const Config &cfg) {
+    if (cfg.matrix_file_name.rfind("gen:", 0) == 0) {
+        char kind[32];
+        long n = 0;
+        if (sscanf(cfg.matrix_file_name.c_str(), "gen:%31[^:]:%ld", kind, &n) != 2 || n < 1) die("ERROR: generator syntax is gen:laplace7:<n> or gen:stencil27:<n>");
+        return n * n * n;
+    }
+    std::ifstream f(cfg.matrix_file_name);
+    if (!f) die("Unable to open file");
+    std::string line;
+    std::getline(f, line);
+    do { if (!std::getline(f, line)) die("read_unsymmetric_sparse(): could not parse matrix size."); } while (line.empty() || line[0] == '%');
+    long M = 0, N = 0, nz = 0;
+    std::istringstream s(line);
+    if (!(s >> M >> N >> nz)) die("read_unsymmetric_sparse(): could not parse matrix size.");
+    return M;
+}
+
+int rank_main(Config cfg, const int rank, const int P, Shared *sh) {
+    auto barrier = [&] { pthread_barrier_wait(&sh->bar); };
+    uspmv_ctx *ctx = nullptr;
+    ck(uspmv_ctx_create(rank, &ctx));
+    const bool ap = is_ap(cfg.value_type);
+    const int ap_mode = cfg.value_type == "ap[dp_sp]" ? USPMV_AP_DP_SP : cfg.value_type == "ap[dp_hp]" ? USPMV_AP_DP_HP
+                        : cfg.value_type == "ap[sp_hp]" ? USPMV_AP_SP_HP : USPMV_AP_DP_SP_HP;
+    const int vt = cfg.value_type == "sp" ? USPMV_F32 : cfg.value_type == "hp" ? USPMV_F16 : USPMV_F64;
+    const int seg = cfg.seg_method == "seg-nnz" ? USPMV_SEG_NNZ : USPMV_SEG_ROWS;
+
+    // ---- global matrix -> work_sharing_arr -> this rank's slab (seg_work_sharing_arr, seg_mtx_struct, localize_row_idx) ------------
+    std::vector<int> wsa(P + 1, 0);
+    uspmv_coo *coo = nullptr;  // rows [wsa[rank], wsa[rank+1]), local row ids, GLOBAL columns
+    Coo host;                  // the whole matrix on the host (files only; rank 0 validates against it)
+    bool have_host = false;
+    long n_glob = 0;
+    const bool gen = cfg.matrix_file_name.rfind("gen:", 0) == 0;
+    int pts = 0;
+    long gn = 0;
+    if (gen) {
+        char kind[32];
+        sscanf(cfg.matrix_file_name.c_str(), "gen:%31[^:]:%ld", kind, &gn);
+        pts = !strcmp(kind, "laplace7") ? 7 : !strcmp(kind, "stencil27") ? 27 : 0;
+        if (!pts) die("ERROR: unknown generator");
+        n_glob = gn * gn * gn;
+        cfg.matrix_min = -1.0; cfg.matrix_max = pts - 1.0; cfg.matrix_mean = 0.0;
+    }
+    if (gen && seg == USPMV_SEG_ROWS && !cfg.equilibrate) {
+        // seg-rows needs no look at the matrix (mpi_funcs.hpp:446-465): floor(n/P) rows per rank, the remainder on the last one —
+        // every rank generates only its own rows, so matrices that do not fit one GPU (512^3 27-point) can be run
+        if (n_glob > 2147483647L) die("ERROR: more than 2^31-1 rows (IT = int, like the reference)");
+        for (int k = 0; k < P; ++k) wsa[k] = (int)(k * (n_glob / P));
+        wsa[P] = (int)n_glob;
+        ck(uspmv_coo_stencil(ctx, pts, gn, gn, gn, wsa[rank], wsa[rank + 1], &coo));
+    } else {
+        uspmv_coo *full = nullptr;
+        if (gen) ck(uspmv_coo_stencil(ctx, pts, gn, gn, gn, 0, n_glob, &full));
+        else {
+            MtxFile file = read_mtx(cfg.matrix_file_name);
+            if (file.entries.V.empty()) die("ERROR: empty matrix");
+            if (cfg.dropout) {
+                Coo k; k.n_rows = file.entries.n_rows; k.n_cols = file.entries.n_cols;
+                for (size_t i = 0; i < file.entries.V.size(); ++i)
+                    if (std::fabs(file.entries.V[i]) >= cfg.dropout_threshold) {
+                        k.I.push_back(file.entries.I[i]); k.J.push_back(file.entries.J[i]); k.V.push_back(file.entries.V[i]);
+                    }
+                file.entries = k;
+                if (file.entries.V.empty()) die("ERROR: dropout removed every element");
+            }
+            ck(uspmv_coo_from_entries(ctx, file.entries.n_rows, file.entries.n_cols, (long)file.entries.V.size(), file.entries.I.data(),
+                                      file.entries.J.data(), file.entries.V.data(), file.symmetric ? 1 : 0, &full));
+        }
+        if (cfg.equilibrate) ck(uspmv_coo_equilibrate(full, nullptr, nullptr));
+        long d3[3];
+        ck(uspmv_coo_dims(full, d3));
+        n_glob = d3[0];
+        host.n_rows = d3[0]; host.n_cols = d3[1];
+        host.I.resize(d3[2]); host.J.resize(d3[2]); host.V.resize(d3[2]);
+        ck(uspmv_coo_export(full, host.I.data(), host.J.data(), host.V.data()));
+        uspmv_coo_destroy(full);
+        have_host = true;
+        if (!gen) {
+            cfg.matrix_min = *std::min_element(host.V.begin(), host.V.end());
+            cfg.matrix_max = *std::max_element(host.V.begin(), host.V.end());
+            cfg.matrix_mean = std::accumulate(host.V.begin(), host.V.end(), 0.0) / host.V.size();
+        }
+        ck(uspmv_seg_work_sharing_arr(seg, d3[0], d3[2], host.I.data(), P, wsa.data()));
+        const long lo = std::lower_bound(host.I.begin(), host.I.end(), wsa[rank]) - host.I.begin();
+        const long hi = std::lower_bound(host.I.begin(), host.I.end(), wsa[rank + 1]) - host.I.begin();
+        std::vector<int> Il(host.I.begin() + lo, host.I.begin() + hi);
+        for (int &v : Il) v -= wsa[rank];
+        ck(uspmv_coo_from_host(ctx, wsa[rank + 1] - wsa[rank], d3[1], hi - lo, Il.data(), host.J.data() + lo, host.V.data() + lo, USPMV_F64, &coo));
+        if (rank != 0 || !(cfg.mode == 's' && cfg.validate_result)) { Coo().I.swap(host.I); Coo().J.swap(host.J); Coo().V.swap(host.V); have_host = false; }
+    }
+    if (rank == 0) {
+        printf("work_sharing_arr (%s):", cfg.seg_method.c_str());
+        for (int k = 0; k <= P; ++k) printf(" %d", wsa[k]);
+        printf("\n");
+    }
+    long cd[3];
+    ck(uspmv_coo_dims(coo, cd));
+    const long n_local = cd[0], nnz_local = cd[2];
+    if (n_local < 1) die("ERROR: a rank received no rows; use fewer GPUs for this matrix");
+
+    // ---- local format + halo discovery (convert_to_scs -> collect_local_needed_heri -> permute_scs_cols; main.cpp:1271-1308) ----------
+    uspmv_scs *scs = nullptr, *part[3] = {nullptr, nullptr, nullptr};
+    uspmv_halo *plan = nullptr;
+    long dims[8];
+    long part_nnz[3] = {0, 0, 0};
+    const int first = ap && ap_mode == USPMV_AP_SP_HP ? 1 : 0;
+    double t0 = now();
+    if (!ap) {
+        ck(uspmv_scs_build(ctx, coo, cfg.chunk_size, cfg.sigma, vt, nullptr, &scs));
+        ck(uspmv_halo_plan_create(scs, wsa.data(), rank, P, &plan));
+        ck(uspmv_scs_permute_cols(scs, nullptr));
+        ck(uspmv_scs_dims(scs, dims));
+    } else {
+        // AP under MPI is refused by the reference (utilities.hpp:1445-1451); here: per-rank partition_precisions, one halo numbering
+        // over the parts, x in the original local row order
+        uspmv_coo *pc[3] = {nullptr, nullptr, nullptr};
+        ck(uspmv_partition_precisions(ctx, coo, ap_mode, cfg.ap_threshold_1, cfg.ap_threshold_2, nullptr, nullptr, &pc[0], &pc[1], &pc[2]));
+        const int vts[3] = {USPMV_F64, USPMV_F32, USPMV_F16};
+        ck(uspmv_scs_build(ctx, pc[first], cfg.chunk_size, cfg.sigma, vts[first], nullptr, &part[first]));
+        ck(uspmv_scs_dims(part[first], dims));
+        std::vector<int> perm(dims[2]);
+        ck(uspmv_scs_export(part[first], nullptr, nullptr, nullptr, nullptr, perm.data(), nullptr));
+        std::vector<uspmv_scs *> used;
+        for (int p = 0; p < 3; ++p) {
+            if (!pc[p]) continue;
+            long d3[3];
+            ck(uspmv_coo_dims(pc[p], d3));
+            part_nnz[p] = d3[2];
+            if (p != first) ck(uspmv_scs_build(ctx, pc[p], cfg.chunk_size, cfg.sigma, vts[p], perm.data(), &part[p]));
+            uspmv_coo_destroy(pc[p]);
+            used.push_back(part[p]);
+        }
+        ck(uspmv_halo_plan_create_multi(used.data(), (int)used.size(), wsa.data(), rank, P, 0, &plan));
+    }
+    uspmv_coo_destroy(coo);
+    const double t_convert = now() - t0;
+    const long n_pad = dims[4], n_chunks = dims[5];
+    long n_elements = dims[6];
+    if (ap) { n_elements = 0; for (int p = 0; p < 3; ++p) if (part[p]) { long d[8]; ck(uspmv_scs_dims(part[p], d)); n_elements += d[6]; } }
+
+    // ---- comm schedule (collect_comm_idxs / organize_cumsums, mpi_funcs.hpp:117-232): the need lists are transposed through the
+    //      shared segment — send list to peer q = what q needs from this rank ----------------------------------------------------------
+    RankInfo &me = sh->info[rank];
+    long n_halo = 0;
+    ck(uspmv_halo_plan_counts(plan, me.recv_cumsum, &n_halo));
+    if (n_halo > sh->cap) die("ERROR: halo larger than the exchange area");
+    {
+        std::vector<int> flat(std::max<long>(n_halo, 1));
+        ck(uspmv_halo_plan_need(plan, flat.data(), me.need_ptr));
+        std::copy(flat.begin(), flat.begin() + n_halo, need_area(sh, rank));
+    }
+    me.n_local = n_local; me.n_halo = n_halo; me.nnz = nnz_local; me.n_elements = n_elements; me.n_chunks = n_chunks; me.n_pad = n_pad;
+    for (int p = 0; p < 3; ++p) me.part_nnz[p] = part_nnz[p];
+    barrier();
+    std::vector<int> send_flat, send_ptr(P + 1, 0);
+    for (int q = 0; q < P; ++q) {
+        const int *nq = need_area(sh, q);
+        const int a = sh->info[q].need_ptr[rank], b = sh->info[q].need_ptr[rank + 1];
+        send_flat.insert(send_flat.end(), nq + a, nq + b);
+        send_ptr[q + 1] = (int)send_flat.size();
+    }
+    if (send_flat.empty()) send_flat.push_back(0);
+    ck(uspmv_halo_plan_set_send(plan, send_flat.data(), send_ptr.data()));
+    if (cfg.print_comm_vol)
+        printf("rank %d: receives %ld halo elements, sends %d\n", rank, n_halo, send_ptr[P]);
+    long n_int = 0, n_bnd = 0;
+    if (!ap) ck(uspmv_scs_split_chunks(scs, &n_int, &n_bnd));
+
+    // ---- vectors + NVLink arena (main.cpp:1405-1431; init/finalize_halo_exchange, classes_structs.hpp:857-995) ---------------------------
+    const int bvs = cfg.block_vec_size;
+    const int layout = cfg.block_vec_layout == "rowwise" ? USPMV_ROWWISE : USPMV_COLWISE;
+    const int xvt = ap ? (ap_mode == USPMV_AP_SP_HP ? USPMV_F32 : USPMV_F64) : vt;
+    const long vec_length = n_local + std::max(n_pad - n_local, n_halo);  // n_local + max(scs_padding, halo_count)
+    const bool two_buf = cfg.mode == 's' && !ap && bvs == 1 && cfg.n_repetitions > 1;
+    uspmv_p2p *p2p = nullptr;
+    void *xb[2] = {nullptr, nullptr};
+    ck(uspmv_p2p_create_ex(plan, xvt, vec_length, bvs, layout, two_buf ? 2 : 1, &p2p, me.ipc, xb));
+    me.vec_length = vec_length;
+    me.x_bytes = ((long)vec_length * bvs * (long)vt_bytes(xvt) + 255) / 256 * 256;
+    barrier();
+    {
+        std::vector<unsigned char> handles((size_t)P * 64);
+        std::vector<long> pxb(P), pbase(P), pld(P);
+        for (int q = 0; q < P; ++q) {
+            memcpy(handles.data() + (size_t)q * 64, sh->info[q].ipc, 64);
+            pxb[q] = sh->info[q].x_bytes;
+            pbase[q] = sh->info[q].n_local + sh->info[q].recv_cumsum[rank];
+            pld[q] = sh->info[q].vec_length;
+        }
+        ck(uspmv_p2p_connect_ex(p2p, handles.data(), pxb.data(), pbase.data(), pld.data()));
+    }
+    barrier();
+    long nnz_total = 0, nel_total = 0, npad_total = 0, pn[3] = {0, 0, 0};
+    for (int q = 0; q < P; ++q) {
+        nnz_total += sh->info[q].nnz; nel_total += sh->info[q].n_elements; npad_total += sh->info[q].n_pad;
+        for (int p = 0; p < 3; ++p) pn[p] += sh->info[q].part_nnz[p];
+    }
+    const double beta = nel_total ? (double)nnz_total / (double)nel_total : 0.0;
+    printf("rank %d: rows [%d, %d), %ld nnz, %ld chunks (%ld interior / %ld boundary), %ld elements, halo %ld; conversion %.3f s\n", rank, wsa[rank],
+           wsa[rank + 1], nnz_local, n_chunks, n_int, n_bnd, n_elements, n_halo, t_convert);
+
+    std::vector<double> x_user(vec_length * bvs, 0.0);
+    {
+        std::mt19937 engine;  // every rank draws the same default-seeded sequence over ITS vector, like random_init under MPI
+        std::uniform_real_distribution<double> dist(cfg.matrix_min, cfg.matrix_max);
+        for (long i = 0; i < vec_length * bvs; ++i) {
+            double v = cfg.random_init_x == '1' ? dist(engine) : cfg.random_init_x == 'm' ? cfg.matrix_mean : 5.0;
+            const long r = layout == USPMV_ROWWISE ? i / bvs : i % vec_length;
+            x_user[i] = r < n_local ? v : 0.0;
+        }
+    }
+    std::vector<int> old_to_new(n_local), new_to_old(n_pad);
+    ck(uspmv_scs_export(ap ? part[first] : scs, nullptr, nullptr, nullptr, nullptr, old_to_new.data(), new_to_old.data()));
+    std::vector<double> x_perm(vec_length * bvs, 0.0);
+    for (long v = 0; v < bvs; ++v)
+        for (long i = 0; i < n_local; ++i) {
+            const long dst = ap ? i : old_to_new[i];
+            if (layout == USPMV_ROWWISE) x_perm[dst * bvs + v] = x_user[i * bvs + v];
+            else x_perm[dst + v * vec_length] = x_user[i + v * vec_length];
+        }
+    upload(ctx, xb[0], x_perm, xvt);
+    void *y_d = nullptr, *comm = nullptr;
+    ck(uspmv_malloc(ctx, vec_length * bvs * vt_bytes(xvt), &y_d));
+    ck(uspmv_memset(ctx, y_d, 0, vec_length * bvs * vt_bytes(xvt), nullptr));
+    ck(uspmv_stream_create(ctx, &comm));
+    ck(uspmv_ctx_sync(ctx));
+    barrier();
+
+    auto execute = [&]() {  // begin/finish halo exchange + kernel (main.cpp:464-468), one call
+        if (ap) ck(uspmv_p2p_ap_spmv(p2p, ap_mode, part[0], part[1], part[2], y_d, nullptr, comm));
+        else if (bvs > 1) ck(uspmv_p2p_spmmv(p2p, scs, 0, y_d, nullptr, comm));
+        else ck(uspmv_p2p_spmv(p2p, scs, y_d, nullptr, comm));
+    };
+    auto max_runtime = [&](double mine) {
+        me.runtime = mine;
+        barrier();
+        double m = 0.0;
+        for (int q = 0; q < P; ++q) m = std::max(m, sh->info[q].runtime);
+        barrier();
+        return m;
+    };
+    int rc = 0;
+    if (cfg.mode == 'b') {
+        const int WARM_UP_REPS = 100;
+        double tw = now();
+        for (int k = 0; k < WARM_UP_REPS; ++k) execute();
+        ck(uspmv_ctx_sync(ctx));
+        const double t_warm = max_runtime(now() - tw);
+        if (rank == 0) std::cout << "warm up time: " << t_warm << std::endl;
+        long n_iter = 2;
+        double runtime = 0.0;
+        do {
+            ck(uspmv_ctx_sync(ctx));
+            barrier();  // ba_synch: MPI_Barrier before the timed loop (main.cpp:440-447)
+            const double tb = now();
+            for (long k = 0; k < n_iter; ++k) execute();
+            ck(uspmv_ctx_sync(ctx));
+            runtime = max_runtime(now() - tb);  // the slowest rank decides, so every rank takes the same branch
+            n_iter *= 2;
+        } while (runtime < cfg.bench_time);
+        n_iter /= 2;
+        int err = 0;
+        long ep = 0;
+        ck(uspmv_p2p_status(p2p, &err, &ep));
+        if (err) { fprintf(stderr, "rank %d: halo exchange timed out (a peer never signalled)\n", rank); rc = 3; }
+        if (rank == 0) {
+            const double t_kernel = runtime / n_iter;
+            const double gflops = (double)nnz_total * 2.0 * bvs / t_kernel / 1e9;
+            printf("Total Gflops: %.6f   time per SpM(M)V: %.3f us   revisions: %ld   ranks: %d\n", gflops, t_kernel * 1e6, n_iter, P);
+            std::fstream out(cfg.output_filename_bench, std::fstream::in | std::fstream::out | std::fstream::app);
+            const int width = 32;
+            out << cfg.matrix_file_name << " with " << P << " MPI processes, and " << (npad_total + 255) / 256 << " block(s), and " << 256
+                << " thread(s) per block" << std::endl;
+            out << "kernel: " << cfg.kernel_format << ", block_vec_size: " << bvs;
+            if (cfg.kernel_format == "scs") out << ", C: " << cfg.chunk_size << " sigma: " << cfg.sigma << std::fixed << std::setprecision(8) << ", beta: " << beta;
+            out << ", block_vec_layout: " << cfg.block_vec_layout;
+            const double pct[3] = {nnz_total ? 100.0 * pn[0] / nnz_total : 0, nnz_total ? 100.0 * pn[1] / nnz_total : 0, nnz_total ? 100.0 * pn[2] / nnz_total : 0};
+            out << std::fixed << std::setprecision(2);
+            if (cfg.value_type == "ap[dp_sp]") out << ", data_type: ap[dp_sp], threshold: " << cfg.ap_threshold_1 << ", % dp elems: " << pct[0] << ", % sp elems: " << pct[1];
+            else if (cfg.value_type == "ap[dp_hp]") out << ", data_type: ap[dp_hp], threshold: " << cfg.ap_threshold_1 << ", % dp elems: " << pct[0] << ", % hp elems: " << pct[2];
+            else if (cfg.value_type == "ap[sp_hp]") out << ", data_type: ap[sp_hp], threshold: " << cfg.ap_threshold_1 << ", % sp elems: " << pct[1] << ", % hp elems: " << pct[2];
+            else if (cfg.value_type == "ap[dp_sp_hp]") out << ", data_type: ap[dp_sp_hp], threshold 1: " << cfg.ap_threshold_1 << ", threshold 2: " << cfg.ap_threshold_2 << ", % dp elems: " << pct[0] << ", % sp elems: " << pct[1] << ", % hp elems: " << pct[2];
+            else out << ", data_type: " << (cfg.value_type == "dp" ? "double" : cfg.value_type == "sp" ? "float" : "half");
+            out << ", revisions: " << n_iter << ", seg_method: " << cfg.seg_method << std::endl << std::endl;
+            out << std::left << std::setw(width) << "Total Gflops:" << std::left << std::setw(width) << "Total Walltime:" << std::endl;
+            out << std::left << std::setw(width) << "-------------" << std::left << std::setw(width) << "-------------" << std::endl;
+            out << std::left << std::setprecision(16) << std::left << std::setw(width) << gflops << std::left << std::setw(width) << runtime << std::endl;
+            out << std::endl << std::endl;
+        }
+    } else {
+        // ---- solve mode: rev x { exchange ; SpMV ; swap } (main.cpp:528-631), then every rank un-permutes its rows into the
+        //      shared result vector and rank 0 validates against the host COO product ----------------------------------------
+        if (cfg.n_repetitions > 1 && (ap || bvs > 1)) die("ERROR: multi-GPU solve mode with -rev > 1 supports plain SpMV only");
+        const void *result = y_d;
+        if (two_buf) {
+            int b = 0;
+            for (unsigned long it = 0; it < cfg.n_repetitions; ++it, b ^= 1) ck(uspmv_p2p_spmv_buf(p2p, scs, b, b ^ 1, nullptr, nullptr, comm));
+            result = xb[b];  // the last y, in permuted row order, rows < n_local
+        } else execute();
+        ck(uspmv_ctx_sync(ctx));
+        int err = 0;
+        long ep = 0;
+        ck(uspmv_p2p_status(p2p, &err, &ep));
+        if (err) { fprintf(stderr, "rank %d: halo exchange timed out\n", rank); rc = 3; }
+        std::vector<double> y_perm = download(ctx, result, (two_buf ? n_local : vec_length * bvs), xvt);
+        double *yg = y_area(sh, P);  // global y, vector v at yg[v * n_glob + row]
+        for (long v = 0; v < bvs; ++v)
+            for (long i = 0; i < n_local; ++i)
+                // (an empty row that tied with the padding rows of the last sigma-window may sit at a position >= n_local, which the
+                //  two-buffer loop does not store: its y is 0 by definition)
+                yg[v * n_glob + wsa[rank] + i] = two_buf ? (old_to_new[i] < n_local ? y_perm[old_to_new[i]] : 0.0)
+                                                 : layout == USPMV_ROWWISE ? y_perm[(long)old_to_new[i] * bvs + v] : y_perm[old_to_new[i] + v * vec_length];
+        // the x every rank used (identical local sequences), for the validator
+        double *xg = yg + (size_t)bvs * n_glob;
+        for (long v = 0; v < bvs; ++v)
+            for (long i = 0; i < n_local; ++i)
+                xg[v * n_glob + wsa[rank] + i] = layout == USPMV_ROWWISE ? x_user[i * bvs + v] : x_user[i + v * vec_length];
+        barrier();
+        if (rank == 0) {
+            printf("solve mode: %lu revision(s) on %d GPUs; y[0..3] =", cfg.n_repetitions, P);
+            for (long i = 0; i < std::min<long>(4, n_glob); ++i) printf(" %.10g", yg[i]);
+            printf("\n");
+            if (cfg.validate_result && have_host) {
+                double max_rel = 0.0;
+                const bool sp_x = ap && ap_mode == USPMV_AP_SP_HP;
+                for (long v = 0; v < bvs; ++v) {
+                    std::vector<double> xa(xg + v * n_glob, xg + (v + 1) * n_glob), ya(n_glob);
+                    if (sp_x) for (double &t : xa) t = (double)(float)t;
+                    for (unsigned long it = 0; it < cfg.n_repetitions; ++it) {
+                        std::fill(ya.begin(), ya.end(), 0.0);
+                        for (size_t k = 0; k < host.V.size(); ++k) ya[host.I[k]] += host.V[k] * xa[host.J[k]];
+                        if (it + 1 < cfg.n_repetitions) std::swap(xa, ya);
+                    }
+                    for (long i = 0; i < n_glob; ++i) {
+                        const double d = std::fabs(yg[v * n_glob + i] - ya[i]) / std::max(std::fabs(ya[i]), 1e-300);
+                        if (ya[i] != 0.0 && d > max_rel) max_rel = d;
+                    }
+                }
+                const char *verdict = max_rel > 1e-2 ? "ERROR" : max_rel > 1e-4 ? "WARNING" : "OK";
+                printf("validation vs host COO product: max relative difference %.3e -> %s\n", max_rel, verdict);
+                std::ofstream vf("spmv_validate_" + (ap ? std::string("ap") : cfg.value_type) + ".txt", std::ios::app);
+                vf << cfg.matrix_file_name << " ranks: " << P << " kernel: " << cfg.kernel_format << " C: " << cfg.chunk_size << " sigma: " << cfg.sigma
+                   << " data_type: " << cfg.value_type << " block_vec_size: " << bvs << " revisions: " << cfg.n_repetitions << " max_rel_diff: " << max_rel << " "
+                   << verdict << std::endl;
+                if (max_rel > 1e-2 && cfg.value_type == "dp") rc = 2;
+            }
+        }
+    }
+    fflush(stdout);
+    barrier();  // nobody unmaps a peer's arena while that peer may still be in its last exchange
+    uspmv_stream_destroy(ctx, comm);
+    uspmv_free(ctx, y_d);
+    uspmv_p2p_destroy(p2p);
+    uspmv_halo_destroy(plan);
+    if (scs) uspmv_scs_destroy(scs);
+    for (auto *p : part) if (p) uspmv_scs_destroy(p);
+    uspmv_ctx_destroy(ctx);
+    return rc;
+}
+
+int run_multi(const Config &cfg) {
+    const int P = cfg.n_gpus;
+    const long n_glob = peek_rows(cfg);
+    if (n_glob < P) die("ERROR: fewer rows than GPUs");
+    const int bvs = cfg.block_vec_size;
+    // shared segment: control block | need lists (P x n_glob ints, sparse) | y and x for the validator (2 x bvs x n_glob doubles)
+    const size_t bytes = 65536 + (size_t)P * n_glob * sizeof(int) + 2 * (size_t)bvs * n_glob * sizeof(double) + 4096;
+    void *mem = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+    if (mem == MAP_FAILED) die("ERROR: mmap of the rank exchange segment failed");
+    static_assert(sizeof(Shared) <= 65536, "control block");
+    Shared *sh = new (mem) Shared();
+    sh->cap = n_glob;
+    sh->y_len = (long)bvs * n_glob;
+    pthread_barrierattr_t at;
+    pthread_barrierattr_init(&at);
+    pthread_barrierattr_setpshared(&at, PTHREAD_PROCESS_SHARED);
+    pthread_barrier_init(&sh->bar, &at, P);
+    fflush(stdout);
+    fflush(stderr);
+    std::vector<pid_t> kids(P, 0);
+    for (int r = 0; r < P; ++r) {
+        pid_t pid = fork();
+        if (pid < 0) die("ERROR: fork failed");
+        if (pid == 0) {
+            int rc = rank_main(cfg, r, P, sh);
+            fflush(stdout);
+            _exit(rc);
+        }
+        kids[r] = pid;
+    }
+    // a rank that dies would leave the others at a barrier forever: the first failure takes the rest down (exact PIDs)
+    int worst = 0, left = P;
+    while (left > 0) {
+        int st = 0;
+        pid_t pid = wait(&st);
+        if (pid < 0) break;
+        --left;
+        const int rc = WIFEXITED(st) ? WEXITSTATUS(st) : 128 + (WIFSIGNALED(st) ? WTERMSIG(st) : 0);
+        for (pid_t &k : kids) if (k == pid) k = 0;
+        if (rc != 0) {
+            worst = std::max(worst, rc);
+            if (rc != 2)  // 2 = validation verdict ERROR on rank 0, the others finish normally
+                for (pid_t k : kids) if (k > 0) kill(k, SIGKILL);
+        }
+    }
+    munmap(mem, bytes);
+    return worst;
+}
+
 }  // namespace
 
 int main(int argc, char **argv) {
     Config cfg;
     parse_cli(argc, argv, cfg);
+    if (cfg.n_gpus > 1) return run_multi(cfg);
     uspmv_ctx *ctx = nullptr;
     ck(uspmv_ctx_create(0, &ctx));
 

@@ -43,6 +43,7 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=8.0, help="CPU baseline time box")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true", help="e2e: do not restrict the CPU affinity to the GPU's NUMA node while allocating pinned buffers")
     ap.add_argument("--strong", action="store_true", help="N>1: ONE n^3 grid cut into N z-slabs (config 5) instead of n^3 per GPU")
     ap.add_argument("--no-overlap", action="store_true", help="N>1: exchange first, then one full SpMV (the reference's order)")
     ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"], help="N>1: NVLink peer stores + epoch flags, or NCCL send/recv")
@@ -262,7 +263,8 @@ def run_ours(args):
         runner = pkg.engine.SingleGpuSpmv(ctx, pts, n, args.C, args.sigma, vt)
     else:
         runner = pkg.dist.DistributedSpmv(ctx, pts, n, args.C, args.sigma, vt, rank, world, halo=args.halo, overlap=not args.no_overlap,
-                                          strong=args.strong, bvs=args.bvs, layout=args.layout, n_buf=2 if args.solve else 1)
+                                          strong=args.strong, bvs=args.bvs, layout=args.layout,
+                                          n_buf=2 if (args.solve or (args.bvs == 1 and args.halo == "p2p")) else 1)
         if args.solve:
             state = {"buf": 0}
 
@@ -327,6 +329,8 @@ def run_ours(args):
     e2e = None
     if not args.no_e2e and not args.solve and not is_ap:
         e2e_steps = max(3, min(args.steps, 20))
+        # pinned staging buffers next to the GPU's PCIe root: first-touch under an affinity restricted to the GPU's NUMA node
+        bound = None if args.no_numa_bind else pkg.dist.bind_to_gpu_numa_node(local_rank)
         sec = runner.time_e2e(e2e_steps, barrier)
         te = torch.tensor([sec], dtype=torch.float64, device="cuda")
         if world > 1:
@@ -335,11 +339,16 @@ def run_ours(args):
                "d2h_bytes_per_step": int(runner.e2e_d2h_bytes), "steps": e2e_steps,
                "api": ("uspmv_spmv_host_submit/_wait (C ABI, pinned host x/y; every step copies its own x in and its own y out, "
                        "3 steps in flight so H2D / kernel / D2H of neighbouring steps overlap)") if (world == 1 and not block_or_solve) else
-                      "host x slab -> device, halo exchange + SpMV, y -> host, sync, per step"}
+                      ("uspmv_p2p_spmv_host_submit/_wait (C ABI, pinned host x/y per rank; every step copies its rank's x slab in and its y out, "
+                       "2 steps in flight over the two arena buffers, halo exchange inside every step)") if getattr(runner, "e2e_pipelined", False) else
+                      "host x slab -> device, halo exchange + SpMV, y -> host, sync, per step",
+               "host_numa": ({"node": bound["node"], "cpus": bound["cpus"]} if bound else None)}
         if world == 1 and not block_or_solve:
             sec1 = runner.time_e2e(max(3, e2e_steps // 2), barrier, pipelined=False)
             e2e["single_call_value"] = 2.0 * nnz_total / sec1 / 1e9
             e2e["single_call_api"] = "uspmv_spmv_host: H2D(x) + SpMV + D2H(y) + sync, one step at a time"
+        if bound:
+            os.sched_setaffinity(0, bound["previous"])  # the CPU baseline below uses all host cores again
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and not is_ap:

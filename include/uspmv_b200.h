@@ -237,6 +237,12 @@ int uspmv_p2p_spmmv(uspmv_p2p *p2p, const uspmv_scs *scs, int x_buf, void *Y_d, 
 /* The halo exchange alone — init_halo_exchange + finalize_halo_exchange (classes_structs.hpp:857-995): push the halo rows of
  * buffer x_buf into the neighbours' vectors over NVLink, wait for the own halo, acknowledge. */
 int uspmv_p2p_exchange(uspmv_p2p *p2p, int x_buf, void *stream, void *comm_stream);
+/* Host-buffer distributed SpMV, pipelined over the two buffers of the arena (n_buf = 2): call k uses slot k & 1 on every rank;
+ * x_h holds this rank's n_local x values (permuted order), y_h receives n_rows_padded values; both should be pinned.  H2D, the
+ * exchange + SpMV and D2H of neighbouring calls overlap.  (The harness copies x / y once around the whole loop,
+ * main.cpp:727-767; this is the per-call host-buffer form an application with host-resident vectors would use.) */
+int uspmv_p2p_spmv_host_submit(uspmv_p2p *p2p, const uspmv_scs *scs, const void *x_h, void *y_h, int slot);
+int uspmv_p2p_spmv_host_wait(uspmv_p2p *p2p, int slot);
 int uspmv_p2p_status(uspmv_p2p *p2p, int *error_flag, long *epoch);
 void uspmv_p2p_destroy(uspmv_p2p *p2p);
 

@@ -88,6 +88,27 @@ def _run_rank(rank, world, port, out_dir, C=32):
             err, ep = r.p2p.status()
             assert err == 0 and ep == 3
             np.save(os.path.join(out_dir, f"solve{rank}_{mode}.npy"), xf[: r.scs.n_rows][perm].cpu().numpy())
+            # ---- host-buffer calls pipelined over the same two buffers (uspmv_p2p_spmv_host_submit / _wait): 5 calls with different x,
+            #      two in flight; every y must equal the device-resident SpMV of that x
+            nl = r.scs.n_rows
+            xs_h = [((torch.sin(rows * (0.21 + 0.05 * k)) + 1.5).cpu()) for k in range(5)]
+            xh = [torch.empty(nl, dtype=torch.float64).pin_memory() for _ in range(5)]
+            yh = [torch.zeros(r.scs.n_rows_padded, dtype=torch.float64).pin_memory() for _ in range(5)]
+            pc = perm.cpu()
+            for k in range(5):
+                xh[k][pc] = xs_h[k]
+            torch.cuda.synchronize()
+            dist.barrier()
+            for k in range(5):
+                capi.call("uspmv_p2p_spmv_host_wait", r.p2p.h, k & 1)
+                capi.call("uspmv_p2p_spmv_host_submit", r.p2p.h, r.scs.h, xh[k].data_ptr(), yh[k].data_ptr(), k & 1)
+            for sl in (0, 1):
+                capi.call("uspmv_p2p_spmv_host_wait", r.p2p.h, sl)
+            with pytest.raises(capi.UspmvError):  # the slots alternate with the arena buffers
+                capi.call("uspmv_p2p_spmv_host_submit", r.p2p.h, r.scs.h, xh[0].data_ptr(), yh[0].data_ptr(), 0)  # call 5 belongs to slot 1
+            err, ep2 = r.p2p.status()
+            assert err == 0 and ep2 == ep + 5
+            np.save(os.path.join(out_dir, f"hosty{rank}_{mode}.npy"), np.stack([yh[k][: r.scs.n_rows_padded][pc].numpy() for k in range(5)]))
             del r
         dist.barrier()
     finally:
@@ -124,6 +145,11 @@ def _check(out_dir, world, mats):
     for mode in (2, 1, 0):
         got = np.concatenate([np.load(os.path.join(out_dir, f"solve{r}_{mode}.npy")) for r in range(world)])
         assert np.max(np.abs(got - x3)) <= 1e-11 * np.max(np.abs(x3)), mode
+        hy = np.concatenate([np.load(os.path.join(out_dir, f"hosty{r}_{mode}.npy")) for r in range(world)], axis=1)
+        for k in range(5):
+            xk = np.sin(np.arange(nr) * (0.21 + 0.05 * k)) + 1.5
+            ref = A @ xk
+            assert np.max(np.abs(hy[k] - ref)) <= 1e-12 * np.max(np.abs(ref)), (mode, k)
 
 
 @pytest.mark.parametrize("C", [32, 16])

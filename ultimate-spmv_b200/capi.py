@@ -88,6 +88,8 @@ _sigs = {
     "uspmv_spmmv_part_supported": [vp, C.c_int],
     "uspmv_p2p_status": [vp, C.POINTER(C.c_int), C.POINTER(C.c_long)],
     "uspmv_p2p_exchange": [vp, C.c_int, vp, vp],
+    "uspmv_p2p_spmv_host_submit": [vp, vp, vp, vp, C.c_int],
+    "uspmv_p2p_spmv_host_wait": [vp, C.c_int],
     "uspmv_halo_pack": [vp, vp, vp, C.c_int, C.c_int, C.c_long, C.c_int, vp],
 }
 for _name, _args in _sigs.items():

@@ -356,6 +356,12 @@ struct uspmv_p2p {
     bool connected = false;
     int mode = 2;  // 0: exchange, then one full SpMV; 1: push/wait kernels next to the interior kernel; 2: ONE fused kernel (C = 32)
     DevBuf<unsigned int> fused_counters;
+    // pipelined host-buffer steps (uspmv_p2p_spmv_host_submit / _wait): two slots = the two arena buffers
+    cudaStream_t s_h2d = nullptr, s_run = nullptr, s_d2h = nullptr, s_comm = nullptr;
+    cudaEvent_t ev_x[2] = {nullptr, nullptr}, ev_y[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    DevBuf<unsigned char> slot_y[2];
+    bool slot_busy[2] = {false, false};
+    long host_submits = 0;
     long n_push_tiles = 0, n_push_tiles_4k = 0;  // tiles (2048 / 4096 elements) of the large-halo push kernels (k_p2p_push_tiles)
     unsigned char *buffer(int b) const { return arena + (size_t)b * x_bytes; }
 };
@@ -876,6 +882,58 @@ int uspmv_p2p_exchange(uspmv_p2p *p, int x_buf, void *stream, void *comm_stream)
     });
 }
 
+/* Host-buffer distributed SpMV, pipelined (the e2e path of bench.py at N > 1; single GPU: uspmv_spmv_host_submit): the arena needs
+ * two buffers; call k (slot = k & 1 on EVERY rank — the buffers alternate like in the solve loop) copies this rank's x rows from
+ * pinned host memory into buffer `slot`, runs the distributed SpMV (exchange included) and copies y (n_rows_padded entries, permuted
+ * order) back, on three streams, so the PCIe transfers of call k overlap the kernel and the opposite-direction copy of call k +- 1. */
+int uspmv_p2p_spmv_host_submit(uspmv_p2p *p, const uspmv_scs *scs, const void *x_h, void *y_h, int slot) {
+    return guarded([&] {
+        if (!p || !scs || !x_h || !y_h) fail("uspmv_p2p_spmv_host_submit: NULL argument");
+        if (!p->connected) fail("uspmv_p2p_spmv_host_submit: call uspmv_p2p_connect first");
+        if (p->n_buf != 2 || p->bvs != 1) fail("uspmv_p2p_spmv_host_submit: needs an arena with two single-vector buffers (uspmv_p2p_create_ex, n_buf = 2)");
+        if (slot != (int)(p->host_submits & 1)) fail("uspmv_p2p_spmv_host_submit: slot must alternate 0, 1, 0, ... on every rank (expected %d)", (int)(p->host_submits & 1));
+        if (p->slot_busy[slot]) fail("uspmv_p2p_spmv_host_submit: slot %d is still in flight (call uspmv_p2p_spmv_host_wait)", slot);
+        uspmv_halo *h = p->plan;
+        USPMV_CUDA(cudaSetDevice(h->ctx->device));
+        const size_t es = vt_size(p->vt);
+        if (!p->s_run) {
+            USPMV_CUDA(cudaStreamCreateWithFlags(&p->s_h2d, cudaStreamNonBlocking));
+            USPMV_CUDA(cudaStreamCreateWithFlags(&p->s_run, cudaStreamNonBlocking));
+            USPMV_CUDA(cudaStreamCreateWithFlags(&p->s_d2h, cudaStreamNonBlocking));
+            USPMV_CUDA(cudaStreamCreateWithFlags(&p->s_comm, cudaStreamNonBlocking));
+            for (int k = 0; k < 2; ++k) {
+                USPMV_CUDA(cudaEventCreateWithFlags(&p->ev_x[k], cudaEventDisableTiming));
+                USPMV_CUDA(cudaEventCreateWithFlags(&p->ev_y[k], cudaEventDisableTiming));
+                USPMV_CUDA(cudaEventCreateWithFlags(&p->ev_done[k], cudaEventDisableTiming));
+            }
+        }
+        const size_t y_bytes = (size_t)scs->n_rows_padded * es;
+        if (p->slot_y[slot].n < y_bytes) p->slot_y[slot].alloc(y_bytes);
+        // buffer `slot` was last read by the SpMV of two calls ago (ev_y[slot]); its D2H (ev_done[slot]) was waited for by the caller
+        if (p->host_submits >= 2) USPMV_CUDA(cudaStreamWaitEvent(p->s_h2d, p->ev_y[slot], 0));
+        USPMV_CUDA(cudaMemcpyAsync(p->buffer(slot), x_h, (size_t)h->n_local * es, cudaMemcpyHostToDevice, p->s_h2d));
+        USPMV_CUDA(cudaEventRecord(p->ev_x[slot], p->s_h2d));
+        USPMV_CUDA(cudaStreamWaitEvent(p->s_run, p->ev_x[slot], 0));
+        if (uspmv_p2p_spmv_buf(p, scs, slot, -1, p->slot_y[slot].p, p->s_run, p->s_comm)) throw Error(uspmv_last_error());
+        USPMV_CUDA(cudaEventRecord(p->ev_y[slot], p->s_run));
+        USPMV_CUDA(cudaStreamWaitEvent(p->s_d2h, p->ev_y[slot], 0));
+        USPMV_CUDA(cudaMemcpyAsync(y_h, p->slot_y[slot].p, y_bytes, cudaMemcpyDeviceToHost, p->s_d2h));
+        USPMV_CUDA(cudaEventRecord(p->ev_done[slot], p->s_d2h));
+        p->slot_busy[slot] = true;
+        ++p->host_submits;
+    });
+}
+
+int uspmv_p2p_spmv_host_wait(uspmv_p2p *p, int slot) {
+    return guarded([&] {
+        if (!p) fail("uspmv_p2p_spmv_host_wait: NULL argument");
+        if (slot < 0 || slot > 1) fail("uspmv_p2p_spmv_host_wait: slot must be 0 or 1");
+        if (!p->slot_busy[slot]) return;
+        USPMV_CUDA(cudaEventSynchronize(p->ev_done[slot]));
+        p->slot_busy[slot] = false;
+    });
+}
+
 int uspmv_p2p_set_overlap(uspmv_p2p *p, int overlap) {
     return guarded([&] {
         if (!p) fail("uspmv_p2p_set_overlap: NULL argument");
@@ -899,6 +957,11 @@ void uspmv_p2p_destroy(uspmv_p2p *p) {
     if (!p) return;
     for (unsigned char *q : p->peer_arena)
         if (q) cudaIpcCloseMemHandle(q);
+    for (cudaStream_t st : {p->s_h2d, p->s_run, p->s_d2h, p->s_comm})
+        if (st) cudaStreamDestroy(st);
+    for (int k = 0; k < 2; ++k)
+        for (cudaEvent_t ev : {p->ev_x[k], p->ev_y[k], p->ev_done[k]})
+            if (ev) cudaEventDestroy(ev);
     if (p->ev_main) cudaEventDestroy(p->ev_main);
     if (p->ev_comm) cudaEventDestroy(p->ev_comm);
     if (p->arena) cudaFree(p->arena);

@@ -56,6 +56,41 @@ def seg_nnz_from_row_counts(counts, world: int) -> np.ndarray:
     return wsa.astype(np.int32)
 
 
+def bind_to_gpu_numa_node(device_index: int):
+    """Restricts this process's CPU affinity to the cores of the NUMA node the GPU hangs off, so that pinned host buffers allocated
+    afterwards are first-touched next to the GPU's PCIe root (8 ranks staging 268 MB per SpMV through one socket's memory is what
+    bounds the host-buffer path otherwise).  Returns {"node", "cpus", "previous"} or None when the topology is not exposed."""
+    import os
+    import subprocess
+    try:
+        bdf = None
+        try:
+            import torch
+            pr = torch.cuda.get_device_properties(device_index)
+            bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        except Exception:
+            out = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(device_index)],
+                                 capture_output=True, text=True, timeout=20).stdout.strip().lower()
+            bdf = out[-12:] if len(out) >= 12 else None
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        previous = os.sched_getaffinity(0)
+        allowed = previous & cpus
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return {"node": node, "cpus": len(allowed), "previous": previous, "bdf": bdf}
+    except Exception:
+        return None
+
+
 def comm_schedule(need_lists, rank: int, world: int, group=None):
     """collect_comm_idxs (mpi_funcs.hpp:117-172): every rank tells every owner which owner-local x indices it needs.
     need_lists[p] = indices this rank needs from owner p.  Returns send_lists[q] = indices rank q needs from us."""
@@ -311,11 +346,36 @@ class DistributedSpmv:
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / steps
 
-    def time_e2e(self, steps, barrier):
-        """Host-buffer step: H2D of this rank's x slab, halo exchange + SpMV, D2H of y."""
+    def time_e2e(self, steps, barrier, pipelined=None):
+        """Host-buffer step: H2D of this rank's x slab, halo exchange + SpMV, D2H of y.  pipelined (needs the two-buffer P2P arena,
+        single vector): uspmv_p2p_spmv_host_submit / _wait, two calls in flight, each still copying its own x in and its own y out."""
         import time
         torch = self._torch
         n = self.scs.n_rows
+        if pipelined is None:
+            pipelined = self.p2p is not None and self.p2p.n_buf == 2 and self.bvs == 1
+        self.e2e_pipelined = bool(pipelined)
+        if pipelined:
+            xh = [torch.full((n,), 5.0, dtype=self.x.dtype).pin_memory() for _ in range(2)]
+            yh = [torch.zeros(self.scs.n_rows_padded, dtype=self.y.dtype).pin_memory() for _ in range(2)]
+            self._e2e_k = getattr(self, "_e2e_k", 0)
+
+            def run(k):
+                for _ in range(k):
+                    sl = self._e2e_k & 1
+                    call("uspmv_p2p_spmv_host_wait", self.p2p.h, sl)
+                    call("uspmv_p2p_spmv_host_submit", self.p2p.h, self.scs.h, vp(xh[sl].data_ptr()), vp(yh[sl].data_ptr()), sl)
+                    self._e2e_k += 1
+                for sl in range(2):
+                    call("uspmv_p2p_spmv_host_wait", self.p2p.h, sl)
+            run(2)
+            barrier()
+            t0 = time.perf_counter()
+            run(steps)
+            barrier()
+            dt = (time.perf_counter() - t0) / steps
+            self.e2e_y = yh[(self._e2e_k - 1) & 1]
+            return dt
         rowwise = self.bvs > 1 and self.layout == capi.ROWWISE
         n_in = n * self.bvs if (self.bvs == 1 or rowwise) else n  # column-major: the local part of every vector
         xh = torch.full((n_in,), 5.0, dtype=self.x.dtype).pin_memory()
@@ -336,6 +396,7 @@ class DistributedSpmv:
         for _ in range(steps):
             one()
         barrier()
+        self.e2e_y = yh
         return (time.perf_counter() - t0) / steps
 
 

@@ -163,8 +163,9 @@ def cpu_reference_run(pts, n, C, sigma, vt, steps, warmup, time_box=None):
     """Builds the matrix with the reference's convert_to_scs and times its OpenMP kernel (spmv_omp_scs_adv,
     kernels.hpp:265-301) on all host cores.  Returns (seconds_per_spmv, steps_done, nnz, threads, build_seconds)."""
     import numpy as np
-    ncpu = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(ncpu))
+    ncpu = len(os.sched_getaffinity(0)) or os.cpu_count() or 1
+    if os.environ.get("TORCHELASTIC_RUN_ID") or os.environ.get("OMP_NUM_THREADS") in (None, "1"):
+        os.environ["OMP_NUM_THREADS"] = str(ncpu)  # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every host core
     os.environ.setdefault("OMP_PROC_BIND", "close")
     os.environ.setdefault("OMP_PLACES", "cores")
     from oracle import bindings
@@ -172,6 +173,11 @@ def cpu_reference_run(pts, n, C, sigma, vt, steps, warmup, time_box=None):
         raise RuntimeError("oracle/_ref is not built (run __graft_entry__.build() where /root/reference exists)")
     orc = bindings.Oracle()
     ref = bindings.Ref("col")
+    try:  # libgomp may have been initialised (with torchrun's OMP_NUM_THREADS=1) before the lines above ran
+        import ctypes
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(int(os.environ["OMP_NUM_THREADS"]))
+    except (OSError, KeyError, ValueError):
+        pass
     t0 = time.time()
     n_rows, n_cols, I, J, V = orc.stencil_coo(pts, n, n, n)
     s = ref.convert_to_scs(n_rows, n_cols, I, J, V, C, sigma, vt, permute_cols=True)

@@ -43,8 +43,19 @@ int main() {
     const long n = 1L << 28;  // 268 M gathers per launch (1 GB of indices: streamed, larger than L2)
     int *idx; cudaMalloc(&idx, n * 4);
     double *out; cudaMalloc(&out, 64);
-    for (int mode = 0; mode < 2; ++mode)
+    size_t g0 = 0;
+    cudaDeviceGetLimit(&g0, cudaLimitMaxL2FetchGranularity);
+    printf("default cudaLimitMaxL2FetchGranularity = %zu B\n", g0);
+    for (size_t gran : {(size_t)0, (size_t)128, (size_t)64, (size_t)32}) {
+      if (gran) {
+          cudaError_t e = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
+          size_t g1 = 0;
+          cudaDeviceGetLimit(&g1, cudaLimitMaxL2FetchGranularity);
+          printf("---- cudaLimitMaxL2FetchGranularity set to %zu (%s), reads back %zu\n", gran, cudaGetErrorString(e), g1);
+      }
+    for (int mode = 0; mode < (gran ? 1 : 2); ++mode)
         for (long mb : {32, 96, 134, 268, 1024}) {
+            if (gran && mb != 268 && mb != 1024) continue;
             const long m = mb * 1024 * 1024 / 8;
             double *x; cudaMalloc(&x, m * 8); cudaMemset(x, 0, m * 8);
             k_fill<<<(unsigned)((n + 255) / 256), 256>>>(idx, n, m, mode);
@@ -55,5 +66,6 @@ int main() {
             }
             cudaFree(x);
         }
+    }
     return 0;
 }

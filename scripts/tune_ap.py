@@ -29,14 +29,18 @@ for mode in os.environ.get("PL_MODES", "ap[dp_sp_hp],ap[dp_sp]").split(","):
     n_pad = P[used[0]].n_rows_padded
     x = torch.full((max(n_pad, n),), 1.0, dtype=torch.float64, device="cuda"); y = torch.zeros(n_pad, dtype=torch.float64, device="cuda")
     print(mode, "n_elements", [p.n_elements if p is not None else 0 for p in P], "nnz", nnz, flush=True)
-    for var in (0, 1, 2, 3, 4):
-        line = f"  variant {var}: "
-        for split in [int(v) for v in os.environ.get("PL_SPLITS", "0,64,128,256,512").split(",")]:
-            capi.set_option("ap_variant", var); capi.set_option("split_long_chunks", split)
-            us = timeit(lambda: eng.ap_spmv(mode, P[0], P[1], P[2], x, y))
-            res[f"{mode}|v{var}|split{split}"] = us
-            line += f"split{split}={us:.0f} "
-        print(line, flush=True)
+    for gran in [int(v) for v in os.environ.get("PL_L2", "0").split(",")]:
+        if gran:
+            capi.set_option("l2_fetch_granularity", gran)
+            print(f" cudaLimitMaxL2FetchGranularity = {gran}", flush=True)
+        for var in [int(v) for v in os.environ.get("PL_VARIANTS", "0,1,2,3,4").split(",")]:
+            line = f"  variant {var}: "
+            for split in [int(v) for v in os.environ.get("PL_SPLITS", "0,64,128,256,512").split(",")]:
+                capi.set_option("ap_variant", var); capi.set_option("split_long_chunks", split)
+                us = timeit(lambda: eng.ap_spmv(mode, P[0], P[1], P[2], x, y))
+                res[f"{mode}|v{var}|split{split}|l2gran{gran}"] = us
+                line += f"split{split}={us:.0f} "
+            print(line, flush=True)
     del coos, P
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 json.dump(res, open(os.path.join(ROOT, "gpurun_out", f"tune_ap_{n}.json"), "w"), indent=1)

@@ -113,6 +113,7 @@ struct Options {
                                  // direct peer stores, 2 = tiles gathered into shared memory and written to the peer by the bulk-copy
                                  // engine, 3 = like 1 with tiles of 4096 elements
     int push_ctas_per_sm = 0;    // CTAs per SM of the large-halo push kernels (0 = default)
+    int l2_fetch_granularity = 0; // cudaLimitMaxL2FetchGranularity (32 / 64 / 128 bytes; 0 = leave the driver default)
     long push_min_elements = 1L << 20;  // halos with at least this many elements to send use the tiled push kernels
 };
 Options &options();

@@ -16,6 +16,7 @@ Options &options() {
         if (const char *e = std::getenv("USPMV_STREAM_VARIANT")) c.stream_variant = std::atoi(e);
         if (const char *e = std::getenv("USPMV_STREAM_BPS")) c.stream_blocks_per_sm = std::max(1, std::atoi(e));
         if (const char *e = std::getenv("USPMV_STRICT_REFERENCE_HALO")) c.strict_reference_halo = std::atoi(e) != 0;
+        if (const char *e = std::getenv("USPMV_L2_FETCH")) c.l2_fetch_granularity = std::atoi(e);
         if (const char *e = std::getenv("USPMV_PUSH_VARIANT")) c.push_variant = std::atoi(e);
         if (const char *e = std::getenv("USPMV_PUSH_CTAS_PER_SM")) c.push_ctas_per_sm = std::max(0, std::atoi(e));
         return c;
@@ -47,6 +48,11 @@ int uspmv_set_option(const char *name, long value) {
         else if (!std::strcmp(name, "push_variant")) c.push_variant = (int)value;
         else if (!std::strcmp(name, "push_ctas_per_sm")) c.push_ctas_per_sm = (int)std::max(0L, value);
         else if (!std::strcmp(name, "push_min_elements")) c.push_min_elements = std::max(0L, value);
+        else if (!std::strcmp(name, "l2_fetch_granularity")) {
+            if (value != 0 && value != 32 && value != 64 && value != 128) fail("uspmv_set_option: l2_fetch_granularity must be 0, 32, 64 or 128");
+            c.l2_fetch_granularity = (int)value;
+            if (value) USPMV_CUDA(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)value));  // current device
+        }
         else fail("uspmv_set_option: unknown option '%s'", name);
     });
 }
@@ -83,6 +89,8 @@ int uspmv_ctx_create(int device, uspmv_ctx **out) {
         if (prop.major != 10)
             fail("uspmv_ctx_create: device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major,
                  prop.minor);
+        if (options().l2_fetch_granularity)
+            USPMV_CUDA(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)options().l2_fetch_granularity));
         auto *ctx = new uspmv_ctx();
         ctx->device = device;
         ctx->n_sm = prop.multiProcessorCount;

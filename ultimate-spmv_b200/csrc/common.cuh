@@ -102,6 +102,7 @@ struct DevBuf {
 // run-time knobs (uspmv_set_option / environment), defined in context.cu
 struct Options {
     bool scs_stream = true;      // C = 32: bulk-copy streamed kernel (false: direct-load kernel)
+    bool scs_stream_wide = true; // C = 64 / 128: wide-chunk streamed kernel (false: direct-load kernel)
     int stream_variant = 0;      // (slots per piece, ring depth, warps per CTA) instantiation
     int stream_blocks_per_sm = 2;
     int mmv_variant = 0;         // SpMMV streamed kernel: 0 = tuned default, 1..4 force a variant (see spmv_kernels.cu)

@@ -550,6 +550,132 @@ k_scs32_stream(long n_items, const int *__restrict__ chunk_list, int chunk_offse
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Wide chunks: C = 32 * H (H = 2, 4: C = 64, 128).  A chunk of C rows is still ONE contiguous range (slot j holds C consecutive
+// elements), so the same per-warp ring applies: a stage keeps 8 / H slots of C elements (the stage size of the C = 32 kernel),
+// lane l owns the H rows l, l + 32, ... of the chunk with one accumulator each and walks its slots in order (bit-identical to the
+// direct kernel and to the oracle).  8 gathers in flight per lane like the C = 32 kernel.
+// ---------------------------------------------------------------------------------------------------------------------
+template <typename VT, typename A, int H, int D, int WARPS, bool UNPERM>
+__global__ void __launch_bounds__(WARPS * 32, (1024 / (WARPS * 32)) > 0 ? (1024 / (WARPS * 32)) : 1)
+k_scsw_stream(int n_items, const int *__restrict__ chunk_list, int chunk_offset, const int *__restrict__ chunk_ptrs,
+              const int *__restrict__ chunk_lengths, const int *__restrict__ col_idxs, const VT *__restrict__ values,
+              const VT *__restrict__ x, VT *__restrict__ y, const int *__restrict__ new_to_old) {
+    constexpr int LS = 8;         // slot-rows (32 elements each) per stage
+    constexpr int LW = LS / H;    // slots of a wide chunk per piece
+    constexpr int C = 32 * H;
+    using R = WarpRing<VT, LS, D>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char *base = smem_raw + (size_t)warp * R::BYTES_ALIGNED;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(base + D * R::STAGE_BYTES);
+    PieceHdr *hdrs = reinterpret_cast<PieceHdr *>(base + D * R::STAGE_BYTES + D * 8);
+    const int W = (int)gridDim.x * WARPS;
+    const int first = (int)blockIdx.x * WARPS + warp;
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < D; ++s) mbar_init(&bars[s], 1);
+        fence_barrier_init();
+    }
+    __syncwarp();
+    const uint64_t pol = policy_evict_first();
+    uint32_t phase_bits = 0;
+    auto item_chunk = [&](int k) -> int { return chunk_list ? chunk_list[k] : k + chunk_offset; };
+
+    // ---- producer (lane 0), three-deep metadata lookahead as in stream_items ----------------------------------------
+    int pc = first;
+    int pj = 0, plen = 0, pcs = 0, pchunk = 0, nlen = 0, ncs = 0, nchunk = 0, n2chunk = 0;
+    if (lane == 0) {
+        if (pc < n_items) { pchunk = item_chunk(pc); plen = chunk_lengths[pchunk]; pcs = chunk_ptrs[pchunk]; }
+        if (pc + W < n_items) { nchunk = item_chunk(pc + W); nlen = chunk_lengths[nchunk]; ncs = chunk_ptrs[nchunk]; }
+        if (pc + 2 * W < n_items) n2chunk = item_chunk(pc + 2 * W);
+    }
+    auto issue = [&](int s) {
+        PieceHdr h;
+        if (pc >= n_items) {
+            h.ns = 0; h.flags = 0; h.chunk = 0; h.pad = 0;
+            hdrs[s] = h;
+            return;
+        }
+        const int ns = min(LW, plen - pj);
+        h.ns = ns;
+        h.flags = 4 | (pj == 0 ? 1 : 0) | (pj + ns >= plen ? 2 : 0);
+        h.chunk = pchunk;
+        h.pad = 0;
+        hdrs[s] = h;
+        if (ns > 0) {
+            const int e0 = pcs + pj * C;
+            const uint32_t vb = (uint32_t)(ns * C) * (uint32_t)sizeof(VT), cb = (uint32_t)(ns * C) * 4u;
+            unsigned char *st = base + s * R::STAGE_BYTES;
+            mbar_expect_tx(&bars[s], vb + cb);
+            bulk_g2s(st, values + e0, vb, &bars[s], pol);
+            bulk_g2s(st + R::VAL_BYTES, col_idxs + e0, cb, &bars[s], pol);
+        }
+        pj += ns;
+        if (pj >= plen) {
+            pc += W;
+            pj = 0;
+            pchunk = nchunk; plen = nlen; pcs = ncs;
+            nchunk = n2chunk;
+            if (pc + W < n_items) { nlen = chunk_lengths[nchunk]; ncs = chunk_ptrs[nchunk]; }
+            if (pc + 2 * W < n_items) n2chunk = item_chunk(pc + 2 * W);
+        }
+    };
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < D; ++s) issue(s);
+    }
+    __syncwarp();
+
+    // ---- consumer ----------------------------------------------------------------------------------------------------
+    typename A::acc_t acc[H];
+#pragma unroll
+    for (int h = 0; h < H; ++h) acc[h] = A::zero();
+    for (int s = 0;; s = (s + 1 == D) ? 0 : s + 1) {
+        const PieceHdr hd = hdrs[s];
+        if (hd.flags == 0) break;
+        if (hd.flags & 1) {
+#pragma unroll
+            for (int h = 0; h < H; ++h) acc[h] = A::zero();
+        }
+        if (hd.ns > 0) {
+            mbar_wait(&bars[s], (phase_bits >> s) & 1u);
+            phase_bits ^= (1u << s);
+            const VT *sv = reinterpret_cast<const VT *>(base + s * R::STAGE_BYTES) + lane;
+            const int *sc = reinterpret_cast<const int *>(base + s * R::STAGE_BYTES + R::VAL_BYTES) + lane;
+            VT v[LS], xv[LS];
+            int col[LS];
+            // slot-row r = j * H + h of the stage: slot j, rows h * 32 + lane
+#pragma unroll
+            for (int r = 0; r < LS; ++r)
+                if (r < hd.ns * H) col[r] = sc[r * 32];
+#pragma unroll
+            for (int r = 0; r < LS; ++r)
+                if (r < hd.ns * H) xv[r] = __ldg(x + col[r]);
+#pragma unroll
+            for (int r = 0; r < LS; ++r)
+                if (r < hd.ns * H) v[r] = sv[r * 32];
+#pragma unroll
+            for (int r = 0; r < LS; ++r)
+                if (r < hd.ns * H) acc[r % H] = A::mad(v[r], xv[r], acc[r % H]);
+        }
+        if (hd.flags & 2) {
+#pragma unroll
+            for (int h = 0; h < H; ++h) {
+                const long row = (long)hd.chunk * C + h * 32 + lane;
+                if (UNPERM) {
+                    const int o = new_to_old[row];
+                    if (o >= 0) y[o] = A::out(acc[h]);
+                } else
+                    y[row] = A::out(acc[h]);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) issue(s);
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // Variant with SOFTWARE-PIPELINED x gathers (D >= 3).  ncu on k_scs32_stream (profiles/r01i_*): 46 % of the stall samples
 // sit on the first FMA of a piece, i.e. warps wait for the x gathers they have just issued.  Here the gathers of piece p+1
 // are issued BEFORE the FMAs of piece p, so a piece's gathers have one whole piece-time to come back:

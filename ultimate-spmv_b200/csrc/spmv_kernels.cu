@@ -292,6 +292,27 @@ void launch_stream_v(long n_chunks, const int *list, int off, const int *cp, con
     kern<<<(unsigned)grid, WARPS * 32, smem, st>>>(n_chunks, list, off, cp, cl, ci, v, x, y, n2o, stream::FusedArgs{});
 }
 
+// C = 64 / 128: the wide-chunk streamed kernel (scs_stream.cuh, k_scsw_stream)
+template <typename VT, bool UNPERM, int H>
+void launch_stream_wide(long n_chunks, const int *list, int off, const int *cp, const int *cl, const int *ci, const VT *v, const VT *x, VT *y,
+                        const int *n2o, cudaStream_t st) {
+    constexpr int D = 2, WARPS = 16;
+    using R = stream::WarpRing<VT, 8, D>;
+    auto kern = stream::k_scsw_stream<VT, Arith<VT>, H, D, WARPS, UNPERM>;
+    constexpr int smem = WARPS * R::BYTES_ALIGNED;
+    static bool configured = false;
+    if (!configured) {
+        USPMV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    int dev = 0;
+    USPMV_CUDA(cudaGetDevice(&dev));
+    long grid = (long)sm_count(dev) * options().stream_blocks_per_sm;
+    const long need = (n_chunks + WARPS - 1) / WARPS;
+    if (grid > need) grid = need;
+    kern<<<(unsigned)grid, WARPS * 32, smem, st>>>((int)n_chunks, list, off, cp, cl, ci, v, x, y, n2o);
+}
+
 template <typename VT, bool UNPERM, int LMAX, int D, int WARPS>
 void launch_stream_pf(long n_chunks, const int *list, int off, const int *cp, const int *cl, const int *ci, const VT *v, const VT *x, VT *y,
                       const int *n2o, cudaStream_t st, int bps_req) {
@@ -414,6 +435,12 @@ void launch_scs(long C, long n_chunks, const int *cp, const int *cl, const int *
     VT *yy = static_cast<VT *>(y);
     if (C == 32 && options().scs_stream) {
         launch_stream<VT, UNPERM>(n_chunks, list, off, cp, cl, ci, v, xx, yy, n2o, st);
+        USPMV_LAUNCH_CHECK();
+        return;
+    }
+    if ((C == 64 || C == 128) && options().scs_stream && options().scs_stream_wide) {
+        if (C == 64) launch_stream_wide<VT, UNPERM, 2>(n_chunks, list, off, cp, cl, ci, v, xx, yy, n2o, st);
+        else launch_stream_wide<VT, UNPERM, 4>(n_chunks, list, off, cp, cl, ci, v, xx, yy, n2o, st);
         USPMV_LAUNCH_CHECK();
         return;
     }

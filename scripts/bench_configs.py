@@ -42,7 +42,7 @@ if "spmmv" in which:
         del scs
 
 if "formats" in which:
-    for (C, sigma, vt) in ((1, 1, "dp"), (16, 1, "dp"), (64, 1, "dp"), (128, 1, "dp"), (64, 1, "sp"), (128, 1, "sp"), (64, 1, "hp"), (32, 1, "sp"), (32, 1, "hp"), (1, 1, "sp"), (32, 512, "dp")):
+    for (C, sigma, vt) in ((1, 1, "dp"), (16, 1, "dp"), (8, 1, "dp"), (16, 1, "sp"), (16, 1, "hp"), (64, 1, "dp"), (128, 1, "dp"), (64, 1, "sp"), (128, 1, "sp"), (64, 1, "hp"), (32, 1, "sp"), (32, 1, "hp"), (1, 1, "sp"), (32, 512, "dp")):
         mtx = eng.MtxData.stencil(7, N, N, N)
         t0 = time.time(); scs = eng.convert_to_scs(mtx, C, sigma, vt); eng.permute_scs_cols(scs); torch.cuda.synchronize(); tb = time.time() - t0
         del mtx

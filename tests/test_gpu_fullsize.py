@@ -86,12 +86,14 @@ def test_full_size_linearity_and_formats(eng, lap, t):
     eng.spmv(crs, x1, yc)
     assert t.equal(yc, y1)
     del crs
-    # C = 128 through the direct kernel
-    s128 = eng.convert_to_scs(mtx, 128, 1, "dp")
-    eng.permute_scs_cols(s128)
-    eng.spmv(s128, x1, yc)
-    assert t.equal(yc, y1)
-    del s128
+    # C = 128 / 64 through the wide-chunk streamed kernel, C = 16 / 8 through the narrow-chunk one (same per-row FMA order)
+    for Cw in (128, 64, 16, 8):
+        sw = eng.convert_to_scs(mtx, Cw, 1, "dp")
+        eng.permute_scs_cols(sw)
+        yc.zero_()
+        eng.spmv(sw, x1, yc)
+        assert t.equal(yc, y1), Cw
+        del sw
     # SpMMV: every column of the block product equals the SpMV of that column (same FMA order), both layouts
     for layout in ("rowwise", "colwise"):
         bvs = 4

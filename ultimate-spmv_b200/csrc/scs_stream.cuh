@@ -676,6 +676,167 @@ k_scsw_stream(int n_items, const int *__restrict__ chunk_list, int chunk_offset,
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Narrow chunks: C = 32 / G (G = 2, 4: C = 16 — a half-warp —, 8).  A warp takes G ADJACENT chunks at once (work item k = chunks
+// G k ... G k + G - 1 of a contiguous chunk range): lane l belongs to sub-chunk g = l / C, so the 32 rows of an item are the 32
+// consecutive padded rows 32 k + l.  Every piece covers the same slot window [pj, pj + 8) of all G sub-chunks; sub-chunk g
+// contributes ns_g = clamp(len_g - pj, 0, 8) slots, fetched by its own pair of bulk copies into region g of the stage (regions
+// are one slot-row apart modulo the bank window, so the two half-warps never meet in a shared-memory bank).  Per row the slots
+// are consumed in order: bit-identical to the direct kernel and the oracle.
+// ---------------------------------------------------------------------------------------------------------------------
+template <typename VT, int G, int D>
+struct NarrowRing {  // per-warp ring of the narrow-chunk kernel: G regions per array, one slot-row of padding BETWEEN regions
+    static constexpr int LMAX = 8, C = 32 / G;
+    static constexpr int RV = (LMAX + 1) * C * (int)sizeof(VT), RC = (LMAX + 1) * C * 4;  // region strides
+    static constexpr int VAL_BYTES = G * LMAX * C * (int)sizeof(VT) + (G - 1) * C * (int)sizeof(VT);
+    static constexpr int COL_BYTES = G * LMAX * C * 4 + (G - 1) * C * 4;
+    static constexpr int STAGE_BYTES = VAL_BYTES + COL_BYTES;
+    static constexpr int META_BYTES = 4 * G * 4;  // producer state of lane 0: {len, ptr} of the current item (+ spare)
+    static constexpr int BYTES = D * STAGE_BYTES + D * 8 + D * (int)sizeof(PieceHdr) + META_BYTES;
+    static constexpr int BYTES_ALIGNED = (BYTES + 127) / 128 * 128;
+};
+
+template <typename VT, typename A, int G, int D, int WARPS, bool UNPERM>
+__global__ void __launch_bounds__(WARPS * 32, (1024 / (WARPS * 32)) > 0 ? (1024 / (WARPS * 32)) : 1)
+k_scsn_stream(int n_chunks, int chunk_offset, const int *__restrict__ chunk_ptrs, const int *__restrict__ chunk_lengths,
+              const int *__restrict__ col_idxs, const VT *__restrict__ values, const VT *__restrict__ x, VT *__restrict__ y,
+              const int *__restrict__ new_to_old) {
+    using R = NarrowRing<VT, G, D>;
+    constexpr int LMAX = R::LMAX, C = R::C, RV = R::RV, RC = R::RC;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char *base = smem_raw + (size_t)warp * R::BYTES_ALIGNED;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(base + D * R::STAGE_BYTES);
+    PieceHdr *hdrs = reinterpret_cast<PieceHdr *>(base + D * R::STAGE_BYTES + D * 8);
+    int *meta = reinterpret_cast<int *>(base + D * R::STAGE_BYTES + D * 8 + D * (int)sizeof(PieceHdr));
+    int *plen = meta, *pcs = meta + G;  // current item: shared memory, touched by lane 0 only
+    int nlen[G], ncs[G];                // next item: registers, so that its loads stay in flight until the item becomes current
+    const int W = (int)gridDim.x * WARPS;
+    const int first = (int)blockIdx.x * WARPS + warp;
+    const int n_items = (n_chunks + G - 1) / G;
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < D; ++s) mbar_init(&bars[s], 1);
+        fence_barrier_init();
+    }
+    __syncwarp();
+    const uint64_t pol = policy_evict_first();
+    uint32_t phase_bits = 0;
+
+    // ---- producer (lane 0): current item + one item of metadata lookahead ---------------------------------------------
+    int pc = first, pj = 0;
+    auto load_meta = [&](int item, int *len, int *cs) {
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const int c = item * G + g;
+            const bool ok = c < n_chunks;
+            len[g] = ok ? chunk_lengths[chunk_offset + c] : 0;
+            cs[g] = ok ? chunk_ptrs[chunk_offset + c] : 0;
+        }
+    };
+#pragma unroll
+    for (int g = 0; g < G; ++g) { nlen[g] = 0; ncs[g] = 0; }
+    if (lane == 0) {
+#pragma unroll
+        for (int g = 0; g < 2 * G; ++g) meta[g] = 0;
+        if (pc < n_items) load_meta(pc, plen, pcs);
+        if (pc + W < n_items) load_meta(pc + W, nlen, ncs);
+    }
+    auto issue = [&](int s) {
+        PieceHdr h;
+        if (pc >= n_items) {
+            h.ns = 0; h.flags = 0; h.chunk = 0; h.pad = 0;
+            hdrs[s] = h;
+            return;
+        }
+        int maxlen = 0;
+#pragma unroll
+        for (int g = 0; g < G; ++g) maxlen = max(maxlen, plen[g]);
+        unsigned int packed = 0, bytes = 0;
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const int n = min(LMAX, max(0, plen[g] - pj));
+            packed |= (unsigned int)n << (8 * g);
+            bytes += (unsigned int)(n * C) * ((unsigned int)sizeof(VT) + 4u);
+        }
+        const int ns = min(LMAX, maxlen - pj);
+        h.ns = ns;
+        h.flags = 4 | (pj == 0 ? 1 : 0) | (pj + ns >= maxlen ? 2 : 0);
+        h.chunk = pc;
+        h.pad = (int)packed;
+        hdrs[s] = h;
+        if (bytes > 0) {
+            unsigned char *st = base + s * R::STAGE_BYTES;
+            mbar_expect_tx(&bars[s], bytes);
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                const int n = (int)((packed >> (8 * g)) & 0xffu);
+                if (n > 0) {
+                    const int e0 = pcs[g] + pj * C;
+                    bulk_g2s(st + g * RV, values + e0, (uint32_t)(n * C) * (uint32_t)sizeof(VT), &bars[s], pol);
+                    bulk_g2s(st + R::VAL_BYTES + g * RC, col_idxs + e0, (uint32_t)(n * C) * 4u, &bars[s], pol);
+                }
+            }
+        }
+        pj += ns;
+        if (pj >= maxlen) {
+            pc += W;
+            pj = 0;
+#pragma unroll
+            for (int g = 0; g < G; ++g) { plen[g] = nlen[g]; pcs[g] = ncs[g]; }
+            if (pc + W < n_items) load_meta(pc + W, nlen, ncs);
+        }
+    };
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < D; ++s) issue(s);
+    }
+    __syncwarp();
+
+    // ---- consumer ----------------------------------------------------------------------------------------------------
+    const int g = lane / C, l = lane % C;
+    typename A::acc_t acc = A::zero();
+    for (int s = 0;; s = (s + 1 == D) ? 0 : s + 1) {
+        const PieceHdr hd = hdrs[s];
+        if (hd.flags == 0) break;
+        if (hd.flags & 1) acc = A::zero();
+        if (hd.pad != 0) {  // some sub-chunk has slots in this piece
+            mbar_wait(&bars[s], (phase_bits >> s) & 1u);
+            phase_bits ^= (1u << s);
+            const int my_ns = ((unsigned int)hd.pad >> (8 * g)) & 0xff;
+            const VT *sv = reinterpret_cast<const VT *>(base + s * R::STAGE_BYTES + g * RV) + l;
+            const int *sc = reinterpret_cast<const int *>(base + s * R::STAGE_BYTES + R::VAL_BYTES + g * RC) + l;
+            VT v[LMAX], xv[LMAX];
+            int col[LMAX];
+#pragma unroll
+            for (int j = 0; j < LMAX; ++j)
+                if (j < my_ns) col[j] = sc[j * C];
+#pragma unroll
+            for (int j = 0; j < LMAX; ++j)
+                if (j < my_ns) xv[j] = __ldg(x + col[j]);
+#pragma unroll
+            for (int j = 0; j < LMAX; ++j)
+                if (j < my_ns) v[j] = sv[j * C];
+#pragma unroll
+            for (int j = 0; j < LMAX; ++j)
+                if (j < my_ns) acc = A::mad(v[j], xv[j], acc);
+        }
+        if (hd.flags & 2) {
+            const long row = ((long)chunk_offset + (long)hd.chunk * G) * C + lane;  // the item's 32 consecutive padded rows
+            if (row < ((long)chunk_offset + n_chunks) * C) {
+                if (UNPERM) {
+                    const int o = new_to_old[row];
+                    if (o >= 0) y[o] = A::out(acc);
+                } else
+                    y[row] = A::out(acc);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) issue(s);
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // Variant with SOFTWARE-PIPELINED x gathers (D >= 3).  ncu on k_scs32_stream (profiles/r01i_*): 46 % of the stall samples
 // sit on the first FMA of a piece, i.e. warps wait for the x gathers they have just issued.  Here the gathers of piece p+1
 // are issued BEFORE the FMAs of piece p, so a piece's gathers have one whole piece-time to come back:

@@ -313,6 +313,28 @@ void launch_stream_wide(long n_chunks, const int *list, int off, const int *cp, 
     kern<<<(unsigned)grid, WARPS * 32, smem, st>>>((int)n_chunks, list, off, cp, cl, ci, v, x, y, n2o);
 }
 
+// C = 16 / 8: the narrow-chunk streamed kernel (scs_stream.cuh, k_scsn_stream); contiguous chunk ranges only
+template <typename VT, bool UNPERM, int G>
+void launch_stream_narrow(long n_chunks, int off, const int *cp, const int *cl, const int *ci, const VT *v, const VT *x, VT *y, const int *n2o,
+                          cudaStream_t st) {
+    constexpr int D = 2, WARPS = 16;
+    using R = stream::NarrowRing<VT, G, D>;
+    auto kern = stream::k_scsn_stream<VT, Arith<VT>, G, D, WARPS, UNPERM>;
+    constexpr int smem = WARPS * R::BYTES_ALIGNED;
+    static bool configured = false;
+    if (!configured) {
+        USPMV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    int dev = 0;
+    USPMV_CUDA(cudaGetDevice(&dev));
+    long grid = (long)sm_count(dev) * options().stream_blocks_per_sm;
+    const long n_items = (n_chunks + G - 1) / G;
+    const long need = (n_items + WARPS - 1) / WARPS;
+    if (grid > need) grid = need;
+    kern<<<(unsigned)grid, WARPS * 32, smem, st>>>((int)n_chunks, off, cp, cl, ci, v, x, y, n2o);
+}
+
 template <typename VT, bool UNPERM, int LMAX, int D, int WARPS>
 void launch_stream_pf(long n_chunks, const int *list, int off, const int *cp, const int *cl, const int *ci, const VT *v, const VT *x, VT *y,
                       const int *n2o, cudaStream_t st, int bps_req) {
@@ -435,6 +457,15 @@ void launch_scs(long C, long n_chunks, const int *cp, const int *cl, const int *
     VT *yy = static_cast<VT *>(y);
     if (C == 32 && options().scs_stream) {
         launch_stream<VT, UNPERM>(n_chunks, list, off, cp, cl, ci, v, xx, yy, n2o, st);
+        USPMV_LAUNCH_CHECK();
+        return;
+    }
+    // narrow chunks: G adjacent chunks per warp need a contiguous chunk range that starts at a multiple of G
+    // Measured at 256^3 (scripts/narrow_vs_direct.py): C = 16 streamed / direct: dp 340 / 342 us, sp 203 / 215, hp 204 / 230; C = 8 (G = 4):
+    // 410 / 349, 255 / 228, 281 / 234 — the producer of the narrow kernel issues 2 G bulk copies per piece and its instruction count,
+    // not bandwidth, bounds it.  So: C = 16 in sp / hp only; everything else narrow stays on the direct kernel.
+    if (C == 16 && sizeof(VT) < 8 && options().scs_stream && options().scs_stream_wide && !list && off % 2 == 0) {
+        launch_stream_narrow<VT, UNPERM, 2>(n_chunks, off, cp, cl, ci, v, xx, yy, n2o, st);
         USPMV_LAUNCH_CHECK();
         return;
     }

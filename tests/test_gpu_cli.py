@@ -34,7 +34,8 @@ def test_interface_shim_example(eng):
     assert "max|y - y_coo|" in r.stdout
 
 
-@pytest.mark.parametrize("fmt_args", [["scs", "-c", "32", "-s", "512"], ["scs", "-c", "16", "-s", "64"], ["crs"], ["scs", "-c", "4", "-s", "1"]])
+@pytest.mark.parametrize("fmt_args", [["scs", "-c", "32", "-s", "512"], ["scs", "-c", "16", "-s", "64"], ["scs", "-c", "128", "-s", "128"], ["crs"],
+                                      ["scs", "-c", "4", "-s", "1"]])
 @pytest.mark.parametrize("vt", ["-dp", "-sp"])
 def test_cli_solve_mode_validates(eng, tmp_path, fmt_args, vt):
     m = write_mtx(str(tmp_path / "bcsstk13.mtx"), "bcsstk13")
@@ -119,7 +120,7 @@ def _two_gpus():
 
 
 @pytest.mark.parametrize("seg", ["-seg_rows", "-seg_nnz"])
-@pytest.mark.parametrize("fmt_args", [["scs", "-c", "32", "-s", "128"], ["scs", "-c", "16", "-s", "64"], ["crs"]])
+@pytest.mark.parametrize("fmt_args", [["scs", "-c", "32", "-s", "128"], ["scs", "-c", "16", "-s", "64"], ["scs", "-c", "64", "-s", "64"], ["crs"]])
 def test_cli_multi_gpu_solve_validates(eng, tmp_path, seg, fmt_args):
     """`uspmv ... -gpus 2` = the reference's `mpirun -n 2 ./uspmv ...`: forked ranks, row partition, device halo discovery, need
     lists / IPC handles through shared memory, NVLink exchange inside every SpMV; validated against the host COO product."""

@@ -50,6 +50,14 @@ if "formats" in which:
         sec = timeit(lambda: eng.spmv(scs, x, y))
         nb = scs.n_elements * (VS[vt] + 4) + 8 * scs.n_chunks + 2 * VS[vt] * scs.n_rows_padded
         report(f"spmv 7pt{N} C{C} s{sigma} {vt} (build {tb*1e3:.0f} ms)", sec, nb, 2.0 * scs.nnz)
+        if C == 1 and vt == "dp":  # the raw-array entry point uspmv_csr_gpu on caller-owned arrays of exactly nnz elements
+            e = scs.export()
+            nnz = int(e.chunk_ptrs[scs.n_rows])
+            rp, ci, va = (torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (e.chunk_ptrs[: scs.n_rows + 1], e.col_idxs[:nnz], e.values[:nnz]))
+            del e
+            sec = timeit(lambda: eng.uspmv_csr_gpu(scs.n_rows, rp, ci, va, x, y))
+            report(f"uspmv_csr_gpu (caller-owned arrays) 7pt{N} dp", sec, nb, 2.0 * scs.nnz)
+            del rp, ci, va
         del scs, x, y
 
 if "ap" in which:

@@ -226,6 +226,33 @@ def test_spmv_raw_array_entry_points(eng, orc, mats):
     assert np.all(np.abs(y2.cpu().numpy() - y_ref) <= 1e-12 * np.maximum(scale, 1e-300))
 
 
+@pytest.mark.parametrize("vt", ["dp", "sp", "hp"])
+@pytest.mark.parametrize("n", [37, 1000, 4099])
+def test_csr_raw_arrays_exact_size(eng, orc, mats, vt, n):
+    """uspmv_csr_gpu on caller-owned arrays of EXACTLY nnz elements (no slack): the streamed kernel stops its bulk copies at nnz & ~7 and
+    reads the last elements with plain loads -> sequential per row, bit-identical to the reference loop (kernels.hpp:46-57), for every
+    nnz mod 8; a base pointer that is not 16-byte aligned falls back to the split-row kernel (tolerance)."""
+    t = torch_()
+    for seed in range(4):
+        coo = positive_coo(mats, n, 5, seed=100 + seed)  # positive data: the split-row fallback below is compared relative to |y|
+        crs = orc.convert_to_scs(*coo, 1, 1, vt)
+        nnz = int(crs.chunk_ptrs[crs.n_rows])
+        x = np.random.default_rng(seed).uniform(0.1, 1.0, crs.n_rows).astype(NPT[vt])
+        rp, ci, va = dev(crs.chunk_ptrs[: crs.n_rows + 1].copy()), dev(crs.col_idxs[:nnz].copy()), dev(crs.values[:nnz].copy())
+        y = t.zeros(crs.n_rows, dtype=va.dtype, device="cuda")
+        eng.uspmv_csr_gpu(crs.n_rows, rp, ci, va, dev(x), y)
+        t.cuda.synchronize()
+        y_ref = orc.spmv_csr(crs.n_rows, crs.chunk_ptrs, crs.col_idxs, crs.values, x)
+        assert np.array_equal(y.cpu().numpy().view(np.uint8), y_ref.view(np.uint8)), ("streamed", vt, n, seed, nnz % 8)
+        # misaligned bases: one element into a larger buffer
+        ci2 = t.empty(nnz + 1, dtype=t.int32, device="cuda"); ci2[1:] = ci
+        va2 = t.empty(nnz + 1, dtype=va.dtype, device="cuda"); va2[1:] = va
+        y.zero_()
+        eng.uspmv_csr_gpu(crs.n_rows, rp, ci2[1:], va2[1:], dev(x), y)
+        t.cuda.synchronize()
+        assert rel_err(y.cpu().numpy(), y_ref) <= TOL[vt], ("misaligned fallback", vt, n, seed)
+
+
 def test_spmv_unpermuted_fused(eng, orc, mats):
     """Fused form: x and y in user numbering, columns not permuted, y[new_to_old[row]] written directly."""
     t = torch_()

@@ -1079,7 +1079,8 @@ __global__ void k_reduce_partials(long n_split, const int *__restrict__ split_ch
 // ---------------------------------------------------------------------------------------------------------------------
 // CRS (C = 1, sigma = 1) through the same per-warp ring.  A warp takes blocks of 32 consecutive rows; their elements are
 // one contiguous range [row_ptrs[r0], row_ptrs[r0+32]) which is streamed in tiles of LMAX*32 elements (tile starts aligned to
-// 8 elements so that every bulk copy is 16-byte aligned for fp64 / fp32 / fp16; the arrays carry 8 elements of slack).
+// 8 elements so that every bulk copy is 16-byte aligned for fp64 / fp32 / fp16; copies stop at nnz & ~7, the last < 8 elements of
+// the matrix are read with plain loads, so caller-owned arrays without slack are fine).
 // Lane l walks the part of ITS row that lies inside the current tile sequentially, so the per-row summation order is the
 // reference's (kernels.hpp:46-57): bit-identical to the sequential loop, unlike the split-row vector kernel.
 // ---------------------------------------------------------------------------------------------------------------------
@@ -1105,6 +1106,7 @@ k_csr_stream(long n_rows, const int *__restrict__ row_ptrs, const int *__restric
     __syncwarp();
     const uint64_t pol = policy_evict_first();
 
+    const int nnz8 = row_ptrs[n_rows] & ~7;  // elements below this index are fetched by (16-byte granular) bulk copies
     auto block_range = [&](long rb, int &b0, int &b1) {
         const long r0 = rb * 32, r1 = min(r0 + 32, n_rows);
         b0 = row_ptrs[r0];
@@ -1125,8 +1127,8 @@ k_csr_stream(long n_rows, const int *__restrict__ row_ptrs, const int *__restric
             return;
         }
         int n = 0;
-        if (pt < pb1) {
-            const int end8 = (pb1 + 7) & ~7;
+        if (pt < pb1 && pt < nnz8) {
+            const int end8 = min((pb1 + 7) & ~7, nnz8);  // never read past the arrays: the last (< 8) elements go through global loads
             n = min(TILE, end8 - pt);
             unsigned char *st = base + s * R::STAGE_BYTES;
             const uint32_t vb = (uint32_t)n * (uint32_t)sizeof(VT), cb = (uint32_t)n * 4u;
@@ -1135,7 +1137,7 @@ k_csr_stream(long n_rows, const int *__restrict__ row_ptrs, const int *__restric
             bulk_g2s(st + R::VAL_BYTES, col_idxs + pt, cb, &bars[s], pol);
         }
         const bool first = pt == (pb0 & ~7);
-        const bool last = pt + n >= pb1;
+        const bool last = pt + n >= pb1 || pt + n >= nnz8;
         h.ns = n;                 // elements in this tile (0: the block has no elements at all)
         h.flags = 4 | (first ? 1 : 0) | (last ? 2 : 0);
         h.chunk = (int)pb;        // row block
@@ -1191,6 +1193,9 @@ k_csr_stream(long n_rows, const int *__restrict__ row_ptrs, const int *__restric
             }
         }
         if (h.flags & 2) {
+            // the final nnz % 8 elements of the matrix are not covered by a bulk copy (caller-owned arrays have no slack):
+            // the rows that own them finish through global loads, in order
+            for (int e = max(beg, h.pad + h.ns); e < end; ++e) acc = A::mad(values[e], __ldg(x + col_idxs[e]), acc);
             const long r = (long)h.chunk * 32 + lane;
             if (r < n_rows) y[r] = A::out(acc);
         }

@@ -21,6 +21,7 @@
 #include "scs_stream.cuh"
 
 #include <algorithm>
+#include <cstdint>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -688,10 +689,13 @@ int uspmv_csr_gpu(uspmv_ctx *ctx, int vt, long n_rows, const int *rp, const int 
     return guarded([&] {
         if (!ctx) fail("uspmv_csr_gpu: ctx is NULL");
         cudaStream_t st = as_stream(stream);
+        // caller-owned arrays: the streamed kernel (sequential per row, bit-identical to kernels.hpp:46-57) needs 16-byte aligned
+        // bases for its bulk copies; otherwise the split-row vector kernel
+        const bool streamed = options().scs_stream && reinterpret_cast<uintptr_t>(ci) % 16 == 0 && reinterpret_cast<uintptr_t>(vals) % 16 == 0;
         switch (vt) {
-        case USPMV_F64: launch_csr<double>(n_rows, -1, rp, ci, vals, x, y, st); break;
-        case USPMV_F32: launch_csr<float>(n_rows, -1, rp, ci, vals, x, y, st); break;
-        case USPMV_F16: launch_csr<__half>(n_rows, -1, rp, ci, vals, x, y, st); break;
+        case USPMV_F64: streamed ? launch_csr_stream<double>(n_rows, rp, ci, vals, x, y, st) : launch_csr<double>(n_rows, -1, rp, ci, vals, x, y, st); break;
+        case USPMV_F32: streamed ? launch_csr_stream<float>(n_rows, rp, ci, vals, x, y, st) : launch_csr<float>(n_rows, -1, rp, ci, vals, x, y, st); break;
+        case USPMV_F16: streamed ? launch_csr_stream<__half>(n_rows, rp, ci, vals, x, y, st) : launch_csr<__half>(n_rows, -1, rp, ci, vals, x, y, st); break;
         default: fail("uspmv_csr_gpu: invalid value type %d", vt);
         }
     });

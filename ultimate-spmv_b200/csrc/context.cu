@@ -39,6 +39,7 @@ int uspmv_set_option(const char *name, long value) {
         Options &c = options();
         if (!std::strcmp(name, "scs_stream")) c.scs_stream = value != 0;
         else if (!std::strcmp(name, "scs_stream_wide")) c.scs_stream_wide = value != 0;
+        else if (!std::strcmp(name, "narrow_dp")) c.narrow_dp = value != 0;
         else if (!std::strcmp(name, "stream_variant")) c.stream_variant = (int)value;
         else if (!std::strcmp(name, "stream_blocks_per_sm")) c.stream_blocks_per_sm = (int)std::max(1L, value);
         else if (!std::strcmp(name, "mmv_variant")) c.mmv_variant = (int)std::max(0L, value);

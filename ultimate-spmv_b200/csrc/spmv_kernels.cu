@@ -315,10 +315,10 @@ void launch_stream_wide(long n_chunks, const int *list, int off, const int *cp, 
 }
 
 // C = 16 / 8: the narrow-chunk streamed kernel (scs_stream.cuh, k_scsn_stream); contiguous chunk ranges only
-template <typename VT, bool UNPERM, int G>
+template <typename VT, bool UNPERM, int G, int WARPS = 16>
 void launch_stream_narrow(long n_chunks, int off, const int *cp, const int *cl, const int *ci, const VT *v, const VT *x, VT *y, const int *n2o,
                           cudaStream_t st) {
-    constexpr int D = 2, WARPS = 16;
+    constexpr int D = 2;
     using R = stream::NarrowRing<VT, G, D>;
     auto kern = stream::k_scsn_stream<VT, Arith<VT>, G, D, WARPS, UNPERM>;
     constexpr int smem = WARPS * R::BYTES_ALIGNED;
@@ -465,8 +465,10 @@ void launch_scs(long C, long n_chunks, const int *cp, const int *cl, const int *
     // Measured at 256^3 (scripts/narrow_vs_direct.py): C = 16 streamed / direct: dp 340 / 342 us, sp 203 / 215, hp 204 / 230; C = 8 (G = 4):
     // 410 / 349, 255 / 228, 281 / 234 — the producer of the narrow kernel issues 2 G bulk copies per piece and its instruction count,
     // not bandwidth, bounds it.  So: C = 16 in sp / hp only; everything else narrow stays on the direct kernel.
-    if (C == 16 && sizeof(VT) < 8 && options().scs_stream && options().scs_stream_wide && !list && off % 2 == 0) {
-        launch_stream_narrow<VT, UNPERM, 2>(n_chunks, off, cp, cl, ci, v, xx, yy, n2o, st);
+    if (C == 16 && (sizeof(VT) < 8 || options().narrow_dp) && options().scs_stream && options().scs_stream_wide && !list && off % 2 == 0) {
+        // fp64: 12 warps per CTA (<= 85 registers, nothing spilled); 16 warps / 64 registers spill the pending metadata loads
+        if (sizeof(VT) == 8) launch_stream_narrow<VT, UNPERM, 2, 12>(n_chunks, off, cp, cl, ci, v, xx, yy, n2o, st);
+        else launch_stream_narrow<VT, UNPERM, 2>(n_chunks, off, cp, cl, ci, v, xx, yy, n2o, st);
         USPMV_LAUNCH_CHECK();
         return;
     }

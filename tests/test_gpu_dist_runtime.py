@@ -22,7 +22,12 @@ def _run_rank(rank, world, port, out_dir, C=32):
         eng, capi, d = pkg.engine, pkg.capi, pkg.dist
         n = 48
         results = {}
-        for halo, mode in (("p2p", 2), ("p2p", 1), ("p2p", 0), ("nccl", True), ("nccl", False)):
+        # pv > 0: the large-halo push kernels (tiled direct stores / shared memory + bulk copy / 4096-element tiles) forced onto this
+        # small halo, here with the permuted-x gather (perm != NULL); the un-permuted form is covered by the AP test below
+        for halo, mode, pv in (("p2p", 2, 0), ("p2p", 1, 0), ("p2p", 0, 0), ("nccl", True, 0), ("nccl", False, 0), ("p2p", 1, 1), ("p2p", 0, 2),
+                               ("p2p", 1, 3)):
+            capi.set_option("push_variant", pv if pv else -1)
+            capi.set_option("push_min_elements", 0 if pv else 1 << 20)
             r = d.DistributedSpmv(eng.default_context(rank), 27, n, C, 64, "dp", rank, world, overlap=mode, halo=halo)
             # x = global row index pattern so that halo values are distinguishable
             rows = torch.arange(rank * n ** 3, (rank + 1) * n ** 3, device="cuda", dtype=torch.float64)
@@ -36,9 +41,11 @@ def _run_rank(rank, world, port, out_dir, C=32):
             if r.p2p is not None:
                 err, ep = r.p2p.status()
                 assert err == 0 and ep == 3
-            results[f"{halo}{mode}"] = r.y[: r.scs.n_rows_padded][perm].cpu().numpy()
+            results[f"{halo}{mode}pv{pv}"] = r.y[: r.scs.n_rows_padded][perm].cpu().numpy()
             del r
-        base = results["p2p2"]
+        capi.set_option("push_variant", -1)
+        capi.set_option("push_min_elements", 1 << 20)
+        base = results["p2p2pv0"]
         for k, v in results.items():
             assert np.array_equal(v, base), k
         np.save(os.path.join(out_dir, f"y{rank}.npy"), base)

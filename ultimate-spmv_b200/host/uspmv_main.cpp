@@ -285,7 +285,10 @@ struct Shared {
     long y_len;      // doubles in the result area
 };
 inline int *need_area(Shared *sh, int q) { return reinterpret_cast<int *>(reinterpret_cast<unsigned char *>(sh) + 65536) + (size_t)q * sh->cap; }
-inline double *y_area(Shared *sh, int P) { return reinterpret_cast<double *>(need_area(sh, P)); }
+inline double *y_area(Shared *sh, int P) {  // behind the need lists, 8-byte aligned
+    const size_t off = (65536 + (size_t)P * sh->cap * sizeof(int) + 7) / 8 * 8;
+    return reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(sh) + off);
+}
 
 // global problem size without touching CUDA (the parent must not create a context before fork)
 long peek_rows(const Config &cfg) {

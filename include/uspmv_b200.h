@@ -168,6 +168,23 @@ int uspmv_partition_precisions(uspmv_ctx *ctx, const uspmv_coo *coo, int ap_mode
 int uspmv_ap_spmv(int ap_mode, const uspmv_scs *dp, const uspmv_scs *sp, const uspmv_scs *hp, const void *x_d, void *y_d,
                   void *stream);
 
+/* ---- column-banded execution plan (EXPERIMENTAL) ------------------------------------------------------ */
+/* For matrices whose x does not fit the L2 (BASELINE config 4 on one GPU: every missing 8-byte gather costs a 128-byte DRAM fill):
+ * the columns are cut into n_bands ranges, every band becomes its own SELL-C-sigma structure (AP: one per precision part) built with
+ * the reference's fixed_permutation mechanism (utilities.hpp:1911-1928; main.cpp:1175-1219) on the sigma-sorted row order of the
+ * whole matrix, and y = sum over bands, band by band, so that one band of x stays cache resident.  x in the original column
+ * numbering, y (n_rows_padded values) in the permuted row order (old_to_new from uspmv_banded_perm).  ap_mode < 0: one precision
+ * `vt`; otherwise USPMV_AP_* with thresholds t1 / t2.  n_bands == 0: about 32 MB of x per band.  Within 1e-12 / 1e-5 / 1e-2 of
+ * the un-banded result (band sums are added in band order); the un-banded kernels stay the bit-identical default. */
+typedef struct uspmv_banded uspmv_banded;
+int uspmv_banded_build(uspmv_ctx *ctx, const uspmv_coo *coo, long C, long sigma, int vt, int ap_mode, double t1, double t2, int n_bands,
+                       uspmv_banded **out);
+/* out8 = n_bands, band_width, n_rows, n_cols, n_rows_padded, nnz, n_elements over all bands and parts, value type of x / y */
+int uspmv_banded_dims(const uspmv_banded *plan, long out8[8]);
+int uspmv_banded_perm(const uspmv_banded *plan, int *old_to_new_h);
+int uspmv_banded_spmv(const uspmv_banded *plan, const void *x_d, void *y_d, void *stream);
+void uspmv_banded_destroy(uspmv_banded *plan);
+
 /* ---- row partitioning and halo exchange (one rank per GPU) ------------------------------------------ */
 /* seg_work_sharing_arr (mpi_funcs.hpp:424-622): wsa_h has P+1 entries.  I_h is the row array of the
  * row-sorted global COO. */

@@ -88,6 +88,10 @@ _sigs = {
     "uspmv_spmmv_part_supported": [vp, C.c_int],
     "uspmv_p2p_status": [vp, C.POINTER(C.c_int), C.POINTER(C.c_long)],
     "uspmv_p2p_exchange": [vp, C.c_int, vp, vp],
+    "uspmv_banded_build": [vp, vp, C.c_long, C.c_long, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.POINTER(vp)],
+    "uspmv_banded_dims": [vp, vp],
+    "uspmv_banded_perm": [vp, vp],
+    "uspmv_banded_spmv": [vp, vp, vp, vp],
     "uspmv_p2p_spmv_host_submit": [vp, vp, vp, vp, C.c_int],
     "uspmv_p2p_spmv_host_wait": [vp, C.c_int],
     "uspmv_halo_pack": [vp, vp, vp, C.c_int, C.c_int, C.c_long, C.c_int, vp],
@@ -97,7 +101,7 @@ for _name, _args in _sigs.items():
     if _fn is not None:  # symbol presence is asserted by tests/test_capi_symbols.py against the header
         _fn.argtypes = _args
         _fn.restype = C.c_int
-for _name in ("uspmv_ctx_destroy", "uspmv_coo_destroy", "uspmv_scs_destroy", "uspmv_halo_destroy", "uspmv_p2p_destroy"):
+for _name in ("uspmv_ctx_destroy", "uspmv_coo_destroy", "uspmv_scs_destroy", "uspmv_halo_destroy", "uspmv_p2p_destroy", "uspmv_banded_destroy"):
     _fn = getattr(lib, _name, None)
     if _fn is not None:
         _fn.argtypes = [vp]

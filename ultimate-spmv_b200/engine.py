@@ -266,6 +266,32 @@ def ap_spmv(ap_value_type, dp: ScsData | None, sp: ScsData | None, hp: ScsData |
     call("uspmv_ap_spmv", mode, dp.h if dp else None, sp.h if sp else None, hp.h if hp else None, _dp(x), _dp(y), _stream())
 
 
+class BandedPlan:
+    """Column-banded execution plan (EXPERIMENTAL; uspmv_banded_*): for matrices whose x does not fit the L2.  x in the original
+    column numbering, y (n_rows_padded) in the permuted row order given by `old_to_new`."""
+
+    def __init__(self, mtx: MtxData, C_: int, sigma: int, vt: str = "dp", ap: str | None = None, t1: float = 0.0, t2: float = 0.0,
+                 n_bands: int = 0):
+        h = vp()
+        call("uspmv_banded_build", mtx.ctx.h, mtx.h, int(C_), int(sigma), VT_CODE[vt], AP_MODE[ap] if ap else -1, float(t1), float(t2),
+             int(n_bands), C.byref(h))
+        self.h, self.ctx = h, mtx.ctx
+        d = (C.c_long * 8)()
+        call("uspmv_banded_dims", self.h, d)
+        (self.n_bands, self.band_width, self.n_rows, self.n_cols, self.n_rows_padded, self.nnz, self.n_elements, self.vt) = [int(v) for v in d]
+        self.old_to_new = np.zeros(max(self.n_rows, 1), np.int32)
+        call("uspmv_banded_perm", self.h, _hp(self.old_to_new))
+        self.old_to_new = self.old_to_new[: self.n_rows]
+
+    def spmv(self, x, y) -> None:
+        call("uspmv_banded_spmv", self.h, _dp(x), _dp(y), _stream())
+
+    def __del__(self):
+        if getattr(self, "h", None) and capi is not None:
+            capi.lib.uspmv_banded_destroy(self.h)
+            self.h = None
+
+
 def execute_uspmv(scs: ScsData, x, y, ap=None) -> None:
     """execute_uspmv (interface.hpp:1871-2187): SCS kernels iff C > 1 or sigma > 1, else CRS; AP by ap_value_type.
     `ap` = (ap_value_type, dp, sp, hp) for adaptive precision."""

@@ -37,6 +37,7 @@
 #include <unistd.h>
 
 #include "../../include/uspmv_b200.h"
+#include "result_report.hpp"
 
 using ST = long;
 
@@ -616,8 +617,8 @@ int rank_main(Config cfg, const int rank, const int P, Shared *sh) {
             for (long i = 0; i < std::min<long>(4, n_glob); ++i) printf(" %.10g", yg[i]);
             printf("\n");
             if (cfg.validate_result && have_host) {
-                double max_rel = 0.0;
                 const bool sp_x = ap && ap_mode == USPMV_AP_SP_HP;
+                std::vector<double> ref((size_t)bvs * n_glob), got(yg, yg + (size_t)bvs * n_glob);
                 for (long v = 0; v < bvs; ++v) {
                     std::vector<double> xa(xg + v * n_glob, xg + (v + 1) * n_glob), ya(n_glob);
                     if (sp_x) for (double &t : xa) t = (double)(float)t;
@@ -626,17 +627,15 @@ int rank_main(Config cfg, const int rank, const int P, Shared *sh) {
                         for (size_t k = 0; k < host.V.size(); ++k) ya[host.I[k]] += host.V[k] * xa[host.J[k]];
                         if (it + 1 < cfg.n_repetitions) std::swap(xa, ya);
                     }
-                    for (long i = 0; i < n_glob; ++i) {
-                        const double d = std::fabs(yg[v * n_glob + i] - ya[i]) / std::max(std::fabs(ya[i]), 1e-300);
-                        if (ya[i] != 0.0 && d > max_rel) max_rel = d;
-                    }
+                    std::copy(ya.begin(), ya.end(), ref.begin() + v * n_glob);
                 }
+                ResultReport rr;
+                rr.matrix_file_name = cfg.matrix_file_name; rr.kernel_format = cfg.kernel_format; rr.value_type = cfg.value_type;
+                rr.block_vec_layout = cfg.block_vec_layout; rr.seg_method = cfg.seg_method; rr.chunk_size = cfg.chunk_size; rr.sigma = cfg.sigma;
+                rr.n_blocks = (npad_total + 255) / 256; rr.ranks = P; rr.verbose = cfg.verbose; rr.revisions = cfg.n_repetitions; rr.beta = beta;
+                const double max_rel = write_result_to_file(rr, ref, got, n_glob);  // spmv_mkl_compare_<type>.txt, write_results.hpp:160-440
                 const char *verdict = max_rel > 1e-2 ? "ERROR" : max_rel > 1e-4 ? "WARNING" : "OK";
                 printf("validation vs host COO product: max relative difference %.3e -> %s\n", max_rel, verdict);
-                std::ofstream vf("spmv_validate_" + (ap ? std::string("ap") : cfg.value_type) + ".txt", std::ios::app);
-                vf << cfg.matrix_file_name << " ranks: " << P << " kernel: " << cfg.kernel_format << " C: " << cfg.chunk_size << " sigma: " << cfg.sigma
-                   << " data_type: " << cfg.value_type << " block_vec_size: " << bvs << " revisions: " << cfg.n_repetitions << " max_rel_diff: " << max_rel << " "
-                   << verdict << std::endl;
                 if (max_rel > 1e-2 && cfg.value_type == "dp") rc = 2;
             }
         }
@@ -901,7 +900,7 @@ int main(int argc, char **argv) {
         printf("\n");
         if (cfg.validate_result && have_host) {
             // host-side COO reference in double (stands in for the reference's MKL validator, write_results.hpp:442-556)
-            double max_rel = 0.0;
+            std::vector<double> ref((size_t)bvs * n_rows);
             for (long v = 0; v < bvs; ++v) {
                 std::vector<double> xa(n_rows), ya(n_rows);
                 for (long i = 0; i < n_rows; ++i) xa[i] = layout == USPMV_ROWWISE ? x_user[i * bvs + v] : x_user[i + v * vec_length];
@@ -910,17 +909,16 @@ int main(int argc, char **argv) {
                     for (size_t k = 0; k < host.V.size(); ++k) ya[host.I[k]] += host.V[k] * xa[host.J[k]];
                     if (it + 1 < cfg.n_repetitions) std::swap(xa, ya);
                 }
-                for (long i = 0; i < n_rows; ++i) {
-                    const double d = std::fabs(y[i + v * n_rows] - ya[i]) / std::max(std::fabs(ya[i]), 1e-300);
-                    if (ya[i] != 0.0 && d > max_rel) max_rel = d;
-                }
+                std::copy(ya.begin(), ya.end(), ref.begin() + v * n_rows);
             }
-            // thresholds of write_result_to_file (write_results.hpp:378-383,422-428)
+            ResultReport rr;
+            rr.matrix_file_name = cfg.matrix_file_name; rr.kernel_format = cfg.kernel_format; rr.value_type = cfg.value_type;
+            rr.block_vec_layout = cfg.block_vec_layout; rr.seg_method = cfg.seg_method; rr.chunk_size = cfg.chunk_size; rr.sigma = cfg.sigma;
+            rr.n_blocks = (n_pad + 255) / 256; rr.ranks = 1; rr.verbose = cfg.verbose; rr.revisions = cfg.n_repetitions; rr.beta = beta;
+            // same file and table as write_result_to_file (write_results.hpp:160-440); thresholds :378-383,422-428
+            const double max_rel = write_result_to_file(rr, ref, y, n_rows);
             const char *verdict = max_rel > 1e-2 ? "ERROR" : max_rel > 1e-4 ? "WARNING" : "OK";
             printf("validation vs host COO product: max relative difference %.3e -> %s\n", max_rel, verdict);
-            std::ofstream vf("spmv_validate_" + (ap ? std::string("ap") : cfg.value_type) + ".txt", std::ios::app);
-            vf << cfg.matrix_file_name << " kernel: " << cfg.kernel_format << " C: " << cfg.chunk_size << " sigma: " << cfg.sigma << " data_type: "
-               << cfg.value_type << " block_vec_size: " << bvs << " revisions: " << cfg.n_repetitions << " max_rel_diff: " << max_rel << " " << verdict << std::endl;
             if (max_rel > 1e-2 && cfg.value_type == "dp") return 2;
         }
     }

@@ -634,9 +634,9 @@ int rank_main(Config cfg, const int rank, const int P, Shared *sh) {
                 rr.block_vec_layout = cfg.block_vec_layout; rr.seg_method = cfg.seg_method; rr.chunk_size = cfg.chunk_size; rr.sigma = cfg.sigma;
                 rr.n_blocks = (npad_total + 255) / 256; rr.ranks = P; rr.verbose = cfg.verbose; rr.revisions = cfg.n_repetitions; rr.beta = beta;
                 const double max_rel = write_result_to_file(rr, ref, got, n_glob);  // spmv_mkl_compare_<type>.txt, write_results.hpp:160-440
-                const char *verdict = max_rel > 1e-2 ? "ERROR" : max_rel > 1e-4 ? "WARNING" : "OK";
+                const char *verdict = (max_rel > 1e-2 || std::isnan(max_rel)) ? "ERROR" : max_rel > 1e-4 ? "WARNING" : "OK";
                 printf("validation vs host COO product: max relative difference %.3e -> %s\n", max_rel, verdict);
-                if (max_rel > 1e-2 && cfg.value_type == "dp") rc = 2;
+                if ((max_rel > 1e-2 || std::isnan(max_rel)) && cfg.value_type == "dp") rc = 2;
             }
         }
     }
@@ -917,9 +917,9 @@ int main(int argc, char **argv) {
             rr.n_blocks = (n_pad + 255) / 256; rr.ranks = 1; rr.verbose = cfg.verbose; rr.revisions = cfg.n_repetitions; rr.beta = beta;
             // same file and table as write_result_to_file (write_results.hpp:160-440); thresholds :378-383,422-428
             const double max_rel = write_result_to_file(rr, ref, y, n_rows);
-            const char *verdict = max_rel > 1e-2 ? "ERROR" : max_rel > 1e-4 ? "WARNING" : "OK";
+            const char *verdict = (max_rel > 1e-2 || std::isnan(max_rel)) ? "ERROR" : max_rel > 1e-4 ? "WARNING" : "OK";
             printf("validation vs host COO product: max relative difference %.3e -> %s\n", max_rel, verdict);
-            if (max_rel > 1e-2 && cfg.value_type == "dp") return 2;
+            if ((max_rel > 1e-2 || std::isnan(max_rel)) && cfg.value_type == "dp") return 2;
         }
     }
     uspmv_free(ctx, x_d);

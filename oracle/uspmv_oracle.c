@@ -5,7 +5,7 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load
  * this library; nothing under ultimate-spmv_b200/ or include/ links, loads or calls it.
  *
- * PARITY PIN: every function here is checked (tests/test_oracle_vs_ref.py, tests/test_golden.py)
+ * PARITY PIN: every function here is checked (tests/test_oracle_pinning.py, all CPU)
  *   - against the reference itself, compiled unmodified from /root/reference into oracle/_ref/ by
  *     oracle/Makefile (bit-exact for all index structures; bit-exact y for SCS kernels), and
  *   - against the reference's own unit-test goldens (test_suite/test_data/M_big.cpp, M1.cpp),

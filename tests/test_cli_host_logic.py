@@ -101,3 +101,15 @@ int main() {
     assert len(rows) == 8 and rows[5].split()[:2] == ["1", "1"] and rows[5].rstrip().endswith("WARNING") and not rows[0].rstrip().endswith("WARNING")
     ap = (tmp_path / "spmv_mkl_compare_ap.txt").read_text()
     assert "data_type: ap[dp_sp]" in ap and ap.rstrip().endswith("ERROR")
+
+
+def test_bench_report_block_is_scrapable_like_the_reference():
+    """tests/golden/spmv_bench_sample.txt is a block this harness appended to spmv_bench.txt on two B200s (`-gpus 2`).  The reference's
+    scripts/scrape_perf.py finds the line holding "Total Gflops:" and reads the first token two lines below it; its nvcc / MPI builds
+    start a block with "<matrix> with N MPI processes, and B block(s), and T thread(s) per block" (write_results.hpp:66-75)."""
+    import re
+    lines = open(os.path.join(ROOT, "tests", "golden", "spmv_bench_sample.txt")).read().splitlines(keepends=True)
+    vals = [float(lines[k + 2].split()[0]) for k, ln in enumerate(lines) if "Total Gflops:" in ln]
+    assert vals == [1683.3778070149201085]
+    assert re.match(r"\S+ with 2 MPI processes, and \d+ block\(s\), and 256 thread\(s\) per block$", lines[0].rstrip("\n"))
+    assert re.match(r"kernel: scs, block_vec_size: 1, C: 32 sigma: 1, beta: 0\.\d{8}, block_vec_layout: colwise, data_type: double, revisions: \d+", lines[1])

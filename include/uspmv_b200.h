@@ -52,7 +52,8 @@ long uspmv_kernel_launches(void);
 int uspmv_set_option(const char *name, long value);
 
 /* ---- context and device memory --------------------------------------------------------------- */
-/* cudaSetDevice(rank % ndev) in the reference: main.cpp:1838-1842 */
+/* cudaGetDeviceCount + cudaSetDevice(rank % ndev) in the reference: main.cpp:1838-1842 */
+int uspmv_device_count(int *out_ndev);
 int uspmv_ctx_create(int device, uspmv_ctx **out);
 void uspmv_ctx_destroy(uspmv_ctx *ctx);
 int uspmv_ctx_sync(uspmv_ctx *ctx);
@@ -82,6 +83,15 @@ int uspmv_coo_from_device(uspmv_ctx *ctx, long n_rows, long n_cols, long nnz, co
  * points-1, off-diagonals -1; dp values.  I is made slab-local (I - row0), J stays global
  * (localize_row_idx, mpi_funcs.hpp:862-877). */
 int uspmv_coo_stencil(uspmv_ctx *ctx, int points, long nx, long ny, long nz, long row0, long row1, uspmv_coo **out);
+/* Synthetic irregular power-law matrix generated on the device (BASELINE.json config 4): n x n, rows
+ * [row0, row1) with local row ids and global columns; row degree clamp(floor(d_min (1-u)^(-1/(alpha-1))), 1, max_deg), half of a
+ * row's columns within +-1024 of the diagonal, half uniform, de-duplicated and ascending; values sign * 10^w, w ~ U(-4, 2); all
+ * randomness splitmix64(seed, row, k), so every rank can generate its own rows.  (The reference reads such matrices from .mtx files,
+ * utilities.hpp:2148-2309; a 5e8-element file is not practical on the benchmark box.) */
+int uspmv_coo_powerlaw(uspmv_ctx *ctx, long n, long row0, long row1, double d_min, double alpha, int max_deg, unsigned long seed,
+                       uspmv_coo **out);
+/* raw device pointers of the COO arrays (MtxData::I / J / values, interface.hpp:16-56); any out pointer may be NULL */
+int uspmv_coo_device_arrays(const uspmv_coo *coo, const int **I_d, const int **J_d, const void **values_d);
 /* read_mtx's post-processing (utilities.hpp:2214-2290) on the device: entries in file order (0-based), symmetric != 0 expands
  * (i,j) into (i,j),(j,i) for i != j, then a stable sort by row.  Text parsing stays with the caller. */
 int uspmv_coo_from_entries(uspmv_ctx *ctx, long n_rows, long n_cols, long nz, const int *I_h, const int *J_h, const double *values_h,
@@ -261,6 +271,14 @@ int uspmv_p2p_exchange(uspmv_p2p *p2p, int x_buf, void *stream, void *comm_strea
 int uspmv_p2p_spmv_host_submit(uspmv_p2p *p2p, const uspmv_scs *scs, const void *x_h, void *y_h, int slot);
 int uspmv_p2p_spmv_host_wait(uspmv_p2p *p2p, int slot);
 int uspmv_p2p_status(uspmv_p2p *p2p, int *error_flag, long *epoch);
+/* cudaDeviceSynchronize + FAIL when a bounded flag wait of any step timed out (the kernels only raise the arena's error word);
+ * uspmv_p2p_spmv_host_wait reports the same condition for its slot.  The reference would sit in MPI_Waitall instead
+ * (classes_structs.hpp:926-995). */
+int uspmv_p2p_sync(uspmv_p2p *p2p);
+/* Teardown is COLLECTIVE (the arena is CUDA-IPC-exported; neighbours write acknowledgements into it after this rank's last step):
+ *   uspmv_p2p_sync -> barrier over all ranks -> uspmv_p2p_disconnect (closes the imported arenas) -> barrier -> uspmv_p2p_destroy.
+ * The harness does this after its bench loop (MPI_Barrier + MPI_Finalize in the reference, main.cpp:1895-1899). */
+int uspmv_p2p_disconnect(uspmv_p2p *p2p);
 void uspmv_p2p_destroy(uspmv_p2p *p2p);
 
 #ifdef __cplusplus

@@ -382,3 +382,34 @@ class RefIface:
             if ne >= 0:
                 return SimpleNamespace(chunk_ptrs=cp, chunk_lengths=cl, col_idxs=ci[:ne], values=v[:ne], old_to_new=o2n, n_elements=int(ne))
             cap = -ne
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference's own CUDA kernels, recompiled for sm_100 (oracle/ref_gpu_driver.cu) — bench.py's gpu_baseline
+# ------------------------------------------------------------------------------------------------
+def ref_gpu_available():
+    return os.path.exists(os.path.join(HERE, "_ref", "libuspmv_ref_gpu.so"))
+
+
+class RefGpu:
+    """spmv_gpu_scs_adv / spmv_gpu_scs / spmv_gpu_csr (code/kernels.hpp:579-775) through the reference's own launchers."""
+
+    KERNELS = {"scs_adv": 0, "scs": 1, "csr": 2}
+
+    def __init__(self):
+        self.lib = L = C.CDLL(os.path.join(HERE, "_ref", "libuspmv_ref_gpu.so"))
+        L.refgpu_last_error.restype = C.c_char_p
+        L.refgpu_spmv.argtypes = [C.c_int, C.c_int, C.c_long, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_void_p,
+                                  C.c_long, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double)]
+        self.threads_per_block = int(L.refgpu_threads_per_block())
+
+    def spmv(self, kernel, vt, C_, n_chunks, chunk_ptrs, chunk_lengths, col_idxs, values, x, warmup=3, steps=20):
+        """Returns (y, ms per launch)."""
+        y = np.zeros(int(n_chunks) * int(C_), NPT[_vt(vt)])
+        ms = C.c_double(0.0)
+        rc = self.lib.refgpu_spmv(self.KERNELS[kernel], _vt(vt), int(C_), int(n_chunks), _p(_i32(chunk_ptrs)),
+                                  _p(_i32(chunk_lengths)) if chunk_lengths is not None else None, _p(_i32(col_idxs)), _p(values), len(col_idxs),
+                                  _p(x), len(x), _p(y), int(warmup), int(steps), C.byref(ms))
+        if rc:
+            raise RuntimeError(self.lib.refgpu_last_error().decode())
+        return y, float(ms.value)

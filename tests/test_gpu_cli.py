@@ -115,8 +115,10 @@ def test_cli_symmetric_file_equilibrate_and_dropout(eng, tmp_path):
 
 
 def _two_gpus():
-    import torch
-    return torch.cuda.device_count() >= 2
+    """`-gpus 2` needs no second GPU: like the reference's `mpirun -n 2` on a one-GPU node the ranks take device rank % ndev
+    (main.cpp:1838-1842), share the GPU time-sliced and still exchange their arenas through CUDA IPC — so the push / wait /
+    acknowledge protocol of every exchange mode runs against a real peer process on the driver's one-GPU test box too."""
+    return True
 
 
 @pytest.mark.parametrize("seg", ["-seg_rows", "-seg_nnz"])

@@ -11,12 +11,27 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _run_rank(rank, world, port, out_dir, C=32):
+def _init(rank, world, port, same_device):
+    """same_device: every rank on cuda:0 (the driver's one-GPU test box).  The ranks are still separate processes whose arenas are
+    exchanged through CUDA IPC, so pushes, flag waits and acknowledgements run against a real peer; the GPU time-slices between the
+    two contexts (a rank spinning on a flag is preempted so that its neighbour can raise it).  NCCL refuses two ranks on one device,
+    so the plumbing (all_gather_object / barrier) runs over gloo there."""
+    import torch
+    import torch.distributed as dist
+    dev = 0 if same_device else rank
+    torch.cuda.set_device(dev)
+    if same_device:
+        dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    else:
+        dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world, device_id=torch.device("cuda", dev))
+    return dev
+
+
+def _run_rank(rank, world, port, out_dir, C=32, same_device=False):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
-    torch.cuda.set_device(rank)
-    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    dev = _init(rank, world, port, same_device)
     try:
         pkg = importlib.import_module("ultimate-spmv_b200")
         eng, capi, d = pkg.engine, pkg.capi, pkg.dist
@@ -24,11 +39,13 @@ def _run_rank(rank, world, port, out_dir, C=32):
         results = {}
         # pv > 0: the large-halo push kernels (tiled direct stores / shared memory + bulk copy / 4096-element tiles) forced onto this
         # small halo, here with the permuted-x gather (perm != NULL); the un-permuted form is covered by the AP test below
-        for halo, mode, pv in (("p2p", 2, 0), ("p2p", 1, 0), ("p2p", 0, 0), ("nccl", True, 0), ("nccl", False, 0), ("p2p", 1, 1), ("p2p", 0, 2),
-                               ("p2p", 1, 3)):
+        cases = (("p2p", 2, 0), ("p2p", 1, 0), ("p2p", 0, 0), ("nccl", True, 0), ("nccl", False, 0), ("p2p", 1, 1), ("p2p", 0, 2), ("p2p", 1, 3))
+        if same_device:
+            cases = tuple(c for c in cases if c[0] == "p2p")
+        for halo, mode, pv in cases:
             capi.set_option("push_variant", pv if pv else -1)
             capi.set_option("push_min_elements", 0 if pv else 1 << 20)
-            r = d.DistributedSpmv(eng.default_context(rank), 27, n, C, 64, "dp", rank, world, overlap=mode, halo=halo)
+            r = d.DistributedSpmv(eng.default_context(dev), 27, n, C, 64, "dp", rank, world, overlap=mode, halo=halo)
             # x = global row index pattern so that halo values are distinguishable
             rows = torch.arange(rank * n ** 3, (rank + 1) * n ** 3, device="cuda", dtype=torch.float64)
             xs = torch.sin(rows * 0.37) + 1.5
@@ -42,6 +59,9 @@ def _run_rank(rank, world, port, out_dir, C=32):
                 err, ep = r.p2p.status()
                 assert err == 0 and ep == 3
             results[f"{halo}{mode}pv{pv}"] = r.y[: r.scs.n_rows_padded][perm].cpu().numpy()
+            # the runner's own checked step (what bench.py runs before timing): NaN-poisoned halo, y against the stencil formula
+            assert r.validate() <= 1e-12, (halo, mode, pv)
+            r.close()  # collective teardown: sync, barrier, unmap the neighbours' arenas, barrier, free
             del r
         capi.set_option("push_variant", -1)
         capi.set_option("push_min_elements", 1 << 20)
@@ -54,7 +74,7 @@ def _run_rank(rank, world, port, out_dir, C=32):
         rows = torch.arange(rank * n ** 3, (rank + 1) * n ** 3, device="cuda", dtype=torch.float64)
         for layout in ("rowwise", "colwise"):
             for bvs, mode in ((4, 1), (4, 0), (3, 1)):
-                r = d.DistributedSpmv(eng.default_context(rank), 27, n, C, 64, "dp", rank, world, overlap=mode, halo="p2p", bvs=bvs, layout=layout)
+                r = d.DistributedSpmv(eng.default_context(dev), 27, n, C, 64, "dp", rank, world, overlap=mode, halo="p2p", bvs=bvs, layout=layout)
                 perm = torch.from_numpy(r.scs.export().old_to_new.astype(np.int64)).cuda()
                 nl, ld = r.scs.n_rows, r.vec_length
                 r.x.zero_()
@@ -79,11 +99,13 @@ def _run_rank(rank, world, port, out_dir, C=32):
                     else:
                         out[v] = r.y[v * ld: v * ld + r.scs.n_rows_padded][perm].cpu().numpy()
                 np.save(os.path.join(out_dir, f"Y{rank}_{layout}_{bvs}_{mode}.npy"), out)
+                assert r.validate() <= 1e-12, (layout, bvs, mode)
+                r.close()
                 del r
 
         # ---- device-resident solve loop: 3 x { exchange ; SpMV ; swap } over the two arena buffers, every overlap mode
         for mode in (2, 1, 0):
-            r = d.DistributedSpmv(eng.default_context(rank), 27, n, C, 64, "dp", rank, world, overlap=mode, halo="p2p", n_buf=2)
+            r = d.DistributedSpmv(eng.default_context(dev), 27, n, C, 64, "dp", rank, world, overlap=mode, halo="p2p", n_buf=2)
             perm = torch.from_numpy(r.scs.export().old_to_new.astype(np.int64)).cuda()
             for b in r.p2p.bufs:
                 b.zero_()
@@ -116,6 +138,7 @@ def _run_rank(rank, world, port, out_dir, C=32):
             err, ep2 = r.p2p.status()
             assert err == 0 and ep2 == ep + 5
             np.save(os.path.join(out_dir, f"hosty{rank}_{mode}.npy"), np.stack([yh[k][: r.scs.n_rows_padded][pc].numpy() for k in range(5)]))
+            r.close()
             del r
         dist.barrier()
     finally:
@@ -178,6 +201,17 @@ def test_two_ranks_over_nvlink(eng, mats, tmp_path, C):
     _check(str(tmp_path), 2, mats)
 
 
+@pytest.mark.parametrize("C", [32, 16])
+def test_two_ranks_on_one_gpu(eng, mats, tmp_path, C):
+    """The same two-rank run with both processes on cuda:0 (see _init): every exchange mode — fused kernel, push / wait / ack kernels,
+    exchange-then-SpMV, the tiled and bulk-copy push kernels, block vectors, the two-buffer solve loop and the pipelined host-buffer
+    calls — against a real peer, on a box with ONE GPU."""
+    import torch.multiprocessing as mp
+    port = 29800 + os.getpid() % 100 + C
+    mp.spawn(_run_rank, args=(2, port, str(tmp_path), C, True), nprocs=2, join=True)
+    _check(str(tmp_path), 2, mats)
+
+
 # ---- adaptive precision, row-partitioned with seg-nnz (BASELINE config 4) --------------------------------------------------------
 def _ap_matrix(n=6000, seed=5):
     rng = np.random.default_rng(seed)
@@ -189,12 +223,11 @@ def _ap_matrix(n=6000, seed=5):
     return n, I, J, V, cnt
 
 
-def _run_ap_rank(rank, world, port, out_dir):
+def _run_ap_rank(rank, world, port, out_dir, same_device=False):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
-    torch.cuda.set_device(rank)
-    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    dev = _init(rank, world, port, same_device)
     try:
         pkg = importlib.import_module("ultimate-spmv_b200")
         eng, d = pkg.engine, pkg.dist
@@ -204,8 +237,8 @@ def _run_ap_rank(rank, world, port, out_dir):
         n_loc = int(wsa[rank + 1] - wsa[rank])
         x_glob = np.sin(np.arange(n) * 0.37) + 1.5
         for mode in ("ap[dp_sp_hp]", "ap[dp_sp]", "ap[sp_hp]"):
-            r = d.DistributedApSpmv(eng.default_context(rank), wsa, (n_loc, n, (I[sel] - wsa[rank]).astype(np.int32), J[sel], V[sel]), mode, 0.5, 0.01,
-                                    32, 64, rank, world)
+            r = d.DistributedApSpmv(eng.default_context(dev), wsa, (n_loc, n, (I[sel] - wsa[rank]).astype(np.int32), J[sel], V[sel]), mode, 0.5, 0.01,
+                                    32, 64, rank, world, keep_coo=True)
             r.x.zero_()
             r.x[:n_loc] = torch.from_numpy(x_glob[wsa[rank]:wsa[rank + 1]]).to(r.x.dtype).cuda()   # original local row order
             torch.cuda.synchronize()
@@ -234,6 +267,8 @@ def _run_ap_rank(rank, world, port, out_dir):
             assert err == 0 and ep == 6
             y = r.y.cpu().numpy()[r.old_to_new]
             np.save(os.path.join(out_dir, f"ap{rank}_{mode}.npy"), y.astype(np.float64))
+            assert r.validate() <= (1e-5 if mode == "ap[sp_hp]" else 1e-12), mode
+            r.close()
             del r
         np.save(os.path.join(out_dir, f"apwsa{rank}.npy"), wsa)
         dist.barrier()
@@ -277,4 +312,10 @@ def test_ap_two_ranks_seg_nnz(eng, tmp_path):
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
     mp.spawn(_run_ap_rank, args=(2, 29350 + os.getpid() % 100, str(tmp_path)), nprocs=2, join=True)
+    _check_ap(str(tmp_path), 2)
+
+
+def test_ap_two_ranks_on_one_gpu(eng, tmp_path):
+    import torch.multiprocessing as mp
+    mp.spawn(_run_ap_rank, args=(2, 29250 + os.getpid() % 100, str(tmp_path), True), nprocs=2, join=True)
     _check_ap(str(tmp_path), 2)

@@ -8,6 +8,7 @@ Layout
     engine.py    Python mirror of the reference's interface.hpp names (tests / bench plumbing)
     matrices.py  Matrix Market reader + synthetic generators (host logic)
     dist.py      one-process-per-GPU row partitioning + halo exchange plumbing (torch.distributed)
+    validate.py  checked steps: y against the stencil formula / the COO triplets with x = f(global row)
 
 The directory name contains a hyphen, so import it with
     importlib.import_module("ultimate-spmv_b200")
@@ -19,7 +20,7 @@ from . import matrices  # noqa: F401  (pure host logic, importable without the C
 def __getattr__(name):
     # capi/engine need the built shared library; import lazily so host-only logic stays importable,
     # but fail loudly (ImportError from capi) the moment a compute entry point is requested.
-    if name in ("capi", "engine", "dist"):
+    if name in ("capi", "engine", "dist", "validate"):
         import importlib
         return importlib.import_module(f"{__name__}.{name}")
     raise AttributeError(name)

@@ -34,6 +34,7 @@ lib.uspmv_kernel_launches.restype = C.c_long
 vp = C.c_void_p
 _sigs = {
     "uspmv_set_option": [C.c_char_p, C.c_long],
+    "uspmv_device_count": [C.POINTER(C.c_int)],
     "uspmv_ctx_create": [C.c_int, C.POINTER(vp)],
     "uspmv_ctx_sync": [vp],
     "uspmv_malloc": [vp, C.c_size_t, C.POINTER(vp)],
@@ -46,6 +47,8 @@ _sigs = {
     "uspmv_coo_from_host": [vp, C.c_long, C.c_long, C.c_long, vp, vp, vp, C.c_int, C.POINTER(vp)],
     "uspmv_coo_from_device": [vp, C.c_long, C.c_long, C.c_long, vp, vp, vp, C.c_int, C.POINTER(vp)],
     "uspmv_coo_stencil": [vp, C.c_int, C.c_long, C.c_long, C.c_long, C.c_long, C.c_long, C.POINTER(vp)],
+    "uspmv_coo_powerlaw": [vp, C.c_long, C.c_long, C.c_long, C.c_double, C.c_double, C.c_int, C.c_ulong, C.POINTER(vp)],
+    "uspmv_coo_device_arrays": [vp] + [C.POINTER(vp)] * 3,
     "uspmv_coo_from_entries": [vp, C.c_long, C.c_long, C.c_long, vp, vp, vp, C.c_int, C.POINTER(vp)],
     "uspmv_coo_equilibrate": [vp, vp, vp],
     "uspmv_coo_dims": [vp, C.POINTER(C.c_long)],
@@ -88,6 +91,8 @@ _sigs = {
     "uspmv_spmmv_part_supported": [vp, C.c_int],
     "uspmv_p2p_status": [vp, C.POINTER(C.c_int), C.POINTER(C.c_long)],
     "uspmv_p2p_exchange": [vp, C.c_int, vp, vp],
+    "uspmv_p2p_sync": [vp],
+    "uspmv_p2p_disconnect": [vp],
     "uspmv_banded_build": [vp, vp, C.c_long, C.c_long, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.POINTER(vp)],
     "uspmv_banded_dims": [vp, vp],
     "uspmv_banded_perm": [vp, vp],

@@ -76,6 +76,18 @@ int uspmv_stream_destroy(uspmv_ctx *ctx, void *stream) {
     });
 }
 
+int uspmv_device_count(int *out) {
+    return guarded([&] {
+        if (!out) fail("uspmv_device_count: out is NULL");
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || ndev == 0)
+            fail("uspmv_device_count: no CUDA device available (%s); this library has no CPU fallback",
+                 e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        *out = ndev;
+    });
+}
+
 int uspmv_ctx_create(int device, uspmv_ctx **out) {
     return guarded([&] {
         if (!out) fail("uspmv_ctx_create: out is NULL");

@@ -361,6 +361,7 @@ struct uspmv_p2p {
     cudaEvent_t ev_x[2] = {nullptr, nullptr}, ev_y[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     DevBuf<unsigned char> slot_y[2];
     bool slot_busy[2] = {false, false};
+    unsigned int *err_h = nullptr;   // pinned: the arena's error word as of the end of each slot's step
     long host_submits = 0;
     long n_push_tiles = 0, n_push_tiles_4k = 0;  // tiles (2048 / 4096 elements) of the large-halo push kernels (k_p2p_push_tiles)
     unsigned char *buffer(int b) const { return arena + (size_t)b * x_bytes; }
@@ -901,6 +902,8 @@ int uspmv_p2p_spmv_host_submit(uspmv_p2p *p, const uspmv_scs *scs, const void *x
             USPMV_CUDA(cudaStreamCreateWithFlags(&p->s_run, cudaStreamNonBlocking));
             USPMV_CUDA(cudaStreamCreateWithFlags(&p->s_d2h, cudaStreamNonBlocking));
             USPMV_CUDA(cudaStreamCreateWithFlags(&p->s_comm, cudaStreamNonBlocking));
+            USPMV_CUDA(cudaMallocHost(&p->err_h, 2 * sizeof(unsigned int)));
+            p->err_h[0] = p->err_h[1] = 0;
             for (int k = 0; k < 2; ++k) {
                 USPMV_CUDA(cudaEventCreateWithFlags(&p->ev_x[k], cudaEventDisableTiming));
                 USPMV_CUDA(cudaEventCreateWithFlags(&p->ev_y[k], cudaEventDisableTiming));
@@ -918,6 +921,7 @@ int uspmv_p2p_spmv_host_submit(uspmv_p2p *p, const uspmv_scs *scs, const void *x
         USPMV_CUDA(cudaEventRecord(p->ev_y[slot], p->s_run));
         USPMV_CUDA(cudaStreamWaitEvent(p->s_d2h, p->ev_y[slot], 0));
         USPMV_CUDA(cudaMemcpyAsync(y_h, p->slot_y[slot].p, y_bytes, cudaMemcpyDeviceToHost, p->s_d2h));
+        USPMV_CUDA(cudaMemcpyAsync(p->err_h + slot, p->error, sizeof(unsigned int), cudaMemcpyDeviceToHost, p->s_d2h));  // checked by _wait
         USPMV_CUDA(cudaEventRecord(p->ev_done[slot], p->s_d2h));
         p->slot_busy[slot] = true;
         ++p->host_submits;
@@ -931,6 +935,8 @@ int uspmv_p2p_spmv_host_wait(uspmv_p2p *p, int slot) {
         if (!p->slot_busy[slot]) return;
         USPMV_CUDA(cudaEventSynchronize(p->ev_done[slot]));
         p->slot_busy[slot] = false;
+        if (p->err_h && p->err_h[slot])
+            fail("uspmv_p2p_spmv_host_wait: halo exchange error word = %u (a bounded flag wait timed out; y of slot %d is not valid)", p->err_h[slot], slot);
     });
 }
 
@@ -939,6 +945,34 @@ int uspmv_p2p_set_overlap(uspmv_p2p *p, int overlap) {
         if (!p) fail("uspmv_p2p_set_overlap: NULL argument");
         if (overlap < 0 || overlap > 2) fail("uspmv_p2p_set_overlap: mode must be 0, 1 or 2");
         p->mode = overlap;
+    });
+}
+
+/* Waits for everything queued on the device and FAILS if a bounded spin of any step timed out (a peer never signalled): the
+ * kernels only raise the arena's error word and carry on, so this is where a lost push becomes a return code. */
+int uspmv_p2p_sync(uspmv_p2p *p) {
+    return guarded([&] {
+        if (!p) fail("uspmv_p2p_sync: NULL argument");
+        USPMV_CUDA(cudaSetDevice(p->plan->ctx->device));
+        USPMV_CUDA(cudaDeviceSynchronize());
+        unsigned int v[2] = {0, 0};
+        USPMV_CUDA(cudaMemcpy(v, p->epoch, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost));
+        if (v[1]) fail("uspmv_p2p_sync: halo exchange error word = %u at epoch %u (a bounded flag wait timed out: a neighbour never pushed / acknowledged)", v[1], v[0]);
+    });
+}
+
+/* Teardown is COLLECTIVE (freeing CUDA-IPC-exported memory while an importer still has it mapped, or while a neighbour's last
+ * kernel still writes its acknowledgement into it, is undefined behaviour):
+ *     uspmv_p2p_sync  ->  barrier over all ranks  ->  uspmv_p2p_disconnect  ->  barrier  ->  uspmv_p2p_destroy
+ * disconnect waits for this rank's device and closes the neighbours' imported arenas; after it the handle only frees. */
+int uspmv_p2p_disconnect(uspmv_p2p *p) {
+    return guarded([&] {
+        if (!p) fail("uspmv_p2p_disconnect: NULL argument");
+        USPMV_CUDA(cudaSetDevice(p->plan->ctx->device));
+        USPMV_CUDA(cudaDeviceSynchronize());
+        for (unsigned char *&q : p->peer_arena)
+            if (q) { USPMV_CUDA(cudaIpcCloseMemHandle(q)); q = nullptr; }
+        p->connected = false;
     });
 }
 
@@ -953,6 +987,8 @@ int uspmv_p2p_status(uspmv_p2p *p, int *error_flag, long *epoch) {
     });
 }
 
+/* Collective, see uspmv_p2p_disconnect.  (Still closes the imported handles itself when disconnect was skipped, e.g. on an error
+ * path — the safe order is the caller's job.) */
 void uspmv_p2p_destroy(uspmv_p2p *p) {
     if (!p) return;
     for (unsigned char *q : p->peer_arena)
@@ -962,6 +998,7 @@ void uspmv_p2p_destroy(uspmv_p2p *p) {
     for (int k = 0; k < 2; ++k)
         for (cudaEvent_t ev : {p->ev_x[k], p->ev_y[k], p->ev_done[k]})
             if (ev) cudaEventDestroy(ev);
+    if (p->err_h) cudaFreeHost(p->err_h);
     if (p->ev_main) cudaEventDestroy(p->ev_main);
     if (p->ev_comm) cudaEventDestroy(p->ev_comm);
     if (p->arena) cudaFree(p->arena);

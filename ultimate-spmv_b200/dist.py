@@ -185,6 +185,7 @@ class P2PHalo:
         import torch.distributed as dist
         from .engine import NP_OF
         self.plan, self.bvs, self.layout, self.n_buf, self.vec_length = plan, int(bvs), int(layout), int(n_buf), int(vec_length)
+        self.group = group
         h = vp()
         xptr = (vp * n_buf)()
         handle = (C.c_ubyte * 64)()
@@ -224,7 +225,35 @@ class P2PHalo:
         call("uspmv_p2p_status", self.h, C.byref(err), C.byref(ep))
         return int(err.value), int(ep.value)
 
+    def sync(self):
+        """Device sync; raises when a bounded flag wait of any step timed out (a neighbour never pushed / acknowledged)."""
+        call("uspmv_p2p_sync", self.h)
+
+    def close(self):
+        """COLLECTIVE teardown (every rank of the group must call it): the arena is CUDA-IPC-exported and the neighbours' last
+        kernels still write acknowledgements into it after this rank's last step has completed, so: device sync -> barrier ->
+        close the imported arenas -> barrier -> free.  Raises if the arena's error word was raised."""
+        if not getattr(self, "h", None):
+            return
+        import torch.distributed as dist
+        err = None
+        try:
+            self.sync()
+        except capi.UspmvError as e:
+            err = e
+        if dist.is_initialized():
+            dist.barrier(group=self.group)
+        capi.lib.uspmv_p2p_disconnect(self.h)
+        if dist.is_initialized():
+            dist.barrier(group=self.group)
+        self.bufs, self.x = [], None
+        capi.lib.uspmv_p2p_destroy(self.h)
+        self.h = None
+        if err is not None:
+            raise err
+
     def __del__(self):
+        # not collective: only safe once every rank is idle (close() is the supported path)
         if getattr(self, "h", None) and capi is not None:
             capi.lib.uspmv_p2p_destroy(self.h)
             self.h = None
@@ -255,6 +284,7 @@ class DistributedSpmv:
         if strong and n % world:
             raise ValueError("strong scaling needs n divisible by the number of ranks")
         wsa = seg_rows_equal(n * n * nz_total, world)
+        self.grid, self.row0, self.row1, self.group = (points, n, n, nz_total), int(wsa[rank]), int(wsa[rank + 1]), group
         mtx = eng.MtxData.stencil(points, n, n, nz_total, int(wsa[rank]), int(wsa[rank + 1]), ctx=ctx)
         self.scs = eng.convert_to_scs(mtx, C_, sigma, vt)
         del mtx
@@ -319,6 +349,77 @@ class DistributedSpmv:
         main.wait_stream(self.comm_stream)
         call("uspmv_spmv_part", self.scs.h, 2, vp(self.x.data_ptr()), vp(self.y.data_ptr()), vp(main.cuda_stream))
 
+    def _perm_tensor(self):
+        from .validate import device_int_tensor
+        return device_int_tensor(self.scs.device_arrays()["old_to_new"].value, self.scs.n_rows, self.x.device).long()
+
+    def set_x(self, xs_of_v, poison_halo=False):
+        """x_v (original local row order, one tensor per block-vector column) -> the permuted / laid-out device vector.
+        poison_halo: NaN in every halo slot, so that a step whose exchange does not deliver cannot produce a finite y."""
+        perm, nl, ld, bvs = self._perm_tensor(), self.scs.n_rows, self.vec_length, self.bvs
+        rowwise = bvs > 1 and self.layout == capi.ROWWISE
+        nan = float("nan")
+        for v in range(bvs):
+            xs = xs_of_v(v).to(self.x.dtype)
+            if rowwise:
+                self.x[: nl * bvs].view(nl, bvs)[perm, v] = xs
+            else:
+                self.x[v * ld: v * ld + nl][perm] = xs
+                if poison_halo:
+                    self.x[v * ld + nl: (v + 1) * ld] = nan
+        if rowwise and poison_halo:
+            self.x[nl * bvs:] = nan
+
+    def get_y(self, v=0):
+        """Column v of the result in the original local row order."""
+        perm, npad, ld, bvs = self._perm_tensor(), self.scs.n_rows_padded, self.vec_length, self.bvs
+        if bvs > 1 and self.layout == capi.ROWWISE:
+            return self.y[: npad * bvs].view(npad, bvs)[perm, v]
+        return self.y[v * ld: v * ld + npad][perm] if bvs > 1 else self.y[:npad][perm]
+
+    def validate(self, steps: int = 2):
+        """Checked steps (COLLECTIVE): x = f(global row), NaN-poisoned halo, `steps` distributed steps (epochs, acks and buffer
+        reuse), y of every rank against the stencil formula.  Returns this rank's max relative error |y - ref| / sum|a||x|
+        (inf if y holds a NaN or the arena's error word was raised); x is restored to the timing default 5.0 afterwards."""
+        import torch
+        import torch.distributed as dist
+        from . import validate as V
+        pts, nx, ny, nz = self.grid
+        refs = [V.stencil_product(pts, nx, ny, nz, self.row0, self.row1, v, self.x.device, self.x.dtype) for v in range(self.bvs)]
+        self.set_x(lambda v: refs[v][0], poison_halo=True)
+        torch.cuda.synchronize()
+        if dist.is_initialized():
+            dist.barrier(group=self.group)  # no neighbour pushes into x before it has been poisoned
+        ep0 = self.p2p.status()[1] if self.p2p is not None else 0
+        for _ in range(steps):
+            self.y.fill_(float("nan"))
+            self.step()
+        torch.cuda.synchronize()
+        worst = 0.0
+        for v in range(self.bvs):
+            worst = max(worst, V.max_rel_err(self.get_y(v), refs[v][1], refs[v][2]))
+        self._refs = refs  # the host-buffer path (time_e2e) is checked against the same products
+        if self.p2p is not None:
+            err, ep = self.p2p.status()
+            if err != 0 or ep != ep0 + steps:
+                worst = float("inf")
+        if dist.is_initialized():
+            dist.barrier(group=self.group)
+        for b in (self.p2p.bufs if self.p2p is not None else [self.x]):
+            b.fill_(5.0)
+        self.y.zero_()
+        torch.cuda.synchronize()
+        if dist.is_initialized():
+            dist.barrier(group=self.group)
+        return worst
+
+    def close(self):
+        """COLLECTIVE teardown of the P2P arena (see P2PHalo.close)."""
+        if self.p2p is not None:
+            self.x = None
+            self.p2p.close()
+            self.p2p = None
+
     def solve(self, revisions: int, first_buf: int = 0):
         """Solve mode (main.cpp:528-631): `revisions` x { halo exchange ; SpMV ; swap }, device resident: step k reads buffer
         k & 1 of the arena and writes its y (the next x, already in permuted order) into the other buffer, so the swap is free.
@@ -355,10 +456,19 @@ class DistributedSpmv:
         if pipelined is None:
             pipelined = self.p2p is not None and self.p2p.n_buf == 2 and self.bvs == 1
         self.e2e_pipelined = bool(pipelined)
+        refs = getattr(self, "_refs", None)
+        from . import validate as V
         if pipelined:
             xh = [torch.full((n,), 5.0, dtype=self.x.dtype).pin_memory() for _ in range(2)]
             yh = [torch.zeros(self.scs.n_rows_padded, dtype=self.y.dtype).pin_memory() for _ in range(2)]
             self._e2e_k = getattr(self, "_e2e_k", 0)
+            if refs is not None:  # host x = the validation vector (permuted): the y that comes back is checked below
+                perm = self._perm_tensor()
+                xp = torch.zeros(n, dtype=self.x.dtype, device=self.x.device)
+                xp[perm] = refs[0][0].to(self.x.dtype)
+                for b in xh:
+                    b.copy_(xp)
+                del xp
 
             def run(k):
                 for _ in range(k):
@@ -375,11 +485,16 @@ class DistributedSpmv:
             barrier()
             dt = (time.perf_counter() - t0) / steps
             self.e2e_y = yh[(self._e2e_k - 1) & 1]
+            if refs is not None:
+                self.e2e_max_rel_err = max(V.max_rel_err(b.to(self.x.device)[: self.scs.n_rows_padded][perm], refs[0][1], refs[0][2]) for b in yh)
             return dt
         rowwise = self.bvs > 1 and self.layout == capi.ROWWISE
         n_in = n * self.bvs if (self.bvs == 1 or rowwise) else n  # column-major: the local part of every vector
         xh = torch.full((n_in,), 5.0, dtype=self.x.dtype).pin_memory()
         yh = torch.zeros(self.y.numel(), dtype=self.y.dtype).pin_memory()
+        if refs is not None:  # row-major: the validation block vector; column-major: x_0 in every column (one host vector)
+            self.set_x((lambda v: refs[v][0]) if rowwise or self.bvs == 1 else (lambda v: refs[0][0]))
+            xh.copy_(self.x[:n_in])
 
         def one():
             if self.bvs > 1 and not rowwise:
@@ -396,8 +511,13 @@ class DistributedSpmv:
         for _ in range(steps):
             one()
         barrier()
+        dt = (time.perf_counter() - t0) / steps
         self.e2e_y = yh
-        return (time.perf_counter() - t0) / steps
+        if refs is not None:
+            self.y.copy_(yh)
+            self.e2e_max_rel_err = max(V.max_rel_err(self.get_y(v), refs[v if (rowwise or self.bvs == 1) else 0][1],
+                                                     refs[v if (rowwise or self.bvs == 1) else 0][2]) for v in range(self.bvs))
+        return dt
 
 
 class DistributedApSpmv:
@@ -410,14 +530,19 @@ class DistributedApSpmv:
 
     kernel_name = "k_scs32_stream_ap"
 
-    def __init__(self, ctx, wsa, local_coo, mode, t1, t2, C_, sigma, rank, world, group=None):
+    def __init__(self, ctx, wsa, local_coo, mode, t1, t2, C_, sigma, rank, world, group=None, keep_coo=False):
         import torch
         import torch.distributed as dist
         from . import engine as eng
         self.ctx, self.rank, self.world, self.mode = ctx, rank, world, mode
-        n_loc, n_glob, I, J, V = local_coo
-        mtx = eng.MtxData.from_host(n_loc, n_glob, I, J, V, ctx=ctx)
+        if isinstance(local_coo, eng.MtxData):  # already on the device (uspmv_coo_powerlaw)
+            n_loc, n_glob, I, J, V = local_coo.n_rows, local_coo.n_cols, None, None, None
+        else:
+            n_loc, n_glob, I, J, V = local_coo
+        mtx = local_coo if isinstance(local_coo, eng.MtxData) else eng.MtxData.from_host(n_loc, n_glob, I, J, V, ctx=ctx)
         self.nnz = mtx.nnz
+        self.group, self.row0, self.t1, self.t2 = group, int(wsa[rank]), float(t1), float(t2)
+        self._coo = mtx if keep_coo else None   # validate() forms the reference product from the COO triplets
         coos = eng.partition_precisions(mtx, mode, t1, t2)
         del mtx
         self.used = [k for k in range(3) if coos[k] is not None]
@@ -462,6 +587,50 @@ class DistributedApSpmv:
         self._torch, self._eng = torch, eng
         dist.barrier(group=group)
 
+    def validate(self, steps: int = 2):
+        """Checked steps (COLLECTIVE; needs keep_coo=True): x = f(global row) with a NaN-poisoned halo, y against the product formed
+        from the COO triplets with the values as partition_precisions stores them (dp / fp32 / fp16 by |v| against t1, t2).
+        Returns this rank's max |y - ref| / sum|a||x| (inf on NaN or a raised error word); x is restored to 1.0."""
+        import torch
+        import torch.distributed as dist
+        from . import validate as V
+        if self._coo is None:
+            raise ValueError("validate() needs keep_coo=True")
+        dev = self.x.device
+        nl = self.n_rows
+        ref, scale = V.coo_ap_product(self._coo, self.mode, self.t1, self.t2, self.x.dtype, dev)
+        g = torch.arange(self.row0, self.row0 + nl, device=dev, dtype=torch.float64)
+        self.x[:nl] = V.x_of(g).to(self.x.dtype)
+        self.x[nl:] = float("nan")
+        torch.cuda.synchronize()
+        if dist.is_initialized():
+            dist.barrier(group=self.group)
+        ep0 = self.p2p.status()[1]
+        for _ in range(steps):
+            self.y.fill_(float("nan"))
+            self.step()
+        torch.cuda.synchronize()
+        o2n = V.device_int_tensor(self.parts[self.used[0]].device_arrays()["old_to_new"].value, nl, dev).long()
+        worst = V.max_rel_err(self.y[o2n], ref, scale)
+        err, ep = self.p2p.status()
+        if err != 0 or ep != ep0 + steps:
+            worst = float("inf")
+        if dist.is_initialized():
+            dist.barrier(group=self.group)
+        self.x.fill_(1.0)
+        self.y.zero_()
+        torch.cuda.synchronize()
+        if dist.is_initialized():
+            dist.barrier(group=self.group)
+        return worst
+
+    def close(self):
+        """COLLECTIVE teardown of the P2P arena (see P2PHalo.close)."""
+        if self.p2p is not None:
+            self.x = None
+            self.p2p.close()
+            self.p2p = None
+
     def algorithmic_bytes(self):
         vs = (8, 4, 2)
         xs = self.x.element_size()
@@ -485,3 +654,71 @@ class DistributedApSpmv:
         e1.record()
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / steps
+
+
+class BandedApSpmv:
+    """One-GPU runner of the column-banded execution plan (uspmv_banded_*) for matrices whose x does not fit the L2 (BASELINE config 4
+    at 2^25 rows): same interface as DistributedApSpmv (step / validate / time_kernel / close) so that bench.py measures both plans with
+    one protocol.  mode None: plain dp."""
+
+    kernel_name = "k_scs32_stream_ap (one launch per column band)"
+    p2p = None
+
+    def __init__(self, ctx, mtx, mode, t1, t2, C_, sigma, n_bands=0, algorithmic_bytes=None):
+        import torch
+        from . import engine as eng
+        self.ctx, self.mode, self.t1, self.t2 = ctx, mode, float(t1), float(t2)
+        self._coo = mtx
+        self.nnz = mtx.nnz
+        self.plan = eng.BandedPlan(mtx, C_, sigma, "dp", ap=mode, t1=t1, t2=t2, n_bands=n_bands)
+        p = self.plan
+        self.n_rows, self.n_rows_padded, self.n_halo, self.n_cols_local = p.n_rows, p.n_rows_padded, 0, p.n_cols
+        self.n_elements, self.n_chunks = [p.n_elements], p.n_rows_padded // C_
+        dt = torch.float32 if mode == "ap[sp_hp]" else torch.float64
+        dev = f"cuda:{ctx.device}"
+        self.x = torch.full((p.n_cols,), 1.0, dtype=dt, device=dev)
+        self.y = torch.zeros(p.n_rows_padded, dtype=dt, device=dev)
+        self._alg_bytes = algorithmic_bytes
+        self._torch = torch
+
+    def step(self):
+        self.plan.spmv(self.x, self.y)
+
+    def describe(self):
+        return {"n_bands": self.plan.n_bands, "band_width": self.plan.band_width, "stored_elements_all_bands": int(self.plan.n_elements)}
+
+    def algorithmic_bytes(self):
+        if self._alg_bytes is not None:
+            return self._alg_bytes
+        raise ValueError("pass the un-banded structures' algorithmic bytes (the roofline denominator is the reference format's)")
+
+    def validate(self, steps: int = 2):
+        import torch
+        from . import validate as V
+        dev = self.x.device
+        ref, scale = V.coo_ap_product(self._coo, self.mode, self.t1, self.t2, self.x.dtype, dev)
+        self.x.copy_(V.x_of(torch.arange(self.plan.n_cols, device=dev, dtype=torch.float64)).to(self.x.dtype))
+        for _ in range(steps):
+            self.y.fill_(float("nan"))
+            self.step()
+        torch.cuda.synchronize()
+        o2n = torch.from_numpy(self.plan.old_to_new.astype(np.int64)).to(dev)
+        worst = V.max_rel_err(self.y[o2n], ref, scale)
+        self.x.fill_(1.0)
+        self.y.zero_()
+        torch.cuda.synchronize()
+        return worst
+
+    def time_kernel(self, steps):
+        torch = self._torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(steps):
+            self.step()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+
+    def close(self):
+        self.plan = None

@@ -131,6 +131,21 @@ class MtxData:
         call("uspmv_coo_stencil", ctx.h, int(points), int(nx), int(ny), int(nz), int(row0), int(row1), C.byref(h))
         return cls(h, ctx)
 
+    @classmethod
+    def powerlaw(cls, n, row0=0, row1=None, d_min=None, alpha=2.2, max_deg=4096, seed=0x5EED, ctx: Context | None = None):
+        """BASELINE config 4's power-law matrix, rows [row0, row1) generated on the device (uspmv_coo_powerlaw)."""
+        from .matrices import POWERLAW_D_MIN_CONFIG4
+        ctx = ctx or default_context()
+        h = vp()
+        call("uspmv_coo_powerlaw", ctx.h, int(n), int(row0), int(n if row1 is None else row1), float(d_min or POWERLAW_D_MIN_CONFIG4),
+             float(alpha), int(max_deg), int(seed), C.byref(h))
+        return cls(h, ctx)
+
+    def device_arrays(self):
+        ptrs = [vp() for _ in range(3)]
+        call("uspmv_coo_device_arrays", self.h, *[C.byref(p) for p in ptrs])
+        return dict(zip(("I", "J", "values"), ptrs))
+
     def to_host(self, mt=np.float64):
         I = np.zeros(self.nnz, np.int32)
         J = np.zeros(self.nnz, np.int32)
@@ -305,7 +320,11 @@ def seg_work_sharing_arr(seg_method: str, n_rows: int, I: np.ndarray, comm_size:
     """seg_work_sharing_arr — mpi_funcs.hpp:424-622 ('seg-rows' / 'seg-nnz')."""
     I = np.ascontiguousarray(I, np.int32)
     wsa = np.zeros(comm_size + 1, np.int32)
-    m = capi.SEG_NNZ if seg_method.replace("_", "-") == "seg-nnz" else capi.SEG_ROWS
+    methods = {"seg-nnz": capi.SEG_NNZ, "seg-rows": capi.SEG_ROWS}
+    key = seg_method.replace("_", "-")
+    if key not in methods:  # seg-metis (mpi_funcs.hpp:494-600) is out of scope; typos must not fall back silently
+        raise ValueError(f"seg_work_sharing_arr: unknown seg_method {seg_method!r} (supported: seg-rows, seg-nnz)")
+    m = methods[key]
     call("uspmv_seg_work_sharing_arr", m, int(n_rows), len(I), _hp(I), int(comm_size), _hp(wsa))
     return wsa
 
@@ -349,7 +368,7 @@ class SingleGpuSpmv:
 
     def __init__(self, ctx: Context, points: int, n: int, C_: int, sigma: int, vt: str):
         t = _torch()
-        self.ctx = ctx
+        self.ctx, self.points, self.n = ctx, points, n
         mtx = MtxData.stencil(points, n, n, n, ctx=ctx)
         if vt != "dp":  # the stencil generator emits doubles; convert_to_scs narrows (MT -> VT)
             pass
@@ -372,6 +391,29 @@ class SingleGpuSpmv:
     def step(self):
         spmv(self.scs, self.x, self.y)
 
+    def validate(self, steps: int = 2) -> float:
+        """Checked steps: x = f(row) (permuted like the harness does, main.cpp:86-93), y against the stencil formula.  Returns
+        max |y - ref| / sum|a||x|; x is restored to the timing default 5.0."""
+        from . import validate as V
+        t = _torch()
+        s = self.scs
+        x_loc, y_ref, scale = V.stencil_product(self.points, self.n, self.n, self.n, 0, s.n_rows, 0, self.x.device, self.x.dtype)
+        perm = V.device_int_tensor(s.device_arrays()["old_to_new"].value, s.n_rows, self.x.device).long()
+        self.x[: s.n_rows][perm] = x_loc.to(self.x.dtype)
+        for _ in range(steps):
+            self.y.fill_(float("nan"))
+            self.step()
+        t.cuda.synchronize()
+        worst = V.max_rel_err(self.y[: s.n_rows_padded][perm], y_ref, scale)
+        self._vref = (x_loc, y_ref, scale, perm)  # the host-buffer path (time_e2e) is checked against the same product
+        self.x.fill_(5.0)
+        self.y.zero_()
+        t.cuda.synchronize()
+        return worst
+
+    def close(self):
+        pass
+
     def time_kernel(self, steps: int) -> float:
         """Average device time of the SpMV kernel (ms), CUDA events on the launching stream."""
         t = _torch()
@@ -392,6 +434,13 @@ class SingleGpuSpmv:
         nslots = 3 if pipelined else 1
         xh = [t.full((self.x.numel(),), 5.0, dtype=self.x.dtype).pin_memory() for _ in range(nslots)]
         yh = [t.zeros(self.y.numel(), dtype=self.y.dtype).pin_memory() for _ in range(nslots)]
+        vref = getattr(self, "_vref", None)
+        if vref is not None:  # host x = the validation vector (permuted), so the y that comes back can be checked
+            xp = t.zeros_like(self.x)
+            xp[: self.scs.n_rows][vref[3]] = vref[0].to(self.x.dtype)
+            for b in xh:
+                b.copy_(xp)
+            del xp
 
         def run(k):
             if not pipelined:
@@ -411,4 +460,7 @@ class SingleGpuSpmv:
         barrier()
         dt = (time.perf_counter() - t0) / steps
         self.e2e_checksum = float(yh[0][: self.n_rows].double().sum())
+        if vref is not None:
+            from . import validate as V
+            self.e2e_max_rel_err = max(V.max_rel_err(b.to(self.x.device)[: self.scs.n_rows_padded][vref[3]], vref[1], vref[2]) for b in yh)
         return dt

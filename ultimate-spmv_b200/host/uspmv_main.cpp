@@ -313,7 +313,11 @@ long peek_rows(const Config &cfg) {
 int rank_main(Config cfg, const int rank, const int P, Shared *sh) {
     auto barrier = [&] { pthread_barrier_wait(&sh->bar); };
     uspmv_ctx *ctx = nullptr;
-    ck(uspmv_ctx_create(rank, &ctx));
+    int ndev = 0;
+    ck(uspmv_device_count(&ndev));
+    // cudaSetDevice(my_rank % ndev) like the reference (main.cpp:1838-1842): more ranks than GPUs share devices (time-sliced; the
+    // arenas are still exchanged through CUDA IPC, so the whole push / wait / acknowledge protocol runs with a real peer)
+    ck(uspmv_ctx_create(rank % ndev, &ctx));
     const bool ap = is_ap(cfg.value_type);
     const int ap_mode = cfg.value_type == "ap[dp_sp]" ? USPMV_AP_DP_SP : cfg.value_type == "ap[dp_hp]" ? USPMV_AP_DP_HP
                         : cfg.value_type == "ap[sp_hp]" ? USPMV_AP_SP_HP : USPMV_AP_DP_SP_HP;
@@ -641,7 +645,12 @@ int rank_main(Config cfg, const int rank, const int P, Shared *sh) {
         }
     }
     fflush(stdout);
-    barrier();  // nobody unmaps a peer's arena while that peer may still be in its last exchange
+    // collective teardown of the IPC arenas: every rank's device is idle (sync) before anybody unmaps a neighbour's arena, and
+    // every mapping is closed before anybody frees
+    if (uspmv_p2p_sync(p2p)) { fprintf(stderr, "rank %d: %s\n", rank, uspmv_last_error()); rc = 3; }
+    barrier();
+    uspmv_p2p_disconnect(p2p);
+    barrier();
     uspmv_stream_destroy(ctx, comm);
     uspmv_free(ctx, y_d);
     uspmv_p2p_destroy(p2p);

@@ -126,17 +126,23 @@ def _u01(h: np.ndarray) -> np.ndarray:
     return (h >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
 
 
-def powerlaw_coo(n: int, target_nnz: int, alpha: float = 2.2, max_deg: int = 4096, seed: int = 0x5EED, row0: int = 0, row1: int | None = None):
+POWERLAW_D_MIN_CONFIG4 = 3.28  # calibrated: ~14.9 stored elements per row after the clamp and de-duplication (5.0e8 at 2^25 rows)
+
+
+def powerlaw_coo(n: int, target_nnz: int, alpha: float = 2.2, max_deg: int = 4096, seed: int = 0x5EED, row0: int = 0, row1: int | None = None,
+                 d_min: float | None = None):
     """Irregular power-law matrix of BASELINE.json config 4: row degree
     d = clamp(floor(d_min * (1-u)^(-1/(alpha-1))), 1, max_deg); columns: half within +-1024 of the diagonal,
     half uniform, de-duplicated, ascending; values sign * 10^w, w ~ U(-4, 2).  All randomness is
-    splitmix64(seed, row, k), so any row range can be generated independently."""
+    splitmix64(seed, row, k), so any row range can be generated independently.  d_min overrides the density derived from
+    target_nnz.  Device twin: uspmv_coo_powerlaw (same matrix)."""
     row1 = n if row1 is None else row1
     with np.errstate(over="ignore"):
         rows = np.arange(row0, row1, dtype=np.uint64)
         u = _u01(_splitmix64(np.uint64(seed) ^ (rows * np.uint64(0xD1342543DE82EF95))))
         # mean of floor(d_min*(1-u)^(-1/(a-1))) ~ d_min*(a-1)/(a-2); pick d_min for the target density
-        d_min = max(1.0, (target_nnz / n) * (alpha - 2.0) / (alpha - 1.0))
+        if d_min is None:
+            d_min = max(1.0, (target_nnz / n) * (alpha - 2.0) / (alpha - 1.0))
         deg = np.clip(np.floor(d_min * (1.0 - u) ** (-1.0 / (alpha - 1.0))), 1, max_deg).astype(np.int64)
         deg = np.minimum(deg, n)
         ptr = np.concatenate(([0], np.cumsum(deg)))

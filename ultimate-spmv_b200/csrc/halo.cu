@@ -180,7 +180,8 @@ int uspmv_halo_plan_create_multi(uspmv_scs **parts, int n_parts, const int *wsa_
                 fail("uspmv_halo_plan_create: the parts do not share n_rows / C");
             slots_total += parts[q]->n_elements;
         }
-        if (slots_total > INT32_MAX - 1024) fail("uspmv_halo_plan_create: more than 2^31 stored elements on one rank");
+        // first-seen order is tracked as a 32-bit storage position over all parts; a single rank has no remote column at all
+        if (P > 1 && slots_total > INT32_MAX - 1024) fail("uspmv_halo_plan_create: more than 2^31 stored elements on one rank");
         USPMV_CUDA(cudaSetDevice(s0->ctx->device));
         const int lo = wsa_h[rank], hi = wsa_h[rank + 1], n_glob = wsa_h[P];
         const long n_local = hi - lo;
@@ -200,7 +201,7 @@ int uspmv_halo_plan_create_multi(uspmv_scs **parts, int n_parts, const int *wsa_
             const bool strict = options().strict_reference_halo;
             const long n_pad = s0->n_rows_padded;
             long slot_base = 0;
-            for (int q = 0; q < n_parts; ++q) {
+            for (int q = 0; q < n_parts && P > 1; ++q) {
                 uspmv_scs *s = parts[q];
                 if (s->n_elements) {
                     k_mark_remote<<<blocks_for(n_pad), TPB>>>(s->chunk_ptrs.p, s->chunk_lengths.p, s->row_lengths.p, s->col_idxs.p, n_pad, (int)s->C,
@@ -210,7 +211,7 @@ int uspmv_halo_plan_create_multi(uspmv_scs **parts, int n_parts, const int *wsa_
                 slot_base += s->n_elements;
             }
             long n_halo = 0;
-            if (n_glob) {
+            if (n_glob && P > 1) {
                 k_flag_seen<<<blocks_for(n_glob), TPB>>>(first.p, n_glob, flag.p);
                 USPMV_LAUNCH_CHECK();
                 USPMV_CUDA(cudaMemset(flag.p + n_glob, 0, sizeof(int)));

@@ -74,6 +74,23 @@ def device_int_tensor(ptr, n, device):
     return torch.as_tensor(a, device=device)
 
 
+def to_half_rn(v):
+    """double -> fp16 with ONE rounding (what static_cast<_Float16>(double) and __double2half do; torch's .half() on a double tensor
+    goes through float and double-rounds).  Among the double-rounded value and its two fp16 neighbours the one nearest to v wins; a v
+    exactly on an fp16 tie is exact in fp32, so the second rounding of the detour already applied ties-to-even correctly."""
+    import torch
+    c = v.float().half()
+    bits = c.view(torch.int16)
+    best, best_err = c, (c.double() - v).abs()
+    for delta in (1, -1):
+        cand = (bits + delta).view(torch.float16)
+        err = (cand.double() - v).abs()
+        take = (err < best_err) & torch.isfinite(cand)
+        best = torch.where(take, cand, best)
+        best_err = torch.where(take, err, best_err)
+    return best
+
+
 def coo_ap_product(mtx, mode, t1, t2, x_dtype, device):
     """(y_ref, scale) per local row for the adaptive-precision product of a device COO (engine.MtxData holding doubles) with
     x[j] = x_of(GLOBAL column j) stored in x_dtype: values as partition_precisions stores them (interface.hpp:938-964: dp / fp32 / fp16
@@ -90,13 +107,13 @@ def coo_ap_product(mtx, mode, t1, t2, x_dtype, device):
     vals = torch.as_tensor(a_, device=device)
     a = vals.abs()
     if mode == "ap[dp_sp_hp]":
-        vs = torch.where(a >= t1, vals, torch.where(a >= t2, vals.float().double(), vals.half().double()))
+        vs = torch.where(a >= t1, vals, torch.where(a >= t2, vals.float().double(), to_half_rn(vals).double()))
     elif mode == "ap[dp_sp]":
         vs = torch.where(a >= t1, vals, vals.float().double())
     elif mode == "ap[dp_hp]":
-        vs = torch.where(a >= t1, vals, vals.half().double())
+        vs = torch.where(a >= t1, vals, to_half_rn(vals).double())
     elif mode == "ap[sp_hp]":
-        vs = torch.where(a >= t1, vals.float().double(), vals.half().double())
+        vs = torch.where(a >= t1, vals.float().double(), to_half_rn(vals).double())
     else:
         vs = vals
     del a

@@ -187,7 +187,7 @@ def test_powerlaw_device_generator_equals_host_generator(eng, mats, big_gpu):
     gI, gJ, gV = mtx.to_host()
     _, _, I, J, V = mats.powerlaw_coo(n, 0, d_min=mats.POWERLAW_D_MIN_CONFIG4)
     assert np.array_equal(gI, I) and np.array_equal(gJ, J)
-    assert np.all(np.abs(gV - V) <= 4e-16 * np.abs(V))
+    assert np.all(np.abs(gV - V) <= 1e-15 * np.abs(V))   # CUDA pow: <= 2 ulp, glibc pow: < 1 ulp
     # any row range generates independently (what every rank does at N > 1)
     a, b = n // 3, n // 3 + 5000
     part = eng.MtxData.powerlaw(n, a, b, d_min=mats.POWERLAW_D_MIN_CONFIG4)

@@ -147,6 +147,11 @@ __device__ __forceinline__ double part_sum_f32prod(const PartArgs &p, long c, in
     return acc;
 }
 
+__global__ void k_diff_lengths(const int *__restrict__ ptrs, long n, int *__restrict__ len) {
+    long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (i < n) len[i] = ptrs[i + 1] - ptrs[i];
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(TPB)
 k_ap_spmv(long n_pad, int C, PartArgs dp, PartArgs sp, PartArgs hp, const void *__restrict__ x, void *__restrict__ y) {
@@ -419,6 +424,66 @@ int uspmv_ap_spmv(int ap_mode, const uspmv_scs *dp, const uspmv_scs *sp, const u
         default: k_ap_spmv<USPMV_AP_DP_SP_HP><<<g, TPB, 0, st>>>(n_pad, C, a, b, c, x, y);
         }
         USPMV_LAUNCH_CHECK();
+    });
+}
+
+/* uspmv_scs_ap{dpsp,dphp,sphp,dpsphp}_gpu / uspmv_csr_ap*_gpu on caller-owned DEVICE arrays — the reference's AP kernels take the raw
+ * arrays of every precision part per call (interface.hpp:1129-1733; GPU: ap_kernels.hpp:637-953, MultiPrecKernelArgs
+ * classes_structs.hpp:238-261).  arrays[4 * p + {0,1,2,3}] = chunk_ptrs, chunk_lengths, col_idxs, values of part p (0 dp, 1 sp, 2 hp;
+ * parts the mode does not use are ignored).  All parts share C and n_chunks.  C == 1 is CRS (chunk_ptrs = row_ptrs; a NULL
+ * chunk_lengths is derived).  One fused pass; very long chunks are NOT cut into segments here (no per-matrix plan without a handle). */
+int uspmv_scs_ap_gpu(uspmv_ctx *ctx, int ap_mode, long C, long n_chunks, const void *const *arrays, const void *x, void *y, void *stream) {
+    return guarded([&] {
+        if (!ctx || !arrays) fail("uspmv_scs_ap_gpu: NULL argument");
+        if (ap_mode < 0 || ap_mode > 3) fail("uspmv_scs_ap_gpu: invalid ap mode %d", ap_mode);
+        if (C < 1) fail("uspmv_scs_ap_gpu: C must be >= 1");
+        const long n_pad = n_chunks * C;
+        if (n_pad == 0) return;
+        if (!x || !y) fail("uspmv_scs_ap_gpu: NULL vector");
+        USPMV_CUDA(cudaSetDevice(ctx->device));
+        cudaStream_t st = as_stream(stream);
+        const bool use[3] = {ap_mode != USPMV_AP_SP_HP, ap_mode != USPMV_AP_DP_HP, ap_mode != USPMV_AP_DP_SP};
+        PartArgs pa[3];
+        DevBuf<int> cl_tmp[3];
+        bool aligned = true, derived = false;
+        for (int p = 0; p < 3; ++p) {
+            pa[p] = PartArgs{nullptr, nullptr, nullptr, nullptr};
+            if (!use[p]) continue;
+            const int *cp = static_cast<const int *>(arrays[4 * p]), *cl = static_cast<const int *>(arrays[4 * p + 1]);
+            const int *ci = static_cast<const int *>(arrays[4 * p + 2]);
+            const void *v = arrays[4 * p + 3];
+            if (!cp || !ci || !v) fail("uspmv_scs_ap_gpu: an array of part %d (required by the mode) is NULL", p);
+            if (!cl) {
+                if (C != 1) fail("uspmv_scs_ap_gpu: chunk_lengths of part %d is NULL", p);
+                cl_tmp[p].alloc(n_chunks);
+                k_diff_lengths<<<blocks_for(n_chunks), TPB, 0, st>>>(cp, n_chunks, cl_tmp[p].p);
+                USPMV_LAUNCH_CHECK();
+                cl = cl_tmp[p].p;
+                derived = true;
+            }
+            pa[p] = PartArgs{cp, cl, ci, v};
+            aligned = aligned && reinterpret_cast<uintptr_t>(ci) % 16 == 0 && reinterpret_cast<uintptr_t>(v) % 16 == 0;
+        }
+        if (C == 32 && options().scs_stream && aligned) {
+            const stream::ApPart sa{pa[0].cp, pa[0].cl, pa[0].ci, pa[0].v}, sb{pa[1].cp, pa[1].cl, pa[1].ci, pa[1].v}, sc{pa[2].cp, pa[2].cl, pa[2].ci, pa[2].v};
+            switch (ap_mode) {
+            case USPMV_AP_DP_SP: launch_ap_stream<USPMV_AP_DP_SP>(n_chunks, nullptr, nullptr, sa, sb, sc, x, y, st); break;
+            case USPMV_AP_DP_HP: launch_ap_stream<USPMV_AP_DP_HP>(n_chunks, nullptr, nullptr, sa, sb, sc, x, y, st); break;
+            case USPMV_AP_SP_HP: launch_ap_stream<USPMV_AP_SP_HP>(n_chunks, nullptr, nullptr, sa, sb, sc, x, y, st); break;
+            default: launch_ap_stream<USPMV_AP_DP_SP_HP>(n_chunks, nullptr, nullptr, sa, sb, sc, x, y, st);
+            }
+            USPMV_LAUNCH_CHECK();
+        } else {
+            const unsigned g = blocks_for(n_pad);
+            switch (ap_mode) {
+            case USPMV_AP_DP_SP: k_ap_spmv<USPMV_AP_DP_SP><<<g, TPB, 0, st>>>(n_pad, (int)C, pa[0], pa[1], pa[2], x, y); break;
+            case USPMV_AP_DP_HP: k_ap_spmv<USPMV_AP_DP_HP><<<g, TPB, 0, st>>>(n_pad, (int)C, pa[0], pa[1], pa[2], x, y); break;
+            case USPMV_AP_SP_HP: k_ap_spmv<USPMV_AP_SP_HP><<<g, TPB, 0, st>>>(n_pad, (int)C, pa[0], pa[1], pa[2], x, y); break;
+            default: k_ap_spmv<USPMV_AP_DP_SP_HP><<<g, TPB, 0, st>>>(n_pad, (int)C, pa[0], pa[1], pa[2], x, y);
+            }
+            USPMV_LAUNCH_CHECK();
+        }
+        if (derived) USPMV_CUDA(cudaStreamSynchronize(st));  // the temporaries are freed on return
     });
 }
 

@@ -161,6 +161,81 @@ int uspmv_memset(uspmv_ctx *ctx, void *dst_d, int byte, size_t bytes, void *stre
     });
 }
 
+/* 1 if ptr is device (or managed) memory of some CUDA device, 0 for ordinary / pinned host memory and NULL */
+int uspmv_pointer_is_device(const void *ptr, int *out) {
+    return guarded([&] {
+        if (!out) fail("uspmv_pointer_is_device: out is NULL");
+        *out = 0;
+        if (!ptr) return;
+        cudaPointerAttributes a;
+        cudaError_t e = cudaPointerGetAttributes(&a, ptr);
+        if (e != cudaSuccess) { cudaGetLastError(); return; }
+        *out = (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) ? 1 : 0;
+    });
+}
+
+/* random_init (utilities.hpp:880-912) + the padding rule of init_std_vec_with_ptr_or_value (:914-981), HOST logic: a DEFAULT-seeded
+ * std::mt19937 and uniform_real_distribution<double>(min, max) drawn sequentially over all n values, each converted to the vector's
+ * type; then, per vector of vec_length values (colwise) / over the first n_rows * bvs values (rowwise), everything past the real rows
+ * is zeroed.  libstdc++'s distribution draws two 32-bit words per double: u = (a0 + a1 2^32) / 2^64 rounded to double (1.0 is replaced
+ * by the largest double below it), value = (max - min) * u + min. */
+int uspmv_random_init_host(double vmin, double vmax, long n, int vt, void *out_h, long n_rows, long vec_length, int bvs, int layout) {
+    return guarded([&] {
+        if (n < 0 || (n > 0 && !out_h)) fail("uspmv_random_init_host: NULL output");
+        vt_size(vt);
+        // mt19937 (32-bit Mersenne twister, seed 5489) restated: the standard fixes its output sequence
+        unsigned int mt[624];
+        mt[0] = 5489u;
+        for (int i = 1; i < 624; ++i) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (unsigned int)i;
+        int idx = 624;
+        auto next = [&]() -> unsigned int {
+            if (idx >= 624) {
+                for (int k = 0; k < 624; ++k) {
+                    const unsigned int yv = (mt[k] & 0x80000000u) | (mt[(k + 1) % 624] & 0x7fffffffu);
+                    mt[k] = mt[(k + 397) % 624] ^ (yv >> 1) ^ ((yv & 1u) ? 0x9908b0dfu : 0u);
+                }
+                idx = 0;
+            }
+            unsigned int yv = mt[idx++];
+            yv ^= yv >> 11;
+            yv ^= (yv << 7) & 0x9d2c5680u;
+            yv ^= (yv << 15) & 0xefc60000u;
+            yv ^= yv >> 18;
+            return yv;
+        };
+        for (long i = 0; i < n; ++i) {
+            const unsigned long long a0 = next(), a1 = next();
+            const long double sum = (long double)a0 + (long double)a1 * 4294967296.0L;
+            double u = (double)(sum / 18446744073709551616.0L);
+            if (u >= 1.0) u = 0.99999999999999988897769753748434595763683319091796875;  // nextafter(1, 0)
+            const double v = (vmax - vmin) * u + vmin;
+            switch (vt) {
+            case USPMV_F64: static_cast<double *>(out_h)[i] = v; break;
+            case USPMV_F32: static_cast<float *>(out_h)[i] = (float)v; break;
+            default: {
+                // double -> fp16, one rounding (static_cast<_Float16>(double))
+                const __half h = __double2half(v);
+                static_cast<__half *>(out_h)[i] = h;
+            }
+            }
+        }
+        if (n_rows < 0 || vec_length <= 0) return;  // no padding rule requested
+        auto zero = [&](long i) {
+            switch (vt) {
+            case USPMV_F64: static_cast<double *>(out_h)[i] = 0.0; break;
+            case USPMV_F32: static_cast<float *>(out_h)[i] = 0.0f; break;
+            default: static_cast<unsigned short *>(out_h)[i] = 0;
+            }
+        };
+        if (layout == USPMV_ROWWISE) {
+            for (long i = n_rows * (long)bvs; i < n; ++i) zero(i);
+        } else {
+            for (long i = 0; i < n; ++i)
+                if (i % vec_length >= n_rows) zero(i);
+        }
+    });
+}
+
 int uspmv_host_alloc(size_t bytes, void **out_h) {
     return guarded([&] {
         if (!out_h) fail("uspmv_host_alloc: out is NULL");

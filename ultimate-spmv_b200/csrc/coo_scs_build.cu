@@ -263,6 +263,21 @@ __global__ void k_perms(const RC *__restrict__ rc, long n_rows, long n_pad, bool
         new_to_old[p] = -1;
 }
 
+// adopted matrices: pass 0 clears new_to_old and sets row_lengths to the chunk length (padding is unknown: every slot counts),
+// pass 1 scatters the inverse permutation
+__global__ void k_adopt_perms(const int *__restrict__ old_to_new, long n_rows, long n_pad, const int *__restrict__ chunk_lengths, int C,
+                              int *__restrict__ new_to_old, int *__restrict__ row_lengths, int pass) {
+    long p = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (p >= n_pad) return;
+    if (pass == 0) {
+        new_to_old[p] = -1;
+        row_lengths[p] = chunk_lengths[p / C];
+    } else if (p < n_rows) {
+        const int q = old_to_new[p];
+        if (q >= 0 && q < n_pad) new_to_old[q] = (int)p;
+    }
+}
+
 template <typename T> struct Cvt;
 template <> struct Cvt<double> {
     __device__ static double from(double v) { return v; }
@@ -398,7 +413,7 @@ __global__ void k_powerlaw_raw(long n, long row0, long n_local, unsigned long lo
         } else
             col = (long long)(h % (unsigned long long)n);
         const unsigned long long h2 = splitmix64(h);
-        const double wexp = u01(h2) * 6.0 - 4.0;
+        const double wexp = __dsub_rn(__dmul_rn(u01(h2), 6.0), 4.0);  // no FMA contraction: the host generator rounds twice
         const double sign = (h2 & 1ull) == 0 ? 1.0 : -1.0;
         keys[b + k] = ((unsigned long long)w << 32) | (unsigned long long)col;
         vals[b + k] = sign * pow(10.0, wexp);
@@ -419,6 +434,26 @@ __global__ void k_compact_keys(const unsigned long long *__restrict__ keys, cons
     I[o] = (int)(keys[i] >> 32);
     J[o] = (int)(keys[i] & 0xffffffffull);
     V[o] = vals[i];
+}
+
+// ---- slab extraction (seg_mtx_struct + localize_row_idx, mpi_funcs.hpp:636-674,862-877) ---------------------------------
+// lower_bound of two row ids in the row-sorted I array, one thread each
+__global__ void k_row_bounds(const int *__restrict__ I, long nnz, int r0, int r1, long long *__restrict__ out2) {
+    const int t = threadIdx.x;
+    if (t > 1) return;
+    const int key = t == 0 ? r0 : r1;
+    long lo = 0, hi = nnz;
+    while (lo < hi) {
+        const long mid = (lo + hi) >> 1;
+        if (I[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    out2[t] = lo;
+}
+__global__ void k_localize_rows(const int *__restrict__ I, long n, int first_row, int *__restrict__ out, int *__restrict__ new_row_flag) {
+    long k = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    out[k] = I[k] - first_row;
+    new_row_flag[k] = (k == 0 || I[k] != I[k - 1]) ? 1 : 0;
 }
 
 // ---- host helpers --------------------------------------------------------------------------------
@@ -694,6 +729,66 @@ int uspmv_coo_powerlaw(uspmv_ctx *ctx, long n, long row0, long row1, double d_mi
     });
 }
 
+/* seg_mtx_struct + localize_row_idx (mpi_funcs.hpp:636-674,862-877) on the device: the rows [wsa[rank], wsa[rank+1]) of a ROW-SORTED
+ * COO as a new COO with process-local row ids and GLOBAL columns (input order kept).  n_distinct_rows (optional) receives the number
+ * of distinct rows present, which is what the reference stores as local n_rows (mpi_funcs.hpp:770); the returned COO has
+ * n_rows = wsa[rank+1] - wsa[rank] (the two differ only when the slab contains empty rows, where the reference's n_rows no longer
+ * covers its own row ids).  The reference makes rows local by subtracting the FIRST STORED row id and finds the slab with a linear
+ * search for the row ids wsa[rank] / wsa[rank+1] (get_index, utilities.hpp:855-878: -1 when such a row is empty); here local row =
+ * row - wsa[rank], identical whenever the reference is defined. */
+int uspmv_coo_seg_mtx(const uspmv_coo *total, const int *wsa_h, int rank, int P, uspmv_coo **out, long *n_distinct_rows) {
+    return guarded([&] {
+        if (!total || !wsa_h || !out) fail("uspmv_coo_seg_mtx: NULL argument");
+        if (P < 1 || rank < 0 || rank >= P) fail("uspmv_coo_seg_mtx: bad rank / comm_size");
+        const int r0 = wsa_h[rank], r1 = wsa_h[rank + 1];
+        if (r0 < 0 || r1 < r0 || r1 > total->n_rows) fail("uspmv_coo_seg_mtx: work_sharing_arr [%d, %d) outside the matrix (%ld rows)", r0, r1, total->n_rows);
+        USPMV_CUDA(cudaSetDevice(total->ctx->device));
+        const long nnz = total->nnz;
+        if (nnz) {
+            DevBuf<int> flags(2);
+            USPMV_CUDA(cudaMemset(flags.p, 0, 2 * sizeof(int)));
+            k_check_sorted<<<blocks_for(nnz), TPB>>>(total->I.p, nnz, total->n_rows, flags.p);
+            USPMV_LAUNCH_CHECK();
+            int hf[2];
+            check_flags(flags, hf);
+            if (hf[0] || hf[1]) fail("uspmv_coo_seg_mtx: the COO matrix must be sorted by row (read_mtx / uspmv_coo_from_entries order)");
+        }
+        long long b[2] = {0, 0};
+        if (nnz) {
+            DevBuf<long long> bd(2);
+            k_row_bounds<<<1, 32>>>(total->I.p, nnz, r0, r1, bd.p);
+            USPMV_LAUNCH_CHECK();
+            USPMV_CUDA(cudaMemcpy(b, bd.p, 2 * sizeof(long long), cudaMemcpyDeviceToHost));
+        }
+        const long lo = (long)b[0], n = (long)(b[1] - b[0]);
+        const size_t es = vt_size(total->mt);
+        auto c = new uspmv_coo();
+        try {
+            coo_common(total->ctx, r1 - r0, total->n_cols, n, total->mt, c);
+            long distinct = 0;
+            if (n) {
+                DevBuf<int> flag(n + 1), pos(n + 1);
+                USPMV_CUDA(cudaMemset(flag.p + n, 0, sizeof(int)));
+                k_localize_rows<<<blocks_for(n), TPB>>>(total->I.p + lo, n, r0, c->I.p, flag.p);
+                USPMV_LAUNCH_CHECK();
+                USPMV_CUDA(cudaMemcpy(c->J.p, total->J.p + lo, n * sizeof(int), cudaMemcpyDeviceToDevice));
+                USPMV_CUDA(cudaMemcpy(c->values.p, total->values.p + (size_t)lo * es, n * es, cudaMemcpyDeviceToDevice));
+                size_t bytes = 0;
+                USPMV_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, flag.p, pos.p, (int)(n + 1)));
+                DevBuf<unsigned char> tmp(bytes);
+                USPMV_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, bytes, flag.p, pos.p, (int)(n + 1)));
+                g_launches.fetch_add(2);
+                int tot = 0;
+                USPMV_CUDA(cudaMemcpy(&tot, pos.p + n, sizeof(int), cudaMemcpyDeviceToHost));
+                distinct = tot;
+            }
+            if (n_distinct_rows) *n_distinct_rows = distinct;
+            USPMV_CUDA(cudaDeviceSynchronize());
+        } catch (...) { delete c; throw; }
+        *out = c;
+    });
+}
+
 /* raw device pointers of the COO arrays (any out pointer may be NULL); values are `mt`-typed */
 int uspmv_coo_device_arrays(const uspmv_coo *coo, const int **I_d, const int **J_d, const void **values_d) {
     return guarded([&] {
@@ -934,6 +1029,73 @@ int uspmv_scs_build(uspmv_ctx *ctx, const uspmv_coo *coo, long C, long sigma, in
                 default: dispatch_fill_vt<__half>(coo, s, rc.p, row_ptr.p, ord); break;
                 }
             }
+            USPMV_CUDA(cudaDeviceSynchronize());
+            build_balanced_order(s);
+        } catch (...) { delete s; throw; }
+        *out = s;
+    });
+}
+
+/* Adopt a SELL-C-sigma matrix that somebody else built (e.g. the reference's own convert_to_scs on the host, or a file): the arrays
+ * are COPIED into a device-resident handle that every kernel entry point accepts.  Host or device pointers (`on_device`).  old_to_new
+ * may be NULL (identity).  chunk_ptrs has n_chunks + 1 entries, n_elements = chunk_ptrs[n_chunks]. */
+int uspmv_scs_from_arrays(uspmv_ctx *ctx, int vt, long C, long sigma, long n_rows, long n_cols, long n_chunks, const int *chunk_ptrs,
+                          const int *chunk_lengths, const int *col_idxs, const void *values, const int *old_to_new, int on_device,
+                          uspmv_scs **out) {
+    return guarded([&] {
+        if (!ctx || !out) fail("uspmv_scs_from_arrays: NULL argument");
+        if (C < 1 || sigma < 1 || n_rows < 0 || n_chunks != (n_rows + C - 1) / C) fail("uspmv_scs_from_arrays: inconsistent C / n_rows / n_chunks");
+        if (n_chunks > 0 && (!chunk_ptrs || !chunk_lengths)) fail("uspmv_scs_from_arrays: NULL chunk array");
+        const size_t es = vt_size(vt);
+        USPMV_CUDA(cudaSetDevice(ctx->device));
+        const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+        int n_el = 0;
+        if (n_chunks) {
+            if (on_device) USPMV_CUDA(cudaMemcpy(&n_el, chunk_ptrs + n_chunks, sizeof(int), cudaMemcpyDeviceToHost));
+            else n_el = chunk_ptrs[n_chunks];
+        }
+        if (n_el < 0) fail("uspmv_scs_from_arrays: negative n_elements");
+        if (n_el > 0 && (!col_idxs || !values)) fail("uspmv_scs_from_arrays: NULL element array");
+        auto s = new uspmv_scs();
+        try {
+            s->ctx = ctx; s->C = C; s->sigma = sigma; s->n_rows = n_rows; s->n_cols = n_cols; s->n_rows_padded = n_chunks * C;
+            s->n_chunks = n_chunks; s->n_elements = n_el; s->vt = vt;
+            s->cols_permuted = true;  // whatever numbering the arrays carry is final
+            s->chunk_ptrs.alloc(n_chunks + 1);
+            s->chunk_lengths.alloc(n_chunks);
+            s->old_to_new.alloc(n_rows);
+            s->new_to_old.alloc(s->n_rows_padded);
+            s->row_lengths.alloc(s->n_rows_padded);
+            s->col_idxs.alloc((size_t)n_el + 8);
+            s->values.alloc(((size_t)n_el + 8) * es);
+            USPMV_CUDA(cudaMemset(s->col_idxs.p + n_el, 0, 8 * sizeof(int)));
+            USPMV_CUDA(cudaMemset(s->values.p + (size_t)n_el * es, 0, 8 * es));
+            if (n_chunks) {
+                USPMV_CUDA(cudaMemcpy(s->chunk_ptrs.p, chunk_ptrs, (n_chunks + 1) * sizeof(int), kind));
+                USPMV_CUDA(cudaMemcpy(s->chunk_lengths.p, chunk_lengths, n_chunks * sizeof(int), kind));
+            } else
+                USPMV_CUDA(cudaMemset(s->chunk_ptrs.p, 0, sizeof(int)));
+            if (n_el) {
+                USPMV_CUDA(cudaMemcpy(s->col_idxs.p, col_idxs, (size_t)n_el * sizeof(int), kind));
+                USPMV_CUDA(cudaMemcpy(s->values.p, values, (size_t)n_el * es, kind));
+            }
+            if (n_rows) {
+                if (old_to_new) USPMV_CUDA(cudaMemcpy(s->old_to_new.p, old_to_new, n_rows * sizeof(int), kind));
+                else {
+                    k_iota<<<blocks_for(n_rows), TPB>>>(s->old_to_new.p, n_rows);
+                    USPMV_LAUNCH_CHECK();
+                }
+            }
+            if (s->n_rows_padded) {
+                k_adopt_perms<<<blocks_for(s->n_rows_padded), TPB>>>(s->old_to_new.p, n_rows, s->n_rows_padded, s->chunk_lengths.p, (int)C,
+                                                                    s->new_to_old.p, s->row_lengths.p, 0);
+                USPMV_LAUNCH_CHECK();
+                k_adopt_perms<<<blocks_for(s->n_rows_padded), TPB>>>(s->old_to_new.p, n_rows, s->n_rows_padded, s->chunk_lengths.p, (int)C,
+                                                                    s->new_to_old.p, s->row_lengths.p, 1);
+                USPMV_LAUNCH_CHECK();
+            }
+            // nnz is not recoverable without the row lengths; the stored-element count stands in (only used for reporting)
+            s->nnz = n_el;
             USPMV_CUDA(cudaDeviceSynchronize());
             build_balanced_order(s);
         } catch (...) { delete s; throw; }

@@ -550,8 +550,15 @@ struct ChunkSel {
     int off;
 };
 
+// the arrays of a SELL-C-sigma matrix, library-built (view_of) or caller-owned (the raw-array entry points)
+struct ScsView {
+    long C, n_chunks, n_rows_padded;
+    const int *cp, *cl, *ci;
+    const void *vals;
+};
+
 template <typename VT, int BVS, bool ROWWISE, int LMAX, int WARPS, bool WIDE, int D = 2>
-void launch_spmmv_stream_v(const uspmv_scs *s, const VT *X, VT *Y, long ld, cudaStream_t st, const ChunkSel &sel) {
+void launch_spmmv_stream_v(const ScsView &s, const VT *X, VT *Y, long ld, cudaStream_t st, const ChunkSel &sel) {
     using R = stream::WarpRing<VT, LMAX, D>;
     auto kern = stream::k_scs32_stream_mmv<VT, Arith<VT>, LMAX, D, WARPS, BVS, ROWWISE, WIDE>;
     constexpr int smem = WARPS * R::BYTES_ALIGNED;
@@ -570,13 +577,13 @@ void launch_spmmv_stream_v(const uspmv_scs *s, const VT *X, VT *Y, long ld, cuda
     const long need = (sel.n + WARPS - 1) / WARPS;
     if (grid > need) grid = need;
     if (grid < 1) return;
-    kern<<<(unsigned)grid, WARPS * 32, smem, st>>>(sel.n, sel.list, sel.off, s->chunk_ptrs.p, s->chunk_lengths.p, s->col_idxs.p,
-                                                  reinterpret_cast<const VT *>(s->values.p), X, Y, ld);
+    kern<<<(unsigned)grid, WARPS * 32, smem, st>>>(sel.n, sel.list, sel.off, s.cp, s.cl, s.ci,
+                                                  static_cast<const VT *>(s.vals), X, Y, ld);
 }
 
 // variant: 0 = tuned default per (precision, bvs, layout); 1..4 force (wide body?, slots per stage)
 template <typename VT, int BVS, bool ROWWISE>
-void launch_spmmv_stream(const uspmv_scs *s, const VT *X, VT *Y, long ld, cudaStream_t st, const ChunkSel &sel) {
+void launch_spmmv_stream(const ScsView &s, const VT *X, VT *Y, long ld, cudaStream_t st, const ChunkSel &sel) {
     int v = options().mmv_variant;
     if (v == 0) v = mmv_default_variant(sizeof(VT), BVS, ROWWISE);
     switch (v) {
@@ -597,20 +604,23 @@ void launch_spmmv_stream(const uspmv_scs *s, const VT *X, VT *Y, long ld, cudaSt
     }
 }
 
-inline bool spmmv_streamed(const uspmv_scs *s, int bvs) {
-    return s->C == 32 && options().scs_stream && (bvs == 2 || bvs == 4 || bvs == 8 || bvs == 16);
+inline bool spmmv_streamed(long C, int bvs) {
+    return C == 32 && options().scs_stream && (bvs == 2 || bvs == 4 || bvs == 8 || bvs == 16);
 }
 
 template <typename VT, int LAYOUT>
-void launch_spmmv_l(const uspmv_scs *s, const void *X, void *Y, int bvs, long ld, cudaStream_t st, const ChunkSel *subset = nullptr) {
-    const long n_pad = s->n_rows_padded;
+void launch_spmmv_l(const ScsView &s, const void *X, void *Y, int bvs, long ld, cudaStream_t st, const ChunkSel *subset = nullptr) {
+    const long n_pad = s.n_rows_padded;
     if (n_pad == 0) return;
-    if (subset && !spmmv_streamed(s, bvs)) fail("uspmv_spmmv_part: chunk subsets need the streamed kernel (C = 32, block_vec_size 2/4/8/16)");
-    const ChunkSel sel = subset ? *subset : ChunkSel{s->n_chunks, nullptr, 0};
-    const VT *v = reinterpret_cast<const VT *>(s->values.p);
+    if (subset && !spmmv_streamed(s.C, bvs)) fail("uspmv_spmmv_part: chunk subsets need the streamed kernel (C = 32, block_vec_size 2/4/8/16)");
+    const ChunkSel sel = subset ? *subset : ChunkSel{s.n_chunks, nullptr, 0};
+    const VT *v = static_cast<const VT *>(s.vals);
     const VT *xx = static_cast<const VT *>(X);
     VT *yy = static_cast<VT *>(Y);
-    if (spmmv_streamed(s, bvs)) {
+    // the bulk copies of the streamed kernel need 16-byte aligned array bases (always true for library-built matrices)
+    const bool aligned = reinterpret_cast<uintptr_t>(s.ci) % 16 == 0 && reinterpret_cast<uintptr_t>(s.vals) % 16 == 0;
+    if (subset && !aligned) fail("uspmv_spmmv_part: misaligned matrix arrays");
+    if (spmmv_streamed(s.C, bvs) && aligned) {
         constexpr bool RW = LAYOUT == USPMV_ROWWISE;
         switch (bvs) {
         case 2: launch_spmmv_stream<VT, 2, RW>(s, xx, yy, ld, st, sel); break;
@@ -622,26 +632,31 @@ void launch_spmmv_l(const uspmv_scs *s, const void *X, void *Y, int bvs, long ld
         return;
     }
     const unsigned g = blocks_for(n_pad);
-    const int C = (int)s->C;
+    const int C = (int)s.C;
 #define USPMV_MMV_CASE(BB)                                                                                                      \
-    case BB: k_scs_spmmv<VT, BB, LAYOUT><<<g, TPB, 0, st>>>(n_pad, C, s->chunk_ptrs.p, s->chunk_lengths.p, s->col_idxs.p, v, xx, yy, \
+    case BB: k_scs_spmmv<VT, BB, LAYOUT><<<g, TPB, 0, st>>>(n_pad, C, s.cp, s.cl, s.ci, v, xx, yy, \
                                                            bvs, ld); break;
     switch (bvs) {
         USPMV_MMV_CASE(2)
         USPMV_MMV_CASE(4)
         USPMV_MMV_CASE(8)
         USPMV_MMV_CASE(16)
-    default: k_scs_spmmv<VT, 0, LAYOUT><<<g, TPB, 0, st>>>(n_pad, C, s->chunk_ptrs.p, s->chunk_lengths.p, s->col_idxs.p, v, xx, yy, bvs, ld);
+    default: k_scs_spmmv<VT, 0, LAYOUT><<<g, TPB, 0, st>>>(n_pad, C, s.cp, s.cl, s.ci, v, xx, yy, bvs, ld);
     }
 #undef USPMV_MMV_CASE
     USPMV_LAUNCH_CHECK();
 }
 
 template <typename VT>
-void launch_spmmv(const uspmv_scs *s, const void *X, void *Y, int bvs, long ld, int layout, cudaStream_t st, const ChunkSel *subset = nullptr) {
+void launch_spmmv(const ScsView &s, const void *X, void *Y, int bvs, long ld, int layout, cudaStream_t st, const ChunkSel *subset = nullptr) {
     if (layout == USPMV_ROWWISE) launch_spmmv_l<VT, USPMV_ROWWISE>(s, X, Y, bvs, ld, st, subset);
     else launch_spmmv_l<VT, USPMV_COLWISE>(s, X, Y, bvs, ld, st, subset);
 }
+
+inline ScsView view_of(const uspmv_scs *s) {
+    return ScsView{s->C, s->n_chunks, s->n_rows_padded, s->chunk_ptrs.p, s->chunk_lengths.p, s->col_idxs.p, s->values.p};
+}
+inline bool spmmv_streamed(const uspmv_scs *s, int bvs) { return spmmv_streamed(s->C, bvs); }
 
 // ---- permutation kernels -----------------------------------------------------------------------
 template <typename VT>
@@ -650,6 +665,27 @@ __global__ void k_apply_perm(VT *__restrict__ out, const VT *__restrict__ in, co
     if (i >= n) return;
     int p = perm[i];
     out[i] = p >= 0 ? in[p] : VT(0.0);
+}
+
+__global__ void k_row_lengths(const int *__restrict__ row_ptrs, long n, int *__restrict__ len) {
+    long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (i < n) len[i] = row_ptrs[i + 1] - row_ptrs[i];
+}
+
+template <typename VT>
+__global__ void k_apply_perm_strided(VT *__restrict__ out, const VT *__restrict__ in, const int *__restrict__ perm, long n, long stride) {
+    long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (i < n) out[i * stride] = in[(long)perm[i] * stride];
+}
+
+__global__ void k_inv_perm(const int *__restrict__ perm, int *__restrict__ inv, long n) {
+    long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (i < n) inv[perm[i]] = (int)i;
+}
+
+__global__ void k_check_perm_range(const int *__restrict__ perm, long n, long limit, int *flag) {
+    long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (i < n && (perm[i] < 0 || perm[i] >= limit)) atomicOr(flag, 1);
 }
 
 template <typename VT>
@@ -809,9 +845,9 @@ int uspmv_spmmv(const uspmv_scs *s, const void *X, void *Y, int bvs, long vec_le
         if (layout == USPMV_COLWISE && vec_length < s->n_rows_padded) fail("uspmv_spmmv: vec_length %ld < n_rows_padded %ld", vec_length, s->n_rows_padded);
         cudaStream_t st = as_stream(stream);
         switch (s->vt) {
-        case USPMV_F64: launch_spmmv<double>(s, X, Y, bvs, vec_length, layout, st); break;
-        case USPMV_F32: launch_spmmv<float>(s, X, Y, bvs, vec_length, layout, st); break;
-        default: launch_spmmv<__half>(s, X, Y, bvs, vec_length, layout, st);
+        case USPMV_F64: launch_spmmv<double>(view_of(s), X, Y, bvs, vec_length, layout, st); break;
+        case USPMV_F32: launch_spmmv<float>(view_of(s), X, Y, bvs, vec_length, layout, st); break;
+        default: launch_spmmv<__half>(view_of(s), X, Y, bvs, vec_length, layout, st);
         }
     });
 }
@@ -838,10 +874,43 @@ int uspmv_spmmv_part(const uspmv_scs *s, int which, const void *X, void *Y, int 
         const ChunkSel sel{(long)l.n, contig ? nullptr : l.p, contig ? (which == 1 ? s->interior_off : s->boundary_off) : 0};
         cudaStream_t st = as_stream(stream);
         switch (s->vt) {
-        case USPMV_F64: launch_spmmv<double>(s, X, Y, bvs, vec_length, layout, st, &sel); break;
-        case USPMV_F32: launch_spmmv<float>(s, X, Y, bvs, vec_length, layout, st, &sel); break;
-        default: launch_spmmv<__half>(s, X, Y, bvs, vec_length, layout, st, &sel);
+        case USPMV_F64: launch_spmmv<double>(view_of(s), X, Y, bvs, vec_length, layout, st, &sel); break;
+        case USPMV_F32: launch_spmmv<float>(view_of(s), X, Y, bvs, vec_length, layout, st, &sel); break;
+        default: launch_spmmv<__half>(view_of(s), X, Y, bvs, vec_length, layout, st, &sel);
         }
+    });
+}
+
+/* block_spmv_{scs,csr} on caller-owned DEVICE arrays (the reference's block kernels take raw arrays per call, kernels.hpp:68-154,
+ * 306-398; its GPU launchers are stubs, :777-844).  C == 1 is CRS (chunk_ptrs = row_ptrs, chunk_lengths may be NULL and is then not
+ * read).  Y has n_chunks * C block rows.  The streamed kernel needs 16-byte aligned col_idxs / values (cudaMalloc gives 256). */
+int uspmv_block_spmv_gpu(uspmv_ctx *ctx, int vt, long C, long n_chunks, const int *cp, const int *cl, const int *ci, const void *vals,
+                         const void *X, void *Y, int bvs, long vec_length, int layout, void *stream) {
+    return guarded([&] {
+        if (!ctx) fail("uspmv_block_spmv_gpu: ctx is NULL");
+        if (C < 1) fail("uspmv_block_spmv_gpu: C must be >= 1");
+        if (bvs < 1 || bvs > 16) fail("uspmv_block_spmv_gpu: block_vec_size must be in [1,16] (got %d)", bvs);
+        if (layout != USPMV_COLWISE && layout != USPMV_ROWWISE) fail("uspmv_block_spmv_gpu: invalid layout %d", layout);
+        if (n_chunks > 0 && (!cp || !ci || !vals || !X || !Y)) fail("uspmv_block_spmv_gpu: NULL array");
+        if (C > 1 && n_chunks > 0 && !cl) fail("uspmv_block_spmv_gpu: chunk_lengths is NULL");
+        if (layout == USPMV_COLWISE && vec_length < n_chunks * C) fail("uspmv_block_spmv_gpu: vec_length %ld < n_chunks * C = %ld", vec_length, n_chunks * C);
+        USPMV_CUDA(cudaSetDevice(ctx->device));
+        cudaStream_t st = as_stream(stream);
+        DevBuf<int> cl_tmp;
+        if (!cl && n_chunks > 0) {  // CRS without a length array: lengths = row_ptrs[r + 1] - row_ptrs[r]
+            cl_tmp.alloc(n_chunks);
+            k_row_lengths<<<blocks_for(n_chunks), TPB, 0, st>>>(cp, n_chunks, cl_tmp.p);
+            USPMV_LAUNCH_CHECK();
+            cl = cl_tmp.p;
+        }
+        const ScsView v{C, n_chunks, n_chunks * C, cp, cl, ci, vals};
+        switch (vt) {
+        case USPMV_F64: launch_spmmv<double>(v, X, Y, bvs, vec_length, layout, st); break;
+        case USPMV_F32: launch_spmmv<float>(v, X, Y, bvs, vec_length, layout, st); break;
+        case USPMV_F16: launch_spmmv<__half>(v, X, Y, bvs, vec_length, layout, st); break;
+        default: fail("uspmv_block_spmv_gpu: invalid value type %d", vt);
+        }
+        if (cl_tmp.p) USPMV_CUDA(cudaStreamSynchronize(st));  // the temporary is freed on return
     });
 }
 
@@ -937,6 +1006,47 @@ int uspmv_apply_permutation_block(uspmv_ctx *ctx, void *out, const void *in, con
         case USPMV_F16: k_apply_perm_block<__half><<<g, TPB, 0, st>>>((__half *)out, (const __half *)in, perm, n, bvs, ld, layout); break;
         default: fail("uspmv_apply_permutation_block: invalid value type %d", vt);
         }
+        USPMV_LAUNCH_CHECK();
+    });
+}
+
+/* apply_strided_permutation (utilities.hpp:1784-1799), literally: out[i * stride] = in[perm[i] * stride], i < n — ONE element per
+ * row; the harness calls it once per vector of a row-major block vector with the base pointers offset by the vector index. */
+int uspmv_apply_strided_permutation(uspmv_ctx *ctx, void *out, const void *in, const int *perm, long n, long stride, int vt, void *stream) {
+    return guarded([&] {
+        if (!ctx) fail("uspmv_apply_strided_permutation: ctx is NULL");
+        if (stride < 1) fail("uspmv_apply_strided_permutation: stride must be >= 1");
+        if (n == 0) return;
+        cudaStream_t st = as_stream(stream);
+        const unsigned g = blocks_for(n);
+        switch (vt) {
+        case USPMV_F64: k_apply_perm_strided<double><<<g, TPB, 0, st>>>((double *)out, (const double *)in, perm, n, stride); break;
+        case USPMV_F32: k_apply_perm_strided<float><<<g, TPB, 0, st>>>((float *)out, (const float *)in, perm, n, stride); break;
+        case USPMV_F16: k_apply_perm_strided<__half><<<g, TPB, 0, st>>>((__half *)out, (const __half *)in, perm, n, stride); break;
+        default: fail("uspmv_apply_strided_permutation: invalid value type %d", vt);
+        }
+        USPMV_LAUNCH_CHECK();
+    });
+}
+
+/* generate_inv_perm (utilities.hpp:1755-1766): inv_perm[perm[i]] = i, i < perm_len (device arrays).  Entries of perm outside
+ * [0, inv_len) are an error here (the reference writes out of bounds); positions of inv_perm that no perm[i] names are left alone. */
+int uspmv_generate_inv_perm(uspmv_ctx *ctx, const int *perm_d, int *inv_perm_d, long perm_len, long inv_len, void *stream) {
+    return guarded([&] {
+        if (!ctx) fail("uspmv_generate_inv_perm: ctx is NULL");
+        if (perm_len == 0) return;
+        if (!perm_d || !inv_perm_d) fail("uspmv_generate_inv_perm: NULL array");
+        USPMV_CUDA(cudaSetDevice(ctx->device));
+        cudaStream_t st = as_stream(stream);
+        DevBuf<int> flag(1);
+        USPMV_CUDA(cudaMemsetAsync(flag.p, 0, sizeof(int), st));
+        k_check_perm_range<<<blocks_for(perm_len), TPB, 0, st>>>(perm_d, perm_len, inv_len, flag.p);
+        USPMV_LAUNCH_CHECK();
+        int bad = 0;
+        USPMV_CUDA(cudaMemcpyAsync(&bad, flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        USPMV_CUDA(cudaStreamSynchronize(st));
+        if (bad) fail("uspmv_generate_inv_perm: perm has an entry outside [0, %ld)", inv_len);
+        k_inv_perm<<<blocks_for(perm_len), TPB, 0, st>>>(perm_d, inv_perm_d, perm_len);
         USPMV_LAUNCH_CHECK();
     });
 }

@@ -111,6 +111,12 @@ void uspmv_coo_destroy(uspmv_coo *coo);
  * the stored matrix (MT -> VT conversion of utilities.hpp:2033 is a single rounding). */
 int uspmv_scs_build(uspmv_ctx *ctx, const uspmv_coo *coo, long C, long sigma, int vt, const int *fixed_perm_h,
                     uspmv_scs **out);
+/* Adopt a SELL-C-sigma matrix built elsewhere — e.g. a ScsData filled by the reference's own host convert_to_scs
+ * (interface.hpp:401-656) — into a device-resident handle: the arrays (host, or device when on_device != 0) are copied.
+ * chunk_ptrs has n_chunks + 1 entries; n_elements = chunk_ptrs[n_chunks]; old_to_new may be NULL (identity). */
+int uspmv_scs_from_arrays(uspmv_ctx *ctx, int vt, long C, long sigma, long n_rows, long n_cols, long n_chunks, const int *chunk_ptrs,
+                          const int *chunk_lengths, const int *col_idxs, const void *values, const int *old_to_new, int on_device,
+                          uspmv_scs **out);
 /* out8 = C, sigma, n_rows, n_cols, n_rows_padded, n_chunks, n_elements, nnz (ScsData scalars) */
 int uspmv_scs_dims(const uspmv_scs *scs, long out8[8]);
 /* Copy the arrays to the host (any pointer may be NULL).  Sizes: chunk_ptrs n_chunks+1, chunk_lengths
@@ -137,6 +143,20 @@ int uspmv_apply_permutation(uspmv_ctx *ctx, void *out_d, const void *in_d, const
 int uspmv_apply_permutation_block(uspmv_ctx *ctx, void *out_d, const void *in_d, const int *perm_d, long n, int vt,
                                   int bvs, long ld, int layout, void *stream);
 
+/* apply_strided_permutation (utilities.hpp:1784-1799), literally: out[i * stride] = in[perm[i] * stride], i < n. */
+int uspmv_apply_strided_permutation(uspmv_ctx *ctx, void *out_d, const void *in_d, const int *perm_d, long n, long stride, int vt,
+                                    void *stream);
+/* generate_inv_perm (utilities.hpp:1755-1766): inv_perm[perm[i]] = i, i < perm_len; inv_perm has inv_len entries (an entry of perm
+ * outside [0, inv_len) is an error here, an out-of-bounds write in the reference). */
+int uspmv_generate_inv_perm(uspmv_ctx *ctx, const int *perm_d, int *inv_perm_d, long perm_len, long inv_len, void *stream);
+/* random_init (utilities.hpp:880-912) + the padding rule of init_std_vec_with_ptr_or_value (:914-981) — HOST logic, no GPU needed:
+ * a DEFAULT-seeded std::mt19937 feeding uniform_real_distribution<double>(vmin, vmax), drawn sequentially over all n values of the
+ * (block) vector, converted to `vt`; then everything past the real rows is zeroed (colwise: positions >= n_rows of every
+ * vec_length-long vector; rowwise: everything from n_rows * bvs on).  n_rows < 0 skips the padding rule. */
+int uspmv_random_init_host(double vmin, double vmax, long n, int vt, void *out_h, long n_rows, long vec_length, int bvs, int layout);
+/* 1 if ptr is device (or managed) memory, 0 for host memory / NULL — lets the C++ shim accept either kind of array */
+int uspmv_pointer_is_device(const void *ptr, int *out);
+
 /* ---- kernels ------------------------------------------------------------------------------------- */
 /* uspmv_scs_gpu / uspmv_csr_gpu (interface.hpp:1741-1867) == spmv_gpu_scs[_adv] / spmv_gpu_csr
  * (kernels.hpp:579-775): raw device arrays, y has n_chunks*C entries in permuted order. */
@@ -154,6 +174,11 @@ int uspmv_spmv_unpermuted(const uspmv_scs *scs, const void *x_d, void *y_d, void
  * kernels.hpp:777-844).  bvs = block_vec_size, vec_length = n_local + per_vector_padding
  * (classes_structs.hpp:1024), layout = USPMV_COLWISE / USPMV_ROWWISE. */
 int uspmv_spmmv(const uspmv_scs *scs, const void *X_d, void *Y_d, int bvs, long vec_length, int layout, void *stream);
+/* The same on caller-owned DEVICE arrays, like every kernel of the reference (raw arrays per call, kernels.hpp:68-154,306-398).
+ * C == 1 is CRS (chunk_ptrs = row_ptrs; chunk_lengths may be NULL).  Y has n_chunks * C block rows. */
+int uspmv_block_spmv_gpu(uspmv_ctx *ctx, int vt, long C, long n_chunks, const int *chunk_ptrs_d, const int *chunk_lengths_d,
+                         const int *col_idxs_d, const void *values_d, const void *X_d, void *Y_d, int bvs, long vec_length, int layout,
+                         void *stream);
 /* Host-buffer call (the reference-facing path measured as "e2e"): copies x to the device, runs the
  * kernel, copies y (n_rows_padded entries) back, synchronises. */
 int uspmv_spmv_host(const uspmv_scs *scs, const void *x_h, long x_len, void *y_h, long y_len);
@@ -178,6 +203,13 @@ int uspmv_partition_precisions(uspmv_ctx *ctx, const uspmv_coo *coo, int ap_mode
 int uspmv_ap_spmv(int ap_mode, const uspmv_scs *dp, const uspmv_scs *sp, const uspmv_scs *hp, const void *x_d, void *y_d,
                   void *stream);
 
+/* The same on caller-owned DEVICE arrays — uspmv_scs_ap{dpsp,dphp,sphp,dpsphp}_gpu / uspmv_csr_ap*_gpu in the reference's argument
+ * style (raw arrays of every precision part per call: interface.hpp:1129-1733, ap_kernels.hpp:637-953, MultiPrecKernelArgs
+ * classes_structs.hpp:238-261).  arrays[4 p + 0..3] = chunk_ptrs, chunk_lengths, col_idxs, values of part p (0 dp, 1 sp, 2 hp); parts
+ * the mode does not use are ignored.  The parts share C and n_chunks.  C == 1 is CRS (a NULL chunk_lengths is derived). */
+int uspmv_scs_ap_gpu(uspmv_ctx *ctx, int ap_mode, long C, long n_chunks, const void *const *arrays12, const void *x_d, void *y_d,
+                     void *stream);
+
 /* ---- column-banded execution plan (EXPERIMENTAL) ------------------------------------------------------ */
 /* For matrices whose x does not fit the L2 (BASELINE config 4 on one GPU: every missing 8-byte gather costs a 128-byte DRAM fill):
  * the columns are cut into n_bands ranges, every band becomes its own SELL-C-sigma structure (AP: one per precision part) built with
@@ -199,6 +231,11 @@ void uspmv_banded_destroy(uspmv_banded *plan);
 /* seg_work_sharing_arr (mpi_funcs.hpp:424-622): wsa_h has P+1 entries.  I_h is the row array of the
  * row-sorted global COO. */
 int uspmv_seg_work_sharing_arr(int seg_method, long n_rows, long nnz, const int *I_h, int P, int *wsa_h);
+/* seg_mtx_struct + localize_row_idx (mpi_funcs.hpp:636-674,862-877) on the device: rows [wsa[rank], wsa[rank+1]) of a ROW-SORTED
+ * COO as a new COO with process-local row ids and GLOBAL columns, input order kept.  n_distinct_rows (optional) = number of distinct
+ * rows present — what the reference stores as the local n_rows (mpi_funcs.hpp:770); the returned COO has n_rows = wsa[rank+1] -
+ * wsa[rank] (different only when the slab holds empty rows, where the reference's n_rows no longer covers its own row ids). */
+int uspmv_coo_seg_mtx(const uspmv_coo *total, const int *wsa_h, int rank, int P, uspmv_coo **out, long *n_distinct_rows);
 /* collect_local_needed_heri (mpi_funcs.hpp:242-415) on the device: rewrites the matrix' global
  * columns to local/halo numbering (first-seen order, grouped by owner) and records the need lists. */
 int uspmv_halo_plan_create(uspmv_scs *scs, const int *wsa_h, int rank, int P, uspmv_halo **out);

@@ -17,38 +17,19 @@
 #ifndef USPMV_INTERFACE_HPP
 #define USPMV_INTERFACE_HPP
 
+#include <algorithm>
 #include <cstring>
+#include <map>
 #include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <type_traits>
 #include <vector>
 
-#include "uspmv_b200.h"
+#include "uspmv_detail.hpp"
 
-using ST = long;  // mmio.h:21
 
-namespace uspmv_detail {
-inline void check(int rc) {
-    if (rc) throw std::runtime_error(uspmv_last_error());
-}
-template <typename VT> struct vt_of;
-template <> struct vt_of<double> { static constexpr int value = USPMV_F64; };
-template <> struct vt_of<float> { static constexpr int value = USPMV_F32; };
-#if defined(__FLT16_MAX__)
-template <> struct vt_of<_Float16> { static constexpr int value = USPMV_F16; };
-#endif
-struct uspmv_half_bits { unsigned short bits; };  // opaque fp16 storage for compilers without _Float16
-template <> struct vt_of<uspmv_half_bits> { static constexpr int value = USPMV_F16; };
-
-inline uspmv_ctx *default_ctx(int device = 0) {
-    static uspmv_ctx *ctx = nullptr;
-    if (!ctx) check(uspmv_ctx_create(device, &ctx));
-    return ctx;
-}
-struct coo_deleter { void operator()(uspmv_coo *p) const { uspmv_coo_destroy(p); } };
-struct scs_deleter { void operator()(uspmv_scs *p) const { uspmv_scs_destroy(p); } };
-}  // namespace uspmv_detail
 
 // interface.hpp:16-56
 template <typename VT, typename IT>
@@ -105,6 +86,15 @@ void export_into(ScsData<VT, IT> *scs) {
         if (v < 0) v = 0;  // positions no real row maps to are uninitialised in the reference; 0 is a safe index
     scs->new_to_old_idx = scs->new_to_old_storage.data();
 }
+template <typename VT, typename IT>
+void register_twin(const ScsData<VT, IT> *scs) {
+    long mx = -1;
+    for (ST e = 0; e < scs->n_elements; ++e) mx = scs->col_idxs[e] > mx ? scs->col_idxs[e] : mx;
+    std::lock_guard<std::mutex> g(twins_mutex());
+    twin &t = twins()[scs->values.data()];
+    t.dev = scs->device; t.adopted.reset();
+    t.n_chunks = scs->n_chunks; t.n_elements = scs->n_elements; t.x_len = std::max<long>(mx + 1, scs->n_cols);  // x has n_cols entries
+}
 }  // namespace uspmv_detail
 
 // convert_to_scs — interface.hpp:401-656 / utilities.hpp:1842-2104
@@ -120,6 +110,7 @@ void convert_to_scs(const MtxData<MT, IT> *local_mtx, ST C, ST sigma, ScsData<VT
     check(uspmv_scs_build(ctx, coo.get(), C, sigma, vt_of<VT>::value, fixed_permutation, &s));
     scs->device = std::shared_ptr<uspmv_scs>(s, scs_deleter());
     export_into(scs);
+    register_twin(scs);
 }
 
 // permute_scs_cols — interface.hpp:659-688 / utilities.hpp:1802-1831
@@ -129,6 +120,7 @@ void permute_scs_cols(ScsData<VT, IT> *scs, IT *perm) {
     if (!scs->device) throw std::runtime_error("permute_scs_cols: ScsData was not built by convert_to_scs");
     check(uspmv_scs_permute_cols(scs->device.get(), perm));
     check(uspmv_scs_export(scs->device.get(), nullptr, nullptr, scs->col_idxs.data(), nullptr, nullptr, nullptr));
+    register_twin(scs);
 }
 
 // apply_permutation — interface.hpp:379-392 (HOST vectors; the gather itself runs on the device)
@@ -149,6 +141,34 @@ void apply_permutation(VT *permuted_vec, VT *vec_to_permute, IT *perm, int num_e
     check(uspmv_apply_permutation(ctx, d_out, d_in, static_cast<const int *>(d_perm), n, vt_of<VT>::value, nullptr));
     check(uspmv_memcpy_d2h(ctx, permuted_vec, d_out, n * sizeof(VT), nullptr));
     uspmv_free(ctx, d_in); uspmv_free(ctx, d_out); uspmv_free(ctx, d_perm);
+}
+
+// apply_strided_permutation — utilities.hpp:1784-1799 (HOST vectors): permuted_vec[i*stride] = vec_to_permute[perm[i]*stride]
+template <typename VT, typename IT>
+void apply_strided_permutation(VT *permuted_vec, VT *vec_to_permute, IT *perm, int num_elems_to_permute, int stride) {
+    using namespace uspmv_detail;
+    uspmv_ctx *ctx = default_ctx();
+    const long n = num_elems_to_permute;
+    if (n <= 0) return;
+    long src_rows = 0;
+    for (long i = 0; i < n; ++i) src_rows = perm[i] + 1 > src_rows ? perm[i] + 1 : src_rows;
+    const long src_len = (src_rows - 1) * stride + 1, dst_len = (n - 1) * stride + 1;
+    void *d_in = nullptr, *d_out = nullptr, *d_perm = nullptr;
+    check(uspmv_malloc(ctx, src_len * sizeof(VT), &d_in));
+    check(uspmv_malloc(ctx, dst_len * sizeof(VT), &d_out));
+    check(uspmv_malloc(ctx, n * sizeof(IT), &d_perm));
+    check(uspmv_memcpy_h2d(ctx, d_in, vec_to_permute, src_len * sizeof(VT), nullptr));
+    check(uspmv_memcpy_h2d(ctx, d_out, permuted_vec, dst_len * sizeof(VT), nullptr));  // the elements between the strides are kept
+    check(uspmv_memcpy_h2d(ctx, d_perm, perm, n * sizeof(IT), nullptr));
+    check(uspmv_apply_strided_permutation(ctx, d_out, d_in, static_cast<const int *>(d_perm), n, stride, vt_of<VT>::value, nullptr));
+    check(uspmv_memcpy_d2h(ctx, permuted_vec, d_out, dst_len * sizeof(VT), nullptr));
+    uspmv_free(ctx, d_in); uspmv_free(ctx, d_out); uspmv_free(ctx, d_perm);
+}
+
+// generate_inv_perm — utilities.hpp:1755-1766 (HOST arrays; tiny, done in place on the host like the reference)
+template <typename IT>
+void generate_inv_perm(int *perm, int *inv_perm, int perm_len) {
+    for (int i = 0; i < perm_len; ++i) inv_perm[perm[i]] = i;
 }
 
 // partition_precisions — interface.hpp:690-978.  The reference compares `char*` with string literals (dead branches);
@@ -227,6 +247,64 @@ void execute_uspmv(const ScsData<VT, IT> *scs, const VT *x, VT *y, const ScsData
     if (mode < 0) throw std::runtime_error("execute_uspmv: unknown ap_value_type '" + t + "'");
     check(uspmv_ap_spmv(mode, dp ? dp->device.get() : nullptr, sp ? sp->device.get() : nullptr, hp ? hp->device.get() : nullptr, ap_x, ap_y,
                         stream));
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// execute_uspmv with the reference's OWN signatures (interface.hpp:1871-1910): a pointer bundle of 8 entries per precision and
+// `char *ap_value_type`.  The reference has three spellings, selected by its USE_AP / HAVE_HALF_MATH macros; all three exist here as
+// overloads, so a call site compiles unchanged whichever way the reference was configured.
+//   * arrays on the HOST (what a user of the reference's CPU library passes): the matrix runs from its device twin — registered by
+//     convert_to_scs, or adopted from the raw arrays on first use — and x / y are staged through the device (uspmv_spmv_host);
+//   * arrays on the DEVICE (what the reference's GPU launchers get, classes_structs.hpp:213-261): the raw-array kernels directly.
+// Kernel choice as in the reference (interface.hpp:1911): SELL-C-sigma kernels iff C > 1 (CHUNK_SIZE / SIGMA are macros there; with
+// C == 1 the arrays ARE the CRS arrays), else CRS.  ap_value_type is compared as a string (the reference compares pointers).
+// ---------------------------------------------------------------------------------------------------------------------------
+
+
+// (1) the reference built without USE_AP
+template <typename VT, typename IT>
+void execute_uspmv(const ST *C, const ST *n_chunks, const IT *chunk_ptrs, const IT *chunk_lengths, const IT *col_idxs, const VT *values, VT *x, VT *y,
+                   char *ap_value_type) {
+    (void)ap_value_type;
+    uspmv_detail::execute_one_prec<VT, IT>(C, n_chunks, chunk_ptrs, chunk_lengths, col_idxs, values, x, y);
+}
+
+// (2) USE_AP and HAVE_HALF_MATH: dp, sp and hp bundles (HT: _Float16 where the compiler has it, else the opaque 16-bit storage type)
+template <typename VT, typename IT, typename HT>
+void execute_uspmv(const ST *C, const ST *n_chunks, const IT *chunk_ptrs, const IT *chunk_lengths, const IT *col_idxs, const VT *values, VT *x, VT *y,
+                   const ST *dp_C, const ST *dp_n_chunks, const IT *dp_chunk_ptrs, const IT *dp_chunk_lengths, const IT *dp_col_idxs,
+                   const double *dp_values, double *dp_x, double *dp_y,
+                   const ST *sp_C, const ST *sp_n_chunks, const IT *sp_chunk_ptrs, const IT *sp_chunk_lengths, const IT *sp_col_idxs,
+                   const float *sp_values, float *sp_x, float *sp_y,
+                   const ST *hp_C, const ST *hp_n_chunks, const IT *hp_chunk_ptrs, const IT *hp_chunk_lengths, const IT *hp_col_idxs,
+                   const HT *hp_values, HT *hp_x, HT *hp_y, char *ap_value_type) {
+    (void)hp_C; (void)hp_n_chunks; (void)hp_x; (void)hp_y;
+    const int mode = uspmv_detail::ap_mode_of(ap_value_type);
+    if (mode < 0) {
+        uspmv_detail::execute_one_prec<VT, IT>(C, n_chunks, chunk_ptrs, chunk_lengths, col_idxs, values, x, y);
+        return;
+    }
+    uspmv_detail::execute_ap<IT, HT>(mode, dp_C, dp_n_chunks, dp_chunk_ptrs, dp_chunk_lengths, dp_col_idxs, dp_values, dp_x, dp_y, sp_C, sp_n_chunks,
+                                     sp_chunk_ptrs, sp_chunk_lengths, sp_col_idxs, sp_values, sp_x, sp_y, hp_chunk_ptrs, hp_chunk_lengths, hp_col_idxs,
+                                     hp_values);
+}
+
+// (3) USE_AP without HAVE_HALF_MATH: dp and sp bundles only
+template <typename VT, typename IT>
+void execute_uspmv(const ST *C, const ST *n_chunks, const IT *chunk_ptrs, const IT *chunk_lengths, const IT *col_idxs, const VT *values, VT *x, VT *y,
+                   const ST *dp_C, const ST *dp_n_chunks, const IT *dp_chunk_ptrs, const IT *dp_chunk_lengths, const IT *dp_col_idxs,
+                   const double *dp_values, double *dp_x, double *dp_y,
+                   const ST *sp_C, const ST *sp_n_chunks, const IT *sp_chunk_ptrs, const IT *sp_chunk_lengths, const IT *sp_col_idxs,
+                   const float *sp_values, float *sp_x, float *sp_y, char *ap_value_type) {
+    const int mode = uspmv_detail::ap_mode_of(ap_value_type);
+    if (mode < 0) {
+        uspmv_detail::execute_one_prec<VT, IT>(C, n_chunks, chunk_ptrs, chunk_lengths, col_idxs, values, x, y);
+        return;
+    }
+    if (mode != USPMV_AP_DP_SP) throw std::runtime_error("execute_uspmv: this overload (no hp bundle) only serves ap[dp_sp]");
+    uspmv_detail::execute_ap<IT, uspmv_detail::uspmv_half_bits>(mode, dp_C, dp_n_chunks, dp_chunk_ptrs, dp_chunk_lengths, dp_col_idxs, dp_values, dp_x,
+                                                               dp_y, sp_C, sp_n_chunks, sp_chunk_ptrs, sp_chunk_lengths, sp_col_idxs, sp_values, sp_x,
+                                                               sp_y, nullptr, nullptr, nullptr, nullptr);
 }
 
 #endif  // USPMV_INTERFACE_HPP

@@ -338,6 +338,13 @@ class Ref:
                                           _p(I), C.c_int(P), _p(wsa))
         return wsa[:P + 1].copy()
 
+    def random_x(self, vt, vmin, vmax, n_x, n_rows, n_rows_padded, bvs=1):
+        """init_std_vec_with_ptr_or_value(..., '1') of this library's block-vector layout (utilities.hpp:914-981)."""
+        x = np.zeros(n_x, NPT[_vt(vt)])
+        self.lib.ref_random_x(C.c_int(_vt(vt)), C.c_double(vmin), C.c_double(vmax), C.c_long(n_x), C.c_int(n_rows), C.c_int(n_rows_padded),
+                              C.c_int(bvs), _p(x))
+        return x
+
     def seg_mtx(self, n_rows, I, J, vals, wsa, rank):
         I, J = _i32(I), _i32(J)
         vals = np.ascontiguousarray(vals, np.float64)

@@ -29,6 +29,7 @@
  *   seg_mtx_struct            mpi_funcs.hpp:636-674
  *   localize_row_idx          mpi_funcs.hpp:862-877
  *   collect_local_needed_heri mpi_funcs.hpp:242-415
+ *   init_std_vec_with_ptr_or_value / random_init  utilities.hpp:880-981
  */
 #include "mmio.h"
 #include "utilities.hpp"
@@ -337,6 +338,25 @@ long ref_seg_mtx(long n_rows, long nnz, const int *I, const int *J, const double
     std::memcpy(lJ, loc.J.data(), sizeof(int) * loc.nnz);
     std::memcpy(lV, loc.values.data(), sizeof(double) * loc.nnz);
     return loc.nnz;
+}
+
+/* init_std_vec_with_ptr_or_value with random numbers (utilities.hpp:914-981 -> random_init :880-912): default-seeded mt19937,
+ * uniform_real_distribution<double>(matrix_min, matrix_max) over all n_x values, then the padding rule of this TU's block-vector
+ * layout.  vt: 0 double, 1 float. */
+void ref_random_x(int vt, double vmin, double vmax, long n_x, int n_rows, int n_rows_padded, int bvs, void *out) {
+    Config cfg;
+    cfg.matrix_min = vmin;
+    cfg.matrix_max = vmax;
+    cfg.block_vec_size = bvs;
+    if (vt == VT_F64) {
+        std::vector<double> x(n_x);
+        init_std_vec_with_ptr_or_value<double>(&cfg, x, n_x, n_rows, n_rows_padded, 5.0, '1');
+        std::memcpy(out, x.data(), sizeof(double) * n_x);
+    } else {
+        std::vector<float> x(n_x);
+        init_std_vec_with_ptr_or_value<float>(&cfg, x, n_x, n_rows, n_rows_padded, 5.0f, '1');
+        std::memcpy(out, x.data(), sizeof(float) * n_x);
+    }
 }
 
 int ref_omp_max_threads(void) {

@@ -54,6 +54,14 @@ _sigs = {
     "uspmv_coo_dims": [vp, C.POINTER(C.c_long)],
     "uspmv_coo_export": [vp, vp, vp, vp],
     "uspmv_scs_build": [vp, vp, C.c_long, C.c_long, C.c_int, vp, C.POINTER(vp)],
+    "uspmv_scs_from_arrays": [vp, C.c_int, C.c_long, C.c_long, C.c_long, C.c_long, C.c_long, vp, vp, vp, vp, vp, C.c_int, C.POINTER(vp)],
+    "uspmv_apply_strided_permutation": [vp, vp, vp, vp, C.c_long, C.c_long, C.c_int, vp],
+    "uspmv_generate_inv_perm": [vp, vp, vp, C.c_long, C.c_long, vp],
+    "uspmv_random_init_host": [C.c_double, C.c_double, C.c_long, C.c_int, vp, C.c_long, C.c_long, C.c_int, C.c_int],
+    "uspmv_pointer_is_device": [vp, C.POINTER(C.c_int)],
+    "uspmv_block_spmv_gpu": [vp, C.c_int, C.c_long, C.c_long, vp, vp, vp, vp, vp, vp, C.c_int, C.c_long, C.c_int, vp],
+    "uspmv_scs_ap_gpu": [vp, C.c_int, C.c_long, C.c_long, C.POINTER(vp), vp, vp, vp],
+    "uspmv_coo_seg_mtx": [vp, vp, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(C.c_long)],
     "uspmv_scs_dims": [vp, C.POINTER(C.c_long)],
     "uspmv_scs_export": [vp, vp, vp, vp, vp, vp, vp],
     "uspmv_scs_permute_cols": [vp, vp],

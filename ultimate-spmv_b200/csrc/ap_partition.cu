@@ -179,13 +179,16 @@ k_ap_spmv(long n_pad, int C, PartArgs dp, PartArgs sp, PartArgs hp, const void *
 // chunk alone (~0.4 ms) while the rest of the GPU idles (ncu r01j: L1 busy 53 % of active but 27 % of elapsed cycles).
 const uspmv_scs::ApPlan *ap_plan_for(int mode, const uspmv_scs *first, const uspmv_scs *o1, const uspmv_scs *o2) {
     const int L = options().split_long_chunks;
+    std::lock_guard<std::mutex> guard(first->ap_plan_mutex);  // built on first use, possibly from several threads
     uspmv_scs::ApPlan *pl = first->ap_plan.get();
     const long ne1 = o1 ? o1->n_elements : -1, ne2 = o2 ? o2->n_elements : -1;
-    if (pl && pl->mode == mode && pl->other[0] == o1 && pl->other[1] == o2 && pl->other_ne[0] == ne1 && pl->other_ne[1] == ne2 && pl->seg_slots == L)
+    // keyed on the other parts' GENERATION ids: an address can be reused by a different matrix after uspmv_scs_destroy
+    const unsigned long long g1 = o1 ? o1->generation : 0, g2 = o2 ? o2->generation : 0;
+    if (pl && pl->mode == mode && pl->other[0] == g1 && pl->other[1] == g2 && pl->other_ne[0] == ne1 && pl->other_ne[1] == ne2 && pl->seg_slots == L)
         return pl;
     first->ap_plan.reset(new uspmv_scs::ApPlan());
     pl = first->ap_plan.get();
-    pl->mode = mode; pl->other[0] = o1; pl->other[1] = o2; pl->other_ne[0] = ne1; pl->other_ne[1] = ne2; pl->seg_slots = L;
+    pl->mode = mode; pl->other[0] = g1; pl->other[1] = g2; pl->other_ne[0] = ne1; pl->other_ne[1] = ne2; pl->seg_slots = L;
     const long nc = first->n_chunks;
     if (L <= 0 || nc < 4096) return pl;
     // parts in dp, sp, hp order; `first` is the dp part (or sp for sp_hp)
@@ -246,8 +249,10 @@ void launch_ap_stream_v(long n_chunks, const int *order, const uspmv_scs::ApPlan
     using R = stream::WarpRing<double, LMAX, D>;
     auto kern = stream::k_scs32_stream_ap<MODE, LMAX, D, WARPS, MINB>;
     constexpr int smem = WARPS * R::BYTES_ALIGNED;
-    static bool configured = false;
-    static int bps = 1;
+    static bool configured_on[uspmv::MAX_DEVICES] = {};
+    bool &configured = configured_on[uspmv::current_device()];
+    static int bps_on[uspmv::MAX_DEVICES];
+    int &bps = bps_on[uspmv::current_device()];
     if (!configured) {
         USPMV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         USPMV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, WARPS * 32, smem));
@@ -395,6 +400,7 @@ int uspmv_ap_spmv(int ap_mode, const uspmv_scs *dp, const uspmv_scs *sp, const u
         check(use_hp ? hp : nullptr, USPMV_F16, "hp");
         const long n_pad = first->n_rows_padded;
         if (n_pad == 0) return;
+        use_device(first->ctx);
         auto args = [](const uspmv_scs *s) {
             PartArgs a{nullptr, nullptr, nullptr, nullptr};
             if (s) a = PartArgs{s->chunk_ptrs.p, s->chunk_lengths.p, s->col_idxs.p, s->values.p};

@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <stdexcept>
 #include <memory>
+#include <mutex>
 #include <string>
 
 #include "../../include/uspmv_b200.h"
@@ -120,6 +121,17 @@ struct Options {
 };
 Options &options();
 
+// per-device once-flags of the launchers (cudaFuncSetAttribute and occupancy are per device; a process may hold contexts on several)
+constexpr int MAX_DEVICES = 64;
+inline int current_device() {
+    int dev = 0;
+    USPMV_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= MAX_DEVICES) fail("device ordinal %d not supported (max %d)", dev, MAX_DEVICES);
+    return dev;
+}
+// compute entry points run on the context's device whatever the caller's current device is
+inline void use_device(const uspmv_ctx *ctx);
+
 inline int sm_count(int device) {
     static int cached[64] = {0};
     if (device >= 0 && device < 64 && cached[device]) return cached[device];
@@ -136,6 +148,17 @@ struct uspmv_ctx {
     int device = 0;
     int n_sm = 0;
 };
+namespace uspmv {
+inline void use_device(const uspmv_ctx *ctx) {
+    int dev = -1;
+    USPMV_CUDA(cudaGetDevice(&dev));
+    if (dev != ctx->device) USPMV_CUDA(cudaSetDevice(ctx->device));
+}
+inline unsigned long long next_generation() {
+    static std::atomic<unsigned long long> g{1};
+    return g.fetch_add(1);
+}
+}  // namespace uspmv
 
 struct uspmv_coo {
     uspmv_ctx *ctx = nullptr;
@@ -147,6 +170,8 @@ struct uspmv_coo {
 
 struct uspmv_scs {
     uspmv_ctx *ctx = nullptr;
+    const unsigned long long generation = uspmv::next_generation();  // identity of this handle (an address can be reused after destroy)
+    long x_min_len = 0;  // smallest x the kernels may be given: n_cols as built, n_local + n_halo after halo renumbering
     long C = 1, sigma = 1, n_rows = 0, n_cols = 0, n_rows_padded = 0, n_chunks = 0, n_elements = 0, nnz = 0;
     int vt = USPMV_F64;
     bool cols_permuted = false;
@@ -186,7 +211,7 @@ struct uspmv_scs {
     // adaptive precision, C = 32, very uneven matrices: work items of the fused kernel (built lazily by the first uspmv_ap_spmv
     // call on this part as the FIRST part, keyed on the other parts), see k_scs32_stream_ap
     struct ApPlan {
-        const uspmv_scs *other[2] = {nullptr, nullptr};
+        unsigned long long other[2] = {0, 0};  // generation ids of the other parts
         long other_ne[2] = {-1, -1};
         int mode = -1, seg_slots = 0;
         bool use = false;
@@ -197,6 +222,7 @@ struct uspmv_scs {
         uspmv::DevBuf<double> partials;
     };
     mutable std::unique_ptr<ApPlan> ap_plan;
+    mutable std::mutex ap_plan_mutex;
     uspmv::DevBuf<int> interior_chunks, boundary_chunks;  // chunk ids without / with halo columns (order kept)
     bool interior_contig = false, boundary_contig = false;
     int interior_off = 0, boundary_off = 0;

@@ -2,6 +2,7 @@
 #include "common.cuh"
 
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 
@@ -208,7 +209,9 @@ int uspmv_random_init_host(double vmin, double vmax, long n, int vt, void *out_h
             const long double sum = (long double)a0 + (long double)a1 * 4294967296.0L;
             double u = (double)(sum / 18446744073709551616.0L);
             if (u >= 1.0) u = 0.99999999999999988897769753748434595763683319091796875;  // nextafter(1, 0)
-            const double v = (vmax - vmin) * u + vmin;
+            // libstdc++: `return (__aurng() * (__p.b() - __p.a())) + __p.a();` — g++ -O3 on an FMA machine (the reference builds with
+            // -march=native) contracts it into one fused multiply-add, so the reference's x is the FMA result
+            const double v = std::fma(u, vmax - vmin, vmin);
             switch (vt) {
             case USPMV_F64: static_cast<double *>(out_h)[i] = v; break;
             case USPMV_F32: static_cast<float *>(out_h)[i] = (float)v; break;

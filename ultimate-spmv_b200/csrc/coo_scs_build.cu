@@ -995,6 +995,7 @@ int uspmv_scs_build(uspmv_ctx *ctx, const uspmv_coo *coo, long C, long sigma, in
             s->ctx = ctx;
             s->C = C; s->sigma = sigma; s->n_rows = n_rows; s->n_cols = coo->n_cols;
             s->n_rows_padded = n_pad; s->n_chunks = n_chunks; s->nnz = nnz; s->vt = vt;
+            s->x_min_len = coo->n_cols;
             s->chunk_ptrs.alloc(n_chunks + 1);
             s->chunk_lengths.alloc(n_chunks);
             s->old_to_new.alloc(n_rows);
@@ -1061,6 +1062,7 @@ int uspmv_scs_from_arrays(uspmv_ctx *ctx, int vt, long C, long sigma, long n_row
             s->ctx = ctx; s->C = C; s->sigma = sigma; s->n_rows = n_rows; s->n_cols = n_cols; s->n_rows_padded = n_chunks * C;
             s->n_chunks = n_chunks; s->n_elements = n_el; s->vt = vt;
             s->cols_permuted = true;  // whatever numbering the arrays carry is final
+            s->x_min_len = n_cols;
             s->chunk_ptrs.alloc(n_chunks + 1);
             s->chunk_lengths.alloc(n_chunks);
             s->old_to_new.alloc(n_rows);

@@ -252,6 +252,7 @@ int uspmv_halo_plan_create_multi(uspmv_scs **parts, int n_parts, const int *wsa_
                                                           lo, hi, n_glob, strict, first.p);
                 USPMV_LAUNCH_CHECK();
             }
+            for (int q = 0; q < n_parts; ++q) parts[q]->x_min_len = n_local + n_halo;  // columns are local / halo ids from here on
             USPMV_CUDA(cudaDeviceSynchronize());
         } catch (...) { delete h; throw; }
         *out = h;

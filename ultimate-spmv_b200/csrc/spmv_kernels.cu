@@ -280,7 +280,8 @@ void launch_stream_v(long n_chunks, const int *list, int off, const int *cp, con
     using R = stream::WarpRing<VT, LMAX, D>;
     auto kern = stream::k_scs32_stream<VT, Arith<VT>, LMAX, D, WARPS, UNPERM, false>;
     constexpr int smem = WARPS * R::BYTES_ALIGNED;
-    static bool configured = false;
+    static bool configured_on[uspmv::MAX_DEVICES] = {};
+    bool &configured = configured_on[uspmv::current_device()];
     if (!configured) {
         USPMV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
@@ -301,7 +302,8 @@ void launch_stream_wide(long n_chunks, const int *list, int off, const int *cp, 
     using R = stream::WarpRing<VT, 8, D>;
     auto kern = stream::k_scsw_stream<VT, Arith<VT>, H, D, WARPS, UNPERM>;
     constexpr int smem = WARPS * R::BYTES_ALIGNED;
-    static bool configured = false;
+    static bool configured_on[uspmv::MAX_DEVICES] = {};
+    bool &configured = configured_on[uspmv::current_device()];
     if (!configured) {
         USPMV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
@@ -322,7 +324,8 @@ void launch_stream_narrow(long n_chunks, int off, const int *cp, const int *cl, 
     using R = stream::NarrowRing<VT, G, D>;
     auto kern = stream::k_scsn_stream<VT, Arith<VT>, G, D, WARPS, UNPERM>;
     constexpr int smem = WARPS * R::BYTES_ALIGNED;
-    static bool configured = false;
+    static bool configured_on[uspmv::MAX_DEVICES] = {};
+    bool &configured = configured_on[uspmv::current_device()];
     if (!configured) {
         USPMV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
@@ -342,8 +345,10 @@ void launch_stream_pf(long n_chunks, const int *list, int off, const int *cp, co
     using R = stream::WarpRing<VT, LMAX, D>;
     auto kern = stream::k_scs32_stream_pf<VT, Arith<VT>, LMAX, D, WARPS, UNPERM>;
     constexpr int smem = WARPS * R::BYTES_ALIGNED;
-    static bool configured = false;
-    static int bps_max = 1;
+    static bool configured_on[uspmv::MAX_DEVICES] = {};
+    bool &configured = configured_on[uspmv::current_device()];
+    static int bps_max_on[uspmv::MAX_DEVICES];
+    int &bps_max = bps_max_on[uspmv::current_device()];
     if (!configured) {
         USPMV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         USPMV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps_max, kern, WARPS * 32, smem));
@@ -389,7 +394,8 @@ static void launch_fused_t(const uspmv_scs *s, const void *x, void *y, const str
     using R = stream::WarpRing<VT, LMAX, D>;
     auto kern = stream::k_scs32_stream<VT, Arith<VT>, LMAX, D, WARPS, false, true>;
     constexpr int smem = WARPS * R::BYTES_ALIGNED;
-    static bool configured = false;
+    static bool configured_on[uspmv::MAX_DEVICES] = {};
+    bool &configured = configured_on[uspmv::current_device()];
     if (!configured) {
         USPMV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
@@ -423,8 +429,10 @@ void launch_split(const uspmv_scs *s, const void *x, void *y, cudaStream_t st) {
     using R = stream::WarpRing<VT, LMAX, D>;
     auto kern = stream::k_scs32_stream_split<VT, Arith<VT>, LMAX, D, WARPS>;
     constexpr int smem = WARPS * R::BYTES_ALIGNED;
-    static bool configured = false;
-    static int bps = 1;
+    static bool configured_on[uspmv::MAX_DEVICES] = {};
+    bool &configured = configured_on[uspmv::current_device()];
+    static int bps_on[uspmv::MAX_DEVICES];
+    int &bps = bps_on[uspmv::current_device()];
     if (!configured) {
         USPMV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         USPMV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, WARPS * 32, smem));
@@ -528,7 +536,8 @@ void launch_csr_stream(long n_rows, const int *rp, const int *ci, const void *va
     using R = stream::WarpRing<VT, LMAX, D>;
     auto kern = stream::k_csr_stream<VT, Arith<VT>, LMAX, D, WARPS>;
     constexpr int smem = WARPS * R::BYTES_ALIGNED;
-    static bool configured = false;
+    static bool configured_on[uspmv::MAX_DEVICES] = {};
+    bool &configured = configured_on[uspmv::current_device()];
     if (!configured) {
         USPMV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
@@ -562,8 +571,10 @@ void launch_spmmv_stream_v(const ScsView &s, const VT *X, VT *Y, long ld, cudaSt
     using R = stream::WarpRing<VT, LMAX, D>;
     auto kern = stream::k_scs32_stream_mmv<VT, Arith<VT>, LMAX, D, WARPS, BVS, ROWWISE, WIDE>;
     constexpr int smem = WARPS * R::BYTES_ALIGNED;
-    static bool configured = false;
-    static int blocks_per_sm = 1;
+    static bool configured_on[uspmv::MAX_DEVICES] = {};
+    bool &configured = configured_on[uspmv::current_device()];
+    static int blocks_per_sm_on[uspmv::MAX_DEVICES];
+    int &blocks_per_sm = blocks_per_sm_on[uspmv::current_device()];
     if (!configured) {
         USPMV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         USPMV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, WARPS * 32, smem));
@@ -712,6 +723,7 @@ int uspmv_scs_gpu(uspmv_ctx *ctx, int vt, long C, long n_chunks, const int *cp, 
     return guarded([&] {
         if (!ctx) fail("uspmv_scs_gpu: ctx is NULL");
         if (C < 1) fail("uspmv_scs_gpu: C must be >= 1");
+        use_device(ctx);
         cudaStream_t st = as_stream(stream);
         switch (vt) {
         case USPMV_F64: launch_scs<double, false>(C, n_chunks, cp, cl, ci, vals, x, y, nullptr, st); break;
@@ -726,6 +738,7 @@ int uspmv_csr_gpu(uspmv_ctx *ctx, int vt, long n_rows, const int *rp, const int 
                   void *stream) {
     return guarded([&] {
         if (!ctx) fail("uspmv_csr_gpu: ctx is NULL");
+        use_device(ctx);
         cudaStream_t st = as_stream(stream);
         // caller-owned arrays: the streamed kernel (sequential per row, bit-identical to kernels.hpp:46-57) needs 16-byte aligned
         // bases for its bulk copies; otherwise the split-row vector kernel
@@ -743,6 +756,7 @@ int uspmv_spmv(const uspmv_scs *s, const void *x, void *y, void *stream) {
     return guarded([&] {
         if (!s) fail("uspmv_spmv: scs is NULL");
         if (s->n_rows_padded && (!x || !y)) fail("uspmv_spmv: NULL vector");
+        use_device(s->ctx);
         cudaStream_t st = as_stream(stream);
         const bool crs = (s->C == 1 && s->sigma == 1);  // execute_uspmv's rule, interface.hpp:1911
         if (s->n_vitems > 0 && options().scs_stream && options().split_long_chunks > 0) {
@@ -810,6 +824,7 @@ int uspmv_spmv_part(const uspmv_scs *s, int which, const void *x, void *y, void 
         }
         if (which != 1 && which != 2) fail("uspmv_spmv_part: which must be 0 (all), 1 (interior) or 2 (boundary)");
         if (!s->chunks_split) fail("uspmv_spmv_part: call uspmv_scs_split_chunks first");
+        use_device(s->ctx);
         const DevBuf<int> &l = which == 1 ? s->interior_chunks : s->boundary_chunks;
         if (l.n == 0) return;
         const bool contig = which == 1 ? s->interior_contig : s->boundary_contig;
@@ -828,6 +843,7 @@ int uspmv_spmv_unpermuted(const uspmv_scs *s, const void *x, void *y, void *stre
     return guarded([&] {
         if (!s) fail("uspmv_spmv_unpermuted: scs is NULL");
         if (s->cols_permuted) fail("uspmv_spmv_unpermuted: columns were already permuted (permute_scs_cols); use uspmv_spmv");
+        use_device(s->ctx);
         cudaStream_t st = as_stream(stream);
         switch (s->vt) {
         case USPMV_F64: launch_scs<double, true>(s->C, s->n_chunks, s->chunk_ptrs.p, s->chunk_lengths.p, s->col_idxs.p, s->values.p, x, y, s->new_to_old.p, st, s->balanced_order.p); break;
@@ -843,6 +859,7 @@ int uspmv_spmmv(const uspmv_scs *s, const void *X, void *Y, int bvs, long vec_le
         if (bvs < 1 || bvs > 16) fail("uspmv_spmmv: block_vec_size must be in [1,16] (got %d)", bvs);
         if (layout != USPMV_COLWISE && layout != USPMV_ROWWISE) fail("uspmv_spmmv: invalid layout %d", layout);
         if (layout == USPMV_COLWISE && vec_length < s->n_rows_padded) fail("uspmv_spmmv: vec_length %ld < n_rows_padded %ld", vec_length, s->n_rows_padded);
+        use_device(s->ctx);
         cudaStream_t st = as_stream(stream);
         switch (s->vt) {
         case USPMV_F64: launch_spmmv<double>(view_of(s), X, Y, bvs, vec_length, layout, st); break;
@@ -865,6 +882,7 @@ int uspmv_spmmv_part(const uspmv_scs *s, int which, const void *X, void *Y, int 
         }
         if (which != 1 && which != 2) fail("uspmv_spmmv_part: which must be 0 (all), 1 (interior) or 2 (boundary)");
         if (!s->chunks_split) fail("uspmv_spmmv_part: call uspmv_scs_split_chunks first");
+        use_device(s->ctx);
         if (bvs < 1 || bvs > 16) fail("uspmv_spmmv_part: block_vec_size must be in [1,16] (got %d)", bvs);
         if (layout != USPMV_COLWISE && layout != USPMV_ROWWISE) fail("uspmv_spmmv_part: invalid layout %d", layout);
         if (layout == USPMV_COLWISE && vec_length < s->n_rows_padded) fail("uspmv_spmmv_part: vec_length %ld < n_rows_padded %ld", vec_length, s->n_rows_padded);
@@ -919,6 +937,7 @@ int uspmv_spmv_host(const uspmv_scs *s_, const void *x_h, long x_len, void *y_h,
         uspmv_scs *s = const_cast<uspmv_scs *>(s_);
         if (!s || !x_h || !y_h) fail("uspmv_spmv_host: NULL argument");
         if (y_len < s->n_rows_padded) fail("uspmv_spmv_host: y_len %ld < n_rows_padded %ld", y_len, s->n_rows_padded);
+        if (x_len < s->x_min_len) fail("uspmv_spmv_host: x_len %ld < %ld (the matrix references columns up to there)", x_len, s->x_min_len);
         USPMV_CUDA(cudaSetDevice(s->ctx->device));
         const size_t es = vt_size(s->vt);
         if (s->h2d_stage_x.n < (size_t)x_len * es) s->h2d_stage_x.alloc((size_t)x_len * es);
@@ -939,6 +958,7 @@ int uspmv_spmv_host_submit(const uspmv_scs *s_, const void *x_h, long x_len, voi
         if (!s || !x_h || !y_h) fail("uspmv_spmv_host_submit: NULL argument");
         if (slot < 0 || slot >= uspmv_scs::HOST_SLOTS) fail("uspmv_spmv_host_submit: slot must be in [0,%d)", uspmv_scs::HOST_SLOTS);
         if (y_len < s->n_rows_padded) fail("uspmv_spmv_host_submit: y_len %ld < n_rows_padded %ld", y_len, s->n_rows_padded);
+        if (x_len < s->x_min_len) fail("uspmv_spmv_host_submit: x_len %ld < %ld (the matrix references columns up to there)", x_len, s->x_min_len);
         if (s->slot_busy[slot]) fail("uspmv_spmv_host_submit: slot %d is still in flight (call uspmv_spmv_host_wait)", slot);
         USPMV_CUDA(cudaSetDevice(s->ctx->device));
         const size_t es = vt_size(s->vt);

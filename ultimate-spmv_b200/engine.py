@@ -329,6 +329,31 @@ def seg_work_sharing_arr(seg_method: str, n_rows: int, I: np.ndarray, comm_size:
     return wsa
 
 
+def seg_mtx_struct(total_mtx: MtxData, work_sharing_arr, loop_rank: int):
+    """seg_mtx_struct + localize_row_idx — mpi_funcs.hpp:636-674,862-877: the slab of `loop_rank` (local row ids, global columns) of a
+    row-sorted device COO.  Returns (local MtxData, number of distinct rows = the reference's local n_rows, mpi_funcs.hpp:770)."""
+    wsa = np.ascontiguousarray(work_sharing_arr, np.int32)
+    h, nd = vp(), C.c_long(0)
+    call("uspmv_coo_seg_mtx", total_mtx.h, _hp(wsa), int(loop_rank), len(wsa) - 1, C.byref(h), C.byref(nd))
+    return MtxData(h, total_mtx.ctx), int(nd.value)
+
+
+def generate_inv_perm(perm_dev_ptr, inv_perm_dev_ptr, perm_len: int, inv_len: int | None = None, ctx: Context | None = None) -> None:
+    """generate_inv_perm(perm, inv_perm, perm_len) — utilities.hpp:1755-1766 (device arrays)."""
+    ctx = ctx or default_context()
+    call("uspmv_generate_inv_perm", ctx.h, perm_dev_ptr, inv_perm_dev_ptr, int(perm_len), int(perm_len if inv_len is None else inv_len), _stream())
+
+
+def random_init(vmin: float, vmax: float, n: int, value_type="dp", n_rows: int = -1, vec_length: int = 0, block_vec_size: int = 1,
+                layout="colwise") -> np.ndarray:
+    """random_init + the padding rule of init_std_vec_with_ptr_or_value — utilities.hpp:880-981 (host logic; bit-identical x)."""
+    vt = vt_code(value_type)
+    out = np.zeros(int(n), NP_OF[vt])
+    lay = LAYOUT[layout] if isinstance(layout, str) else layout
+    call("uspmv_random_init_host", float(vmin), float(vmax), int(n), vt, _hp(out), int(n_rows), int(vec_length), int(block_vec_size), lay)
+    return out
+
+
 @dataclass
 class SpmvKernel:
     """Harness-side kernel object (classes_structs.hpp:280-1166): picks the kernel from the format, owns x/y

@@ -69,5 +69,31 @@ int main() {
     for (int i = 0; i < n; ++i) ap_diff = std::fmax(ap_diff, std::fabs(ya[dp_s.old_to_new_idx[i]] - yr[i]));
     std::printf("example_interface: ap[dp_sp_hp] split %ld / %ld / %ld, max|y - y_coo| = %.3e (fp32/fp16 storage of the small entries)\n",
                 dp_m.nnz, sp_m.nnz, hp_m.nnz, ap_diff);
-    return ap_diff < 5e-3 ? 0 : 3;
+    if (!(ap_diff < 5e-3)) return 3;
+
+    // ---- execute_uspmv with the reference's OWN signature (interface.hpp:1871-1910): pointer bundles of HOST arrays, scalars by pointer,
+    //      `char *ap_value_type` — the call a user of the reference's library makes, unchanged ----
+    char dp_type[] = "dp", ap_type[] = "ap[dp_sp_hp]";
+    ST Cs = scs.C, ncs = scs.n_chunks;
+    std::vector<double> y2(scs.n_rows_padded, -1.0);
+    execute_uspmv<double, int>(&Cs, &ncs, scs.chunk_ptrs.data(), scs.chunk_lengths.data(), scs.col_idxs.data(), scs.values.data(), xp.data(), y2.data(),
+                               dp_type);
+    double d2 = 0.0;
+    for (long i = 0; i < scs.n_rows_padded; ++i) d2 = std::fmax(d2, std::fabs(y2[i] - yp[i]));
+    std::printf("example_interface: execute_uspmv(pointer bundle, host arrays): max|y - y(uspmv_scs_gpu)| = %.3e\n", d2);
+    if (d2 != 0.0) return 4;
+    ST Cd = dp_s.C, ncd = dp_s.n_chunks;
+    std::vector<double> y3(dp_s.n_rows_padded, -1.0);
+    std::vector<float> xs(xa.begin(), xa.end()), ysp(dp_s.n_rows_padded, 0.f);
+    std::vector<half_t> xh(dp_s.n_rows_padded), yh(dp_s.n_rows_padded);
+    execute_uspmv<double, int, half_t>(&Cd, &ncd, dp_s.chunk_ptrs.data(), dp_s.chunk_lengths.data(), dp_s.col_idxs.data(), dp_s.values.data(), xa.data(),
+                                       y3.data(),
+                                       &Cd, &ncd, dp_s.chunk_ptrs.data(), dp_s.chunk_lengths.data(), dp_s.col_idxs.data(), dp_s.values.data(), xa.data(), y3.data(),
+                                       &Cd, &ncd, sp_s.chunk_ptrs.data(), sp_s.chunk_lengths.data(), sp_s.col_idxs.data(), sp_s.values.data(), xs.data(), ysp.data(),
+                                       &Cd, &ncd, hp_s.chunk_ptrs.data(), hp_s.chunk_lengths.data(), hp_s.col_idxs.data(), hp_s.values.data(), xh.data(), yh.data(),
+                                       ap_type);
+    double d3 = 0.0;
+    for (long i = 0; i < dp_s.n_rows_padded; ++i) d3 = std::fmax(d3, std::fabs(y3[i] - ya[i]));
+    std::printf("example_interface: execute_uspmv(dp + sp + hp bundles, host arrays): max|y - y(device call)| = %.3e\n", d3);
+    return d3 == 0.0 ? 0 : 5;
 }

@@ -373,7 +373,6 @@ int rank_main(Config cfg, const int rank, const int P, Shared *sh) {
         host.n_rows = d3[0]; host.n_cols = d3[1];
         host.I.resize(d3[2]); host.J.resize(d3[2]); host.V.resize(d3[2]);
         ck(uspmv_coo_export(full, host.I.data(), host.J.data(), host.V.data()));
-        uspmv_coo_destroy(full);
         have_host = true;
         if (!gen) {
             cfg.matrix_min = *std::min_element(host.V.begin(), host.V.end());
@@ -381,11 +380,9 @@ int rank_main(Config cfg, const int rank, const int P, Shared *sh) {
             cfg.matrix_mean = std::accumulate(host.V.begin(), host.V.end(), 0.0) / host.V.size();
         }
         ck(uspmv_seg_work_sharing_arr(seg, d3[0], d3[2], host.I.data(), P, wsa.data()));
-        const long lo = std::lower_bound(host.I.begin(), host.I.end(), wsa[rank]) - host.I.begin();
-        const long hi = std::lower_bound(host.I.begin(), host.I.end(), wsa[rank + 1]) - host.I.begin();
-        std::vector<int> Il(host.I.begin() + lo, host.I.begin() + hi);
-        for (int &v : Il) v -= wsa[rank];
-        ck(uspmv_coo_from_host(ctx, wsa[rank + 1] - wsa[rank], d3[1], hi - lo, Il.data(), host.J.data() + lo, host.V.data() + lo, USPMV_F64, &coo));
+        // seg_mtx_struct + localize_row_idx (mpi_funcs.hpp:636-674,862-877): this rank's slab, local rows, global columns
+        ck(uspmv_coo_seg_mtx(full, wsa.data(), rank, P, &coo, nullptr));
+        uspmv_coo_destroy(full);
         if (rank != 0 || !(cfg.mode == 's' && cfg.validate_result)) { Coo().I.swap(host.I); Coo().J.swap(host.J); Coo().V.swap(host.V); have_host = false; }
     }
     if (rank == 0) {
@@ -500,13 +497,14 @@ int rank_main(Config cfg, const int rank, const int P, Shared *sh) {
            wsa[rank + 1], nnz_local, n_chunks, n_int, n_bnd, n_elements, n_halo, t_convert);
 
     std::vector<double> x_user(vec_length * bvs, 0.0);
-    {
-        std::mt19937 engine;  // every rank draws the same default-seeded sequence over ITS vector, like random_init under MPI
-        std::uniform_real_distribution<double> dist(cfg.matrix_min, cfg.matrix_max);
+    if (cfg.random_init_x == '1') {
+        // every rank draws the same default-seeded sequence over ITS vector, like random_init under MPI (utilities.hpp:880-981;
+        // bit-identical to the reference's x: tests/test_boundary_cpu.py)
+        ck(uspmv_random_init_host(cfg.matrix_min, cfg.matrix_max, vec_length * bvs, USPMV_F64, x_user.data(), n_local, vec_length, bvs, layout));
+    } else {
         for (long i = 0; i < vec_length * bvs; ++i) {
-            double v = cfg.random_init_x == '1' ? dist(engine) : cfg.random_init_x == 'm' ? cfg.matrix_mean : 5.0;
             const long r = layout == USPMV_ROWWISE ? i / bvs : i % vec_length;
-            x_user[i] = r < n_local ? v : 0.0;
+            x_user[i] = r < n_local ? (cfg.random_init_x == 'm' ? cfg.matrix_mean : 5.0) : 0.0;
         }
     }
     std::vector<int> old_to_new(n_local), new_to_old(n_pad);
@@ -816,13 +814,13 @@ int main(int argc, char **argv) {
     const long vec_length = std::max(n_pad, n_rows);  // n_local + per_vector_padding (no halo in a single process)
     const int xvt = ap ? (ap_mode == USPMV_AP_SP_HP ? USPMV_F32 : USPMV_F64) : vt;
     std::vector<double> x_user(vec_length * bvs, 0.0);
-    {
-        std::mt19937 engine;  // default-seeded, like random_init (utilities.hpp:880-912)
-        std::uniform_real_distribution<double> dist(cfg.matrix_min, cfg.matrix_max);
+    if (cfg.random_init_x == '1') {
+        // random_init + the padding rule (utilities.hpp:880-981), bit-identical to the reference's x (tests/test_boundary_cpu.py)
+        ck(uspmv_random_init_host(cfg.matrix_min, cfg.matrix_max, vec_length * bvs, USPMV_F64, x_user.data(), n_rows, vec_length, bvs, layout));
+    } else {
         for (long i = 0; i < vec_length * bvs; ++i) {
-            double v = cfg.random_init_x == '1' ? dist(engine) : cfg.random_init_x == 'm' ? cfg.matrix_mean : 5.0;  // DefaultValues x = 5.0
             const long r = layout == USPMV_ROWWISE ? i / bvs : i % vec_length;
-            x_user[i] = r < n_rows ? v : 0.0;  // padding slots zeroed (utilities.hpp:948-981)
+            x_user[i] = r < n_rows ? (cfg.random_init_x == 'm' ? cfg.matrix_mean : 5.0) : 0.0;  // DefaultValues x = 5.0; padding zeroed
         }
     }
     std::vector<int> old_to_new(n_rows), new_to_old(n_pad);

@@ -16,6 +16,7 @@
 // order is j = 0..len-1 with one FMA per slot: bit-identical to the direct kernel and to the oracle.
 #pragma once
 #include <cstdint>
+#include <type_traits>
 
 namespace uspmv {
 namespace stream {
@@ -139,21 +140,34 @@ struct SpmvBody {
     typename A::acc_t acc;
     int y_rows = 0;  // BOUNDED: positions >= y_rows are not stored (y aliases the next x, whose tail holds the halo)
     __device__ __forceinline__ void begin_chunk(int = 0) { acc = A::zero(); }
-    __device__ __forceinline__ void piece(const int ns, const VT *sv, const int *sc) {
-        VT v[LMAX], xv[LMAX];
-        int col[LMAX];
+    // The slot count is a template constant: with a run-time count every slot became a predicated load plus a DFMA followed by two
+    // FSELs (ncu / SASS of round 1: 111 instructions for a 7-slot piece); here a piece of NS slots is NS x {LDS, LDG, LDS, FMA}.
+    template <int NS>
+    __device__ __forceinline__ void piece_n(const VT *sv, const int *sc) {
+        VT xv[NS];
+        int col[NS];
 #pragma unroll
-        for (int j = 0; j < LMAX; ++j)
-            if (j < ns) col[j] = sc[j * 32];
+        for (int j = 0; j < NS; ++j) col[j] = sc[j * 32];
 #pragma unroll
-        for (int j = 0; j < LMAX; ++j)
-            if (j < ns) xv[j] = COHERENT ? __ldcg(x + col[j]) : __ldg(x + col[j]);
+        for (int j = 0; j < NS; ++j) xv[j] = COHERENT ? __ldcg(x + col[j]) : __ldg(x + col[j]);
 #pragma unroll
-        for (int j = 0; j < LMAX; ++j)
-            if (j < ns) v[j] = sv[j * 32];
-#pragma unroll
-        for (int j = 0; j < LMAX; ++j)
-            if (j < ns) acc = A::mad(v[j], xv[j], acc);
+        for (int j = 0; j < NS; ++j) acc = A::mad(sv[j * 32], xv[j], acc);
+    }
+    __device__ __forceinline__ void piece(int ns, const VT *sv, const int *sc) {
+        if constexpr (LMAX > 8) {
+            while (ns > 8) { piece_n<8>(sv, sc); sv += 8 * 32; sc += 8 * 32; ns -= 8; }
+        }
+        switch (ns) {
+        case 0: break;
+        case 1: piece_n<1>(sv, sc); break;
+        case 2: piece_n<(LMAX >= 2 ? 2 : 1)>(sv, sc); break;
+        case 3: piece_n<(LMAX >= 3 ? 3 : 1)>(sv, sc); break;
+        case 4: piece_n<(LMAX >= 4 ? 4 : 1)>(sv, sc); break;
+        case 5: piece_n<(LMAX >= 5 ? 5 : 1)>(sv, sc); break;
+        case 6: piece_n<(LMAX >= 6 ? 6 : 1)>(sv, sc); break;
+        case 7: piece_n<(LMAX >= 7 ? 7 : 1)>(sv, sc); break;
+        default: piece_n<(LMAX >= 8 ? 8 : LMAX)>(sv, sc); break;
+        }
     }
     __device__ __forceinline__ void end_chunk(const int chunk) {
         const long row = (long)chunk * 32 + lane;
@@ -367,93 +381,95 @@ struct SpmmvBodyRowWide {
 };
 
 // The streaming loop of one warp over work items first, first + W, ... < n_items (item k -> chunk list[k] or k + off).
-template <typename VT, int LMAX, int D, typename Body>
-__device__ __forceinline__ void stream_items(unsigned char *base, uint64_t *bars, PieceHdr *hdrs, uint32_t &phase_bits, const int W,
-                                             const int first, const int lane, const int n_items, const int *__restrict__ chunk_list,
-                                             const int chunk_offset, const int *__restrict__ chunk_ptrs,
-                                             const int *__restrict__ chunk_lengths, const int *__restrict__ col_idxs,
-                                             const VT *__restrict__ values, Body &body, const uint64_t pol) {
-    using R = WarpRing<VT, LMAX, D>;
-    auto item_chunk = [&](int k) -> int { return chunk_list ? chunk_list[k] : k + chunk_offset; };  // 32-bit index math throughout
+//
+// Round-2 form.  SASS of the round-1 loop: 266 instructions per piece, of which 28 were the arithmetic of a 7-slot piece — lane 0 ran
+// the producer (header stores to shared memory, address arithmetic, three-deep metadata lookahead) inside a divergent branch while 31
+// lanes waited, every lane then re-read the header, and the run-time slot count predicated every load.  Now
+//   * the producer STATE is warp-uniform: every lane keeps the same {item, slot, length, pointer} registers and runs the same few
+//     integer instructions; only the mbarrier.expect_tx and the two bulk copies are issued by one elected lane.  No divergent
+//     region, no header in shared memory, one __syncwarp per piece instead of two;
+//   * the piece header {slots, flags, chunk} of each ring stage lives in registers (the stage loop is unrolled over the D stages, so
+//     stage offsets are immediates);
+//   * the metadata of the next item is loaded (by all lanes, one broadcast transaction) when the current one becomes current, i.e. a
+//     whole chunk before it is needed;
+//   * the bodies take the slot count as a template constant (piece_n<NS>).
+// Per-row accumulation order is unchanged (one FMA per slot in slot order): results stay bit-identical.
+struct PieceReg {
+    int ns, flags, chunk;
+};
 
-    // ---- producer state (meaningful in lane 0 only) --------------------------------------------------
-    // Three-deep metadata lookahead so that no load issued by lane 0 is consumed in the same piece:
-    //   cur  = (pchunk, plen, pcs)  item being cut into pieces
-    //   nxt  = (nchunk, nlen, ncs)  item pc + W, loaded when cur became current
-    //   n2chunk                     chunk id of item pc + 2W (only needed with a chunk list)
-    int pc = first;  // work item of the next piece (n_items + 2W < 2^31: one item per 32 rows)
-    int pj = 0, plen = 0, pcs = 0, pchunk = 0, nlen = 0, ncs = 0, nchunk = 0, n2chunk = 0;
-    if (lane == 0) {
-        if (pc < n_items) {
-            pchunk = item_chunk(pc);
-            plen = chunk_lengths[pchunk];
-            pcs = chunk_ptrs[pchunk];
-        }
-        if (pc + W < n_items) {
-            nchunk = item_chunk(pc + W);
-            nlen = chunk_lengths[nchunk];
-            ncs = chunk_ptrs[nchunk];
-        }
-        if (pc + 2 * W < n_items) n2chunk = item_chunk(pc + 2 * W);
+template <typename VT, int LMAX, int D, typename Body, int H = 1>  // H: a slot holds 32 * H elements (wide chunks, C = 32 * H)
+__device__ __forceinline__ void stream_items(unsigned char *base, uint64_t *bars, PieceHdr *, uint32_t &phase_bits, const int W, const int first,
+                                             const int lane, const int n_items, const int *__restrict__ chunk_list, const int chunk_offset,
+                                             const int *__restrict__ chunk_ptrs, const int *__restrict__ chunk_lengths,
+                                             const int *__restrict__ col_idxs, const VT *__restrict__ values, Body &body, const uint64_t pol) {
+    using R = WarpRing<VT, LMAX * H, D>;
+    if (first >= n_items) return;  // warp-uniform
+    auto item_chunk = [&](int k) -> int { return chunk_list ? __ldg(chunk_list + k) : k + chunk_offset; };  // 32-bit index math throughout
+
+    // ---- producer state, identical in every lane --------------------------------------------------------------------------
+    int pc = first, pj = 0;                       // work item / first slot of the next piece
+    int pchunk = item_chunk(pc);
+    int plen = __ldg(chunk_lengths + pchunk), pcs = __ldg(chunk_ptrs + pchunk);
+    int nchunk = 0, nlen = 0, ncs = 0;            // item pc + W, requested when item pc became current
+    if (pc + W < n_items) {
+        nchunk = item_chunk(pc + W);
+        nlen = __ldg(chunk_lengths + nchunk);
+        ncs = __ldg(chunk_ptrs + nchunk);
     }
-    auto issue = [&](int s) {  // lane 0: fill stage s with the next piece of this warp's stream
-        PieceHdr h;
+    PieceReg hdr[D];
+    auto issue = [&](const int s) {  // fill ring stage s (compile-time constant) with the next piece of this warp's stream
         if (pc >= n_items) {
-            h.ns = 0; h.flags = 0; h.chunk = 0; h.pad = 0;
-            hdrs[s] = h;
+            hdr[s].ns = 0; hdr[s].flags = 0; hdr[s].chunk = 0;
             return;
         }
         const int ns = min(LMAX, plen - pj);
-        h.ns = ns;
-        h.flags = 4 | (pj == 0 ? 1 : 0) | (pj + ns >= plen ? 2 : 0);
-        h.chunk = pchunk;
-        h.pad = 0;
-        hdrs[s] = h;
-        if (ns > 0) {
-            const int e0 = pcs + pj * 32;  // < n_elements < 2^31
-            const uint32_t vb = (uint32_t)ns * 32u * (uint32_t)sizeof(VT), cb = (uint32_t)ns * 128u;
+        hdr[s].ns = ns;
+        hdr[s].flags = 4 | (pj == 0 ? 1 : 0) | (pj + ns >= plen ? 2 : 0);
+        hdr[s].chunk = pchunk;
+        if (ns > 0 && lane == 0) {
+            const int e0 = pcs + pj * (32 * H);  // < n_elements < 2^31
+            const uint32_t vb = (uint32_t)ns * (32u * H) * (uint32_t)sizeof(VT), cb = (uint32_t)ns * (128u * H);
             unsigned char *st = base + s * R::STAGE_BYTES;
             mbar_expect_tx(&bars[s], vb + cb);
             bulk_g2s(st, values + e0, vb, &bars[s], pol);
             bulk_g2s(st + R::VAL_BYTES, col_idxs + e0, cb, &bars[s], pol);
         }
         pj += ns;
-        if (pj >= plen) {  // advance: nxt -> cur, start the loads for the new nxt
+        if (pj >= plen) {  // next item becomes current; request the metadata of the one after it
             pc += W;
             pj = 0;
             pchunk = nchunk; plen = nlen; pcs = ncs;
-            nchunk = n2chunk;
             if (pc + W < n_items) {
-                nlen = chunk_lengths[nchunk];
-                ncs = chunk_ptrs[nchunk];
+                nchunk = item_chunk(pc + W);
+                nlen = __ldg(chunk_lengths + nchunk);
+                ncs = __ldg(chunk_ptrs + nchunk);
             }
-            if (pc + 2 * W < n_items) n2chunk = item_chunk(pc + 2 * W);
         }
     };
-
-    if (lane == 0) {
 #pragma unroll
-        for (int s = 0; s < D; ++s) issue(s);
-    }
-    __syncwarp();
+    for (int s = 0; s < D; ++s) issue(s);
 
-    // ---- consumer -----------------------------------------------------------------------------------------
+    // ---- consumer --------------------------------------------------------------------------------------------------------
     body.begin_chunk();
-    for (int s = 0;; s = (s + 1 == D) ? 0 : s + 1) {
-        const PieceHdr h = hdrs[s];
-        if (h.flags == 0) break;
-        if (h.flags & 1) body.begin_chunk(h.chunk);
-        if (h.ns > 0) {
-            mbar_wait(&bars[s], (phase_bits >> s) & 1u);
-            phase_bits ^= (1u << s);
-            const VT *sv = reinterpret_cast<const VT *>(base + s * R::STAGE_BYTES) + lane;
-            const int *sc = reinterpret_cast<const int *>(base + s * R::STAGE_BYTES + R::VAL_BYTES) + lane;
-            body.piece(h.ns, sv, sc);
+    bool more = true;
+    while (more) {
+#pragma unroll
+        for (int s = 0; s < D; ++s) {
+            const PieceReg h = hdr[s];
+            if (h.flags == 0) { more = false; break; }
+            if (h.flags & 1) body.begin_chunk(h.chunk);
+            if (h.ns > 0) {
+                mbar_wait(&bars[s], (phase_bits >> s) & 1u);
+                phase_bits ^= (1u << s);
+                const VT *sv = reinterpret_cast<const VT *>(base + s * R::STAGE_BYTES) + lane;
+                const int *sc = reinterpret_cast<const int *>(base + s * R::STAGE_BYTES + R::VAL_BYTES) + lane;
+                body.piece(h.ns, sv, sc);
+            }
+            if (h.flags & 2) body.end_chunk(h.chunk);
+            __syncwarp();  // every lane has read stage s before it is refilled
+            issue(s);
         }
-        if (h.flags & 2) body.end_chunk(h.chunk);
-        __syncwarp();  // every lane is done with stage s (data and header) before it is refilled
-        if (lane == 0) issue(s);
-        __syncwarp();
     }
 }
 
@@ -555,20 +571,68 @@ k_scs32_stream(long n_items, const int *__restrict__ chunk_list, int chunk_offse
 // lane l owns the H rows l, l + 32, ... of the chunk with one accumulator each and walks its slots in order (bit-identical to the
 // direct kernel and to the oracle).  8 gathers in flight per lane like the C = 32 kernel.
 // ---------------------------------------------------------------------------------------------------------------------
+// Body of the wide-chunk kernel: lane l owns the H rows l, l + 32, ... of the chunk; a piece of NS slots is NS * H slot-rows of 32
+// elements, slot-row r = j * H + h holds slot j of the rows h * 32 + lane.
+template <typename VT, typename A, int H, bool UNPERM>
+struct WideBody {
+    static constexpr int C = 32 * H;
+    const VT *__restrict__ x;
+    VT *__restrict__ y;
+    const int *__restrict__ new_to_old;
+    int lane;
+    typename A::acc_t acc[H];
+    __device__ __forceinline__ void begin_chunk(int = 0) {
+#pragma unroll
+        for (int h = 0; h < H; ++h) acc[h] = A::zero();
+    }
+    template <int NS>
+    __device__ __forceinline__ void piece_n(const VT *sv, const int *sc) {
+        constexpr int NR = NS * H;
+        VT xv[NR];
+        int col[NR];
+#pragma unroll
+        for (int r = 0; r < NR; ++r) col[r] = sc[r * 32];
+#pragma unroll
+        for (int r = 0; r < NR; ++r) xv[r] = __ldg(x + col[r]);
+#pragma unroll
+        for (int r = 0; r < NR; ++r) acc[r % H] = A::mad(sv[r * 32], xv[r], acc[r % H]);
+    }
+    __device__ __forceinline__ void piece(const int ns, const VT *sv, const int *sc) {
+        static_assert(8 % H == 0 && H <= 8, "a stage holds 8 slot-rows");
+        switch (ns) {
+        case 0: break;
+        case 1: piece_n<1>(sv, sc); break;
+        case 2: piece_n<(8 / H >= 2 ? 2 : 1)>(sv, sc); break;
+        case 3: piece_n<(8 / H >= 3 ? 3 : 1)>(sv, sc); break;
+        default: piece_n<(8 / H >= 4 ? 4 : 1)>(sv, sc); break;
+        }
+    }
+    __device__ __forceinline__ void end_chunk(const int chunk) {
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+            const long row = (long)chunk * C + h * 32 + lane;
+            if (UNPERM) {
+                const int o = new_to_old[row];
+                if (o >= 0) y[o] = A::out(acc[h]);
+            } else
+                y[row] = A::out(acc[h]);
+        }
+    }
+};
+
 template <typename VT, typename A, int H, int D, int WARPS, bool UNPERM>
 __global__ void __launch_bounds__(WARPS * 32, (1024 / (WARPS * 32)) > 0 ? (1024 / (WARPS * 32)) : 1)
 k_scsw_stream(int n_items, const int *__restrict__ chunk_list, int chunk_offset, const int *__restrict__ chunk_ptrs,
               const int *__restrict__ chunk_lengths, const int *__restrict__ col_idxs, const VT *__restrict__ values,
               const VT *__restrict__ x, VT *__restrict__ y, const int *__restrict__ new_to_old) {
+    static_assert(H == 2 || H == 4, "C = 64 or 128");
     constexpr int LS = 8;         // slot-rows (32 elements each) per stage
     constexpr int LW = LS / H;    // slots of a wide chunk per piece
-    constexpr int C = 32 * H;
     using R = WarpRing<VT, LS, D>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned char *base = smem_raw + (size_t)warp * R::BYTES_ALIGNED;
     uint64_t *bars = reinterpret_cast<uint64_t *>(base + D * R::STAGE_BYTES);
-    PieceHdr *hdrs = reinterpret_cast<PieceHdr *>(base + D * R::STAGE_BYTES + D * 8);
     const int W = (int)gridDim.x * WARPS;
     const int first = (int)blockIdx.x * WARPS + warp;
     if (lane == 0) {
@@ -579,100 +643,10 @@ k_scsw_stream(int n_items, const int *__restrict__ chunk_list, int chunk_offset,
     __syncwarp();
     const uint64_t pol = policy_evict_first();
     uint32_t phase_bits = 0;
-    auto item_chunk = [&](int k) -> int { return chunk_list ? chunk_list[k] : k + chunk_offset; };
-
-    // ---- producer (lane 0), three-deep metadata lookahead as in stream_items ----------------------------------------
-    int pc = first;
-    int pj = 0, plen = 0, pcs = 0, pchunk = 0, nlen = 0, ncs = 0, nchunk = 0, n2chunk = 0;
-    if (lane == 0) {
-        if (pc < n_items) { pchunk = item_chunk(pc); plen = chunk_lengths[pchunk]; pcs = chunk_ptrs[pchunk]; }
-        if (pc + W < n_items) { nchunk = item_chunk(pc + W); nlen = chunk_lengths[nchunk]; ncs = chunk_ptrs[nchunk]; }
-        if (pc + 2 * W < n_items) n2chunk = item_chunk(pc + 2 * W);
-    }
-    auto issue = [&](int s) {
-        PieceHdr h;
-        if (pc >= n_items) {
-            h.ns = 0; h.flags = 0; h.chunk = 0; h.pad = 0;
-            hdrs[s] = h;
-            return;
-        }
-        const int ns = min(LW, plen - pj);
-        h.ns = ns;
-        h.flags = 4 | (pj == 0 ? 1 : 0) | (pj + ns >= plen ? 2 : 0);
-        h.chunk = pchunk;
-        h.pad = 0;
-        hdrs[s] = h;
-        if (ns > 0) {
-            const int e0 = pcs + pj * C;
-            const uint32_t vb = (uint32_t)(ns * C) * (uint32_t)sizeof(VT), cb = (uint32_t)(ns * C) * 4u;
-            unsigned char *st = base + s * R::STAGE_BYTES;
-            mbar_expect_tx(&bars[s], vb + cb);
-            bulk_g2s(st, values + e0, vb, &bars[s], pol);
-            bulk_g2s(st + R::VAL_BYTES, col_idxs + e0, cb, &bars[s], pol);
-        }
-        pj += ns;
-        if (pj >= plen) {
-            pc += W;
-            pj = 0;
-            pchunk = nchunk; plen = nlen; pcs = ncs;
-            nchunk = n2chunk;
-            if (pc + W < n_items) { nlen = chunk_lengths[nchunk]; ncs = chunk_ptrs[nchunk]; }
-            if (pc + 2 * W < n_items) n2chunk = item_chunk(pc + 2 * W);
-        }
-    };
-    if (lane == 0) {
-#pragma unroll
-        for (int s = 0; s < D; ++s) issue(s);
-    }
-    __syncwarp();
-
-    // ---- consumer ----------------------------------------------------------------------------------------------------
-    typename A::acc_t acc[H];
-#pragma unroll
-    for (int h = 0; h < H; ++h) acc[h] = A::zero();
-    for (int s = 0;; s = (s + 1 == D) ? 0 : s + 1) {
-        const PieceHdr hd = hdrs[s];
-        if (hd.flags == 0) break;
-        if (hd.flags & 1) {
-#pragma unroll
-            for (int h = 0; h < H; ++h) acc[h] = A::zero();
-        }
-        if (hd.ns > 0) {
-            mbar_wait(&bars[s], (phase_bits >> s) & 1u);
-            phase_bits ^= (1u << s);
-            const VT *sv = reinterpret_cast<const VT *>(base + s * R::STAGE_BYTES) + lane;
-            const int *sc = reinterpret_cast<const int *>(base + s * R::STAGE_BYTES + R::VAL_BYTES) + lane;
-            VT v[LS], xv[LS];
-            int col[LS];
-            // slot-row r = j * H + h of the stage: slot j, rows h * 32 + lane
-#pragma unroll
-            for (int r = 0; r < LS; ++r)
-                if (r < hd.ns * H) col[r] = sc[r * 32];
-#pragma unroll
-            for (int r = 0; r < LS; ++r)
-                if (r < hd.ns * H) xv[r] = __ldg(x + col[r]);
-#pragma unroll
-            for (int r = 0; r < LS; ++r)
-                if (r < hd.ns * H) v[r] = sv[r * 32];
-#pragma unroll
-            for (int r = 0; r < LS; ++r)
-                if (r < hd.ns * H) acc[r % H] = A::mad(v[r], xv[r], acc[r % H]);
-        }
-        if (hd.flags & 2) {
-#pragma unroll
-            for (int h = 0; h < H; ++h) {
-                const long row = (long)hd.chunk * C + h * 32 + lane;
-                if (UNPERM) {
-                    const int o = new_to_old[row];
-                    if (o >= 0) y[o] = A::out(acc[h]);
-                } else
-                    y[row] = A::out(acc[h]);
-            }
-        }
-        __syncwarp();
-        if (lane == 0) issue(s);
-        __syncwarp();
-    }
+    WideBody<VT, A, H, UNPERM> body;
+    body.x = x; body.y = y; body.new_to_old = new_to_old; body.lane = lane;
+    stream_items<VT, LW, D, WideBody<VT, A, H, UNPERM>, H>(base, bars, nullptr, phase_bits, W, first, lane, n_items, chunk_list, chunk_offset, chunk_ptrs,
+                                                           chunk_lengths, col_idxs, values, body, pol);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -1094,7 +1068,6 @@ k_csr_stream(long n_rows, const int *__restrict__ row_ptrs, const int *__restric
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned char *base = smem_raw + (size_t)warp * R::BYTES_ALIGNED;
     uint64_t *bars = reinterpret_cast<uint64_t *>(base + D * R::STAGE_BYTES);
-    PieceHdr *hdrs = reinterpret_cast<PieceHdr *>(base + D * R::STAGE_BYTES + D * 8);
     const long W = (long)gridDim.x * WARPS;
     const long gw = (long)blockIdx.x * WARPS + warp;
     const long n_blocks = (n_rows + 31) / 32;
@@ -1106,43 +1079,44 @@ k_csr_stream(long n_rows, const int *__restrict__ row_ptrs, const int *__restric
     __syncwarp();
     const uint64_t pol = policy_evict_first();
 
-    const int nnz8 = row_ptrs[n_rows] & ~7;  // elements below this index are fetched by (16-byte granular) bulk copies
+    const int nnz8 = __ldg(row_ptrs + n_rows) & ~7;  // elements below this index are fetched by (16-byte granular) bulk copies
+    if (gw >= n_blocks) return;
     auto block_range = [&](long rb, int &b0, int &b1) {
         const long r0 = rb * 32, r1 = min(r0 + 32, n_rows);
-        b0 = row_ptrs[r0];
-        b1 = row_ptrs[r1];
+        b0 = __ldg(row_ptrs + r0);
+        b1 = __ldg(row_ptrs + r1);
     };
-    // ---- producer (lane 0): tiles of the blocks gw, gw + W, ... -------------------------------------------------------
+    // ---- producer: tiles of the blocks gw, gw + W, ...; warp-uniform state, only the copies are elected (see stream_items) ---------
     long pb = gw;
     int pb0 = 0, pb1 = 0, nb0 = 0, nb1 = 0, pt = 0;  // current block's element range, next block's, next tile start
-    if (lane == 0) {
-        if (pb < n_blocks) { block_range(pb, pb0, pb1); pt = pb0 & ~7; }
-        if (pb + W < n_blocks) block_range(pb + W, nb0, nb1);
-    }
-    auto issue = [&](int s) {
-        PieceHdr h;
+    block_range(pb, pb0, pb1);
+    pt = pb0 & ~7;
+    if (pb + W < n_blocks) block_range(pb + W, nb0, nb1);
+    struct TileReg { int ns, flags, chunk, pad; };
+    TileReg hdr[D];
+    auto issue = [&](const int s) {
         if (pb >= n_blocks) {
-            h.ns = 0; h.flags = 0; h.chunk = 0; h.pad = 0;
-            hdrs[s] = h;
+            hdr[s].ns = 0; hdr[s].flags = 0; hdr[s].chunk = 0; hdr[s].pad = 0;
             return;
         }
         int n = 0;
         if (pt < pb1 && pt < nnz8) {
             const int end8 = min((pb1 + 7) & ~7, nnz8);  // never read past the arrays: the last (< 8) elements go through global loads
             n = min(TILE, end8 - pt);
-            unsigned char *st = base + s * R::STAGE_BYTES;
-            const uint32_t vb = (uint32_t)n * (uint32_t)sizeof(VT), cb = (uint32_t)n * 4u;
-            mbar_expect_tx(&bars[s], vb + cb);
-            bulk_g2s(st, values + pt, vb, &bars[s], pol);
-            bulk_g2s(st + R::VAL_BYTES, col_idxs + pt, cb, &bars[s], pol);
+            if (lane == 0) {
+                unsigned char *st = base + s * R::STAGE_BYTES;
+                const uint32_t vb = (uint32_t)n * (uint32_t)sizeof(VT), cb = (uint32_t)n * 4u;
+                mbar_expect_tx(&bars[s], vb + cb);
+                bulk_g2s(st, values + pt, vb, &bars[s], pol);
+                bulk_g2s(st + R::VAL_BYTES, col_idxs + pt, cb, &bars[s], pol);
+            }
         }
         const bool first = pt == (pb0 & ~7);
         const bool last = pt + n >= pb1 || pt + n >= nnz8;
-        h.ns = n;                 // elements in this tile (0: the block has no elements at all)
-        h.flags = 4 | (first ? 1 : 0) | (last ? 2 : 0);
-        h.chunk = (int)pb;        // row block
-        h.pad = pt;               // first element of the tile
-        hdrs[s] = h;
+        hdr[s].ns = n;                 // elements in this tile (0: the block has no elements at all)
+        hdr[s].flags = 4 | (first ? 1 : 0) | (last ? 2 : 0);
+        hdr[s].chunk = (int)pb;        // row block
+        hdr[s].pad = pt;               // first element of the tile
         pt += n;
         if (last) {
             pb += W;
@@ -1150,58 +1124,67 @@ k_csr_stream(long n_rows, const int *__restrict__ row_ptrs, const int *__restric
             if (pb + W < n_blocks) block_range(pb + W, nb0, nb1);
         }
     };
-    if (lane == 0) {
 #pragma unroll
-        for (int s = 0; s < D; ++s) issue(s);
-    }
-    __syncwarp();
+    for (int s = 0; s < D; ++s) issue(s);
 
     // ---- consumer -----------------------------------------------------------------------------------------------------
     uint32_t phase_bits = 0;
     typename A::acc_t acc = A::zero();
     int beg = 0, end = 0;
-    for (int s = 0;; s = (s + 1 == D) ? 0 : s + 1) {
-        const PieceHdr h = hdrs[s];
-        if (h.flags == 0) break;
-        if (h.flags & 1) {
-            acc = A::zero();
-            const long r = (long)h.chunk * 32 + lane;
-            beg = row_ptrs[min(r, n_rows)];
-            end = row_ptrs[min(r + 1, n_rows)];
-        }
-        if (h.ns > 0) {
-            mbar_wait(&bars[s], (phase_bits >> s) & 1u);
-            phase_bits ^= (1u << s);
-            const VT *sv = reinterpret_cast<const VT *>(base + s * R::STAGE_BYTES);
-            const int *sc = reinterpret_cast<const int *>(base + s * R::STAGE_BYTES + R::VAL_BYTES);
-            const int lo = max(beg, h.pad) - h.pad, hi = min(end, h.pad + h.ns) - h.pad;
-            for (int j = lo; j < hi; j += 4) {
-                int col[4];
-                VT v[4], xv[4];
+    bool running = true;
+    while (running) {
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (j + u < hi) col[u] = sc[j + u];
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (j + u < hi) xv[u] = __ldg(x + col[u]);
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (j + u < hi) v[u] = sv[j + u];
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (j + u < hi) acc = A::mad(v[u], xv[u], acc);
+        for (int s = 0; s < D; ++s) {
+            const TileReg h = hdr[s];
+            if (h.flags == 0) { running = false; break; }
+            if (h.flags & 1) {
+                acc = A::zero();
+                const long r = (long)h.chunk * 32 + lane;
+                beg = __ldg(row_ptrs + min(r, n_rows));
+                end = __ldg(row_ptrs + min(r + 1, n_rows));
             }
+            if (h.ns > 0) {
+                mbar_wait(&bars[s], (phase_bits >> s) & 1u);
+                phase_bits ^= (1u << s);
+                const VT *sv = reinterpret_cast<const VT *>(base + s * R::STAGE_BYTES);
+                const int *sc = reinterpret_cast<const int *>(base + s * R::STAGE_BYTES + R::VAL_BYTES);
+                const int lo = max(beg, h.pad) - h.pad, hi = min(end, h.pad + h.ns) - h.pad;
+                constexpr int G = sizeof(VT) == 8 ? 4 : 8;  // gathers in flight per lane (fp64: 4, the 64-register budget)
+                int j = lo;
+                for (; j + G <= hi; j += G) {  // full groups: no predication
+                    int col[G];
+                    VT xv[G];
+#pragma unroll
+                    for (int u = 0; u < G; ++u) col[u] = sc[j + u];
+#pragma unroll
+                    for (int u = 0; u < G; ++u) xv[u] = __ldg(x + col[u]);
+#pragma unroll
+                    for (int u = 0; u < G; ++u) acc = A::mad(sv[j + u], xv[u], acc);
+                }
+                if (j < hi) {  // remainder of 1 .. G-1 elements
+                    int col[G - 1];
+                    VT xv[G - 1];
+#pragma unroll
+                    for (int u = 0; u < G - 1; ++u)
+                        if (j + u < hi) col[u] = sc[j + u];
+#pragma unroll
+                    for (int u = 0; u < G - 1; ++u)
+                        if (j + u < hi) xv[u] = __ldg(x + col[u]);
+#pragma unroll
+                    for (int u = 0; u < G - 1; ++u)
+                        if (j + u < hi) acc = A::mad(sv[j + u], xv[u], acc);
+                }
+            }
+            if (h.flags & 2) {
+                // the final nnz % 8 elements of the matrix are not covered by a bulk copy (caller-owned arrays have no slack):
+                // the rows that own them finish through global loads, in order
+                for (int e = max(beg, h.pad + h.ns); e < end; ++e) acc = A::mad(values[e], __ldg(x + col_idxs[e]), acc);
+                const long r = (long)h.chunk * 32 + lane;
+                if (r < n_rows) y[r] = A::out(acc);
+            }
+            __syncwarp();
+            issue(s);
         }
-        if (h.flags & 2) {
-            // the final nnz % 8 elements of the matrix are not covered by a bulk copy (caller-owned arrays have no slack):
-            // the rows that own them finish through global loads, in order
-            for (int e = max(beg, h.pad + h.ns); e < end; ++e) acc = A::mad(values[e], __ldg(x + col_idxs[e]), acc);
-            const long r = (long)h.chunk * 32 + lane;
-            if (r < n_rows) y[r] = A::out(acc);
-        }
-        __syncwarp();
-        if (lane == 0) issue(s);
-        __syncwarp();
     }
 }
 
@@ -1262,7 +1245,6 @@ k_scs32_stream_ap(long n_items, const int *__restrict__ order, const int4 *__res
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned char *base = smem_raw + (size_t)warp * R::BYTES_ALIGNED;
     uint64_t *bars = reinterpret_cast<uint64_t *>(base + D * R::STAGE_BYTES);
-    PieceHdr *hdrs = reinterpret_cast<PieceHdr *>(base + D * R::STAGE_BYTES + D * 8);
     const long W = (long)gridDim.x * WARPS;
     const long gw = (long)blockIdx.x * WARPS + warp;
     constexpr bool USE0 = MODE != 2, USE1 = MODE != 1, USE2 = MODE != 0;  // dp, sp, hp parts in use
@@ -1276,7 +1258,9 @@ k_scs32_stream_ap(long n_items, const int *__restrict__ order, const int4 *__res
     __syncwarp();
     const uint64_t pol = policy_evict_first();
 
-    // ---- producer (lane 0): items gw, gw + W, ...; per item the parts in order dp, sp, hp ------------------------------
+    // ---- producer: items gw, gw + W, ...; per item the parts in order dp, sp, hp.  The state is WARP-UNIFORM (every lane keeps the
+    //      same registers and runs the same integer instructions, see stream_items); only expect_tx + the bulk copies are elected ----
+    if (gw >= n_items) return;
     long pc = gw;
     int pchunk = 0, nchunk = 0;
     int plen[3] = {0, 0, 0}, pcs[3] = {0, 0, 0}, nlen[3] = {0, 0, 0}, ncs[3] = {0, 0, 0};
@@ -1286,24 +1270,20 @@ k_scs32_stream_ap(long n_items, const int *__restrict__ order, const int4 *__res
 #pragma unroll
         for (int q = 0; q < 3; ++q) {
             const bool use = q == 0 ? USE0 : (q == 1 ? USE1 : USE2);
-            len[q] = use ? parts[q].cl[chunk] : 0;
-            cs[q] = use ? parts[q].cp[chunk] : 0;
+            len[q] = use ? __ldg(parts[q].cl + chunk) : 0;
+            cs[q] = use ? __ldg(parts[q].cp + chunk) : 0;
         }
     };
     // With `items` (very uneven matrices) a work item is either a whole chunk (code < 0) or ONE slot segment of ONE part of a long
     // chunk, {chunk, first slot, slots, code = partial slot << 2 | part}; its sum goes to partial[] and k_reduce_partials_ap adds the
     // segments of a part in slot order.  A segment looks to the producer like a chunk whose other parts are empty.
-    // Three-deep lookahead like the SpMV producer: the DESCRIPTOR of item pc + 2W is fetched one advance before its chunk metadata
-    // (lengths / pointers of up to three parts, which depend on the chunk id) is requested, and that metadata is first used one
-    // advance later again — no load of lane 0 is consumed in the step that issued it (ncu r01p: 30 % of the stall samples of the
-    // two-deep version sat on exactly these dependent loads, with the other 31 lanes parked at the __syncwarp).  Measured gain is
-    // small (384 -> 380 us on the 4 M-row power-law matrix, and only with the kernel capped at 80 registers so that 24 warps stay
-    // resident): the kernel is bound by the L1 cost of the scattered x gathers, not by this chain.
+    // Lookahead: the DESCRIPTOR of item pc + 2W is fetched one advance before its chunk metadata (lengths / pointers of up to three
+    // parts, which depend on the chunk id) is requested, and that metadata is first used one advance later again.
     int pcode = -1, ncode = -1;
     int4 n2it = make_int4(0, 0, 0, -1);
     auto fetch_desc = [&](long k) -> int4 {
-        if (items) return items[k];
-        return make_int4(order ? order[k] : (int)k, 0, 0, -1);
+        if (items) return __ldg(items + k);
+        return make_int4(order ? __ldg(order + k) : (int)k, 0, 0, -1);
     };
     auto load_item = [&](const int4 it, int &chunk, int *len, int *cs, int &code) {
         chunk = it.x;
@@ -1314,41 +1294,41 @@ k_scs32_stream_ap(long n_items, const int *__restrict__ order, const int4 *__res
 #pragma unroll
             for (int q = 0; q < 3; ++q) {
                 len[q] = q == part ? it.z : 0;
-                cs[q] = q == part ? parts[q].cp[chunk] + it.y * 32 : 0;
+                cs[q] = q == part ? __ldg(parts[q].cp + chunk) + it.y * 32 : 0;
             }
         }
     };
-    if (lane == 0) {
-        if (pc < n_items) load_item(fetch_desc(pc), pchunk, plen, pcs, pcode);
-        if (pc + W < n_items) load_item(fetch_desc(pc + W), nchunk, nlen, ncs, ncode);
-        if (pc + 2 * W < n_items) n2it = fetch_desc(pc + 2 * W);
-    }
-    auto issue = [&](int s) {
-        PieceHdr h;
-        h.ns = 0; h.flags = 0; h.chunk = 0; h.pad = 0;
-        if (pc >= n_items) { hdrs[s] = h; return; }
+    load_item(fetch_desc(pc), pchunk, plen, pcs, pcode);
+    if (pc + W < n_items) load_item(fetch_desc(pc + W), nchunk, nlen, ncs, ncode);
+    if (pc + 2 * W < n_items) n2it = fetch_desc(pc + 2 * W);
+    struct ApPieceReg { int ns, flags, chunk, pad; };
+    ApPieceReg hdr[D];
+    auto issue = [&](const int s) {
+        hdr[s].ns = 0; hdr[s].flags = 0; hdr[s].chunk = 0; hdr[s].pad = 0;
+        if (pc >= n_items) return;
         while (pp < 3 && pj >= plen[pp]) { ++pp; pj = 0; }  // skip exhausted / empty parts
         int ns = 0;
         if (pp < 3) {
             ns = min(LMAX, plen[pp] - pj);
-            const long e0 = (long)pcs[pp] + (long)pj * 32;
-            const uint32_t vsz = pp == 0 ? 8u : (pp == 1 ? 4u : 2u);
-            const uint32_t vb = (uint32_t)ns * 32u * vsz, cb = (uint32_t)ns * 128u;
-            unsigned char *st = base + s * R::STAGE_BYTES;
-            mbar_expect_tx(&bars[s], vb + cb);
-            bulk_g2s(st, static_cast<const unsigned char *>(parts[pp].v) + e0 * vsz, vb, &bars[s], pol);
-            bulk_g2s(st + R::VAL_BYTES, parts[pp].ci + e0, cb, &bars[s], pol);
-            h.pad = pp | (pcode < 0 ? 0 : ((pcode >> 2) + 1) << 2);
+            if (lane == 0) {
+                const long e0 = (long)pcs[pp] + (long)pj * 32;
+                const uint32_t vsz = pp == 0 ? 8u : (pp == 1 ? 4u : 2u);
+                const uint32_t vb = (uint32_t)ns * 32u * vsz, cb = (uint32_t)ns * 128u;
+                unsigned char *st = base + s * R::STAGE_BYTES;
+                mbar_expect_tx(&bars[s], vb + cb);
+                bulk_g2s(st, static_cast<const unsigned char *>(parts[pp].v) + e0 * vsz, vb, &bars[s], pol);
+                bulk_g2s(st + R::VAL_BYTES, parts[pp].ci + e0, cb, &bars[s], pol);
+            }
+            hdr[s].pad = pp | (pcode < 0 ? 0 : ((pcode >> 2) + 1) << 2);
             pj += ns;
         }
         // is anything left in this chunk after this piece?
         bool more = false;
 #pragma unroll
         for (int q = 0; q < 3; ++q) more |= (q > pp && plen[q] > 0) || (q == pp && pj < plen[q]);
-        h.ns = ns;
-        h.flags = 4 | (pfirst ? 1 : 0) | (more ? 0 : 2);
-        h.chunk = pchunk;
-        hdrs[s] = h;
+        hdr[s].ns = ns;
+        hdr[s].flags = 4 | (pfirst ? 1 : 0) | (more ? 0 : 2);
+        hdr[s].chunk = pchunk;
         pfirst = false;
         if (!more) {  // next chunk
             pc += W;
@@ -1361,82 +1341,88 @@ k_scs32_stream_ap(long n_items, const int *__restrict__ order, const int4 *__res
             if (pc + 2 * W < n_items) n2it = fetch_desc(pc + 2 * W);
         }
     };
-    if (lane == 0) {
 #pragma unroll
-        for (int s = 0; s < D; ++s) issue(s);
-    }
-    __syncwarp();
+    for (int s = 0; s < D; ++s) issue(s);
 
-    // ---- consumer --------------------------------------------------------------------------------------------------------
+    // ---- consumer: one piece = NS slots of ONE part; the slot count is a template constant (see SpmvBody::piece_n) ----------------
     uint32_t phase_bits = 0;
     double acc[3] = {0.0, 0.0, 0.0};
-    for (int s = 0;; s = (s + 1 == D) ? 0 : s + 1) {
-        const PieceHdr h = hdrs[s];
-        if (h.flags == 0) break;
-        if (h.flags & 1) { acc[0] = 0.0; acc[1] = 0.0; acc[2] = 0.0; }
-        const int part = h.pad & 3, pslot1 = h.pad >> 2;  // pslot1 > 0: segment of a split chunk -> partial[pslot1 - 1]
-        if (h.ns > 0) {
-            mbar_wait(&bars[s], (phase_bits >> s) & 1u);
-            phase_bits ^= (1u << s);
-            const unsigned char *sv = base + s * R::STAGE_BYTES;
-            const int *sc = reinterpret_cast<const int *>(base + s * R::STAGE_BYTES + R::VAL_BYTES) + lane;
-            int col[LMAX];
+    auto piece_n = [&](auto ns_tag, const int part, const unsigned char *sv, const int *sc) {
+        constexpr int NS = decltype(ns_tag)::value;
+        int col[NS];
 #pragma unroll
-            for (int j = 0; j < LMAX; ++j)
-                if (j < h.ns) col[j] = sc[j * 32];
-            if constexpr (MODE == 2) {
-                const float *x = static_cast<const float *>(xv_);
-                float xf[LMAX];
+        for (int j = 0; j < NS; ++j) col[j] = sc[j * 32];
+        if constexpr (MODE == 2) {
+            const float *x = static_cast<const float *>(xv_);
+            float xf[NS];
 #pragma unroll
-                for (int j = 0; j < LMAX; ++j)
-                    if (j < h.ns) xf[j] = __ldg(x + col[j]);
-                if (part == 1) {
-                    const float *v = reinterpret_cast<const float *>(sv) + lane;
+            for (int j = 0; j < NS; ++j) xf[j] = __ldg(x + col[j]);
+            if (part == 1) {
+                const float *v = reinterpret_cast<const float *>(sv) + lane;
 #pragma unroll
-                    for (int j = 0; j < LMAX; ++j)
-                        if (j < h.ns) acc[1] += (double)__fmul_rn(v[j * 32], xf[j]);
-                } else {
-                    const __half *v = reinterpret_cast<const __half *>(sv) + lane;
-#pragma unroll
-                    for (int j = 0; j < LMAX; ++j)
-                        if (j < h.ns) acc[2] += (double)__fmul_rn(__half2float(v[j * 32]), xf[j]);
-                }
+                for (int j = 0; j < NS; ++j) acc[1] += (double)__fmul_rn(v[j * 32], xf[j]);
             } else {
-                const double *x = static_cast<const double *>(xv_);
-                double xd[LMAX];
+                const __half *v = reinterpret_cast<const __half *>(sv) + lane;
 #pragma unroll
-                for (int j = 0; j < LMAX; ++j)
-                    if (j < h.ns) xd[j] = __ldg(x + col[j]);
-                if (part == 0) {
-                    const double *v = reinterpret_cast<const double *>(sv) + lane;
+                for (int j = 0; j < NS; ++j) acc[2] += (double)__fmul_rn(__half2float(v[j * 32]), xf[j]);
+            }
+        } else {
+            const double *x = static_cast<const double *>(xv_);
+            double xd[NS];
 #pragma unroll
-                    for (int j = 0; j < LMAX; ++j)
-                        if (j < h.ns) acc[0] = fma(v[j * 32], xd[j], acc[0]);
-                } else if (part == 1) {
-                    const float *v = reinterpret_cast<const float *>(sv) + lane;
+            for (int j = 0; j < NS; ++j) xd[j] = __ldg(x + col[j]);
+            if (part == 0) {
+                const double *v = reinterpret_cast<const double *>(sv) + lane;
 #pragma unroll
-                    for (int j = 0; j < LMAX; ++j)
-                        if (j < h.ns) acc[1] = fma((double)v[j * 32], xd[j], acc[1]);
-                } else {
-                    const __half *v = reinterpret_cast<const __half *>(sv) + lane;
+                for (int j = 0; j < NS; ++j) acc[0] = fma(v[j * 32], xd[j], acc[0]);
+            } else if (part == 1) {
+                const float *v = reinterpret_cast<const float *>(sv) + lane;
 #pragma unroll
-                    for (int j = 0; j < LMAX; ++j)
-                        if (j < h.ns) acc[2] = fma((double)__half2float(v[j * 32]), xd[j], acc[2]);
-                }
+                for (int j = 0; j < NS; ++j) acc[1] = fma((double)v[j * 32], xd[j], acc[1]);
+            } else {
+                const __half *v = reinterpret_cast<const __half *>(sv) + lane;
+#pragma unroll
+                for (int j = 0; j < NS; ++j) acc[2] = fma((double)__half2float(v[j * 32]), xd[j], acc[2]);
             }
         }
-        if ((h.flags & 2) && pslot1 > 0) {
-            partial[(long)(pslot1 - 1) * 32 + lane] = part == 0 ? acc[0] : (part == 1 ? acc[1] : acc[2]);
-        } else if (h.flags & 2) {
-            const long row = (long)h.chunk * 32 + lane;
-            if constexpr (MODE == 2) static_cast<float *>(yv_)[row] = (float)(acc[1] + acc[2]);
-            else if constexpr (MODE == 0) static_cast<double *>(yv_)[row] = acc[0] + acc[1];
-            else if constexpr (MODE == 1) static_cast<double *>(yv_)[row] = acc[0] + acc[2];
-            else static_cast<double *>(yv_)[row] = acc[0] + acc[1] + acc[2];
+    };
+    static_assert(LMAX == 8, "the AP consumer dispatches on 1..8 slots");
+    bool running = true;
+    while (running) {
+#pragma unroll
+        for (int s = 0; s < D; ++s) {
+            const ApPieceReg h = hdr[s];
+            if (h.flags == 0) { running = false; break; }
+            if (h.flags & 1) { acc[0] = 0.0; acc[1] = 0.0; acc[2] = 0.0; }
+            const int part = h.pad & 3, pslot1 = h.pad >> 2;  // pslot1 > 0: segment of a split chunk -> partial[pslot1 - 1]
+            if (h.ns > 0) {
+                mbar_wait(&bars[s], (phase_bits >> s) & 1u);
+                phase_bits ^= (1u << s);
+                const unsigned char *sv = base + s * R::STAGE_BYTES;
+                const int *sc = reinterpret_cast<const int *>(base + s * R::STAGE_BYTES + R::VAL_BYTES) + lane;
+                switch (h.ns) {
+                case 1: piece_n(std::integral_constant<int, 1>{}, part, sv, sc); break;
+                case 2: piece_n(std::integral_constant<int, 2>{}, part, sv, sc); break;
+                case 3: piece_n(std::integral_constant<int, 3>{}, part, sv, sc); break;
+                case 4: piece_n(std::integral_constant<int, 4>{}, part, sv, sc); break;
+                case 5: piece_n(std::integral_constant<int, 5>{}, part, sv, sc); break;
+                case 6: piece_n(std::integral_constant<int, 6>{}, part, sv, sc); break;
+                case 7: piece_n(std::integral_constant<int, 7>{}, part, sv, sc); break;
+                default: piece_n(std::integral_constant<int, 8>{}, part, sv, sc); break;
+                }
+            }
+            if ((h.flags & 2) && pslot1 > 0) {
+                partial[(long)(pslot1 - 1) * 32 + lane] = part == 0 ? acc[0] : (part == 1 ? acc[1] : acc[2]);
+            } else if (h.flags & 2) {
+                const long row = (long)h.chunk * 32 + lane;
+                if constexpr (MODE == 2) static_cast<float *>(yv_)[row] = (float)(acc[1] + acc[2]);
+                else if constexpr (MODE == 0) static_cast<double *>(yv_)[row] = acc[0] + acc[1];
+                else if constexpr (MODE == 1) static_cast<double *>(yv_)[row] = acc[0] + acc[2];
+                else static_cast<double *>(yv_)[row] = acc[0] + acc[1] + acc[2];
+            }
+            __syncwarp();  // every lane has read stage s before it is refilled
+            issue(s);
         }
-        __syncwarp();
-        if (lane == 0) issue(s);
-        __syncwarp();
     }
 }
 

@@ -56,6 +56,7 @@ def parse_args():
     ap.add_argument("--no-banded", action="store_true", help="other_configs: config 4 with the fused kernel only (no column-banded plan)")
     ap.add_argument("--config4-log2-rows", type=int, default=25)
     ap.add_argument("--config5-n", type=int, default=512, help="other_configs at N > 1: grid edge of the 27-point strong-scaling matrix")
+    ap.add_argument("--steady-steps", type=int, default=1000, help="also report ms per step over this many steps (0 = skip)")
     ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the reference's own CUDA kernel (oracle/_ref, recompiled for sm_100)")
     return ap.parse_args()
 
@@ -301,9 +302,14 @@ def timed_steps(runner, steps, warmup, world, rank, local_rank, capi, sample_clo
     sampler = ClockSampler(local_rank) if (rank == 0 and sample_clocks) else None
     if sampler:
         sampler.start()
-    l0 = capi.kernel_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    if world > 1:
+        # The ranks leave the host barrier 100+ us apart; a rank whose neighbour starts late waits for that neighbour's first push, so
+        # the skew would be charged to the K timed steps (20 x 0.25 ms).  ONE more untimed step after the barrier aligns the device
+        # timelines (every rank's kernel ends only after its neighbours' pushes have arrived); the timed region is still exactly K steps.
+        runner.step()
+    l0 = capi.kernel_launches()
     e0.record()
     for _ in range(steps):
         runner.step()
@@ -470,6 +476,10 @@ def run_ours(args):
     nnz_total, bytes_total = reduce_sum([nnz_local, bytes_local], world)
     sec_per_step = ms_step / 1e3
     gflops = 2.0 * nnz_total / sec_per_step / 1e9
+    # the same protocol over a longer run (informative: how much of `ms_per_step` is start-up of a K-step region)
+    steady_ms = None
+    if args.steady_steps > 0:
+        steady_ms, _, _ = timed_steps(runner, args.steady_steps, 3, world, rank, local_rank, capi, sample_clocks=False)
 
     # kernel-only duration of the dominant kernel (SpMV) measured with CUDA events on its stream
     kern_ms = runner.time_kernel(max(args.steps, 20))
@@ -581,6 +591,11 @@ def run_ours(args):
                           "y against the product formed from the matrix definition (no SELL-C-sigma structure, no exchange involved); max over ranks of "
                           "|y - ref| / sum|a||x|; after the timed steps the arena's error word is read (exchange_errors)",
             "gbs": bytes_total / sec_per_step / 1e9,
+            "timing": ("CUDA events on the launching stream around exactly K steps, max over ranks" +
+                       ("; after the host barrier ONE untimed step aligns the ranks' device timelines (host barrier exit skew is not part of a step)"
+                        if world > 1 else "")),
+            "steady_state": ({"steps": args.steady_steps, "ms_per_step": steady_ms, "value": 2.0 * nnz_total / (steady_ms / 1e3) / 1e9, "unit": UNIT}
+                             if steady_ms else None),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "traffic_source": traffic_src, "kernel": kernel_name, "kernel_ms": kern_ms,
                          "algorithmic_bytes_per_launch": int(bytes_local), "peak_source": peak_src},

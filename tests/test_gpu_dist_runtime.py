@@ -11,6 +11,11 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+# (block_vec_size, exchange mode): 2 = ONE fused kernel (C = 32, block_vec_size 2 / 4 / 8 / 16), 1 = push / wait kernels next to the
+# interior kernel, 0 = exchange first; block_vec_size 3 has no streamed kernel and falls back to exchange + one full SpMMV
+BLOCK_CASES = ((4, 2), (8, 2), (4, 1), (4, 0), (3, 1), (3, 2))
+
+
 def _init(rank, world, port, same_device):
     """same_device: every rank on cuda:0 (the driver's one-GPU test box).  The ranks are still separate processes whose arenas are
     exchanged through CUDA IPC, so pushes, flag waits and acknowledgements run against a real peer; the GPU time-slices between the
@@ -73,7 +78,7 @@ def _run_rank(rank, world, port, out_dir, C=32, same_device=False):
         # ---- block vectors (bulkvec exchange): all bvs vectors of the halo rows in one push, both layouts, with / without overlap
         rows = torch.arange(rank * n ** 3, (rank + 1) * n ** 3, device="cuda", dtype=torch.float64)
         for layout in ("rowwise", "colwise"):
-            for bvs, mode in ((4, 1), (4, 0), (3, 1)):
+            for bvs, mode in BLOCK_CASES:
                 r = d.DistributedSpmv(eng.default_context(dev), 27, n, C, 64, "dp", rank, world, overlap=mode, halo="p2p", bvs=bvs, layout=layout)
                 perm = torch.from_numpy(r.scs.export().old_to_new.astype(np.int64)).cuda()
                 nl, ld = r.scs.n_rows, r.vec_length
@@ -157,7 +162,7 @@ def _check(out_dir, world, mats):
     assert np.all(np.abs(y - y_ref) <= 1e-12 * scale)
     # block vectors
     for layout in ("rowwise", "colwise"):
-        for bvs, mode in ((4, 1), (4, 0), (3, 1)):
+        for bvs, mode in BLOCK_CASES:
             Y = np.concatenate([np.load(os.path.join(out_dir, f"Y{r}_{layout}_{bvs}_{mode}.npy")) for r in range(world)], axis=1)
             for v in range(bvs):
                 xv = np.sin(np.arange(nr) * (0.37 + 0.11 * v)) + 1.5
@@ -182,15 +187,16 @@ def _check(out_dir, world, mats):
             assert np.max(np.abs(hy[k] - ref)) <= 1e-12 * np.max(np.abs(ref)), (mode, k)
 
 
-@pytest.mark.parametrize("C", [32, 16])
+@pytest.mark.parametrize("C", [32, 16, 64])
 def test_world_size_1_fused_kernel(eng, mats, tmp_path, C):
-    """C = 32: fused kernel; C = 16: the P2P step falls back to the push / wait / ack kernels around the direct SpMV kernel."""
+    """C = 32 / 64: fused kernel (SELL-32 / wide-chunk); C = 16: the P2P step falls back to the push / wait / ack kernels around the
+    narrow-chunk SpMV kernel."""
     port = 29700 + os.getpid() % 200 + C
     _run_rank(0, 1, port, str(tmp_path), C)
     _check(str(tmp_path), 1, mats)
 
 
-@pytest.mark.parametrize("C", [32, 16])
+@pytest.mark.parametrize("C", [32, 16, 64])
 def test_two_ranks_over_nvlink(eng, mats, tmp_path, C):
     import torch
     if torch.cuda.device_count() < 2:
@@ -201,7 +207,7 @@ def test_two_ranks_over_nvlink(eng, mats, tmp_path, C):
     _check(str(tmp_path), 2, mats)
 
 
-@pytest.mark.parametrize("C", [32, 16])
+@pytest.mark.parametrize("C", [32, 16, 64])
 def test_two_ranks_on_one_gpu(eng, mats, tmp_path, C):
     """The same two-rank run with both processes on cuda:0 (see _init): every exchange mode — fused kernel, push / wait / ack kernels,
     exchange-then-SpMV, the tiled and bulk-copy push kernels, block vectors, the two-buffer solve loop and the pipelined host-buffer

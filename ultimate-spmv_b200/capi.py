@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libuspmv_b200.so")
+LIB_PATH = os.environ.get("USPMV_B200_LIB") or os.path.join(HERE, "lib", "libuspmv_b200.so")  # the override is for A/B builds of the same ABI
 
 F64, F32, F16 = 0, 1, 2
 COLWISE, ROWWISE = 0, 1

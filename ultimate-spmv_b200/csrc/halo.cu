@@ -23,8 +23,11 @@
 
 using namespace uspmv;
 
-namespace uspmv {
-void launch_scs32_fused(const uspmv_scs *s, const void *x, void *y, const stream::FusedArgs &fa, cudaStream_t st);  // spmv_kernels.cu
+namespace uspmv {  // spmv_kernels.cu
+void launch_scs32_fused(const uspmv_scs *s, const void *x, void *y, const stream::FusedArgs &fa, cudaStream_t st);
+bool scs_fused_supported(const uspmv_scs *s);
+bool spmmv_fused_supported(const uspmv_scs *s, int bvs);
+void launch_spmmv_fused_any(const uspmv_scs *s, const void *X, void *Y, int bvs, long ld, int layout, const stream::FusedArgs &fa, cudaStream_t st);
 }
 
 struct uspmv_halo {
@@ -755,7 +758,7 @@ int uspmv_p2p_spmv_buf(uspmv_p2p *p, const uspmv_scs *scs, int x_buf, int y_buf,
         cudaStream_t main = as_stream(stream), comm = as_stream(comm_stream);
         const int P = h->P;
         const void *x = p->buffer(x_buf);
-        if (p->mode == 2 && scs->C == 32 && P <= 32) {
+        if (p->mode == 2 && scs_fused_supported(scs) && P <= 32) {
             stream::FusedArgs fa{};
             fa.n_int = (long)scs->interior_chunks.n;
             fa.n_bnd = (long)scs->boundary_chunks.n;
@@ -766,7 +769,9 @@ int uspmv_p2p_spmv_buf(uspmv_p2p *p, const uspmv_scs *scs, int x_buf, int y_buf,
             fa.P = P; fa.my_rank = h->rank; fa.n_send = h->n_send;
             fa.send_ptr = p->send_ptr_d.p; fa.is_receiver = p->is_receiver_d.p; fa.is_sender = p->is_sender_d.p;
             fa.send_idx = h->send_idx.p; fa.perm = h->perm_d;
-            fa.peer_x_dst = p->peer_x_dst.p + (size_t)x_buf * P; fa.peer_arrived = p->peer_arrived.p; fa.peer_acked = p->peer_acked.p;
+            fa.peer_x0 = p->peer_x0.p + (size_t)x_buf * P; fa.peer_base = p->peer_base.p; fa.peer_ld = p->peer_ld.p;
+            fa.bvs = 1; fa.layout = USPMV_COLWISE; fa.ld = p->vec_length;
+            fa.peer_arrived = p->peer_arrived.p; fa.peer_acked = p->peer_acked.p;
             fa.acked = p->acked; fa.arrived = p->arrived; fa.epoch = p->epoch; fa.error = p->error; fa.counters = p->fused_counters.p;
             fa.y_rows = (int)(to_buf ? scs->n_rows : scs->n_rows_padded);
             launch_scs32_fused(scs, x, to_buf ? (void *)p->buffer(y_buf) : y_d, fa, main);
@@ -821,6 +826,25 @@ int uspmv_p2p_spmmv(uspmv_p2p *p, const uspmv_scs *scs, int x_buf, void *Y_d, vo
         cudaStream_t main = as_stream(stream), comm = as_stream(comm_stream);
         const int P = h->P;
         const void *X = p->buffer(x_buf);
+        if (p->mode == 2 && spmmv_fused_supported(scs, p->bvs) && P <= 32) {  // ONE fused kernel: push, interior, wait, boundary, ack
+            stream::FusedArgs fa{};
+            fa.n_int = (long)scs->interior_chunks.n;
+            fa.n_bnd = (long)scs->boundary_chunks.n;
+            fa.int_list = scs->interior_contig ? nullptr : scs->interior_chunks.p;
+            fa.bnd_list = scs->boundary_contig ? nullptr : scs->boundary_chunks.p;
+            fa.int_off = scs->interior_off;
+            fa.bnd_off = scs->boundary_off;
+            fa.P = P; fa.my_rank = h->rank; fa.n_send = h->n_send;
+            fa.send_ptr = p->send_ptr_d.p; fa.is_receiver = p->is_receiver_d.p; fa.is_sender = p->is_sender_d.p;
+            fa.send_idx = h->send_idx.p; fa.perm = h->perm_d;
+            fa.peer_x0 = p->peer_x0.p + (size_t)x_buf * P; fa.peer_base = p->peer_base.p; fa.peer_ld = p->peer_ld.p;
+            fa.bvs = p->bvs; fa.layout = p->layout; fa.ld = p->vec_length;
+            fa.peer_arrived = p->peer_arrived.p; fa.peer_acked = p->peer_acked.p;
+            fa.acked = p->acked; fa.arrived = p->arrived; fa.epoch = p->epoch; fa.error = p->error; fa.counters = p->fused_counters.p;
+            fa.y_rows = (int)scs->n_rows_padded;
+            launch_spmmv_fused_any(scs, X, Y_d, p->bvs, p->vec_length, p->layout, fa, main);
+            return;
+        }
         const bool overlap = p->mode != 0 && uspmv_spmmv_part_supported(scs, p->bvs);
         USPMV_CUDA(cudaEventRecord(p->ev_main, main));
         if (overlap && uspmv_spmmv_part(scs, 1, X, Y_d, p->bvs, p->vec_length, p->layout, stream)) throw Error(uspmv_last_error());

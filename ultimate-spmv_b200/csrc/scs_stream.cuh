@@ -93,7 +93,10 @@ struct FusedArgs {
     int P, my_rank;
     long n_send;
     const int *send_ptr, *is_receiver, *is_sender, *send_idx, *perm;
-    const unsigned long long *peer_x_dst, *peer_arrived, *peer_acked;
+    const unsigned long long *peer_x0, *peer_arrived, *peer_acked;  // peer_x0[q]: start of q's (block) vector
+    const long *peer_base, *peer_ld;  // per peer q: row offset of OUR rows in q's vector (q.n_local + q.recv_cumsum[me]); q's vec_length
+    int bvs, layout;              // block vectors: all bvs values of a halo row travel in the same push (bulkvec, classes_structs.hpp:909-970)
+    long ld;                      // own vec_length (column-major block vectors)
     unsigned int *acked, *arrived, *epoch, *error, *counters;  // counters[0] push warps done, [1] warps finished
     int y_rows;                   // rows >= y_rows are not stored (solve loop: y is the other x buffer, see uspmv_p2p_spmv_buf)
 };
@@ -125,6 +128,72 @@ __device__ __forceinline__ void warp_wait_flags(const unsigned int *flags, const
 }
 template <typename T> __device__ __forceinline__ T ld_x_coherent(const T *p) { return __ldcg(p); }  // L2 (coherent with peer stores)
 
+// (a) of the fused step: warp pw handles elements [32 pw, 32 pw + 32) of this rank's send list (x bvs for block vectors: row-major
+// element (i, v) of peer q lands at q.X[(base_q + i) * bvs + v], column-major at q.X[base_q + i + v * ld_q]); the last push warp of the
+// grid raises the neighbours' `arrived` flags.  ROWWISE_LAYOUT value = 1 (USPMV_ROWWISE).
+template <typename VT>
+__device__ __forceinline__ void fused_push(const FusedArgs &fa, const VT *__restrict__ x, const long gw, const long W, const int lane,
+                                           const unsigned int epoch_e) {
+    const long total = fa.n_send * fa.bvs;
+    const long n_push_warps = (total + 31) / 32;
+    for (long pw = gw; pw < n_push_warps; pw += W) {
+        warp_wait_flags(fa.acked, fa.is_receiver, fa.P, epoch_e - 1u, lane, fa.error);  // receivers consumed step e-1
+        const long t = pw * 32 + lane;
+        if (t < total) {
+            long i, v;
+            if (fa.bvs == 1) { i = t; v = 0; }
+            else if (fa.layout == 1) { i = t / fa.bvs; v = t - i * fa.bvs; }
+            else { v = t / fa.n_send; i = t - v * fa.n_send; }
+            int q = 0;
+            while (i >= fa.send_ptr[q + 1]) ++q;
+            const long src = fa.perm ? fa.perm[fa.send_idx[i]] : fa.send_idx[i];
+            const long k = fa.peer_base[q] + (i - fa.send_ptr[q]);
+            VT *dst = reinterpret_cast<VT *>(fa.peer_x0[q]);
+            if (fa.bvs == 1) dst[k] = x[src];
+            else if (fa.layout == 1) dst[k * fa.bvs + v] = x[src * fa.bvs + v];
+            else dst[k + v * fa.peer_ld[q]] = x[src + v * fa.ld];
+        }
+        __threadfence_system();
+        __syncwarp();
+        unsigned int last = 0;
+        if (lane == 0) last = (atomicAdd(&fa.counters[0], 1u) == (unsigned int)(n_push_warps - 1));
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last) {
+            __threadfence_system();
+            if (lane < fa.P && fa.is_receiver[lane]) {
+                volatile unsigned int *f = reinterpret_cast<volatile unsigned int *>(fa.peer_arrived[lane]);
+                *f = epoch_e;
+            }
+            __threadfence_system();
+        }
+    }
+}
+
+// (d) of the fused step: the last warp of the grid acknowledges consumption to the senders and closes the epoch
+__device__ __forceinline__ void fused_finish(const FusedArgs &fa, const long W, const int lane, const unsigned int epoch_e) {
+    __syncwarp();
+    unsigned int last = 0;
+    if (lane == 0) {
+        __threadfence();
+        last = (atomicAdd(&fa.counters[1], 1u) == (unsigned int)(W - 1));
+    }
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (last) {
+        if (fa.n_bnd == 0) warp_wait_flags(fa.arrived, fa.is_sender, fa.P, epoch_e, lane, fa.error);  // keep epochs in step
+        if (lane < fa.P && fa.is_sender[lane]) {
+            volatile unsigned int *f = reinterpret_cast<volatile unsigned int *>(fa.peer_acked[lane]);
+            *f = epoch_e;
+        }
+        __threadfence_system();
+        if (lane == 0) {
+            fa.counters[0] = 0;
+            fa.counters[1] = 0;
+            *reinterpret_cast<volatile unsigned int *>(fa.epoch) = epoch_e;
+            __threadfence();
+        }
+    }
+}
+
 // ---- per-piece arithmetic ("bodies") ----------------------------------------------------------------------------
 // A body owns the accumulators of the 32 rows of the current chunk (one row per lane):
 //   begin_chunk()                       reset
@@ -140,34 +209,25 @@ struct SpmvBody {
     typename A::acc_t acc;
     int y_rows = 0;  // BOUNDED: positions >= y_rows are not stored (y aliases the next x, whose tail holds the halo)
     __device__ __forceinline__ void begin_chunk(int = 0) { acc = A::zero(); }
-    // The slot count is a template constant: with a run-time count every slot became a predicated load plus a DFMA followed by two
-    // FSELs (ncu / SASS of round 1: 111 instructions for a 7-slot piece); here a piece of NS slots is NS x {LDS, LDG, LDS, FMA}.
-    template <int NS>
-    __device__ __forceinline__ void piece_n(const VT *sv, const int *sc) {
-        VT xv[NS];
-        int col[NS];
+    // Slot count at run time (predicated loads): measured FASTER than a switch over template-constant slot counts for the narrow
+    // types on B200 (7-point 256^3, profiles/r02d_ab_stream.log: sp 162 vs 194 us, hp 150 vs 172 us, dp equal) although it executes
+    // more instructions — ncu (profiles/r02e_*): the kernel is latency-, not issue-limited once the predication is gone
+    // (IPC 3.0 -> 2.1, "no eligible" 24 % -> 49 % for hp), so the shorter instruction stream only exposes the gather latency.
+    __device__ __forceinline__ void piece(const int ns, const VT *sv, const int *sc) {
+        VT v[LMAX], xv[LMAX];
+        int col[LMAX];
 #pragma unroll
-        for (int j = 0; j < NS; ++j) col[j] = sc[j * 32];
+        for (int j = 0; j < LMAX; ++j)
+            if (j < ns) col[j] = sc[j * 32];
 #pragma unroll
-        for (int j = 0; j < NS; ++j) xv[j] = COHERENT ? __ldcg(x + col[j]) : __ldg(x + col[j]);
+        for (int j = 0; j < LMAX; ++j)
+            if (j < ns) xv[j] = COHERENT ? __ldcg(x + col[j]) : __ldg(x + col[j]);
 #pragma unroll
-        for (int j = 0; j < NS; ++j) acc = A::mad(sv[j * 32], xv[j], acc);
-    }
-    __device__ __forceinline__ void piece(int ns, const VT *sv, const int *sc) {
-        if constexpr (LMAX > 8) {
-            while (ns > 8) { piece_n<8>(sv, sc); sv += 8 * 32; sc += 8 * 32; ns -= 8; }
-        }
-        switch (ns) {
-        case 0: break;
-        case 1: piece_n<1>(sv, sc); break;
-        case 2: piece_n<(LMAX >= 2 ? 2 : 1)>(sv, sc); break;
-        case 3: piece_n<(LMAX >= 3 ? 3 : 1)>(sv, sc); break;
-        case 4: piece_n<(LMAX >= 4 ? 4 : 1)>(sv, sc); break;
-        case 5: piece_n<(LMAX >= 5 ? 5 : 1)>(sv, sc); break;
-        case 6: piece_n<(LMAX >= 6 ? 6 : 1)>(sv, sc); break;
-        case 7: piece_n<(LMAX >= 7 ? 7 : 1)>(sv, sc); break;
-        default: piece_n<(LMAX >= 8 ? 8 : LMAX)>(sv, sc); break;
-        }
+        for (int j = 0; j < LMAX; ++j)
+            if (j < ns) v[j] = sv[j * 32];
+#pragma unroll
+        for (int j = 0; j < LMAX; ++j)
+            if (j < ns) acc = A::mad(v[j], xv[j], acc);
     }
     __device__ __forceinline__ void end_chunk(const int chunk) {
         const long row = (long)chunk * 32 + lane;
@@ -181,7 +241,7 @@ struct SpmvBody {
 
 // SpMMV: Y = A X with BVS right-hand sides.  ROWWISE: X[col*BVS + v] (one vector load per gathered row); else X[col + v*ld].
 // Slots are consumed SB at a time so that SB*BVS gathered values are in flight per lane without blowing the register file.
-template <typename VT, typename A, int LMAX, int BVS, bool ROWWISE>
+template <typename VT, typename A, int LMAX, int BVS, bool ROWWISE, bool COHERENT = false>
 struct SpmmvBody {
     static constexpr int SB = (BVS * (int)sizeof(VT) >= 64) ? 2 : (BVS * (int)sizeof(VT) >= 32 ? 4 : 8);
     const VT *__restrict__ X;
@@ -199,18 +259,18 @@ struct SpmmvBody {
             if constexpr (BYTES % 16 == 0) {
                 const int4 *p = reinterpret_cast<const int4 *>(X + col * BVS);
 #pragma unroll
-                for (int k = 0; k < BYTES / 16; ++k) reinterpret_cast<int4 *>(xv)[k] = __ldg(p + k);
+                for (int k = 0; k < BYTES / 16; ++k) reinterpret_cast<int4 *>(xv)[k] = COHERENT ? __ldcg(p + k) : __ldg(p + k);
             } else if constexpr (BYTES % 8 == 0) {
                 const int2 *p = reinterpret_cast<const int2 *>(X + col * BVS);
 #pragma unroll
-                for (int k = 0; k < BYTES / 8; ++k) reinterpret_cast<int2 *>(xv)[k] = __ldg(p + k);
+                for (int k = 0; k < BYTES / 8; ++k) reinterpret_cast<int2 *>(xv)[k] = COHERENT ? __ldcg(p + k) : __ldg(p + k);
             } else {
 #pragma unroll
-                for (int v = 0; v < BVS; ++v) xv[v] = __ldg(X + col * BVS + v);
+                for (int v = 0; v < BVS; ++v) xv[v] = COHERENT ? __ldcg(X + col * BVS + v) : __ldg(X + col * BVS + v);
             }
         } else {
 #pragma unroll
-            for (int v = 0; v < BVS; ++v) xv[v] = __ldg(X + col + v * ld);
+            for (int v = 0; v < BVS; ++v) xv[v] = COHERENT ? __ldcg(X + col + v * ld) : __ldg(X + col + v * ld);
         }
     }
     // The slot count is a template constant: with a run-time count every gather became a predicated load into a scratch register
@@ -303,7 +363,7 @@ struct SpmmvBody {
 // one 128-bit load each, so every warp-wide load touches whole 128-byte lines (a lane-per-row int4 load touches 32 different
 // lines per instruction and is L1-wavefront bound: measured 0.47 of peak for dp bvs 8).  Lane l owns the 16-byte slice
 // (l % T) of the rows l/T + (32/T)*k, k = 0..T-1 of the chunk; per (row, vector) the FMA order is unchanged (slot order).
-template <typename VT, typename A, int LMAX, int BVS>
+template <typename VT, typename A, int LMAX, int BVS, bool COHERENT = false>
 struct SpmmvBodyRowWide {
     static constexpr int PER = 16 / (int)sizeof(VT);            // values per 128-bit load
     static constexpr int T = BVS * (int)sizeof(VT) / 16;        // lanes per row == rows per lane
@@ -332,7 +392,8 @@ struct SpmmvBodyRowWide {
 #pragma unroll
                     for (int k = 0; k < T; ++k) {
                         const long col = c0[(j0 + u) * 32 + r0 + RPI * k];
-                        *reinterpret_cast<int4 *>(xv[u][k]) = __ldg(reinterpret_cast<const int4 *>(X + col * BVS) + part);
+                        const int4 *src = reinterpret_cast<const int4 *>(X + col * BVS) + part;
+                        *reinterpret_cast<int4 *>(xv[u][k]) = COHERENT ? __ldcg(src) : __ldg(src);
                     }
                 }
 #pragma unroll
@@ -381,6 +442,97 @@ struct SpmmvBodyRowWide {
 };
 
 // The streaming loop of one warp over work items first, first + W, ... < n_items (item k -> chunk list[k] or k + off).
+template <typename VT, int LMAX, int D, typename Body>
+__device__ __forceinline__ void stream_items(unsigned char *base, uint64_t *bars, PieceHdr *hdrs, uint32_t &phase_bits, const int W,
+                                             const int first, const int lane, const int n_items, const int *__restrict__ chunk_list,
+                                             const int chunk_offset, const int *__restrict__ chunk_ptrs,
+                                             const int *__restrict__ chunk_lengths, const int *__restrict__ col_idxs,
+                                             const VT *__restrict__ values, Body &body, const uint64_t pol) {
+    using R = WarpRing<VT, LMAX, D>;
+    auto item_chunk = [&](int k) -> int { return chunk_list ? chunk_list[k] : k + chunk_offset; };  // 32-bit index math throughout
+
+    // ---- producer state (meaningful in lane 0 only) --------------------------------------------------
+    // Three-deep metadata lookahead so that no load issued by lane 0 is consumed in the same piece:
+    //   cur  = (pchunk, plen, pcs)  item being cut into pieces
+    //   nxt  = (nchunk, nlen, ncs)  item pc + W, loaded when cur became current
+    //   n2chunk                     chunk id of item pc + 2W (only needed with a chunk list)
+    int pc = first;  // work item of the next piece (n_items + 2W < 2^31: one item per 32 rows)
+    int pj = 0, plen = 0, pcs = 0, pchunk = 0, nlen = 0, ncs = 0, nchunk = 0, n2chunk = 0;
+    if (lane == 0) {
+        if (pc < n_items) {
+            pchunk = item_chunk(pc);
+            plen = chunk_lengths[pchunk];
+            pcs = chunk_ptrs[pchunk];
+        }
+        if (pc + W < n_items) {
+            nchunk = item_chunk(pc + W);
+            nlen = chunk_lengths[nchunk];
+            ncs = chunk_ptrs[nchunk];
+        }
+        if (pc + 2 * W < n_items) n2chunk = item_chunk(pc + 2 * W);
+    }
+    auto issue = [&](int s) {  // lane 0: fill stage s with the next piece of this warp's stream
+        PieceHdr h;
+        if (pc >= n_items) {
+            h.ns = 0; h.flags = 0; h.chunk = 0; h.pad = 0;
+            hdrs[s] = h;
+            return;
+        }
+        const int ns = min(LMAX, plen - pj);
+        h.ns = ns;
+        h.flags = 4 | (pj == 0 ? 1 : 0) | (pj + ns >= plen ? 2 : 0);
+        h.chunk = pchunk;
+        h.pad = 0;
+        hdrs[s] = h;
+        if (ns > 0) {
+            const int e0 = pcs + pj * 32;  // < n_elements < 2^31
+            const uint32_t vb = (uint32_t)ns * 32u * (uint32_t)sizeof(VT), cb = (uint32_t)ns * 128u;
+            unsigned char *st = base + s * R::STAGE_BYTES;
+            mbar_expect_tx(&bars[s], vb + cb);
+            bulk_g2s(st, values + e0, vb, &bars[s], pol);
+            bulk_g2s(st + R::VAL_BYTES, col_idxs + e0, cb, &bars[s], pol);
+        }
+        pj += ns;
+        if (pj >= plen) {  // advance: nxt -> cur, start the loads for the new nxt
+            pc += W;
+            pj = 0;
+            pchunk = nchunk; plen = nlen; pcs = ncs;
+            nchunk = n2chunk;
+            if (pc + W < n_items) {
+                nlen = chunk_lengths[nchunk];
+                ncs = chunk_ptrs[nchunk];
+            }
+            if (pc + 2 * W < n_items) n2chunk = item_chunk(pc + 2 * W);
+        }
+    };
+
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < D; ++s) issue(s);
+    }
+    __syncwarp();
+
+    // ---- consumer -----------------------------------------------------------------------------------------
+    body.begin_chunk();
+    for (int s = 0;; s = (s + 1 == D) ? 0 : s + 1) {
+        const PieceHdr h = hdrs[s];
+        if (h.flags == 0) break;
+        if (h.flags & 1) body.begin_chunk(h.chunk);
+        if (h.ns > 0) {
+            mbar_wait(&bars[s], (phase_bits >> s) & 1u);
+            phase_bits ^= (1u << s);
+            const VT *sv = reinterpret_cast<const VT *>(base + s * R::STAGE_BYTES) + lane;
+            const int *sc = reinterpret_cast<const int *>(base + s * R::STAGE_BYTES + R::VAL_BYTES) + lane;
+            body.piece(h.ns, sv, sc);
+        }
+        if (h.flags & 2) body.end_chunk(h.chunk);
+        __syncwarp();  // every lane is done with stage s (data and header) before it is refilled
+        if (lane == 0) issue(s);
+        __syncwarp();
+    }
+}
+
+// The same loop in "lean" form (used by the wide-chunk kernel, where it is the faster one: C = 64 hp 145 -> 131 us).
 //
 // Round-2 form.  SASS of the round-1 loop: 266 instructions per piece, of which 28 were the arithmetic of a 7-slot piece — lane 0 ran
 // the producer (header stores to shared memory, address arithmetic, three-deep metadata lookahead) inside a divergent branch while 31
@@ -399,7 +551,7 @@ struct PieceReg {
 };
 
 template <typename VT, int LMAX, int D, typename Body, int H = 1>  // H: a slot holds 32 * H elements (wide chunks, C = 32 * H)
-__device__ __forceinline__ void stream_items(unsigned char *base, uint64_t *bars, PieceHdr *, uint32_t &phase_bits, const int W, const int first,
+__device__ __forceinline__ void stream_items_u(unsigned char *base, uint64_t *bars, PieceHdr *, uint32_t &phase_bits, const int W, const int first,
                                              const int lane, const int n_items, const int *__restrict__ chunk_list, const int chunk_offset,
                                              const int *__restrict__ chunk_ptrs, const int *__restrict__ chunk_lengths,
                                              const int *__restrict__ col_idxs, const VT *__restrict__ values, Body &body, const uint64_t pol) {
@@ -501,32 +653,9 @@ k_scs32_stream(long n_items, const int *__restrict__ chunk_list, int chunk_offse
         stream_items<VT, LMAX, D>(base, bars, hdrs, phase_bits, (int)W, (int)gw, lane, (int)n_items, chunk_list, chunk_offset,
                                   chunk_ptrs, chunk_lengths, col_idxs, values, body, pol);
     } else {
-        // (a) push: warp pw handles send elements [32 pw, 32 pw + 32)
+        // (a) push this rank's elements into the neighbours' x tails
         const unsigned int epoch_e = ld_flag(fa.epoch) + 1u;
-        const long n_push_warps = (fa.n_send + 31) / 32;
-        for (long pw = gw; pw < n_push_warps; pw += W) {
-            warp_wait_flags(fa.acked, fa.is_receiver, fa.P, epoch_e - 1u, lane, fa.error);  // receivers consumed step e-1
-            const long i = pw * 32 + lane;
-            if (i < fa.n_send) {
-                int q = 0;
-                while (i >= fa.send_ptr[q + 1]) ++q;
-                VT *dst = reinterpret_cast<VT *>(fa.peer_x_dst[q]);
-                dst[i - fa.send_ptr[q]] = x[fa.perm[fa.send_idx[i]]];
-            }
-            __threadfence_system();
-            __syncwarp();
-            unsigned int last = 0;
-            if (lane == 0) last = (atomicAdd(&fa.counters[0], 1u) == (unsigned int)(n_push_warps - 1));
-            last = __shfl_sync(0xffffffffu, last, 0);
-            if (last) {
-                __threadfence_system();
-                if (lane < fa.P && fa.is_receiver[lane]) {
-                    volatile unsigned int *f = reinterpret_cast<volatile unsigned int *>(fa.peer_arrived[lane]);
-                    *f = epoch_e;
-                }
-                __threadfence_system();
-            }
-        }
+        fused_push<VT>(fa, x, gw, W, lane, epoch_e);
         // (b) interior chunks: no halo column, identical code path to the single-GPU kernel
         {
             SpmvBody<VT, A, LMAX, UNPERM, false, true> body{x, y, new_to_old, lane, A::zero(), fa.y_rows};
@@ -541,27 +670,7 @@ k_scs32_stream(long n_items, const int *__restrict__ chunk_list, int chunk_offse
                                       chunk_lengths, col_idxs, values, body, pol);
         }
         // (d) the last warp of the grid acknowledges consumption to the senders and closes the epoch
-        __syncwarp();
-        unsigned int last = 0;
-        if (lane == 0) {
-            __threadfence();
-            last = (atomicAdd(&fa.counters[1], 1u) == (unsigned int)(W - 1));
-        }
-        last = __shfl_sync(0xffffffffu, last, 0);
-        if (last) {
-            if (fa.n_bnd == 0) warp_wait_flags(fa.arrived, fa.is_sender, fa.P, epoch_e, lane, fa.error);  // keep epochs in step
-            if (lane < fa.P && fa.is_sender[lane]) {
-                volatile unsigned int *f = reinterpret_cast<volatile unsigned int *>(fa.peer_acked[lane]);
-                *f = epoch_e;
-            }
-            __threadfence_system();
-            if (lane == 0) {
-                fa.counters[0] = 0;
-                fa.counters[1] = 0;
-                *reinterpret_cast<volatile unsigned int *>(fa.epoch) = epoch_e;
-                __threadfence();
-            }
-        }
+        fused_finish(fa, W, lane, epoch_e);
     }
 }
 
@@ -573,13 +682,14 @@ k_scs32_stream(long n_items, const int *__restrict__ chunk_list, int chunk_offse
 // ---------------------------------------------------------------------------------------------------------------------
 // Body of the wide-chunk kernel: lane l owns the H rows l, l + 32, ... of the chunk; a piece of NS slots is NS * H slot-rows of 32
 // elements, slot-row r = j * H + h holds slot j of the rows h * 32 + lane.
-template <typename VT, typename A, int H, bool UNPERM>
+template <typename VT, typename A, int H, bool UNPERM, bool COHERENT = false, bool BOUNDED = false>
 struct WideBody {
     static constexpr int C = 32 * H;
     const VT *__restrict__ x;
     VT *__restrict__ y;
     const int *__restrict__ new_to_old;
     int lane;
+    int y_rows = 0;  // BOUNDED: positions >= y_rows are not stored (y aliases the next x, whose tail holds the halo)
     typename A::acc_t acc[H];
     __device__ __forceinline__ void begin_chunk(int = 0) {
 #pragma unroll
@@ -593,7 +703,7 @@ struct WideBody {
 #pragma unroll
         for (int r = 0; r < NR; ++r) col[r] = sc[r * 32];
 #pragma unroll
-        for (int r = 0; r < NR; ++r) xv[r] = __ldg(x + col[r]);
+        for (int r = 0; r < NR; ++r) xv[r] = COHERENT ? __ldcg(x + col[r]) : __ldg(x + col[r]);
 #pragma unroll
         for (int r = 0; r < NR; ++r) acc[r % H] = A::mad(sv[r * 32], xv[r], acc[r % H]);
     }
@@ -614,17 +724,17 @@ struct WideBody {
             if (UNPERM) {
                 const int o = new_to_old[row];
                 if (o >= 0) y[o] = A::out(acc[h]);
-            } else
+            } else if (!BOUNDED || row < y_rows)
                 y[row] = A::out(acc[h]);
         }
     }
 };
 
-template <typename VT, typename A, int H, int D, int WARPS, bool UNPERM>
+template <typename VT, typename A, int H, int D, int WARPS, bool UNPERM, bool FUSED = false>
 __global__ void __launch_bounds__(WARPS * 32, (1024 / (WARPS * 32)) > 0 ? (1024 / (WARPS * 32)) : 1)
 k_scsw_stream(int n_items, const int *__restrict__ chunk_list, int chunk_offset, const int *__restrict__ chunk_ptrs,
               const int *__restrict__ chunk_lengths, const int *__restrict__ col_idxs, const VT *__restrict__ values,
-              const VT *__restrict__ x, VT *__restrict__ y, const int *__restrict__ new_to_old) {
+              const VT *__restrict__ x, VT *__restrict__ y, const int *__restrict__ new_to_old, const FusedArgs fa) {
     static_assert(H == 2 || H == 4, "C = 64 or 128");
     constexpr int LS = 8;         // slot-rows (32 elements each) per stage
     constexpr int LW = LS / H;    // slots of a wide chunk per piece
@@ -643,10 +753,32 @@ k_scsw_stream(int n_items, const int *__restrict__ chunk_list, int chunk_offset,
     __syncwarp();
     const uint64_t pol = policy_evict_first();
     uint32_t phase_bits = 0;
-    WideBody<VT, A, H, UNPERM> body;
-    body.x = x; body.y = y; body.new_to_old = new_to_old; body.lane = lane;
-    stream_items<VT, LW, D, WideBody<VT, A, H, UNPERM>, H>(base, bars, nullptr, phase_bits, W, first, lane, n_items, chunk_list, chunk_offset, chunk_ptrs,
-                                                           chunk_lengths, col_idxs, values, body, pol);
+    if constexpr (!FUSED) {
+        WideBody<VT, A, H, UNPERM> body;
+        body.x = x; body.y = y; body.new_to_old = new_to_old; body.lane = lane;
+        stream_items_u<VT, LW, D, WideBody<VT, A, H, UNPERM>, H>(base, bars, nullptr, phase_bits, W, first, lane, n_items, chunk_list, chunk_offset,
+                                                               chunk_ptrs, chunk_lengths, col_idxs, values, body, pol);
+    } else {
+        // ONE kernel per distributed SpMV for C = 64 / 128 (see k_scs32_stream): push, interior chunks, wait, boundary chunks, acknowledge
+        const unsigned int epoch_e = ld_flag(fa.epoch) + 1u;
+        fused_push<VT>(fa, x, first, W, lane, epoch_e);
+        {
+            using B = WideBody<VT, A, H, UNPERM, false, true>;
+            B body;
+            body.x = x; body.y = y; body.new_to_old = new_to_old; body.lane = lane; body.y_rows = fa.y_rows;
+            stream_items_u<VT, LW, D, B, H>(base, bars, nullptr, phase_bits, W, first, lane, (int)fa.n_int, fa.int_list, fa.int_off, chunk_ptrs,
+                                            chunk_lengths, col_idxs, values, body, pol);
+        }
+        if (first < fa.n_bnd) {
+            warp_wait_flags(fa.arrived, fa.is_sender, fa.P, epoch_e, lane, fa.error);
+            using B = WideBody<VT, A, H, UNPERM, true, true>;
+            B body;
+            body.x = x; body.y = y; body.new_to_old = new_to_old; body.lane = lane; body.y_rows = fa.y_rows;
+            stream_items_u<VT, LW, D, B, H>(base, bars, nullptr, phase_bits, W, first, lane, (int)fa.n_bnd, fa.bnd_list, fa.bnd_off, chunk_ptrs,
+                                            chunk_lengths, col_idxs, values, body, pol);
+        }
+        fused_finish(fa, W, lane, epoch_e);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -1189,11 +1321,11 @@ k_csr_stream(long n_rows, const int *__restrict__ row_ptrs, const int *__restric
 }
 
 // SELL-32 SpMMV through the same per-warp bulk-copy ring (smaller stages: the block vectors want the L1 capacity).
-template <typename VT, typename A, int LMAX, int D, int WARPS, int BVS, bool ROWWISE, bool WIDE>
+template <typename VT, typename A, int LMAX, int D, int WARPS, int BVS, bool ROWWISE, bool WIDE, bool FUSED = false>
 __global__ void __launch_bounds__(WARPS * 32)  // ~80 registers, 24 warps/SM: capping at 64 spills and is 30-50 % slower (measured)
 k_scs32_stream_mmv(long n_items, const int *__restrict__ chunk_list, int chunk_offset, const int *__restrict__ chunk_ptrs,
                    const int *__restrict__ chunk_lengths, const int *__restrict__ col_idxs, const VT *__restrict__ values,
-                   const VT *__restrict__ X, VT *__restrict__ Y, long ld) {
+                   const VT *__restrict__ X, VT *__restrict__ Y, long ld, const FusedArgs fa) {
     using R = WarpRing<VT, LMAX, D>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1211,16 +1343,34 @@ k_scs32_stream_mmv(long n_items, const int *__restrict__ chunk_list, int chunk_o
     const uint64_t pol = policy_evict_first();
     uint32_t phase_bits = 0;
     constexpr int ROW_BYTES = BVS * (int)sizeof(VT);
-    if constexpr (WIDE && ROWWISE && ROW_BYTES >= 32 && ROW_BYTES <= 128 && (ROW_BYTES & (ROW_BYTES - 1)) == 0) {
-        SpmmvBodyRowWide<VT, A, LMAX, BVS> body;
-        body.X = X; body.Y = Y; body.lane = lane;
-        stream_items<VT, LMAX, D>(base, bars, hdrs, phase_bits, (int)W, (int)gw, lane, (int)n_items, chunk_list, chunk_offset, chunk_ptrs,
-                                  chunk_lengths, col_idxs, values, body, pol);
+    constexpr bool USE_WIDE = WIDE && ROWWISE && ROW_BYTES >= 32 && ROW_BYTES <= 128 && (ROW_BYTES & (ROW_BYTES - 1)) == 0;
+    auto run = [&](auto coherent, const long n, const int *list, const int off) {
+        constexpr bool COH = decltype(coherent)::value;
+        if constexpr (USE_WIDE) {
+            SpmmvBodyRowWide<VT, A, LMAX, BVS, COH> body;
+            body.X = X; body.Y = Y; body.lane = lane;
+            stream_items<VT, LMAX, D>(base, bars, hdrs, phase_bits, (int)W, (int)gw, lane, (int)n, list, off, chunk_ptrs, chunk_lengths, col_idxs,
+                                      values, body, pol);
+        } else {
+            SpmmvBody<VT, A, LMAX, BVS, ROWWISE, COH> body;
+            body.X = X; body.Y = Y; body.ld = ld; body.lane = lane;
+            stream_items<VT, LMAX, D>(base, bars, hdrs, phase_bits, (int)W, (int)gw, lane, (int)n, list, off, chunk_ptrs, chunk_lengths, col_idxs,
+                                      values, body, pol);
+        }
+    };
+    if constexpr (!FUSED) {
+        run(std::false_type{}, n_items, chunk_list, chunk_offset);
     } else {
-        SpmmvBody<VT, A, LMAX, BVS, ROWWISE> body;
-        body.X = X; body.Y = Y; body.ld = ld; body.lane = lane;
-        stream_items<VT, LMAX, D>(base, bars, hdrs, phase_bits, (int)W, (int)gw, lane, (int)n_items, chunk_list, chunk_offset, chunk_ptrs,
-                                  chunk_lengths, col_idxs, values, body, pol);
+        // ONE kernel per distributed SpMMV (see k_scs32_stream): push all block_vec_size values of the halo rows to the neighbours,
+        // interior chunks, wait for the own halo, boundary chunks with L2-coherent gathers, acknowledge
+        const unsigned int epoch_e = ld_flag(fa.epoch) + 1u;
+        fused_push<VT>(fa, X, gw, W, lane, epoch_e);
+        run(std::false_type{}, fa.n_int, fa.int_list, fa.int_off);
+        if (gw < fa.n_bnd) {
+            warp_wait_flags(fa.arrived, fa.is_sender, fa.P, epoch_e, lane, fa.error);
+            run(std::true_type{}, fa.n_bnd, fa.bnd_list, fa.bnd_off);
+        }
+        fused_finish(fa, W, lane, epoch_e);
     }
 }
 

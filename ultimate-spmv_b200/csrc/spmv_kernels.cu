@@ -313,7 +313,7 @@ void launch_stream_wide(long n_chunks, const int *list, int off, const int *cp, 
     long grid = (long)sm_count(dev) * options().stream_blocks_per_sm;
     const long need = (n_chunks + WARPS - 1) / WARPS;
     if (grid > need) grid = need;
-    kern<<<(unsigned)grid, WARPS * 32, smem, st>>>((int)n_chunks, list, off, cp, cl, ci, v, x, y, n2o);
+    kern<<<(unsigned)grid, WARPS * 32, smem, st>>>((int)n_chunks, list, off, cp, cl, ci, v, x, y, n2o, stream::FusedArgs{});
 }
 
 // C = 16 / 8: the narrow-chunk streamed kernel (scs_stream.cuh, k_scsn_stream); contiguous chunk ranges only
@@ -377,6 +377,8 @@ void launch_stream(long n_chunks, const int *list, int off, const int *cp, const
     case 7: launch_stream_v<VT, UNPERM, 16, 2, 8>(n_chunks, list, off, cp, cl, ci, v, x, y, n2o, st, c.stream_blocks_per_sm); break;
     case 8: launch_stream_v<VT, UNPERM, 8, 2, 32>(n_chunks, list, off, cp, cl, ci, v, x, y, n2o, st, c.stream_blocks_per_sm); break;
     case 9: launch_stream_v<VT, UNPERM, 2, 4, 16>(n_chunks, list, off, cp, cl, ci, v, x, y, n2o, st, c.stream_blocks_per_sm); break;
+    case 13: launch_stream_v<VT, UNPERM, 8, 3, 16>(n_chunks, list, off, cp, cl, ci, v, x, y, n2o, st, c.stream_blocks_per_sm); break;
+    case 14: launch_stream_v<VT, UNPERM, 8, 4, 16>(n_chunks, list, off, cp, cl, ci, v, x, y, n2o, st, c.stream_blocks_per_sm); break;
     case 10: launch_stream_pf<VT, UNPERM, 8, 3, 8>(n_chunks, list, off, cp, cl, ci, v, x, y, n2o, st, c.stream_blocks_per_sm); break;
     case 11: launch_stream_pf<VT, UNPERM, 8, 4, 8>(n_chunks, list, off, cp, cl, ci, v, x, y, n2o, st, c.stream_blocks_per_sm); break;
     case 12: launch_stream_pf<VT, UNPERM, 4, 4, 8>(n_chunks, list, off, cp, cl, ci, v, x, y, n2o, st, c.stream_blocks_per_sm); break;
@@ -410,13 +412,41 @@ static void launch_fused_t(const uspmv_scs *s, const void *x, void *y, const str
     USPMV_LAUNCH_CHECK();
 }
 
-void launch_scs32_fused(const uspmv_scs *s, const void *x, void *y, const stream::FusedArgs &fa, cudaStream_t st) {
-    if (s->C != 32) fail("fused halo exchange kernel needs C = 32 (got %ld)", s->C);
-    switch (s->vt) {
-    case USPMV_F64: launch_fused_t<double>(s, x, y, fa, st); break;
-    case USPMV_F32: launch_fused_t<float>(s, x, y, fa, st); break;
-    default: launch_fused_t<__half>(s, x, y, fa, st);
+// C = 64 / 128: the wide-chunk kernel with the fused exchange
+template <typename VT, int H>
+static void launch_fused_wide_t(const uspmv_scs *s, const void *x, void *y, const stream::FusedArgs &fa, cudaStream_t st) {
+    constexpr int D = 2, WARPS = 16;
+    using R = stream::WarpRing<VT, 8, D>;
+    auto kern = stream::k_scsw_stream<VT, Arith<VT>, H, D, WARPS, false, true>;
+    constexpr int smem = WARPS * R::BYTES_ALIGNED;
+    static bool configured_on[uspmv::MAX_DEVICES] = {};
+    const int dev = uspmv::current_device();
+    if (!configured_on[dev]) {
+        USPMV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured_on[dev] = true;
     }
+    const long grid = (long)sm_count(dev) * 2;  // 2 CTAs of 16 warps per SM, all resident (warps spin on peer flags)
+    kern<<<(unsigned)grid, WARPS * 32, smem, st>>>((int)(fa.n_int + fa.n_bnd), nullptr, 0, s->chunk_ptrs.p, s->chunk_lengths.p, s->col_idxs.p,
+                                                 reinterpret_cast<const VT *>(s->values.p), static_cast<const VT *>(x), static_cast<VT *>(y), nullptr, fa);
+    USPMV_LAUNCH_CHECK();
+}
+
+bool scs_fused_supported(const uspmv_scs *s) { return options().scs_stream && (s->C == 32 || ((s->C == 64 || s->C == 128) && options().scs_stream_wide)); }
+
+void launch_scs32_fused(const uspmv_scs *s, const void *x, void *y, const stream::FusedArgs &fa, cudaStream_t st) {
+    if (!scs_fused_supported(s)) fail("fused halo exchange kernel needs C = 32, 64 or 128 (got %ld)", s->C);
+#define USPMV_FUSED_VT(VT)                                                    \
+    do {                                                                      \
+        if (s->C == 32) launch_fused_t<VT>(s, x, y, fa, st);                  \
+        else if (s->C == 64) launch_fused_wide_t<VT, 2>(s, x, y, fa, st);     \
+        else launch_fused_wide_t<VT, 4>(s, x, y, fa, st);                     \
+    } while (0)
+    switch (s->vt) {
+    case USPMV_F64: USPMV_FUSED_VT(double); break;
+    case USPMV_F32: USPMV_FUSED_VT(float); break;
+    default: USPMV_FUSED_VT(__half);
+    }
+#undef USPMV_FUSED_VT
 }
 }  // namespace uspmv
 
@@ -589,7 +619,38 @@ void launch_spmmv_stream_v(const ScsView &s, const VT *X, VT *Y, long ld, cudaSt
     if (grid > need) grid = need;
     if (grid < 1) return;
     kern<<<(unsigned)grid, WARPS * 32, smem, st>>>(sel.n, sel.list, sel.off, s.cp, s.cl, s.ci,
-                                                  static_cast<const VT *>(s.vals), X, Y, ld);
+                                                  static_cast<const VT *>(s.vals), X, Y, ld, stream::FusedArgs{});
+}
+
+// ONE kernel per distributed SpMMV (push + interior + wait + boundary + ack): every CTA must be resident, so the grid is exactly
+// SMs x resident CTAs per SM
+template <typename VT, int BVS, bool ROWWISE, int LMAX, int WARPS, bool WIDE>
+void launch_spmmv_fused_v(const ScsView &s, const VT *X, VT *Y, long ld, cudaStream_t st, const stream::FusedArgs &fa) {
+    constexpr int D = 2;
+    using R = stream::WarpRing<VT, LMAX, D>;
+    auto kern = stream::k_scs32_stream_mmv<VT, Arith<VT>, LMAX, D, WARPS, BVS, ROWWISE, WIDE, true>;
+    constexpr int smem = WARPS * R::BYTES_ALIGNED;
+    static bool configured_on[uspmv::MAX_DEVICES] = {};
+    static int bps_on[uspmv::MAX_DEVICES];
+    const int dev = uspmv::current_device();
+    if (!configured_on[dev]) {
+        USPMV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        USPMV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps_on[dev], kern, WARPS * 32, smem));
+        if (bps_on[dev] < 1) bps_on[dev] = 1;
+        configured_on[dev] = true;
+    }
+    const int bps = options().mmv_blocks_per_sm > 0 ? std::min(options().mmv_blocks_per_sm, bps_on[dev]) : bps_on[dev];
+    const long grid = (long)sm_count(dev) * bps;
+    kern<<<(unsigned)grid, WARPS * 32, smem, st>>>(fa.n_int + fa.n_bnd, nullptr, 0, s.cp, s.cl, s.ci, static_cast<const VT *>(s.vals), X, Y, ld, fa);
+}
+
+template <typename VT, int BVS, bool ROWWISE>
+void launch_spmmv_fused(const ScsView &s, const VT *X, VT *Y, long ld, cudaStream_t st, const stream::FusedArgs &fa) {
+    switch (mmv_default_variant(sizeof(VT), BVS, ROWWISE)) {  // the tuned instantiation per (precision, block_vec_size, layout)
+    case 2: launch_spmmv_fused_v<VT, BVS, ROWWISE, 8, 8, true>(s, X, Y, ld, st, fa); break;
+    case 6: launch_spmmv_fused_v<VT, BVS, ROWWISE, 8, 24, true>(s, X, Y, ld, st, fa); break;
+    default: launch_spmmv_fused_v<VT, BVS, ROWWISE, 8, 8, false>(s, X, Y, ld, st, fa); break;
+    }
 }
 
 // variant: 0 = tuned default per (precision, bvs, layout); 1..4 force (wide body?, slots per stage)
@@ -668,6 +729,40 @@ inline ScsView view_of(const uspmv_scs *s) {
     return ScsView{s->C, s->n_chunks, s->n_rows_padded, s->chunk_ptrs.p, s->chunk_lengths.p, s->col_idxs.p, s->values.p};
 }
 inline bool spmmv_streamed(const uspmv_scs *s, int bvs) { return spmmv_streamed(s->C, bvs); }
+
+}  // namespace
+
+namespace uspmv {
+bool spmmv_fused_supported(const uspmv_scs *s, int bvs) { return spmmv_streamed(s->C, bvs); }
+
+// One-launch distributed SpMMV over the arena's block vector (C = 32, block_vec_size 2 / 4 / 8 / 16)
+void launch_spmmv_fused_any(const uspmv_scs *s, const void *X, void *Y, int bvs, long ld, int layout, const stream::FusedArgs &fa, cudaStream_t st) {
+    if (!spmmv_fused_supported(s, bvs)) fail("fused SpMMV needs C = 32 and block_vec_size 2 / 4 / 8 / 16");
+    const ScsView v = view_of(s);
+#define USPMV_FUSED_MMV(VT, RW)                                                                                             \
+    switch (bvs) {                                                                                                          \
+    case 2: launch_spmmv_fused<VT, 2, RW>(v, static_cast<const VT *>(X), static_cast<VT *>(Y), ld, st, fa); break;          \
+    case 4: launch_spmmv_fused<VT, 4, RW>(v, static_cast<const VT *>(X), static_cast<VT *>(Y), ld, st, fa); break;          \
+    case 8: launch_spmmv_fused<VT, 8, RW>(v, static_cast<const VT *>(X), static_cast<VT *>(Y), ld, st, fa); break;          \
+    default: launch_spmmv_fused<VT, 16, RW>(v, static_cast<const VT *>(X), static_cast<VT *>(Y), ld, st, fa);               \
+    }
+#define USPMV_FUSED_MMV_L(VT)                                        \
+    do {                                                             \
+        if (layout == USPMV_ROWWISE) { USPMV_FUSED_MMV(VT, true) }   \
+        else { USPMV_FUSED_MMV(VT, false) }                          \
+    } while (0)
+    switch (s->vt) {
+    case USPMV_F64: USPMV_FUSED_MMV_L(double); break;
+    case USPMV_F32: USPMV_FUSED_MMV_L(float); break;
+    default: USPMV_FUSED_MMV_L(__half);
+    }
+#undef USPMV_FUSED_MMV_L
+#undef USPMV_FUSED_MMV
+    USPMV_LAUNCH_CHECK();
+}
+}  // namespace uspmv
+
+namespace {
 
 // ---- permutation kernels -----------------------------------------------------------------------
 template <typename VT>

@@ -131,42 +131,72 @@ template <typename T> __device__ __forceinline__ T ld_x_coherent(const T *p) { r
 // (a) of the fused step: warp pw handles elements [32 pw, 32 pw + 32) of this rank's send list (x bvs for block vectors: row-major
 // element (i, v) of peer q lands at q.X[(base_q + i) * bvs + v], column-major at q.X[base_q + i + v * ld_q]); the last push warp of the
 // grid raises the neighbours' `arrived` flags.  ROWWISE_LAYOUT value = 1 (USPMV_ROWWISE).
+// Stores only: returns the number of 32-unit groups this warp pushed (0: it took no part).  The caller must follow up with
+// fused_push_signal — right away (fused_push) or after some interior work, when the stores have long been acknowledged and the
+// system-scope fence is cheap (SELL-32 SpMV kernel).
 template <typename VT>
-__device__ __forceinline__ void fused_push(const FusedArgs &fa, const VT *__restrict__ x, const long gw, const long W, const int lane,
-                                           const unsigned int epoch_e) {
-    const long total = fa.n_send * fa.bvs;
-    const long n_push_warps = (total + 31) / 32;
-    for (long pw = gw; pw < n_push_warps; pw += W) {
-        warp_wait_flags(fa.acked, fa.is_receiver, fa.P, epoch_e - 1u, lane, fa.error);  // receivers consumed step e-1
+__device__ __forceinline__ unsigned int fused_push_stores(const FusedArgs &fa, const VT *__restrict__ x, const long gw, const long W, const int lane,
+                                                          const unsigned int epoch_e) {
+    // work units: single vectors and column-major block vectors go element by element (coalesced over the rows of one vector);
+    // row-major block vectors go row by row — one index lookup per halo row, its bvs values copied with 128-bit accesses when aligned
+    const bool by_row = fa.bvs > 1 && fa.layout == 1;
+    const long units = by_row ? fa.n_send : fa.n_send * fa.bvs;
+    const long n_push_warps = (units + 31) / 32;
+    if (gw >= n_push_warps) return 0;
+    warp_wait_flags(fa.acked, fa.is_receiver, fa.P, epoch_e - 1u, lane, fa.error);  // receivers consumed step e-1
+    unsigned int mine = 0;  // 32-unit groups this warp pushed
+    for (long pw = gw; pw < n_push_warps; pw += W, ++mine) {
         const long t = pw * 32 + lane;
-        if (t < total) {
-            long i, v;
-            if (fa.bvs == 1) { i = t; v = 0; }
-            else if (fa.layout == 1) { i = t / fa.bvs; v = t - i * fa.bvs; }
-            else { v = t / fa.n_send; i = t - v * fa.n_send; }
+        if (t < units) {
+            long i = t, v = 0;
+            if (!by_row && fa.bvs > 1) { v = t / fa.n_send; i = t - v * fa.n_send; }
             int q = 0;
             while (i >= fa.send_ptr[q + 1]) ++q;
             const long src = fa.perm ? fa.perm[fa.send_idx[i]] : fa.send_idx[i];
             const long k = fa.peer_base[q] + (i - fa.send_ptr[q]);
             VT *dst = reinterpret_cast<VT *>(fa.peer_x0[q]);
             if (fa.bvs == 1) dst[k] = x[src];
-            else if (fa.layout == 1) dst[k * fa.bvs + v] = x[src * fa.bvs + v];
-            else dst[k + v * fa.peer_ld[q]] = x[src + v * fa.ld];
-        }
-        __threadfence_system();
-        __syncwarp();
-        unsigned int last = 0;
-        if (lane == 0) last = (atomicAdd(&fa.counters[0], 1u) == (unsigned int)(n_push_warps - 1));
-        last = __shfl_sync(0xffffffffu, last, 0);
-        if (last) {
-            __threadfence_system();
-            if (lane < fa.P && fa.is_receiver[lane]) {
-                volatile unsigned int *f = reinterpret_cast<volatile unsigned int *>(fa.peer_arrived[lane]);
-                *f = epoch_e;
-            }
-            __threadfence_system();
+            else if (by_row) {
+                const int row_bytes = fa.bvs * (int)sizeof(VT);
+                if (row_bytes % 16 == 0) {  // rows of a 16-byte multiple are 16-byte aligned on both sides (buffers are 256-byte aligned)
+                    const int4 *sp = reinterpret_cast<const int4 *>(x + src * fa.bvs);
+                    int4 *dp = reinterpret_cast<int4 *>(dst + k * fa.bvs);
+                    for (int w = 0; w < row_bytes / 16; ++w) dp[w] = sp[w];
+                } else
+                    for (int w = 0; w < fa.bvs; ++w) dst[k * fa.bvs + w] = x[src * fa.bvs + w];
+            } else
+                dst[k + v * fa.peer_ld[q]] = x[src + v * fa.ld];
         }
     }
+    return mine;
+}
+
+// ONE system-scope fence per warp (every push of this warp is ordered before its counter update), then the warp that completes the
+// count raises the neighbours' `arrived` flags
+__device__ __forceinline__ void fused_push_signal(const FusedArgs &fa, const unsigned int mine, const int lane, const unsigned int epoch_e) {
+    const bool by_row = fa.bvs > 1 && fa.layout == 1;
+    const long units = by_row ? fa.n_send : fa.n_send * fa.bvs;
+    const unsigned int n_push_warps = (unsigned int)((units + 31) / 32);
+    __threadfence_system();
+    __syncwarp();
+    unsigned int last = 0;
+    if (lane == 0) last = (atomicAdd(&fa.counters[0], mine) + mine == n_push_warps);
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (last) {
+        __threadfence_system();
+        if (lane < fa.P && fa.is_receiver[lane]) {
+            volatile unsigned int *f = reinterpret_cast<volatile unsigned int *>(fa.peer_arrived[lane]);
+            *f = epoch_e;
+        }
+        __threadfence_system();
+    }
+}
+
+template <typename VT>
+__device__ __forceinline__ void fused_push(const FusedArgs &fa, const VT *__restrict__ x, const long gw, const long W, const int lane,
+                                           const unsigned int epoch_e) {
+    const unsigned int mine = fused_push_stores<VT>(fa, x, gw, W, lane, epoch_e);
+    if (mine) fused_push_signal(fa, mine, lane, epoch_e);
 }
 
 // (d) of the fused step: the last warp of the grid acknowledges consumption to the senders and closes the epoch
@@ -208,7 +238,7 @@ struct SpmvBody {
     int lane;
     typename A::acc_t acc;
     int y_rows = 0;  // BOUNDED: positions >= y_rows are not stored (y aliases the next x, whose tail holds the halo)
-    __device__ __forceinline__ void begin_chunk(int = 0) { acc = A::zero(); }
+    __device__ __forceinline__ void begin_chunk(int = 0, int = 0) { acc = A::zero(); }
     // Slot count at run time (predicated loads): measured FASTER than a switch over template-constant slot counts for the narrow
     // types on B200 (7-point 256^3, profiles/r02d_ab_stream.log: sp 162 vs 194 us, hp 150 vs 172 us, dp equal) although it executes
     // more instructions — ncu (profiles/r02e_*): the kernel is latency-, not issue-limited once the predication is gone
@@ -239,6 +269,59 @@ struct SpmvBody {
     }
 };
 
+// Body of the fused distributed SELL-32 SpMV (k_scs32_stream<..., FUSED>).  Interior and boundary chunks run through ONE stream
+// (boundary items follow the interior ones in the item list and carry header flag 8): the bulk copies of the first boundary chunks
+// are in flight while the last interior chunks are summed, instead of a cold ring restart after the flag wait.  The first boundary
+// chunk of a warp waits for the neighbours' `arrived` flags; boundary pieces gather x through L2 (ld.global.cg: a peer wrote the halo
+// during this kernel).  The warp's push is SIGNALLED (fence.sys + counter) after its first chunk, when its peer stores have long been
+// acknowledged — or before it waits for anybody else's, whichever comes first.
+template <typename VT, typename A, int LMAX>
+struct SpmvBodyFusedStream {
+    const VT *__restrict__ x;
+    VT *__restrict__ y;
+    int lane, y_rows;
+    const FusedArgs *fa;
+    unsigned int epoch_e, mine;
+    bool sig_pending, halo_ready, bnd;
+    typename A::acc_t acc;
+    __device__ __forceinline__ void signal() {
+        fused_push_signal(*fa, mine, lane, epoch_e);
+        sig_pending = false;
+    }
+    __device__ __forceinline__ void begin_chunk(int = 0, const int flags = 0) {
+        acc = A::zero();
+        bnd = (flags & 8) != 0;
+        if (bnd && !halo_ready) {
+            if (sig_pending) signal();  // never wait for a neighbour while one's own push is unpublished
+            warp_wait_flags(fa->arrived, fa->is_sender, fa->P, epoch_e, lane, fa->error);
+            halo_ready = true;
+        }
+    }
+    __device__ __forceinline__ void piece(const int ns, const VT *sv, const int *sc) {
+        VT xv[LMAX];
+        int col[LMAX];
+#pragma unroll
+        for (int j = 0; j < LMAX; ++j)
+            if (j < ns) col[j] = sc[j * 32];
+        if (bnd) {  // warp-uniform: only the gathers differ between interior and boundary pieces
+#pragma unroll
+            for (int j = 0; j < LMAX; ++j)
+                if (j < ns) xv[j] = __ldcg(x + col[j]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < LMAX; ++j)
+                if (j < ns) xv[j] = __ldg(x + col[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < LMAX; ++j)
+            if (j < ns) acc = A::mad(sv[j * 32], xv[j], acc);  // values read from the stage right before use (64-register budget)
+    }
+    __device__ __forceinline__ void end_chunk(const int chunk) {
+        if (chunk * 32 + lane < y_rows) y[(long)chunk * 32 + lane] = A::out(acc);
+        if (sig_pending) signal();
+    }
+};
+
 // SpMMV: Y = A X with BVS right-hand sides.  ROWWISE: X[col*BVS + v] (one vector load per gathered row); else X[col + v*ld].
 // Slots are consumed SB at a time so that SB*BVS gathered values are in flight per lane without blowing the register file.
 template <typename VT, typename A, int LMAX, int BVS, bool ROWWISE, bool COHERENT = false>
@@ -249,7 +332,7 @@ struct SpmmvBody {
     long ld;
     int lane;
     typename A::acc_t acc[BVS];
-    __device__ __forceinline__ void begin_chunk(int = 0) {
+    __device__ __forceinline__ void begin_chunk(int = 0, int = 0) {
 #pragma unroll
         for (int v = 0; v < BVS; ++v) acc[v] = A::zero();
     }
@@ -373,7 +456,7 @@ struct SpmmvBodyRowWide {
     VT *__restrict__ Y;
     int lane;
     typename A::acc_t acc[T][PER];
-    __device__ __forceinline__ void begin_chunk(int = 0) {
+    __device__ __forceinline__ void begin_chunk(int = 0, int = 0) {
 #pragma unroll
         for (int k = 0; k < T; ++k)
 #pragma unroll
@@ -447,9 +530,15 @@ __device__ __forceinline__ void stream_items(unsigned char *base, uint64_t *bars
                                              const int first, const int lane, const int n_items, const int *__restrict__ chunk_list,
                                              const int chunk_offset, const int *__restrict__ chunk_ptrs,
                                              const int *__restrict__ chunk_lengths, const int *__restrict__ col_idxs,
-                                             const VT *__restrict__ values, Body &body, const uint64_t pol) {
+                                             const VT *__restrict__ values, Body &body, const uint64_t pol, const int n_split = -1,
+                                             const int *__restrict__ chunk_list2 = nullptr, const int chunk_offset2 = 0) {
     using R = WarpRing<VT, LMAX, D>;
-    auto item_chunk = [&](int k) -> int { return chunk_list ? chunk_list[k] : k + chunk_offset; };  // 32-bit index math throughout
+    // n_split >= 0: items [n_split, n_items) come from a SECOND list (chunk_list2 / chunk_offset2) and carry header flag 8 — the
+    // boundary chunks of the fused distributed step, appended to the interior ones so that the ring never drains between them
+    auto item_chunk = [&](int k) -> int {  // 32-bit index math throughout
+        if (n_split >= 0 && k >= n_split) return chunk_list2 ? chunk_list2[k - n_split] : k - n_split + chunk_offset2;
+        return chunk_list ? chunk_list[k] : k + chunk_offset;
+    };
 
     // ---- producer state (meaningful in lane 0 only) --------------------------------------------------
     // Three-deep metadata lookahead so that no load issued by lane 0 is consumed in the same piece:
@@ -480,7 +569,7 @@ __device__ __forceinline__ void stream_items(unsigned char *base, uint64_t *bars
         }
         const int ns = min(LMAX, plen - pj);
         h.ns = ns;
-        h.flags = 4 | (pj == 0 ? 1 : 0) | (pj + ns >= plen ? 2 : 0);
+        h.flags = 4 | (pj == 0 ? 1 : 0) | (pj + ns >= plen ? 2 : 0) | ((n_split >= 0 && pc >= n_split) ? 8 : 0);
         h.chunk = pchunk;
         h.pad = 0;
         hdrs[s] = h;
@@ -517,7 +606,7 @@ __device__ __forceinline__ void stream_items(unsigned char *base, uint64_t *bars
     for (int s = 0;; s = (s + 1 == D) ? 0 : s + 1) {
         const PieceHdr h = hdrs[s];
         if (h.flags == 0) break;
-        if (h.flags & 1) body.begin_chunk(h.chunk);
+        if (h.flags & 1) body.begin_chunk(h.chunk, h.flags);
         if (h.ns > 0) {
             mbar_wait(&bars[s], (phase_bits >> s) & 1u);
             phase_bits ^= (1u << s);
@@ -629,7 +718,8 @@ template <typename VT, typename A, int LMAX, int D, int WARPS, bool UNPERM, bool
 __global__ void __launch_bounds__(WARPS * 32, (1024 / (WARPS * 32)) > 0 ? (1024 / (WARPS * 32)) : 1)  // <= 64 registers: 32 warps/SM
 k_scs32_stream(long n_items, const int *__restrict__ chunk_list, int chunk_offset, const int *__restrict__ chunk_ptrs,
                const int *__restrict__ chunk_lengths, const int *__restrict__ col_idxs, const VT *__restrict__ values,
-               const VT *__restrict__ x, VT *__restrict__ y, const int *__restrict__ new_to_old, const FusedArgs fa) {
+               const VT *__restrict__ x, VT *__restrict__ y, const int *__restrict__ new_to_old, const __grid_constant__ FusedArgs fa) {
+    // (__grid_constant__: the fused body keeps a POINTER to the argument block; without it taking the address copies the struct to the stack)
     using R = WarpRing<VT, LMAX, D>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -653,22 +743,16 @@ k_scs32_stream(long n_items, const int *__restrict__ chunk_list, int chunk_offse
         stream_items<VT, LMAX, D>(base, bars, hdrs, phase_bits, (int)W, (int)gw, lane, (int)n_items, chunk_list, chunk_offset,
                                   chunk_ptrs, chunk_lengths, col_idxs, values, body, pol);
     } else {
-        // (a) push this rank's elements into the neighbours' x tails
+        // (a) store this rank's elements into the neighbours' x tails (published after this warp's first chunk, see the body)
         const unsigned int epoch_e = ld_flag(fa.epoch) + 1u;
-        fused_push<VT>(fa, x, gw, W, lane, epoch_e);
-        // (b) interior chunks: no halo column, identical code path to the single-GPU kernel
-        {
-            SpmvBody<VT, A, LMAX, UNPERM, false, true> body{x, y, new_to_old, lane, A::zero(), fa.y_rows};
-            stream_items<VT, LMAX, D>(base, bars, hdrs, phase_bits, (int)W, (int)gw, lane, (int)fa.n_int, fa.int_list, fa.int_off,
-                                      chunk_ptrs, chunk_lengths, col_idxs, values, body, pol);
-        }
-        // (c) boundary chunks once the neighbours' elements for this step have landed in our x tail
-        if (gw < fa.n_bnd) {
-            warp_wait_flags(fa.arrived, fa.is_sender, fa.P, epoch_e, lane, fa.error);
-            SpmvBody<VT, A, LMAX, UNPERM, true, true> body{x, y, new_to_old, lane, A::zero(), fa.y_rows};
-            stream_items<VT, LMAX, D>(base, bars, hdrs, phase_bits, (int)W, (int)gw, lane, (int)fa.n_bnd, fa.bnd_list, fa.bnd_off, chunk_ptrs,
-                                      chunk_lengths, col_idxs, values, body, pol);
-        }
+        const unsigned int mine = fused_push_stores<VT>(fa, x, gw, W, lane, epoch_e);
+        // (b) + (c) interior chunks, then — in the same stream — the boundary chunks once the neighbours' elements have landed
+        SpmvBodyFusedStream<VT, A, LMAX> body;
+        body.x = x; body.y = y; body.lane = lane; body.y_rows = fa.y_rows; body.fa = &fa; body.epoch_e = epoch_e; body.mine = mine;
+        body.sig_pending = mine > 0; body.halo_ready = false; body.bnd = false; body.acc = A::zero();
+        stream_items<VT, LMAX, D>(base, bars, hdrs, phase_bits, (int)W, (int)gw, lane, (int)(fa.n_int + fa.n_bnd), fa.int_list, fa.int_off, chunk_ptrs,
+                                  chunk_lengths, col_idxs, values, body, pol, (int)fa.n_int, fa.bnd_list, fa.bnd_off);
+        if (body.sig_pending) body.signal();  // a warp without any chunk still publishes its push
         // (d) the last warp of the grid acknowledges consumption to the senders and closes the epoch
         fused_finish(fa, W, lane, epoch_e);
     }
@@ -691,7 +775,7 @@ struct WideBody {
     int lane;
     int y_rows = 0;  // BOUNDED: positions >= y_rows are not stored (y aliases the next x, whose tail holds the halo)
     typename A::acc_t acc[H];
-    __device__ __forceinline__ void begin_chunk(int = 0) {
+    __device__ __forceinline__ void begin_chunk(int = 0, int = 0) {
 #pragma unroll
         for (int h = 0; h < H; ++h) acc[h] = A::zero();
     }

@@ -46,6 +46,8 @@ def parse_args():
     ap.add_argument("--no-numa-bind", action="store_true", help="e2e: do not restrict the CPU affinity to the GPU's NUMA node while allocating pinned buffers")
     ap.add_argument("--strong", action="store_true", help="N>1: ONE n^3 grid cut into N z-slabs (config 5) instead of n^3 per GPU")
     ap.add_argument("--no-overlap", action="store_true", help="N>1: exchange first, then one full SpMV (the reference's order)")
+    ap.add_argument("--p2p-mode", type=int, default=2, choices=[0, 1, 2],
+                    help="N>1, --halo p2p: 2 = ONE fused kernel per step, 1 = push / wait kernels next to the interior kernel, 0 = exchange first")
     ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"], help="N>1: NVLink peer stores + epoch flags, or NCCL send/recv")
     ap.add_argument("--bvs", type=int, default=1, help="block_vec_size > 1: SpMMV (config 3), block-vector halo exchange when N>1")
     ap.add_argument("--layout", default="rowwise", choices=["rowwise", "colwise"], help="block vector layout for --bvs > 1")
@@ -350,7 +352,15 @@ def checked(runner, vt, world):
     return bool(err <= tol), err, tol
 
 
-def other_config(pkg, ctx, args, rank, world, local_rank, peak, name, make_runner, vt, bvs=1, steps=None):
+def traffic_of(key):
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if key and os.path.exists(tp):
+        with open(tp) as f:
+            return json.load(f).get(key)
+    return None
+
+
+def other_config(pkg, ctx, args, rank, world, local_rank, peak, name, make_runner, vt, bvs=1, steps=None, traffic_key=None):
     """One more BASELINE.json config measured with the headline's protocol: build, validate, time, roofline."""
     import torch
     capi = pkg.capi
@@ -375,7 +385,9 @@ def other_config(pkg, ctx, args, rank, world, local_rank, peak, name, make_runne
     out = {"config": name, "value": 2.0 * nnz_total / (ms / 1e3) / 1e9, "unit": UNIT, "ms_per_step": ms, "steps": steps, "n_gpus": world,
            "dtype": {"dp": "f64", "sp": "f32", "hp": "f16"}[vt], "validated": ok, "max_rel_err": err, "tolerance": tol,
            "nnz": int(nnz_total), "gbs": bytes_total / (ms / 1e3) / 1e9,
-           "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+           "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic_of(traffic_key),
+                        "traffic_source": "a committed ncu capture of this kernel on this workload (profiles/traffic.json), NOT measured in this run"
+                                          if traffic_of(traffic_key) else None,
                         "kernel": runner.kernel_name, "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": int(bytes_local)},
            "gpu_launches": int(launches), "clocks": clocks, "build_s": round(build_s, 2)}
     extra = getattr(runner, "describe", None)
@@ -424,7 +436,8 @@ def run_ours(args):
     elif world == 1 and not block_or_solve:
         runner = pkg.engine.SingleGpuSpmv(ctx, pts, n, args.C, args.sigma, vt)
     else:
-        runner = pkg.dist.DistributedSpmv(ctx, pts, n, args.C, args.sigma, vt, rank, world, halo=args.halo, overlap=not args.no_overlap,
+        runner = pkg.dist.DistributedSpmv(ctx, pts, n, args.C, args.sigma, vt, rank, world, halo=args.halo,
+                                          overlap=(False if args.no_overlap else (True if args.p2p_mode == 2 else args.p2p_mode)),
                                           strong=args.strong, bvs=args.bvs, layout=args.layout,
                                           n_buf=2 if (args.solve or (args.bvs == 1 and args.halo == "p2p")) else 1)
     p2p = getattr(runner, "p2p", None)
@@ -554,7 +567,8 @@ def run_ours(args):
                         f"config 4: power-law matrix 2^{args.config4_log2_rows} rows, ap[dp_sp_hp] t1=1.0 t2=1e-2, scs C=32 sigma=512, plan={plan}",
                         lambda plan=plan: build_powerlaw_ap(pkg, ctx, args.config4_log2_rows, "ap[dp_sp_hp]", 32, 512, rank, world, plan=plan,
                                                             alg_bytes=(others[-1]["roofline"]["algorithmic_bytes_per_launch"] if plan == "banded" else None))[0],
-                        "dp", steps=max(10, min(args.steps, 50))))
+                        "dp", steps=max(10, min(args.steps, 50)),
+                        traffic_key=(f"config4|powerlaw_{args.config4_log2_rows}|ap[dp_sp_hp]|C32|s512" if plan == "fused" else None)))
         elif not args.strong and pts == 7:
             n5 = args.config5_n
             if n5 % world == 0:

@@ -15,6 +15,10 @@ template <int V> __device__ __forceinline__ double ld(const double *p) {
     else if (V == 5) asm volatile("ld.global.cs.f64 %0, [%1];" : "=d"(v) : "l"(p));
     else if (V == 6) asm volatile("ld.global.L1::evict_first.f64 %0, [%1];" : "=d"(v) : "l"(p));
     else if (V == 7) asm volatile("ld.global.relaxed.gpu.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    else if (V == 8) asm volatile("ld.global.nc.L2::64B.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    else if (V == 9) asm volatile("ld.global.L2::64B.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    else if (V == 10) asm volatile("ld.global.nc.L2::128B.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    else if (V == 11) asm volatile("ld.global.nc.L1::no_allocate.L2::64B.f64 %0, [%1];" : "=d"(v) : "l"(p));
     return v;
 }
 template <int V, int U>
@@ -55,15 +59,17 @@ int main() {
     const long n = 1L << 28;
     int *idx; cudaMalloc(&idx, n * 4);
     double *out; cudaMalloc(&out, 64);
-    const char *names[8] = {"ld.global.nc (__ldg)", "ld.global", "ld.global.cg", "ld.global.nc.L1::no_allocate", "ld.global.L1::no_allocate", "ld.global.cs",
-                            "ld.global.L1::evict_first", "ld.global.relaxed.gpu"};
+    const char *names[12] = {"ld.global.nc (__ldg)", "ld.global", "ld.global.cg", "ld.global.nc.L1::no_allocate", "ld.global.L1::no_allocate", "ld.global.cs",
+                             "ld.global.L1::evict_first", "ld.global.relaxed.gpu", "ld.global.nc.L2::64B", "ld.global.L2::64B", "ld.global.nc.L2::128B",
+                             "ld.global.nc.L1::no_allocate.L2::64B"};
     for (long mb : {268, 1024}) {
         const long m = mb * 1024 * 1024 / 8;
         double *x; cudaMalloc(&x, m * 8); cudaMemset(x, 0, m * 8);
         k_fill<<<(unsigned)((n + 255) / 256), 256>>>(idx, n, m);
-        float t[8] = {run<0>(idx, x, n, out, sm * 8), run<1>(idx, x, n, out, sm * 8), run<2>(idx, x, n, out, sm * 8), run<3>(idx, x, n, out, sm * 8),
-                      run<4>(idx, x, n, out, sm * 8), run<5>(idx, x, n, out, sm * 8), run<6>(idx, x, n, out, sm * 8), run<7>(idx, x, n, out, sm * 8)};
-        for (int v = 0; v < 8; ++v) printf("table %4ld MB  %-32s %.1f G gathers/s\n", mb, names[v], n / t[v] / 1e6);
+        float t[12] = {run<0>(idx, x, n, out, sm * 8), run<1>(idx, x, n, out, sm * 8), run<2>(idx, x, n, out, sm * 8), run<3>(idx, x, n, out, sm * 8),
+                       run<4>(idx, x, n, out, sm * 8), run<5>(idx, x, n, out, sm * 8), run<6>(idx, x, n, out, sm * 8), run<7>(idx, x, n, out, sm * 8),
+                       run<8>(idx, x, n, out, sm * 8), run<9>(idx, x, n, out, sm * 8), run<10>(idx, x, n, out, sm * 8), run<11>(idx, x, n, out, sm * 8)};
+        for (int v = 0; v < 12; ++v) printf("table %4ld MB  %-32s %.1f G gathers/s\n", mb, names[v], n / t[v] / 1e6);
         cudaFree(x);
     }
     return 0;

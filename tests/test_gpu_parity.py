@@ -413,3 +413,38 @@ def test_device_ingest_and_equilibrate(eng, orc, name):
 def test_device_ingest_rejects_out_of_range(eng, pkg):
     with pytest.raises(pkg.capi.UspmvError, match="outside"):
         eng.MtxData.from_entries(4, 4, [0, 5], [0, 1], [1.0, 2.0], False)
+
+
+@pytest.mark.parametrize("n", [4097, 4128, 33, 64])
+def test_spmv_hp_pair_kernel(eng, pkg, orc, mats, n):
+    """fp16, C = 32: the kernel that takes two adjacent chunks per work item (k_scs32_stream_pair): chunks longer than a stage (slices),
+    empty chunks, an odd number of chunks (no chunk B at the tail), the un-permuted form — bit-identical to the oracle and to the
+    one-chunk kernel."""
+    t = torch_()
+    rng = np.random.default_rng(n)
+    cnt = rng.integers(0, 9, n)
+    cnt[rng.choice(n, max(1, n // 40), replace=False)] = rng.integers(17, 60, max(1, n // 40))   # chunks longer than 16 slots
+    cnt[: min(n, 96)] = 0                                                                        # whole empty chunks
+    I = np.repeat(np.arange(n), cnt).astype(np.int32)
+    J = rng.integers(0, n, len(I)).astype(np.int32)
+    V = rng.uniform(0.05, 1.0, len(I))
+    coo = (n, n, I, J, V)
+    for sigma in (1, 128):
+        scs, ref = build_both(eng, orc, coo, 32, sigma, "hp")
+        x = rng.uniform(0.1, 1.0, n)
+        xp, y = run_spmv(eng, scs, ref, x, "hp")
+        y_ref = orc.spmv_scs(ref, xp)
+        assert np.array_equal(y.view(np.uint8), y_ref.view(np.uint8)), (n, sigma)
+        pkg.capi.set_option("pair_hp", 0)
+        try:
+            _, y1 = run_spmv(eng, scs, ref, x, "hp")
+        finally:
+            pkg.capi.set_option("pair_hp", 1)
+        assert np.array_equal(y.view(np.uint8), y1.view(np.uint8)), (n, sigma)
+    scs, ref = build_both(eng, orc, coo, 32, 128, "hp", permute=False)
+    xh = rng.uniform(0.1, 1.0, n).astype(np.float16)
+    yu = t.full((n,), 7.0, dtype=t.float16, device="cuda")
+    eng.spmv_unpermuted(scs, dev(xh), yu)
+    t.cuda.synchronize()
+    y_ref_perm = orc.spmv_scs(ref, np.concatenate([xh, np.zeros(ref.n_rows_padded, np.float16)]))
+    assert np.array_equal(yu.cpu().numpy().view(np.uint8), y_ref_perm[ref.old_to_new].view(np.uint8))

@@ -826,7 +826,18 @@ int uspmv_p2p_spmmv(uspmv_p2p *p, const uspmv_scs *scs, int x_buf, void *Y_d, vo
         cudaStream_t main = as_stream(stream), comm = as_stream(comm_stream);
         const int P = h->P;
         const void *X = p->buffer(x_buf);
-        if (p->mode == 2 && spmmv_fused_supported(scs, p->bvs) && P <= 32) {  // ONE fused kernel: push, interior, wait, boundary, ack
+        if (h->n_send == 0 && h->n_halo == 0) {  // no neighbour at all (one rank): the tuned single-GPU kernel, then close the epoch
+            if (uspmv_spmmv(scs, X, Y_d, p->bvs, p->vec_length, p->layout, stream)) throw Error(uspmv_last_error());
+            k_p2p_ack<<<1, 256, 0, main>>>(P, p->is_sender_d.p, p->peer_acked.p, p->epoch);
+            USPMV_LAUNCH_CHECK();
+            return;
+        }
+        // ONE fused kernel (push, interior, wait, boundary, ack) where it measured faster than the push / wait kernels next to the
+        // interior kernel: column-major block vectors (N = 2, 256^3 slab, dp bvs 4: 0.483 vs 0.503 ms).  For row-major block vectors
+        // the fused instance of the wide-row body is slower (dp bvs 8: 0.806 vs 0.651 ms, sp bvs 8: 0.556 vs 0.408;
+        // profiles/r02k_n2_*.json), so they keep the multi-kernel overlap unless "mmv_fused_rowwise" asks for the fused kernel.
+        const bool fused_wanted = p->mode == 2 && (p->layout == USPMV_COLWISE || options().mmv_fused_rowwise);
+        if (fused_wanted && spmmv_fused_supported(scs, p->bvs) && P <= 32) {
             stream::FusedArgs fa{};
             fa.n_int = (long)scs->interior_chunks.n;
             fa.n_bnd = (long)scs->boundary_chunks.n;

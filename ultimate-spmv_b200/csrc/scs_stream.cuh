@@ -866,6 +866,133 @@ k_scsw_stream(int n_items, const int *__restrict__ chunk_list, int chunk_offset,
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Narrow value types, short chunks: TWO consecutive SELL-32 chunks per work item ("pair" kernel, used for fp16).
+// ncu on the fp16 instance of k_scs32_stream (profiles/r02e_*): 240 warp instructions per 7-slot piece at IPC 3.0 — a piece carries
+// only 1.3 KB, so the per-piece cost (producer, barrier wait, header) is paid per 1.3 KB and each lane has at most 7 gathers in flight.
+// Chunks 2k and 2k + 1 are adjacent in memory (chunk_ptrs[c + 1] = chunk_ptrs[c] + len * 32), so their len_A + len_B slots form ONE
+// contiguous run that is cut into pieces of <= LMAX (16) slots: one pair of bulk copies, one barrier wait and one producer step now
+// serve up to 14-16 slots, and up to 16 gathers are in flight per lane.  Inside a piece slots [0, a) belong to chunk A, [a, ns) to
+// chunk B; each lane runs ONE accumulator chain in slot order and switches from A's sum to B's at slot a — per row the FMA order is
+// the storage order, bit-identical to the one-chunk kernel and the oracle.  Lean loop form (warp-uniform producer, see stream_items_u).
+// ---------------------------------------------------------------------------------------------------------------------
+template <typename VT, typename A, int LMAX, int D, int WARPS, bool UNPERM>
+__global__ void __launch_bounds__(WARPS * 32, (1024 / (WARPS * 32)) > 0 ? (1024 / (WARPS * 32)) : 1)
+k_scs32_stream_pair(int n_chunks, int chunk_offset, const int *__restrict__ chunk_ptrs, const int *__restrict__ col_idxs,
+                    const VT *__restrict__ values, const VT *__restrict__ x, VT *__restrict__ y, const int *__restrict__ new_to_old) {
+    using R = WarpRing<VT, LMAX, D>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char *base = smem_raw + (size_t)warp * R::BYTES_ALIGNED;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(base + D * R::STAGE_BYTES);
+    const int W = (int)gridDim.x * WARPS;
+    const int first = (int)blockIdx.x * WARPS + warp;
+    const int n_items = (n_chunks + 1) / 2;
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < D; ++s) mbar_init(&bars[s], 1);
+        fence_barrier_init();
+    }
+    __syncwarp();
+    if (first >= n_items) return;
+    const uint64_t pol = policy_evict_first();
+
+    // ---- producer (warp-uniform state): item k = chunks 2k, 2k + 1 of the range; lengths from the pointer differences --------------
+    auto load_item = [&](const int k, int &cs, int &la, int &lb) {
+        const int c = chunk_offset + 2 * k;
+        const int p0 = __ldg(chunk_ptrs + c), p1 = __ldg(chunk_ptrs + c + 1);
+        const int p2 = (2 * k + 1 < n_chunks) ? __ldg(chunk_ptrs + c + 2) : p1;
+        cs = p0; la = (p1 - p0) >> 5; lb = (p2 - p1) >> 5;
+    };
+    int pc = first, pj = 0, pcs, pla, plb, ncs = 0, nla = 0, nlb = 0;
+    load_item(pc, pcs, pla, plb);
+    if (pc + W < n_items) load_item(pc + W, ncs, nla, nlb);
+    struct PairReg { int ns, a, flags, item; };  // flags: 1 A begins, 2 A ends, 4 B begins, 8 B ends, 16 valid
+    PairReg hdr[D];
+    auto issue = [&](const int s) {
+        if (pc >= n_items) {
+            hdr[s].ns = 0; hdr[s].a = 0; hdr[s].flags = 0; hdr[s].item = 0;
+            return;
+        }
+        const int tot = pla + plb;
+        const int ns = min(LMAX, tot - pj);
+        const int a = max(0, min(ns, pla - pj));            // slots of chunk A in this piece
+        int f = 16;
+        if (pj == 0) f |= 1;                                 // A begins with the item
+        if (pj <= pla && pj + ns >= pla) f |= 2 | 4;         // A's last slot (or an empty A) lies in this piece: A ends, B begins
+        if (pj + ns >= tot) f |= 8;                          // B ends
+        hdr[s].ns = ns; hdr[s].a = a; hdr[s].flags = f; hdr[s].item = pc;
+        if (ns > 0 && lane == 0) {
+            const int e0 = pcs + pj * 32;
+            const uint32_t vb = (uint32_t)ns * 32u * (uint32_t)sizeof(VT), cb = (uint32_t)ns * 128u;
+            unsigned char *st = base + s * R::STAGE_BYTES;
+            mbar_expect_tx(&bars[s], vb + cb);
+            bulk_g2s(st, values + e0, vb, &bars[s], pol);
+            bulk_g2s(st + R::VAL_BYTES, col_idxs + e0, cb, &bars[s], pol);
+        }
+        pj += ns;
+        if (pj >= tot) {
+            pc += W;
+            pj = 0;
+            pcs = ncs; pla = nla; plb = nlb;
+            if (pc + W < n_items) load_item(pc + W, ncs, nla, nlb);
+        }
+    };
+#pragma unroll
+    for (int s = 0; s < D; ++s) issue(s);
+
+    // ---- consumer ------------------------------------------------------------------------------------------------------------------
+    uint32_t phase_bits = 0;
+    typename A::acc_t accA = A::zero(), accB = A::zero();
+    auto store = [&](const int chunk, const typename A::acc_t acc) {
+        if (chunk >= chunk_offset + n_chunks) return;  // the odd tail has no chunk B
+        const long row = (long)chunk * 32 + lane;
+        if (UNPERM) {
+            const int o = new_to_old[row];
+            if (o >= 0) y[o] = A::out(acc);
+        } else
+            y[row] = A::out(acc);
+    };
+    bool running = true;
+    while (running) {
+#pragma unroll
+        for (int s = 0; s < D; ++s) {
+            const PairReg h = hdr[s];
+            if (h.flags == 0) { running = false; break; }
+            if (h.flags & 1) accA = A::zero();
+            if (h.flags & 4) accB = A::zero();
+            if (h.ns > 0) {
+                mbar_wait(&bars[s], (phase_bits >> s) & 1u);
+                phase_bits ^= (1u << s);
+                const VT *sv = reinterpret_cast<const VT *>(base + s * R::STAGE_BYTES) + lane;
+                const int *sc = reinterpret_cast<const int *>(base + s * R::STAGE_BYTES + R::VAL_BYTES) + lane;
+                int col[LMAX];
+                VT xv[LMAX];
+#pragma unroll
+                for (int j = 0; j < LMAX; ++j)
+                    if (j < h.ns) col[j] = sc[j * 32];
+#pragma unroll
+                for (int j = 0; j < LMAX; ++j)
+                    if (j < h.ns) xv[j] = __ldg(x + col[j]);
+                // one chain in slot order; at slot a it leaves chunk A's sum and continues chunk B's
+                typename A::acc_t acc = h.a > 0 ? accA : accB;
+#pragma unroll
+                for (int j = 0; j < LMAX; ++j)
+                    if (j < h.ns) {
+                        if (j == h.a && j > 0) { accA = acc; acc = accB; }
+                        acc = A::mad(sv[j * 32], xv[j], acc);
+                    }
+                if (h.a == h.ns) accA = acc; else accB = acc;
+            }
+            const int cA = chunk_offset + 2 * h.item;
+            if (h.flags & 2) store(cA, accA);
+            if (h.flags & 8) store(cA + 1, accB);
+            __syncwarp();  // every lane has read stage s before it is refilled
+            issue(s);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // Narrow chunks: C = 32 / G (G = 2, 4: C = 16 — a half-warp —, 8).  A warp takes G ADJACENT chunks at once (work item k = chunks
 // G k ... G k + G - 1 of a contiguous chunk range): lane l belongs to sub-chunk g = l / C, so the 32 rows of an item are the 32
 // consecutive padded rows 32 k + l.  Every piece covers the same slot window [pj, pj + 8) of all G sub-chunks; sub-chunk g

@@ -316,6 +316,25 @@ void launch_stream_wide(long n_chunks, const int *list, int off, const int *cp, 
     kern<<<(unsigned)grid, WARPS * 32, smem, st>>>((int)n_chunks, list, off, cp, cl, ci, v, x, y, n2o, stream::FusedArgs{});
 }
 
+// C = 32, fp16: two adjacent chunks per work item, pieces of up to 16 slots (scs_stream.cuh, k_scs32_stream_pair); contiguous ranges only
+template <typename VT, bool UNPERM>
+void launch_stream_pair(long n_chunks, int off, const int *cp, const int *ci, const VT *v, const VT *x, VT *y, const int *n2o, cudaStream_t st) {
+    constexpr int LMAX = 16, D = 2, WARPS = 16;
+    using R = stream::WarpRing<VT, LMAX, D>;
+    auto kern = stream::k_scs32_stream_pair<VT, Arith<VT>, LMAX, D, WARPS, UNPERM>;
+    constexpr int smem = WARPS * R::BYTES_ALIGNED;
+    static bool configured_on[uspmv::MAX_DEVICES] = {};
+    const int dev = uspmv::current_device();
+    if (!configured_on[dev]) {
+        USPMV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured_on[dev] = true;
+    }
+    long grid = (long)sm_count(dev) * options().stream_blocks_per_sm;
+    const long need = ((n_chunks + 1) / 2 + WARPS - 1) / WARPS;
+    if (grid > need) grid = need;
+    kern<<<(unsigned)grid, WARPS * 32, smem, st>>>((int)n_chunks, off, cp, ci, v, x, y, n2o);
+}
+
 // C = 16 / 8: the narrow-chunk streamed kernel (scs_stream.cuh, k_scsn_stream); contiguous chunk ranges only
 template <typename VT, bool UNPERM, int G, int WARPS = 16>
 void launch_stream_narrow(long n_chunks, int off, const int *cp, const int *cl, const int *ci, const VT *v, const VT *x, VT *y, const int *n2o,
@@ -494,6 +513,15 @@ void launch_scs(long C, long n_chunks, const int *cp, const int *cl, const int *
     const VT *v = static_cast<const VT *>(vals);
     const VT *xx = static_cast<const VT *>(x);
     VT *yy = static_cast<VT *>(y);
+    if constexpr (sizeof(VT) == 2) {
+        // fp16: pieces of two adjacent chunks (contiguous chunk ranges; chunk lists — longest-first order, interior / boundary
+        // subsets — keep the one-chunk kernel)
+        if (C == 32 && options().scs_stream && options().pair_hp && !list && options().stream_variant == 0) {
+            launch_stream_pair<VT, UNPERM>(n_chunks, off, cp, ci, v, xx, yy, n2o, st);
+            USPMV_LAUNCH_CHECK();
+            return;
+        }
+    }
     if (C == 32 && options().scs_stream) {
         launch_stream<VT, UNPERM>(n_chunks, list, off, cp, cl, ci, v, xx, yy, n2o, st);
         USPMV_LAUNCH_CHECK();

@@ -429,22 +429,24 @@ def test_spmv_hp_pair_kernel(eng, pkg, orc, mats, n):
     J = rng.integers(0, n, len(I)).astype(np.int32)
     V = rng.uniform(0.05, 1.0, len(I))
     coo = (n, n, I, J, V)
-    for sigma in (1, 128):
-        scs, ref = build_both(eng, orc, coo, 32, sigma, "hp")
-        x = rng.uniform(0.1, 1.0, n)
-        xp, y = run_spmv(eng, scs, ref, x, "hp")
-        y_ref = orc.spmv_scs(ref, xp)
-        assert np.array_equal(y.view(np.uint8), y_ref.view(np.uint8)), (n, sigma)
-        pkg.capi.set_option("pair_hp", 0)
-        try:
+    pkg.capi.set_option("pair_hp", 1)  # off by default (not faster); the kernel stays covered here
+    try:
+        for sigma in (1, 128):
+            scs, ref = build_both(eng, orc, coo, 32, sigma, "hp")
+            x = rng.uniform(0.1, 1.0, n)
+            xp, y = run_spmv(eng, scs, ref, x, "hp")
+            y_ref = orc.spmv_scs(ref, xp)
+            assert np.array_equal(y.view(np.uint8), y_ref.view(np.uint8)), (n, sigma)
+            pkg.capi.set_option("pair_hp", 0)
             _, y1 = run_spmv(eng, scs, ref, x, "hp")
-        finally:
             pkg.capi.set_option("pair_hp", 1)
-        assert np.array_equal(y.view(np.uint8), y1.view(np.uint8)), (n, sigma)
-    scs, ref = build_both(eng, orc, coo, 32, 128, "hp", permute=False)
-    xh = rng.uniform(0.1, 1.0, n).astype(np.float16)
-    yu = t.full((n,), 7.0, dtype=t.float16, device="cuda")
-    eng.spmv_unpermuted(scs, dev(xh), yu)
-    t.cuda.synchronize()
+            assert np.array_equal(y.view(np.uint8), y1.view(np.uint8)), (n, sigma)
+        scs, ref = build_both(eng, orc, coo, 32, 128, "hp", permute=False)
+        xh = rng.uniform(0.1, 1.0, n).astype(np.float16)
+        yu = t.full((n,), 7.0, dtype=t.float16, device="cuda")
+        eng.spmv_unpermuted(scs, dev(xh), yu)
+        t.cuda.synchronize()
+    finally:
+        pkg.capi.set_option("pair_hp", 0)
     y_ref_perm = orc.spmv_scs(ref, np.concatenate([xh, np.zeros(ref.n_rows_padded, np.float16)]))
     assert np.array_equal(yu.cpu().numpy().view(np.uint8), y_ref_perm[ref.old_to_new].view(np.uint8))

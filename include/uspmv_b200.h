@@ -50,6 +50,11 @@ long uspmv_kernel_launches(void);
  *                             where padding's column 0 is GLOBAL column 0 and so becomes one spurious halo element
  *                             received from rank 0 on every rank > 0 (utilities.hpp:1991-2002, mpi_funcs.hpp:279-283) */
 int uspmv_set_option(const char *name, long value);
+/* The knobs are per CONTEXT: uspmv_set_option changes the process defaults AND every live context; uspmv_ctx_set_option changes one
+ * context only, so two contexts in one process (two GPUs, two solver instances) can run different variants.  get reads them back
+ * (ctx == NULL: the process defaults). */
+int uspmv_ctx_set_option(uspmv_ctx *ctx, const char *name, long value);
+int uspmv_ctx_get_option(const uspmv_ctx *ctx, const char *name, long *out);
 
 /* ---- context and device memory --------------------------------------------------------------- */
 /* cudaGetDeviceCount + cudaSetDevice(rank % ndev) in the reference: main.cpp:1838-1842 */

@@ -236,3 +236,39 @@ def test_harness_adapter_through_the_reference_typedefs(eng, layout):
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count(" OK ") == 5 and "FAILED" not in r.stdout, r.stdout
+
+
+def test_options_are_per_context(eng, pkg, orc, mats):
+    """Two contexts in one process can run different kernel variants (uspmv_ctx_set_option); uspmv_set_option still reaches every live
+    context; the results are identical either way (the variants are bit-identical)."""
+    t = _t()
+    capi = pkg.capi
+    a, b = eng.Context(0), eng.Context(0)
+
+    def get(ctx, name):
+        v = C.c_long(-99)
+        capi.call("uspmv_ctx_get_option", ctx.h if ctx else None, name.encode(), C.byref(v))
+        return v.value
+    assert get(a, "scs_stream") == 1 and get(b, "scs_stream") == 1
+    capi.call("uspmv_ctx_set_option", a.h, b"scs_stream", 0)          # context a: the direct-load kernel
+    capi.call("uspmv_ctx_set_option", b.h, b"stream_variant", 6)      # context b: another instantiation of the streamed kernel
+    assert (get(a, "scs_stream"), get(b, "scs_stream"), get(None, "scs_stream")) == (0, 1, 1)
+    assert (get(a, "stream_variant"), get(b, "stream_variant")) == (0, 6)
+    coo = mats.random_coo(5000, 7, seed=2)
+    ref = orc.convert_to_scs(*coo, 32, 64, "dp")
+    orc.permute_scs_cols(ref, ref.old_to_new)
+    x = np.random.default_rng(1).uniform(-1, 1, ref.n_rows_padded)
+    y_ref = orc.spmv_scs(ref, x)
+    launches = []
+    for ctx in (a, b):
+        scs = eng.convert_to_scs(eng.MtxData.from_host(*coo, ctx=ctx), 32, 64, "dp")
+        eng.permute_scs_cols(scs)
+        yd = t.zeros(ref.n_rows_padded, dtype=t.float64, device="cuda")
+        eng.spmv(scs, dev(x), yd)
+        t.cuda.synchronize()
+        assert np.array_equal(yd.cpu().numpy(), y_ref)
+        launches.append(scs)
+    capi.set_option("stream_variant", 0)                               # process-wide: defaults and every live context
+    assert (get(a, "stream_variant"), get(b, "stream_variant"), get(None, "stream_variant")) == (0, 0, 0)
+    assert get(a, "scs_stream") == 0                                   # a context-level choice survives an unrelated global change
+    capi.call("uspmv_ctx_set_option", a.h, b"scs_stream", 1)

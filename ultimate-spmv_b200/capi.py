@@ -34,6 +34,8 @@ lib.uspmv_kernel_launches.restype = C.c_long
 vp = C.c_void_p
 _sigs = {
     "uspmv_set_option": [C.c_char_p, C.c_long],
+    "uspmv_ctx_set_option": [vp, C.c_char_p, C.c_long],
+    "uspmv_ctx_get_option": [vp, C.c_char_p, C.POINTER(C.c_long)],
     "uspmv_device_count": [C.POINTER(C.c_int)],
     "uspmv_ctx_create": [C.c_int, C.POINTER(vp)],
     "uspmv_ctx_sync": [vp],

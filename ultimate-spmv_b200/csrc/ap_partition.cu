@@ -361,6 +361,7 @@ extern "C" {
 int uspmv_partition_precisions(uspmv_ctx *ctx, const uspmv_coo *coo, int ap_mode, double t1, double t2, const double *rowmax_h,
                                const double *colmax_h, uspmv_coo **dp, uspmv_coo **sp, uspmv_coo **hp) {
     return guarded([&] {
+        OptScope opt_scope(ctx_of(ctx));  // this context's options govern everything below
         if (!ctx || !coo) fail("uspmv_partition_precisions: NULL argument");
         if (ap_mode < 0 || ap_mode > 3) fail("uspmv_partition_precisions: invalid ap mode %d", ap_mode);
         if (ap_mode == USPMV_AP_DP_SP_HP && !(t1 > t2)) fail("uspmv_partition_precisions: thresholds must satisfy t1 > t2 (utilities.hpp:1514-1517)");
@@ -386,6 +387,7 @@ int uspmv_partition_precisions(uspmv_ctx *ctx, const uspmv_coo *coo, int ap_mode
 
 int uspmv_ap_spmv(int ap_mode, const uspmv_scs *dp, const uspmv_scs *sp, const uspmv_scs *hp, const void *x, void *y, void *stream) {
     return guarded([&] {
+        OptScope opt_scope(ctx_of(dp ? dp : sp));  // this context's options govern everything below
         const bool use_dp = ap_mode != USPMV_AP_SP_HP, use_sp = ap_mode != USPMV_AP_DP_HP, use_hp = ap_mode != USPMV_AP_DP_SP;
         if (ap_mode < 0 || ap_mode > 3) fail("uspmv_ap_spmv: invalid ap mode %d", ap_mode);
         if ((use_dp && !dp) || (use_sp && !sp) || (use_hp && !hp)) fail("uspmv_ap_spmv: a matrix part required by the mode is NULL");
@@ -440,6 +442,7 @@ int uspmv_ap_spmv(int ap_mode, const uspmv_scs *dp, const uspmv_scs *sp, const u
  * chunk_lengths is derived).  One fused pass; very long chunks are NOT cut into segments here (no per-matrix plan without a handle). */
 int uspmv_scs_ap_gpu(uspmv_ctx *ctx, int ap_mode, long C, long n_chunks, const void *const *arrays, const void *x, void *y, void *stream) {
     return guarded([&] {
+        OptScope opt_scope(ctx_of(ctx));  // this context's options govern everything below
         if (!ctx || !arrays) fail("uspmv_scs_ap_gpu: NULL argument");
         if (ap_mode < 0 || ap_mode > 3) fail("uspmv_scs_ap_gpu: invalid ap mode %d", ap_mode);
         if (C < 1) fail("uspmv_scs_ap_gpu: C must be >= 1");

@@ -32,6 +32,8 @@ struct uspmv_banded {
     DevBuf<unsigned char> scratch;   // n_rows_padded values of the y type
 };
 
+const uspmv_ctx *ctx_of(const uspmv_banded *b) { return b ? b->ctx : nullptr; }
+
 namespace {
 
 constexpr int TPB = 256;
@@ -136,6 +138,7 @@ void uspmv_banded_destroy(uspmv_banded *b) {
 int uspmv_banded_build(uspmv_ctx *ctx, const uspmv_coo *coo, long C, long sigma, int vt, int ap_mode, double t1, double t2, int n_bands,
                        uspmv_banded **out) {
     return guarded([&] {
+        OptScope opt_scope(ctx_of(ctx));  // this context's options govern everything below
         if (!ctx || !coo || !out) fail("uspmv_banded_build: NULL argument");
         if (ap_mode > 3) fail("uspmv_banded_build: invalid ap mode %d", ap_mode);
         if (n_bands < 0 || n_bands > 256) fail("uspmv_banded_build: n_bands must be in [0,256]");
@@ -211,6 +214,7 @@ int uspmv_banded_build(uspmv_ctx *ctx, const uspmv_coo *coo, long C, long sigma,
 /* out8 = n_bands, band_width, n_rows, n_cols, n_rows_padded, nnz, n_elements (all bands and parts), value type of x / y */
 int uspmv_banded_dims(const uspmv_banded *b, long out8[8]) {
     return guarded([&] {
+        OptScope opt_scope(ctx_of(b));  // this context's options govern everything below
         if (!b || !out8) fail("uspmv_banded_dims: NULL argument");
         out8[0] = b->n_bands; out8[1] = b->band_width; out8[2] = b->n_rows; out8[3] = b->n_cols; out8[4] = b->n_rows_padded;
         out8[5] = b->nnz; out8[6] = b->n_elements; out8[7] = b->vt;
@@ -220,6 +224,7 @@ int uspmv_banded_dims(const uspmv_banded *b, long out8[8]) {
 /* old_to_new of the plan (n_rows ints): y_user[i] = y[old_to_new[i]] */
 int uspmv_banded_perm(const uspmv_banded *b, int *old_to_new_h) {
     return guarded([&] {
+        OptScope opt_scope(ctx_of(b));  // this context's options govern everything below
         if (!b || !old_to_new_h) fail("uspmv_banded_perm: NULL argument");
         std::copy(b->old_to_new.begin(), b->old_to_new.begin() + b->n_rows, old_to_new_h);
     });
@@ -228,6 +233,7 @@ int uspmv_banded_perm(const uspmv_banded *b, int *old_to_new_h) {
 /* y (n_rows_padded values, permuted row order) = A x, x in the original column numbering (n_cols values) */
 int uspmv_banded_spmv(const uspmv_banded *b, const void *x, void *y, void *stream) {
     return guarded([&] {
+        OptScope opt_scope(ctx_of(b));  // this context's options govern everything below
         if (!b || !x || !y) fail("uspmv_banded_spmv: NULL argument");
         cudaStream_t st = as_stream(stream);
         const long n = b->n_rows_padded;

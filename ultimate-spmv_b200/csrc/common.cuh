@@ -122,7 +122,19 @@ struct Options {
     int l2_fetch_granularity = 0; // cudaLimitMaxL2FetchGranularity (32 / 64 / 128 bytes; 0 = leave the driver default)
     long push_min_elements = 1L << 20;  // halos with at least this many elements to send use the tiled push kernels
 };
-Options &options();
+// Options are per CONTEXT (two contexts in one process can differ): every context owns a copy, taken from the process defaults when it
+// is created.  uspmv_set_option changes the defaults AND every live context (the process-wide knob tests and benchmarks use),
+// uspmv_ctx_set_option one context only.  Inside the library `options()` is the option block of the context whose entry point is
+// executing on this thread (OptScope at the top of every entry point that takes a handle), else the process defaults.
+Options &default_options();
+const Options &options();
+struct OptScope {
+    const Options *prev;
+    explicit OptScope(const uspmv_ctx *ctx);
+    ~OptScope();
+    OptScope(const OptScope &) = delete;
+    OptScope &operator=(const OptScope &) = delete;
+};
 
 // per-device once-flags of the launchers (cudaFuncSetAttribute and occupancy are per device; a process may hold contexts on several)
 constexpr int MAX_DEVICES = 64;
@@ -150,6 +162,7 @@ inline int sm_count(int device) {
 struct uspmv_ctx {
     int device = 0;
     int n_sm = 0;
+    uspmv::Options opts;  // this context's kernel-selection knobs
 };
 namespace uspmv {
 inline void use_device(const uspmv_ctx *ctx) {
@@ -230,3 +243,13 @@ struct uspmv_scs {
     bool interior_contig = false, boundary_contig = false;
     int interior_off = 0, boundary_off = 0;
 };
+
+// the context behind any handle (null-safe), for OptScope
+inline const uspmv_ctx *ctx_of(const uspmv_ctx *c) { return c; }
+inline const uspmv_ctx *ctx_of(const uspmv_scs *s) { return s ? s->ctx : nullptr; }
+inline const uspmv_ctx *ctx_of(const uspmv_coo *c) { return c ? c->ctx : nullptr; }
+const uspmv_ctx *ctx_of(const uspmv_halo *h);    // halo.cu
+const uspmv_ctx *ctx_of(const uspmv_p2p *p);     // halo.cu
+struct uspmv_banded;
+const uspmv_ctx *ctx_of(const uspmv_banded *b);  // column_bands.cu
+

@@ -5,12 +5,20 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <vector>
 
 namespace uspmv {
 static thread_local std::string t_error;
 std::atomic<long> g_launches{0};
 void set_error(const std::string &msg) { t_error = msg; }
-Options &options() {
+static thread_local const Options *t_active = nullptr;
+static std::mutex g_ctx_mutex;
+static std::vector<uspmv_ctx *> g_live_ctxs;
+const Options &options() { return t_active ? *t_active : default_options(); }
+OptScope::OptScope(const uspmv_ctx *ctx) : prev(t_active) { if (ctx) t_active = &ctx->opts; }
+OptScope::~OptScope() { t_active = prev; }
+Options &default_options() {
     static Options o = [] {
         Options c;
         if (const char *e = std::getenv("USPMV_SCS_KERNEL")) c.scs_stream = std::strcmp(e, "direct") != 0;
@@ -34,10 +42,7 @@ const char *uspmv_last_error(void) { return t_error.c_str(); }
 int uspmv_version(void) { return 100; }
 long uspmv_kernel_launches(void) { return g_launches.load(); }
 
-int uspmv_set_option(const char *name, long value) {
-    return guarded([&] {
-        if (!name) fail("uspmv_set_option: name is NULL");
-        Options &c = options();
+static void apply_option(Options &c, const char *name, long value, int device) {
         if (!std::strcmp(name, "scs_stream")) c.scs_stream = value != 0;
         else if (!std::strcmp(name, "scs_stream_wide")) c.scs_stream_wide = value != 0;
         else if (!std::strcmp(name, "narrow_dp")) c.narrow_dp = value != 0;
@@ -56,9 +61,47 @@ int uspmv_set_option(const char *name, long value) {
         else if (!std::strcmp(name, "l2_fetch_granularity")) {
             if (value != 0 && value != 32 && value != 64 && value != 128) fail("uspmv_set_option: l2_fetch_granularity must be 0, 32, 64 or 128");
             c.l2_fetch_granularity = (int)value;
-            if (value) USPMV_CUDA(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)value));  // current device
+            if (value) {
+                if (device >= 0) USPMV_CUDA(cudaSetDevice(device));
+                USPMV_CUDA(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)value));  // a device limit: the context's (or current) device
+            }
         }
         else fail("uspmv_set_option: unknown option '%s'", name);
+}
+
+/* process-wide: the defaults new contexts start from AND every live context */
+int uspmv_set_option(const char *name, long value) {
+    return guarded([&] {
+        if (!name) fail("uspmv_set_option: name is NULL");
+        apply_option(default_options(), name, value, -1);
+        std::lock_guard<std::mutex> g(g_ctx_mutex);
+        for (uspmv_ctx *c : g_live_ctxs) apply_option(c->opts, name, value, -1);
+    });
+}
+
+/* one context only: two contexts (e.g. two GPUs, or two solver instances on one GPU) can run different kernel variants */
+int uspmv_ctx_set_option(uspmv_ctx *ctx, const char *name, long value) {
+    return guarded([&] {
+        if (!ctx || !name) fail("uspmv_ctx_set_option: NULL argument");
+        apply_option(ctx->opts, name, value, ctx->device);
+    });
+}
+
+int uspmv_ctx_get_option(const uspmv_ctx *ctx, const char *name, long *out) {
+    return guarded([&] {
+        if (!name || !out) fail("uspmv_ctx_get_option: NULL argument");
+        const Options &c = ctx ? ctx->opts : default_options();
+        if (!std::strcmp(name, "scs_stream")) *out = c.scs_stream;
+        else if (!std::strcmp(name, "scs_stream_wide")) *out = c.scs_stream_wide;
+        else if (!std::strcmp(name, "stream_variant")) *out = c.stream_variant;
+        else if (!std::strcmp(name, "stream_blocks_per_sm")) *out = c.stream_blocks_per_sm;
+        else if (!std::strcmp(name, "mmv_variant")) *out = c.mmv_variant;
+        else if (!std::strcmp(name, "ap_variant")) *out = c.ap_variant;
+        else if (!std::strcmp(name, "split_long_chunks")) *out = c.split_long_chunks;
+        else if (!std::strcmp(name, "strict_reference_halo")) *out = c.strict_reference_halo;
+        else if (!std::strcmp(name, "push_variant")) *out = c.push_variant;
+        else if (!std::strcmp(name, "pair_hp")) *out = c.pair_hp;
+        else fail("uspmv_ctx_get_option: unknown option '%s'", name);
     });
 }
 
@@ -106,16 +149,28 @@ int uspmv_ctx_create(int device, uspmv_ctx **out) {
         if (prop.major != 10)
             fail("uspmv_ctx_create: device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major,
                  prop.minor);
-        if (options().l2_fetch_granularity)
-            USPMV_CUDA(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)options().l2_fetch_granularity));
+        if (default_options().l2_fetch_granularity)
+            USPMV_CUDA(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)default_options().l2_fetch_granularity));
         auto *ctx = new uspmv_ctx();
         ctx->device = device;
         ctx->n_sm = prop.multiProcessorCount;
+        ctx->opts = default_options();
+        {
+            std::lock_guard<std::mutex> g(g_ctx_mutex);
+            g_live_ctxs.push_back(ctx);
+        }
         *out = ctx;
     });
 }
 
-void uspmv_ctx_destroy(uspmv_ctx *ctx) { delete ctx; }
+void uspmv_ctx_destroy(uspmv_ctx *ctx) {
+    if (!ctx) return;
+    {
+        std::lock_guard<std::mutex> g(g_ctx_mutex);
+        g_live_ctxs.erase(std::remove(g_live_ctxs.begin(), g_live_ctxs.end(), ctx), g_live_ctxs.end());
+    }
+    delete ctx;
+}
 
 int uspmv_ctx_sync(uspmv_ctx *ctx) {
     return guarded([&] {

@@ -229,6 +229,25 @@ __global__ void k_sort_windows(RC *rc, long n_pad, long sigma, long n_windows) {
     d_std_sort(rc + begin, end - begin);
 }
 
+// The same sort with the window staged in SHARED memory: one CTA per window loads its {row, count} records with coalesced accesses,
+// one thread runs the (inherently sequential, data-dependent) introsort restatement on the shared copy — ~30-cycle instead of
+// ~500-cycle dependent accesses — and the CTA writes the window back.  Bit-exact by construction (same code, same order of
+// comparisons and swaps).  sigma = 16 384 at 2^25 rows: seconds -> tens of milliseconds (round 1: 1.1-4.2 s).
+__global__ void __launch_bounds__(64) k_sort_windows_smem(RC *rc, long n_pad, long sigma, long n_windows) {
+    extern __shared__ __align__(8) unsigned char win_raw[];
+    RC *win = reinterpret_cast<RC *>(win_raw);
+    for (long w = blockIdx.x; w < n_windows; w += gridDim.x) {
+        const long begin = w * sigma;
+        const long n = begin + sigma < n_pad ? sigma : n_pad - begin;
+        for (long i = threadIdx.x; i < n; i += blockDim.x) win[i] = rc[begin + i];
+        __syncthreads();
+        if (threadIdx.x == 0) d_std_sort(win, n);
+        __syncthreads();
+        for (long i = threadIdx.x; i < n; i += blockDim.x) rc[begin + i] = win[i];
+        __syncthreads();
+    }
+}
+
 // chunk_lengths[c] = max count in chunk; len64[c] = len*C
 __global__ void k_chunk_lengths(const RC *__restrict__ rc, long n_chunks, int C, int *__restrict__ chunk_lengths,
                                 long long *__restrict__ len64) {
@@ -602,6 +621,7 @@ static void coo_common(uspmv_ctx *ctx, long n_rows, long n_cols, long nnz, int m
 int uspmv_coo_from_host(uspmv_ctx *ctx, long n_rows, long n_cols, long nnz, const int *I_h, const int *J_h, const void *values_h,
                         int mt, uspmv_coo **out) {
     return guarded([&] {
+        OptScope opt_scope(ctx_of(ctx));  // this context's options govern everything below
         if (!out) fail("uspmv_coo_from_host: out is NULL");
         if (nnz > 0 && (!I_h || !J_h || !values_h)) fail("uspmv_coo_from_host: NULL array");
         auto c = new uspmv_coo();
@@ -620,6 +640,7 @@ int uspmv_coo_from_host(uspmv_ctx *ctx, long n_rows, long n_cols, long nnz, cons
 int uspmv_coo_from_device(uspmv_ctx *ctx, long n_rows, long n_cols, long nnz, const int *I_d, const int *J_d, const void *values_d,
                           int mt, uspmv_coo **out) {
     return guarded([&] {
+        OptScope opt_scope(ctx_of(ctx));  // this context's options govern everything below
         if (!out) fail("uspmv_coo_from_device: out is NULL");
         if (nnz > 0 && (!I_d || !J_d || !values_d)) fail("uspmv_coo_from_device: NULL array");
         auto c = new uspmv_coo();
@@ -637,6 +658,7 @@ int uspmv_coo_from_device(uspmv_ctx *ctx, long n_rows, long n_cols, long nnz, co
 
 int uspmv_coo_stencil(uspmv_ctx *ctx, int points, long nx, long ny, long nz, long row0, long row1, uspmv_coo **out) {
     return guarded([&] {
+        OptScope opt_scope(ctx_of(ctx));  // this context's options govern everything below
         if (!ctx || !out) fail("uspmv_coo_stencil: NULL argument");
         if (points != 7 && points != 27) fail("uspmv_coo_stencil: points must be 7 or 27");
         long n = nx * ny * nz;
@@ -673,6 +695,7 @@ int uspmv_coo_stencil(uspmv_ctx *ctx, int points, long nx, long ny, long nz, lon
 int uspmv_coo_powerlaw(uspmv_ctx *ctx, long n, long row0, long row1, double d_min, double alpha, int max_deg, unsigned long seed,
                        uspmv_coo **out) {
     return guarded([&] {
+        OptScope opt_scope(ctx_of(ctx));  // this context's options govern everything below
         if (!ctx || !out) fail("uspmv_coo_powerlaw: NULL argument");
         if (n <= 0 || n > INT32_MAX - 1024 || row0 < 0 || row1 > n || row0 > row1) fail("uspmv_coo_powerlaw: bad size / row range");
         if (!(alpha > 1.0) || !(d_min > 0.0) || max_deg < 1) fail("uspmv_coo_powerlaw: need alpha > 1, d_min > 0, max_deg >= 1");
@@ -738,6 +761,7 @@ int uspmv_coo_powerlaw(uspmv_ctx *ctx, long n, long row0, long row1, double d_mi
  * row - wsa[rank], identical whenever the reference is defined. */
 int uspmv_coo_seg_mtx(const uspmv_coo *total, const int *wsa_h, int rank, int P, uspmv_coo **out, long *n_distinct_rows) {
     return guarded([&] {
+        OptScope opt_scope(ctx_of(total));  // this context's options govern everything below
         if (!total || !wsa_h || !out) fail("uspmv_coo_seg_mtx: NULL argument");
         if (P < 1 || rank < 0 || rank >= P) fail("uspmv_coo_seg_mtx: bad rank / comm_size");
         const int r0 = wsa_h[rank], r1 = wsa_h[rank + 1];
@@ -792,6 +816,7 @@ int uspmv_coo_seg_mtx(const uspmv_coo *total, const int *wsa_h, int rank, int P,
 /* raw device pointers of the COO arrays (any out pointer may be NULL); values are `mt`-typed */
 int uspmv_coo_device_arrays(const uspmv_coo *coo, const int **I_d, const int **J_d, const void **values_d) {
     return guarded([&] {
+        OptScope opt_scope(ctx_of(coo));  // this context's options govern everything below
         if (!coo) fail("uspmv_coo_device_arrays: coo is NULL");
         if (I_d) *I_d = coo->I.p;
         if (J_d) *J_d = coo->J.p;
@@ -801,6 +826,7 @@ int uspmv_coo_device_arrays(const uspmv_coo *coo, const int **I_d, const int **J
 
 int uspmv_coo_dims(const uspmv_coo *coo, long out3[3]) {
     return guarded([&] {
+        OptScope opt_scope(ctx_of(coo));  // this context's options govern everything below
         if (!coo || !out3) fail("uspmv_coo_dims: NULL argument");
         out3[0] = coo->n_rows; out3[1] = coo->n_cols; out3[2] = coo->nnz;
     });
@@ -811,6 +837,7 @@ int uspmv_coo_dims(const uspmv_coo *coo, long out3[3]) {
 int uspmv_coo_from_entries(uspmv_ctx *ctx, long n_rows, long n_cols, long nz, const int *I_h, const int *J_h, const double *V_h,
                            int symmetric, uspmv_coo **out) {
     return guarded([&] {
+        OptScope opt_scope(ctx_of(ctx));  // this context's options govern everything below
         if (!out) fail("uspmv_coo_from_entries: out is NULL");
         if (nz > 0 && (!I_h || !J_h || !V_h)) fail("uspmv_coo_from_entries: NULL array");
         if (!ctx) fail("uspmv_coo_from_entries: ctx is NULL");
@@ -876,6 +903,7 @@ int uspmv_coo_from_entries(uspmv_ctx *ctx, long n_rows, long n_cols, long nz, co
  * what the harness hands to partition_precisions in AP mode (main.cpp:1143-1153). */
 int uspmv_coo_equilibrate(uspmv_coo *coo, double *rowmax_h, double *colmax_h) {
     return guarded([&] {
+        OptScope opt_scope(ctx_of(coo));  // this context's options govern everything below
         if (!coo) fail("uspmv_coo_equilibrate: coo is NULL");
         if (coo->mt != USPMV_F64) fail("uspmv_coo_equilibrate: the COO matrix must hold doubles");
         USPMV_CUDA(cudaSetDevice(coo->ctx->device));
@@ -902,6 +930,7 @@ int uspmv_coo_equilibrate(uspmv_coo *coo, double *rowmax_h, double *colmax_h) {
 
 int uspmv_coo_export(const uspmv_coo *coo, int *I_h, int *J_h, void *values_h) {
     return guarded([&] {
+        OptScope opt_scope(ctx_of(coo));  // this context's options govern everything below
         if (!coo) fail("uspmv_coo_export: coo is NULL");
         USPMV_CUDA(cudaSetDevice(coo->ctx->device));
         if (I_h && coo->nnz) USPMV_CUDA(cudaMemcpy(I_h, coo->I.p, coo->nnz * sizeof(int), cudaMemcpyDeviceToHost));
@@ -917,6 +946,7 @@ void uspmv_coo_destroy(uspmv_coo *coo) { delete coo; }
 // ---------------------------------------------------------------------------------------------
 int uspmv_scs_build(uspmv_ctx *ctx, const uspmv_coo *coo, long C, long sigma, int vt, const int *fixed_perm_h, uspmv_scs **out) {
     return guarded([&] {
+        OptScope opt_scope(ctx_of(ctx));  // this context's options govern everything below
         if (!ctx || !coo || !out) fail("uspmv_scs_build: NULL argument");
         if (C < 1 || sigma < 1) fail("uspmv_scs_build: C and sigma must be >= 1 (got C=%ld sigma=%ld)", C, sigma);
         vt_size(vt);
@@ -985,7 +1015,18 @@ int uspmv_scs_build(uspmv_ctx *ctx, const uspmv_coo *coo, long C, long sigma, in
             USPMV_LAUNCH_CHECK();
             if (sigma > 1) {
                 long n_windows = (n_pad + sigma - 1) / sigma;
-                k_sort_windows<<<blocks_for(n_windows, 64), 64>>>(rc.p, n_pad, sigma, n_windows);
+                const size_t win_bytes = (size_t)std::min<long>(sigma, n_pad) * sizeof(RC);
+                if (sigma >= 64 && win_bytes <= 200 * 1024) {  // window staged in shared memory, one CTA per window
+                    static bool configured_on[uspmv::MAX_DEVICES] = {};
+                    const int dev = uspmv::current_device();
+                    if (!configured_on[dev]) {
+                        USPMV_CUDA(cudaFuncSetAttribute(k_sort_windows_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                        configured_on[dev] = true;
+                    }
+                    const long grid = std::min<long>(n_windows, 32L * sm_count(dev));
+                    k_sort_windows_smem<<<(unsigned)grid, 64, win_bytes>>>(rc.p, n_pad, sigma, n_windows);
+                } else  // tiny windows (insertion-sort regime) or windows beyond the shared-memory size: one thread per window
+                    k_sort_windows<<<blocks_for(n_windows, 64), 64>>>(rc.p, n_pad, sigma, n_windows);
                 USPMV_LAUNCH_CHECK();
             }
         }
@@ -1044,6 +1085,7 @@ int uspmv_scs_from_arrays(uspmv_ctx *ctx, int vt, long C, long sigma, long n_row
                           const int *chunk_lengths, const int *col_idxs, const void *values, const int *old_to_new, int on_device,
                           uspmv_scs **out) {
     return guarded([&] {
+        OptScope opt_scope(ctx_of(ctx));  // this context's options govern everything below
         if (!ctx || !out) fail("uspmv_scs_from_arrays: NULL argument");
         if (C < 1 || sigma < 1 || n_rows < 0 || n_chunks != (n_rows + C - 1) / C) fail("uspmv_scs_from_arrays: inconsistent C / n_rows / n_chunks");
         if (n_chunks > 0 && (!chunk_ptrs || !chunk_lengths)) fail("uspmv_scs_from_arrays: NULL chunk array");
@@ -1107,6 +1149,7 @@ int uspmv_scs_from_arrays(uspmv_ctx *ctx, int vt, long C, long sigma, long n_row
 
 int uspmv_scs_dims(const uspmv_scs *s, long o[8]) {
     return guarded([&] {
+        OptScope opt_scope(ctx_of(s));  // this context's options govern everything below
         if (!s || !o) fail("uspmv_scs_dims: NULL argument");
         o[0] = s->C; o[1] = s->sigma; o[2] = s->n_rows; o[3] = s->n_cols;
         o[4] = s->n_rows_padded; o[5] = s->n_chunks; o[6] = s->n_elements; o[7] = s->nnz;
@@ -1116,6 +1159,7 @@ int uspmv_scs_dims(const uspmv_scs *s, long o[8]) {
 int uspmv_scs_export(const uspmv_scs *s, int *chunk_ptrs_h, int *chunk_lengths_h, int *col_idxs_h, void *values_h, int *old_to_new_h,
                      int *new_to_old_h) {
     return guarded([&] {
+        OptScope opt_scope(ctx_of(s));  // this context's options govern everything below
         if (!s) fail("uspmv_scs_export: scs is NULL");
         USPMV_CUDA(cudaSetDevice(s->ctx->device));
         auto d2h = [](void *dst, const void *src, size_t bytes) {
@@ -1132,6 +1176,7 @@ int uspmv_scs_export(const uspmv_scs *s, int *chunk_ptrs_h, int *chunk_lengths_h
 
 int uspmv_scs_permute_cols(uspmv_scs *s, const int *perm_h) {
     return guarded([&] {
+        OptScope opt_scope(ctx_of(s));  // this context's options govern everything below
         if (!s) fail("uspmv_scs_permute_cols: scs is NULL");
         USPMV_CUDA(cudaSetDevice(s->ctx->device));
         DevBuf<int> perm_d;
@@ -1153,6 +1198,7 @@ int uspmv_scs_permute_cols(uspmv_scs *s, const int *perm_h) {
 int uspmv_scs_device_arrays(const uspmv_scs *s, const int **chunk_ptrs_d, const int **chunk_lengths_d, const int **col_idxs_d,
                             const void **values_d, const int **old_to_new_d, const int **new_to_old_d) {
     return guarded([&] {
+        OptScope opt_scope(ctx_of(s));  // this context's options govern everything below
         if (!s) fail("uspmv_scs_device_arrays: scs is NULL");
         if (chunk_ptrs_d) *chunk_ptrs_d = s->chunk_ptrs.p;
         if (chunk_lengths_d) *chunk_lengths_d = s->chunk_lengths.p;

@@ -172,6 +172,7 @@ int uspmv_seg_work_sharing_arr(int seg_method, long n_rows, long nnz, const int 
  * the original column numbering, main.cpp:1308-1332), so the elements sent to the neighbours are x[send_idx], not x[perm[send_idx]]. */
 int uspmv_halo_plan_create_multi(uspmv_scs **parts, int n_parts, const int *wsa_h, int rank, int P, int x_permuted, uspmv_halo **out) {
     return guarded([&] {
+        OptScope opt_scope(ctx_of(parts && n_parts > 0 ? parts[0] : nullptr));  // this context's options govern everything below
         if (!parts || !wsa_h || !out || n_parts < 1 || n_parts > 3) fail("uspmv_halo_plan_create: NULL argument or bad part count");
         if (P < 1 || rank < 0 || rank >= P) fail("uspmv_halo_plan_create: bad rank/comm_size");
         uspmv_scs *s0 = parts[0];
@@ -272,6 +273,7 @@ int uspmv_halo_plan_create(uspmv_scs *s, const int *wsa_h, int rank, int P, uspm
 
 int uspmv_halo_plan_counts(const uspmv_halo *h, int *recv_counts_cumsum_h, long *n_halo) {
     return guarded([&] {
+        OptScope opt_scope(ctx_of(h));  // this context's options govern everything below
         if (!h) fail("uspmv_halo_plan_counts: plan is NULL");
         if (recv_counts_cumsum_h)
             for (int p = 0; p <= h->P; ++p) recv_counts_cumsum_h[p] = h->recv_cumsum[p];
@@ -281,6 +283,7 @@ int uspmv_halo_plan_counts(const uspmv_halo *h, int *recv_counts_cumsum_h, long 
 
 int uspmv_halo_plan_need(const uspmv_halo *h, int *need_flat_h, int *need_ptr_h) {
     return guarded([&] {
+        OptScope opt_scope(ctx_of(h));  // this context's options govern everything below
         if (!h) fail("uspmv_halo_plan_need: plan is NULL");
         if (need_flat_h)
             for (long k = 0; k < h->n_halo; ++k) need_flat_h[k] = h->need_flat[k];
@@ -291,6 +294,7 @@ int uspmv_halo_plan_need(const uspmv_halo *h, int *need_flat_h, int *need_ptr_h)
 
 int uspmv_halo_plan_set_send(uspmv_halo *h, const int *send_flat_h, const int *send_ptr_h) {
     return guarded([&] {
+        OptScope opt_scope(ctx_of(h));  // this context's options govern everything below
         if (!h || !send_ptr_h) fail("uspmv_halo_plan_set_send: NULL argument");
         USPMV_CUDA(cudaSetDevice(h->ctx->device));
         for (int p = 0; p <= h->P; ++p) h->send_ptr[p] = send_ptr_h[p];
@@ -304,6 +308,7 @@ int uspmv_halo_plan_set_send(uspmv_halo *h, const int *send_flat_h, const int *s
 
 int uspmv_halo_pack(const uspmv_halo *h, const void *x, void *sendbuf, int vt, int bvs, long vec_length, int layout, void *stream) {
     return guarded([&] {
+        OptScope opt_scope(ctx_of(h));  // this context's options govern everything below
         if (!h) fail("uspmv_halo_pack: plan is NULL");
         if (h->n_send == 0) return;
         if (!x || !sendbuf) fail("uspmv_halo_pack: NULL buffer");
@@ -371,6 +376,9 @@ struct uspmv_p2p {
     long n_push_tiles = 0, n_push_tiles_4k = 0;  // tiles (2048 / 4096 elements) of the large-halo push kernels (k_p2p_push_tiles)
     unsigned char *buffer(int b) const { return arena + (size_t)b * x_bytes; }
 };
+
+const uspmv_ctx *ctx_of(const uspmv_halo *h) { return h ? h->ctx : nullptr; }
+const uspmv_ctx *ctx_of(const uspmv_p2p *p) { return p && p->plan ? p->plan->ctx : nullptr; }
 
 namespace {
 
@@ -638,6 +646,7 @@ extern "C" {
 int uspmv_p2p_create_ex(uspmv_halo *plan, int vt, long vec_length, int bvs, int layout, int n_buf, uspmv_p2p **out, void *ipc_handle64,
                         void **x_d) {
     return guarded([&] {
+        OptScope opt_scope(ctx_of(plan));  // this context's options govern everything below
         if (!plan || !out || !ipc_handle64 || !x_d) fail("uspmv_p2p_create: NULL argument");
         if (plan->P > 256) fail("uspmv_p2p_create: at most 256 ranks");
         if (bvs < 1 || bvs > 16) fail("uspmv_p2p_create: block_vec_size must be in [1,16] (got %d)", bvs);
@@ -687,6 +696,7 @@ int uspmv_p2p_create(uspmv_halo *plan, int vt, long x_len, uspmv_p2p **out, void
 int uspmv_p2p_connect_ex(uspmv_p2p *p, const void *all_handles, const long *peer_x_bytes, const long *peer_halo_base,
                          const long *peer_vec_length) {
     return guarded([&] {
+        OptScope opt_scope(ctx_of(p));  // this context's options govern everything below
         if (!p || !all_handles || !peer_x_bytes || !peer_halo_base) fail("uspmv_p2p_connect: NULL argument");
         if (!peer_vec_length && p->bvs > 1 && p->layout == USPMV_COLWISE) fail("uspmv_p2p_connect: column-major block vectors need peer_vec_length");
         uspmv_halo *h = p->plan;
@@ -745,6 +755,7 @@ int uspmv_p2p_connect(uspmv_p2p *p, const void *all_handles, const long *peer_x_
  * device-resident loop with no copy (solve mode, main.cpp:528-631).  Overlap modes as set by uspmv_p2p_set_overlap. */
 int uspmv_p2p_spmv_buf(uspmv_p2p *p, const uspmv_scs *scs, int x_buf, int y_buf, void *y_d, void *stream, void *comm_stream) {
     return guarded([&] {
+        OptScope opt_scope(ctx_of(p));  // this context's options govern everything below
         if (!p || !scs) fail("uspmv_p2p_spmv: NULL argument");
         if (!p->connected) fail("uspmv_p2p_spmv: call uspmv_p2p_connect first");
         if (!scs->chunks_split) fail("uspmv_p2p_spmv: call uspmv_scs_split_chunks first");
@@ -818,6 +829,7 @@ int uspmv_p2p_spmv(uspmv_p2p *p, const uspmv_scs *scs, void *y_d, void *stream, 
  * chunks when the streamed kernel applies (C = 32, block_vec_size 2/4/8/16); otherwise exchange first, then one full SpMMV. */
 int uspmv_p2p_spmmv(uspmv_p2p *p, const uspmv_scs *scs, int x_buf, void *Y_d, void *stream, void *comm_stream) {
     return guarded([&] {
+        OptScope opt_scope(ctx_of(p));  // this context's options govern everything below
         if (!p || !scs || !Y_d) fail("uspmv_p2p_spmmv: NULL argument");
         if (!p->connected) fail("uspmv_p2p_spmmv: call uspmv_p2p_connect first");
         if (!scs->chunks_split) fail("uspmv_p2p_spmmv: call uspmv_scs_split_chunks first");
@@ -877,6 +889,7 @@ int uspmv_p2p_spmmv(uspmv_p2p *p, const uspmv_scs *scs, int x_buf, void *Y_d, vo
 int uspmv_p2p_ap_spmv(uspmv_p2p *p, int ap_mode, const uspmv_scs *dp, const uspmv_scs *sp, const uspmv_scs *hp, void *y_d, void *stream,
                       void *comm_stream) {
     return guarded([&] {
+        OptScope opt_scope(ctx_of(p));  // this context's options govern everything below
         if (!p || !y_d) fail("uspmv_p2p_ap_spmv: NULL argument");
         if (!p->connected) fail("uspmv_p2p_ap_spmv: call uspmv_p2p_connect first");
         if (p->bvs != 1) fail("uspmv_p2p_ap_spmv: the arena was created for block vectors");
@@ -903,6 +916,7 @@ int uspmv_p2p_ap_spmv(uspmv_p2p *p, int ap_mode, const uspmv_scs *dp, const uspm
  * buffer x_buf into the neighbours' vectors, wait for the own halo, acknowledge.  After it x_buf holds local rows + halo. */
 int uspmv_p2p_exchange(uspmv_p2p *p, int x_buf, void *stream, void *comm_stream) {
     return guarded([&] {
+        OptScope opt_scope(ctx_of(p));  // this context's options govern everything below
         if (!p) fail("uspmv_p2p_exchange: NULL argument");
         if (!p->connected) fail("uspmv_p2p_exchange: call uspmv_p2p_connect first");
         if (x_buf < 0 || x_buf >= p->n_buf) fail("uspmv_p2p_exchange: x buffer %d out of range", x_buf);
@@ -926,6 +940,7 @@ int uspmv_p2p_exchange(uspmv_p2p *p, int x_buf, void *stream, void *comm_stream)
  * order) back, on three streams, so the PCIe transfers of call k overlap the kernel and the opposite-direction copy of call k +- 1. */
 int uspmv_p2p_spmv_host_submit(uspmv_p2p *p, const uspmv_scs *scs, const void *x_h, void *y_h, int slot) {
     return guarded([&] {
+        OptScope opt_scope(ctx_of(p));  // this context's options govern everything below
         if (!p || !scs || !x_h || !y_h) fail("uspmv_p2p_spmv_host_submit: NULL argument");
         if (!p->connected) fail("uspmv_p2p_spmv_host_submit: call uspmv_p2p_connect first");
         if (p->n_buf != 2 || p->bvs != 1) fail("uspmv_p2p_spmv_host_submit: needs an arena with two single-vector buffers (uspmv_p2p_create_ex, n_buf = 2)");
@@ -967,6 +982,7 @@ int uspmv_p2p_spmv_host_submit(uspmv_p2p *p, const uspmv_scs *scs, const void *x
 
 int uspmv_p2p_spmv_host_wait(uspmv_p2p *p, int slot) {
     return guarded([&] {
+        OptScope opt_scope(ctx_of(p));  // this context's options govern everything below
         if (!p) fail("uspmv_p2p_spmv_host_wait: NULL argument");
         if (slot < 0 || slot > 1) fail("uspmv_p2p_spmv_host_wait: slot must be 0 or 1");
         if (!p->slot_busy[slot]) return;
@@ -979,6 +995,7 @@ int uspmv_p2p_spmv_host_wait(uspmv_p2p *p, int slot) {
 
 int uspmv_p2p_set_overlap(uspmv_p2p *p, int overlap) {
     return guarded([&] {
+        OptScope opt_scope(ctx_of(p));  // this context's options govern everything below
         if (!p) fail("uspmv_p2p_set_overlap: NULL argument");
         if (overlap < 0 || overlap > 2) fail("uspmv_p2p_set_overlap: mode must be 0, 1 or 2");
         p->mode = overlap;
@@ -989,6 +1006,7 @@ int uspmv_p2p_set_overlap(uspmv_p2p *p, int overlap) {
  * kernels only raise the arena's error word and carry on, so this is where a lost push becomes a return code. */
 int uspmv_p2p_sync(uspmv_p2p *p) {
     return guarded([&] {
+        OptScope opt_scope(ctx_of(p));  // this context's options govern everything below
         if (!p) fail("uspmv_p2p_sync: NULL argument");
         USPMV_CUDA(cudaSetDevice(p->plan->ctx->device));
         USPMV_CUDA(cudaDeviceSynchronize());
@@ -1004,6 +1022,7 @@ int uspmv_p2p_sync(uspmv_p2p *p) {
  * disconnect waits for this rank's device and closes the neighbours' imported arenas; after it the handle only frees. */
 int uspmv_p2p_disconnect(uspmv_p2p *p) {
     return guarded([&] {
+        OptScope opt_scope(ctx_of(p));  // this context's options govern everything below
         if (!p) fail("uspmv_p2p_disconnect: NULL argument");
         USPMV_CUDA(cudaSetDevice(p->plan->ctx->device));
         USPMV_CUDA(cudaDeviceSynchronize());
@@ -1016,6 +1035,7 @@ int uspmv_p2p_disconnect(uspmv_p2p *p) {
 /* 0 = fine; 1 = a bounded spin timed out (a peer never signalled) */
 int uspmv_p2p_status(uspmv_p2p *p, int *error_flag, long *epoch) {
     return guarded([&] {
+        OptScope opt_scope(ctx_of(p));  // this context's options govern everything below
         if (!p) fail("uspmv_p2p_status: NULL argument");
         unsigned int v[2] = {0, 0};
         USPMV_CUDA(cudaMemcpy(v, p->epoch, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost));

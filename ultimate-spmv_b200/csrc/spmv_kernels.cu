@@ -844,6 +844,7 @@ extern "C" {
 int uspmv_scs_gpu(uspmv_ctx *ctx, int vt, long C, long n_chunks, const int *cp, const int *cl, const int *ci, const void *vals,
                   const void *x, void *y, void *stream) {
     return guarded([&] {
+        OptScope opt_scope(ctx_of(ctx));  // this context's options govern everything below
         if (!ctx) fail("uspmv_scs_gpu: ctx is NULL");
         if (C < 1) fail("uspmv_scs_gpu: C must be >= 1");
         use_device(ctx);
@@ -860,6 +861,7 @@ int uspmv_scs_gpu(uspmv_ctx *ctx, int vt, long C, long n_chunks, const int *cp, 
 int uspmv_csr_gpu(uspmv_ctx *ctx, int vt, long n_rows, const int *rp, const int *ci, const void *vals, const void *x, void *y,
                   void *stream) {
     return guarded([&] {
+        OptScope opt_scope(ctx_of(ctx));  // this context's options govern everything below
         if (!ctx) fail("uspmv_csr_gpu: ctx is NULL");
         use_device(ctx);
         cudaStream_t st = as_stream(stream);
@@ -877,6 +879,7 @@ int uspmv_csr_gpu(uspmv_ctx *ctx, int vt, long n_rows, const int *rp, const int 
 
 int uspmv_spmv(const uspmv_scs *s, const void *x, void *y, void *stream) {
     return guarded([&] {
+        OptScope opt_scope(ctx_of(s));  // this context's options govern everything below
         if (!s) fail("uspmv_spmv: scs is NULL");
         if (s->n_rows_padded && (!x || !y)) fail("uspmv_spmv: NULL vector");
         use_device(s->ctx);
@@ -911,6 +914,7 @@ int uspmv_spmv(const uspmv_scs *s, const void *x, void *y, void *stream) {
 
 int uspmv_scs_split_chunks(uspmv_scs *s, long *n_interior, long *n_boundary) {
     return guarded([&] {
+        OptScope opt_scope(ctx_of(s));  // this context's options govern everything below
         if (!s) fail("uspmv_scs_split_chunks: scs is NULL");
         USPMV_CUDA(cudaSetDevice(s->ctx->device));
         const long nc = s->n_chunks;
@@ -940,6 +944,7 @@ int uspmv_scs_split_chunks(uspmv_scs *s, long *n_interior, long *n_boundary) {
 
 int uspmv_spmv_part(const uspmv_scs *s, int which, const void *x, void *y, void *stream) {
     return guarded([&] {
+        OptScope opt_scope(ctx_of(s));  // this context's options govern everything below
         if (!s) fail("uspmv_spmv_part: scs is NULL");
         if (which == 0) {
             if (uspmv_spmv(s, x, y, stream)) throw Error(uspmv_last_error());
@@ -964,6 +969,7 @@ int uspmv_spmv_part(const uspmv_scs *s, int which, const void *x, void *y, void 
 
 int uspmv_spmv_unpermuted(const uspmv_scs *s, const void *x, void *y, void *stream) {
     return guarded([&] {
+        OptScope opt_scope(ctx_of(s));  // this context's options govern everything below
         if (!s) fail("uspmv_spmv_unpermuted: scs is NULL");
         if (s->cols_permuted) fail("uspmv_spmv_unpermuted: columns were already permuted (permute_scs_cols); use uspmv_spmv");
         use_device(s->ctx);
@@ -978,6 +984,7 @@ int uspmv_spmv_unpermuted(const uspmv_scs *s, const void *x, void *y, void *stre
 
 int uspmv_spmmv(const uspmv_scs *s, const void *X, void *Y, int bvs, long vec_length, int layout, void *stream) {
     return guarded([&] {
+        OptScope opt_scope(ctx_of(s));  // this context's options govern everything below
         if (!s) fail("uspmv_spmmv: scs is NULL");
         if (bvs < 1 || bvs > 16) fail("uspmv_spmmv: block_vec_size must be in [1,16] (got %d)", bvs);
         if (layout != USPMV_COLWISE && layout != USPMV_ROWWISE) fail("uspmv_spmmv: invalid layout %d", layout);
@@ -998,6 +1005,7 @@ int uspmv_spmmv_part_supported(const uspmv_scs *s, int bvs) { return s && s->chu
 
 int uspmv_spmmv_part(const uspmv_scs *s, int which, const void *X, void *Y, int bvs, long vec_length, int layout, void *stream) {
     return guarded([&] {
+        OptScope opt_scope(ctx_of(s));  // this context's options govern everything below
         if (!s) fail("uspmv_spmmv_part: scs is NULL");
         if (which == 0) {
             if (uspmv_spmmv(s, X, Y, bvs, vec_length, layout, stream)) throw Error(uspmv_last_error());
@@ -1028,6 +1036,7 @@ int uspmv_spmmv_part(const uspmv_scs *s, int which, const void *X, void *Y, int 
 int uspmv_block_spmv_gpu(uspmv_ctx *ctx, int vt, long C, long n_chunks, const int *cp, const int *cl, const int *ci, const void *vals,
                          const void *X, void *Y, int bvs, long vec_length, int layout, void *stream) {
     return guarded([&] {
+        OptScope opt_scope(ctx_of(ctx));  // this context's options govern everything below
         if (!ctx) fail("uspmv_block_spmv_gpu: ctx is NULL");
         if (C < 1) fail("uspmv_block_spmv_gpu: C must be >= 1");
         if (bvs < 1 || bvs > 16) fail("uspmv_block_spmv_gpu: block_vec_size must be in [1,16] (got %d)", bvs);
@@ -1057,6 +1066,7 @@ int uspmv_block_spmv_gpu(uspmv_ctx *ctx, int vt, long C, long n_chunks, const in
 
 int uspmv_spmv_host(const uspmv_scs *s_, const void *x_h, long x_len, void *y_h, long y_len) {
     return guarded([&] {
+        OptScope opt_scope(ctx_of(s_));  // this context's options govern everything below
         uspmv_scs *s = const_cast<uspmv_scs *>(s_);
         if (!s || !x_h || !y_h) fail("uspmv_spmv_host: NULL argument");
         if (y_len < s->n_rows_padded) fail("uspmv_spmv_host: y_len %ld < n_rows_padded %ld", y_len, s->n_rows_padded);
@@ -1077,6 +1087,7 @@ int uspmv_spmv_host(const uspmv_scs *s_, const void *x_h, long x_len, void *y_h,
 // opposite-direction transfer of its neighbours.  x_h / y_h should be pinned (uspmv_host_alloc) for the copies to be async.
 int uspmv_spmv_host_submit(const uspmv_scs *s_, const void *x_h, long x_len, void *y_h, long y_len, int slot) {
     return guarded([&] {
+        OptScope opt_scope(ctx_of(s_));  // this context's options govern everything below
         uspmv_scs *s = const_cast<uspmv_scs *>(s_);
         if (!s || !x_h || !y_h) fail("uspmv_spmv_host_submit: NULL argument");
         if (slot < 0 || slot >= uspmv_scs::HOST_SLOTS) fail("uspmv_spmv_host_submit: slot must be in [0,%d)", uspmv_scs::HOST_SLOTS);
@@ -1111,6 +1122,7 @@ int uspmv_spmv_host_submit(const uspmv_scs *s_, const void *x_h, long x_len, voi
 
 int uspmv_spmv_host_wait(const uspmv_scs *s_, int slot) {
     return guarded([&] {
+        OptScope opt_scope(ctx_of(s_));  // this context's options govern everything below
         uspmv_scs *s = const_cast<uspmv_scs *>(s_);
         if (!s) fail("uspmv_spmv_host_wait: NULL argument");
         if (slot < 0 || slot >= uspmv_scs::HOST_SLOTS) fail("uspmv_spmv_host_wait: slot must be in [0,%d)", uspmv_scs::HOST_SLOTS);
@@ -1122,6 +1134,7 @@ int uspmv_spmv_host_wait(const uspmv_scs *s_, int slot) {
 
 int uspmv_apply_permutation(uspmv_ctx *ctx, void *out, const void *in, const int *perm, long n, int vt, void *stream) {
     return guarded([&] {
+        OptScope opt_scope(ctx_of(ctx));  // this context's options govern everything below
         if (!ctx) fail("uspmv_apply_permutation: ctx is NULL");
         if (n == 0) return;
         cudaStream_t st = as_stream(stream);
@@ -1139,6 +1152,7 @@ int uspmv_apply_permutation(uspmv_ctx *ctx, void *out, const void *in, const int
 int uspmv_apply_permutation_block(uspmv_ctx *ctx, void *out, const void *in, const int *perm, long n, int vt, int bvs, long ld,
                                   int layout, void *stream) {
     return guarded([&] {
+        OptScope opt_scope(ctx_of(ctx));  // this context's options govern everything below
         if (!ctx) fail("uspmv_apply_permutation_block: ctx is NULL");
         if (n == 0 || bvs == 0) return;
         cudaStream_t st = as_stream(stream);
@@ -1157,6 +1171,7 @@ int uspmv_apply_permutation_block(uspmv_ctx *ctx, void *out, const void *in, con
  * row; the harness calls it once per vector of a row-major block vector with the base pointers offset by the vector index. */
 int uspmv_apply_strided_permutation(uspmv_ctx *ctx, void *out, const void *in, const int *perm, long n, long stride, int vt, void *stream) {
     return guarded([&] {
+        OptScope opt_scope(ctx_of(ctx));  // this context's options govern everything below
         if (!ctx) fail("uspmv_apply_strided_permutation: ctx is NULL");
         if (stride < 1) fail("uspmv_apply_strided_permutation: stride must be >= 1");
         if (n == 0) return;
@@ -1176,6 +1191,7 @@ int uspmv_apply_strided_permutation(uspmv_ctx *ctx, void *out, const void *in, c
  * [0, inv_len) are an error here (the reference writes out of bounds); positions of inv_perm that no perm[i] names are left alone. */
 int uspmv_generate_inv_perm(uspmv_ctx *ctx, const int *perm_d, int *inv_perm_d, long perm_len, long inv_len, void *stream) {
     return guarded([&] {
+        OptScope opt_scope(ctx_of(ctx));  // this context's options govern everything below
         if (!ctx) fail("uspmv_generate_inv_perm: ctx is NULL");
         if (perm_len == 0) return;
         if (!perm_d || !inv_perm_d) fail("uspmv_generate_inv_perm: NULL array");

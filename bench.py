@@ -58,6 +58,7 @@ def parse_args():
     ap.add_argument("--no-banded", action="store_true", help="other_configs: config 4 with the fused kernel only (no column-banded plan)")
     ap.add_argument("--config4-log2-rows", type=int, default=25)
     ap.add_argument("--config5-n", type=int, default=512, help="other_configs at N > 1: grid edge of the 27-point strong-scaling matrix")
+    ap.add_argument("--set", action="append", default=[], metavar="NAME=VALUE", help="library option for A/B runs (uspmv_set_option), repeatable")
     ap.add_argument("--steady-steps", type=int, default=1000, help="also report ms per step over this many steps (0 = skip)")
     ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the reference's own CUDA kernel (oracle/_ref, recompiled for sm_100)")
     return ap.parse_args()
@@ -240,7 +241,19 @@ def gpu_reference_kernel_run(pts, n, C, sigma, vt, steps):
         nnz = int(s.nnz)
         same = bool(np.array_equal(y, y_cpu))
         close = bool(np.allclose(y, y_cpu, rtol={"dp": 1e-12, "sp": 1e-5}[vt], atol=0))
-        return {"value": 2.0 * nnz / (ms / 1e3) / 1e9, "unit": UNIT, "ms_per_step": ms, "kind": "reference CUDA kernel",
+        cusp = None
+        if bindings.cusparse_available():  # the reference's own second GPU baseline: its USE_CUSPARSE mode (utilities.hpp:3380-3550)
+            try:
+                cs = bindings.CuSparse()
+                kind = "csr" if crs else "sell"
+                yc, msc = cs.spmv(kind, vt, s.n_rows, len(x), nnz, C, s.chunk_ptrs, s.col_idxs, s.values, x, warmup=5, steps=min(steps, 100))
+                cusp = {"value": 2.0 * nnz / (msc / 1e3) / 1e9, "unit": UNIT, "ms_per_step": msc,
+                        "kernel": ("cusparseSpMV, CSR" if crs else f"cusparseSpMV on cusparseCreateSlicedEll(slice size {C}) made from the same SELL-C-sigma arrays") +
+                                  ", CUSPARSE_SPMV_ALG_DEFAULT (utilities.hpp:3393-3457)",
+                        "y_close_to_reference_cpu_y": bool(np.allclose(yc, y_cpu[: s.n_rows], rtol={"dp": 1e-12, "sp": 1e-5}[vt], atol=1e-300))}
+            except Exception as e:
+                cusp = {"value": None, "sample": f"unavailable: {e}"}
+        return {"value": 2.0 * nnz / (ms / 1e3) / 1e9, "unit": UNIT, "ms_per_step": ms, "kind": "reference CUDA kernel", "cusparse": cusp,
                 "kernel": {"csr": "spmv_gpu_csr (kernels.hpp:631-659)", "scs_adv": "spmv_gpu_scs_adv / scs_impl_gpu<C> (kernels.hpp:685-775)",
                            "scs": "spmv_gpu_scs (kernels.hpp:579-608)"}[kern],
                 "build": f"unmodified reference source, nvcc -O3 -gencode arch=compute_100,code=sm_100, THREADS_PER_BLOCK={g.threads_per_block}",
@@ -428,6 +441,9 @@ def run_ours(args):
     vt = args.vt
     vsize = {"dp": 8, "sp": 4, "hp": 2}[vt]
     ctx = eng.default_context(local_rank)
+    for kv in args.set:
+        k, _, v = kv.partition("=")
+        capi.set_option(k, int(v))
 
     wsa = None
     if is_ap:
@@ -613,6 +629,7 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "traffic_source": traffic_src, "kernel": kernel_name, "kernel_ms": kern_ms,
                          "algorithmic_bytes_per_launch": int(bytes_local), "peak_source": peak_src},
+            "library_options": args.set or None,
             "cpu_baseline": cpu, "gpu_baseline": gpu_base, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "other_configs": others,
         }

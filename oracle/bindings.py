@@ -420,3 +420,29 @@ class RefGpu:
         if rc:
             raise RuntimeError(self.lib.refgpu_last_error().decode())
         return y, float(ms.value)
+
+
+# ------------------------------------------------------------------------------------------------
+# cuSPARSE, the way the reference's USE_CUSPARSE comparison mode calls it (oracle/cusparse_driver.cu)
+# ------------------------------------------------------------------------------------------------
+def cusparse_available():
+    return os.path.exists(os.path.join(HERE, "_ref", "libuspmv_cusparse.so"))
+
+
+class CuSparse:
+    def __init__(self):
+        self.lib = L = C.CDLL(os.path.join(HERE, "_ref", "libuspmv_cusparse.so"))
+        L.cusp_last_error.restype = C.c_char_p
+        L.cusp_spmv.argtypes = [C.c_int, C.c_int, C.c_long, C.c_long, C.c_long, C.c_long, C.c_int, C.c_void_p, C.c_long, C.c_void_p, C.c_void_p,
+                                C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double)]
+
+    def spmv(self, kind, vt, n_rows, n_cols, nnz, C_, ptrs, cols, vals, x, warmup=3, steps=20):
+        """kind 'csr' (ptrs = row_ptrs) or 'sell' (ptrs = chunk_ptrs, slice size C_).  Returns (y[n_rows], ms per call)."""
+        ptrs, cols = _i32(ptrs), _i32(cols)
+        y = np.zeros(int(n_rows), NPT[_vt(vt)])
+        ms = C.c_double(0.0)
+        rc = self.lib.cusp_spmv(1 if kind == "sell" else 0, _vt(vt), int(n_rows), int(n_cols), int(nnz), len(cols), int(C_), _p(ptrs), len(ptrs),
+                                _p(cols), _p(vals), _p(x), _p(y), int(warmup), int(steps), C.byref(ms))
+        if rc:
+            raise RuntimeError(self.lib.cusp_last_error().decode())
+        return y, float(ms.value)

@@ -870,9 +870,14 @@ int uspmv_p2p_spmmv(uspmv_p2p *p, const uspmv_scs *scs, int x_buf, void *Y_d, vo
         }
         const bool overlap = p->mode != 0 && uspmv_spmmv_part_supported(scs, p->bvs);
         USPMV_CUDA(cudaEventRecord(p->ev_main, main));
-        if (overlap && uspmv_spmmv_part(scs, 1, X, Y_d, p->bvs, p->vec_length, p->layout, stream)) throw Error(uspmv_last_error());
+        // Launch order.  The SpMMV kernels hold ~80 registers x 24 warps per SM: launched first, the persistent interior kernel leaves no
+        // room for the push CTAs, which then run only when it retires — no overlap at all, and the neighbours get their halo one
+        // kernel late.  So the (short) push goes FIRST and the interior CTAs fill the SMs behind it ("mmv_push_first", default on).
+        const bool push_first = options().mmv_push_first;
+        if (overlap && !push_first && uspmv_spmmv_part(scs, 1, X, Y_d, p->bvs, p->vec_length, p->layout, stream)) throw Error(uspmv_last_error());
         USPMV_CUDA(cudaStreamWaitEvent(comm, p->ev_main, 0));
         launch_push(p, X, x_buf, comm);
+        if (overlap && push_first && uspmv_spmmv_part(scs, 1, X, Y_d, p->bvs, p->vec_length, p->layout, stream)) throw Error(uspmv_last_error());
         k_p2p_wait<<<1, 256, 0, comm>>>(P, p->is_sender_d.p, p->arrived, p->epoch, p->error);
         USPMV_LAUNCH_CHECK();
         USPMV_CUDA(cudaEventRecord(p->ev_comm, comm));

@@ -14,4 +14,4 @@ for f in sorted(glob.glob('gpurun_out/r02p_bench_*.json')):
             d = json.loads(line); g = d.get('gpu_baseline') or {}
             print(f.split('/')[-1], 'ours %.1f | ref kernel %s | cusparse %s' % (d['value'], g.get('value'), json.dumps(g.get('cusparse'))))
 PY
-tail -3 gpurun_out/r02p_bench_*.err
+tail -n 3 gpurun_out/r02p_bench_*.err

@@ -79,7 +79,6 @@ def _run_rank(rank, world, port, out_dir, C=32, same_device=False):
         rows = torch.arange(rank * n ** 3, (rank + 1) * n ** 3, device="cuda", dtype=torch.float64)
         for layout in ("rowwise", "colwise"):
             for bvs, mode in BLOCK_CASES:
-                capi.set_option("mmv_fused_rowwise", 1 if mode == 2 else 0)  # row-major defaults to the multi-kernel overlap; keep the fused instance covered
                 r = d.DistributedSpmv(eng.default_context(dev), 27, n, C, 64, "dp", rank, world, overlap=mode, halo="p2p", bvs=bvs, layout=layout)
                 perm = torch.from_numpy(r.scs.export().old_to_new.astype(np.int64)).cuda()
                 nl, ld = r.scs.n_rows, r.vec_length
@@ -108,7 +107,13 @@ def _run_rank(rank, world, port, out_dir, C=32, same_device=False):
                 assert r.validate() <= 1e-12, (layout, bvs, mode)
                 r.close()
                 del r
+        # row-major block vectors through the push / wait kernels next to the interior kernel as well (mode 2 defaults to the fused step)
         capi.set_option("mmv_fused_rowwise", 0)
+        r = d.DistributedSpmv(eng.default_context(dev), 27, n, C, 64, "dp", rank, world, overlap=2, halo="p2p", bvs=4, layout="rowwise")
+        assert r.validate() <= 1e-12
+        r.close()
+        del r
+        capi.set_option("mmv_fused_rowwise", 1)
 
         # ---- device-resident solve loop: 3 x { exchange ; SpMV ; swap } over the two arena buffers, every overlap mode
         for mode in (2, 1, 0):

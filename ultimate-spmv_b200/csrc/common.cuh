@@ -106,7 +106,8 @@ struct Options {
     bool scs_stream_wide = true; // C = 64 / 128: wide-chunk streamed kernel (false: direct-load kernel)
     bool narrow_dp = true;       // C = 16 in fp64 through the narrow-chunk streamed kernel (12 warps per CTA)
     bool mmv_push_first = true;      // distributed SpMMV, multi-kernel overlap: launch the push before the interior kernel (see halo.cu)
-    bool mmv_fused_rowwise = false;  // distributed SpMMV with row-major block vectors through the fused one-kernel step (slower, kept for A/B)
+    int mmv_fused_rowwise = 1;       // distributed SpMMV with row-major block vectors: 1 fused one-kernel step (default), 0 push / wait kernels next to the
+                                     // interior kernel, 2 fused even without a neighbour (profiling the instance)
     bool pair_hp = false;        // C = 32 in fp16: two adjacent chunks per work item (k_scs32_stream_pair) — bit-identical, measured
                                  // no faster than the one-chunk kernel (7-pt 256^3: 154 vs 149 us, profiles/r02l_*), so off by default
     int stream_variant = 0;      // (slots per piece, ring depth, warps per CTA) instantiation

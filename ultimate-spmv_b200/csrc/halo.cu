@@ -838,16 +838,17 @@ int uspmv_p2p_spmmv(uspmv_p2p *p, const uspmv_scs *scs, int x_buf, void *Y_d, vo
         cudaStream_t main = as_stream(stream), comm = as_stream(comm_stream);
         const int P = h->P;
         const void *X = p->buffer(x_buf);
-        if (h->n_send == 0 && h->n_halo == 0) {  // no neighbour at all (one rank): the tuned single-GPU kernel, then close the epoch
+        if (h->n_send == 0 && h->n_halo == 0 && options().mmv_fused_rowwise < 2) {  // no neighbour at all (one rank): the tuned single-GPU kernel, then close the epoch
             if (uspmv_spmmv(scs, X, Y_d, p->bvs, p->vec_length, p->layout, stream)) throw Error(uspmv_last_error());
             k_p2p_ack<<<1, 256, 0, main>>>(P, p->is_sender_d.p, p->peer_acked.p, p->epoch);
             USPMV_LAUNCH_CHECK();
             return;
         }
-        // ONE fused kernel (push, interior, wait, boundary, ack) where it measured faster than the push / wait kernels next to the
-        // interior kernel: column-major block vectors (N = 2, 256^3 slab, dp bvs 4: 0.483 vs 0.503 ms).  For row-major block vectors
-        // the fused instance of the wide-row body is slower (dp bvs 8: 0.806 vs 0.651 ms, sp bvs 8: 0.556 vs 0.408;
-        // profiles/r02k_n2_*.json), so they keep the multi-kernel overlap unless "mmv_fused_rowwise" asks for the fused kernel.
+        // ONE fused kernel (push, interior, publish, wait, boundary, ack) by default for both layouts.  N = 2, 256^3 slab per rank, B200
+        // (profiles/r02A_dist_probe_mmv.txt; us per step: fused / push + wait kernels next to the interior kernel / local kernel):
+        // row-major dp bvs 4 418 / 440 / 365, dp bvs 8 686 / 708 / 586, sp bvs 8 363 / 419 / 325, sp bvs 16 663 / 674 / 595,
+        // sp bvs 4 282 / 280 / 229, dp bvs 2 314 / 312 / 295; column-major dp bvs 4 483 / 503.  "mmv_fused_rowwise" = 0 selects the
+        // multi-kernel overlap for row-major block vectors (A/B runs, tests).
         const bool fused_wanted = p->mode == 2 && (p->layout == USPMV_COLWISE || options().mmv_fused_rowwise);
         if (fused_wanted && spmmv_fused_supported(scs, p->bvs) && P <= 32) {
             stream::FusedArgs fa{};

@@ -134,13 +134,28 @@ template <typename T> __device__ __forceinline__ T ld_x_coherent(const T *p) { r
 // Stores only: returns the number of 32-unit groups this warp pushed (0: it took no part).  The caller must follow up with
 // fused_push_signal — right away (fused_push) or after some interior work, when the stores have long been acknowledged and the
 // system-scope fence is cheap (SELL-32 SpMV kernel).
+// work units of the push.  Single vectors and column-major block vectors: one element.  Row-major block vectors: one SEGMENT of a
+// halo row — 16 bytes when the row is a multiple of 16 bytes (rows are then 16-byte aligned on both sides, the buffers being
+// 256-byte aligned), else one element; consecutive units are consecutive in the PEER's vector, so a warp-wide store covers 512
+// contiguous bytes of NVLink traffic (a lane-per-row copy wrote 16-byte pieces a row apart and gave a quarter of the warps the whole
+// push to do; profiles/r02u_dist_probe_mmv.txt).
+template <typename VT>
+__device__ __forceinline__ int fused_push_seg_bytes(const FusedArgs &fa) {
+    const int row_bytes = fa.bvs * (int)sizeof(VT);
+    return (fa.bvs > 1 && fa.layout == 1 && row_bytes % 16 == 0) ? 16 : (int)sizeof(VT);
+}
+template <typename VT>
+__device__ __forceinline__ long fused_push_units(const FusedArgs &fa) {
+    return fa.n_send * (long)(fa.bvs * (int)sizeof(VT) / fused_push_seg_bytes<VT>(fa));
+}
+
 template <typename VT>
 __device__ __forceinline__ unsigned int fused_push_stores(const FusedArgs &fa, const VT *__restrict__ x, const long gw, const long W, const int lane,
                                                           const unsigned int epoch_e) {
-    // work units: single vectors and column-major block vectors go element by element (coalesced over the rows of one vector);
-    // row-major block vectors go row by row — one index lookup per halo row, its bvs values copied with 128-bit accesses when aligned
     const bool by_row = fa.bvs > 1 && fa.layout == 1;
-    const long units = by_row ? fa.n_send : fa.n_send * fa.bvs;
+    const int seg = fused_push_seg_bytes<VT>(fa);
+    const int spr = fa.bvs * (int)sizeof(VT) / seg;  // units per halo row (1 for single vectors)
+    const long units = fa.n_send * (long)spr;
     const long n_push_warps = (units + 31) / 32;
     if (gw >= n_push_warps) return 0;
     warp_wait_flags(fa.acked, fa.is_receiver, fa.P, epoch_e - 1u, lane, fa.error);  // receivers consumed step e-1
@@ -148,24 +163,17 @@ __device__ __forceinline__ unsigned int fused_push_stores(const FusedArgs &fa, c
     for (long pw = gw; pw < n_push_warps; pw += W, ++mine) {
         const long t = pw * 32 + lane;
         if (t < units) {
-            long i = t, v = 0;
-            if (!by_row && fa.bvs > 1) { v = t / fa.n_send; i = t - v * fa.n_send; }
+            long i, v;  // halo row, unit within the row (row-major) / vector (column-major)
+            if (by_row) { i = t / spr; v = t - i * spr; }
+            else { v = t / fa.n_send; i = t - v * fa.n_send; }
             int q = 0;
             while (i >= fa.send_ptr[q + 1]) ++q;
             const long src = fa.perm ? fa.perm[fa.send_idx[i]] : fa.send_idx[i];
             const long k = fa.peer_base[q] + (i - fa.send_ptr[q]);
             VT *dst = reinterpret_cast<VT *>(fa.peer_x0[q]);
-            if (fa.bvs == 1) dst[k] = x[src];
-            else if (by_row) {
-                const int row_bytes = fa.bvs * (int)sizeof(VT);
-                if (row_bytes % 16 == 0) {  // rows of a 16-byte multiple are 16-byte aligned on both sides (buffers are 256-byte aligned)
-                    const int4 *sp = reinterpret_cast<const int4 *>(x + src * fa.bvs);
-                    int4 *dp = reinterpret_cast<int4 *>(dst + k * fa.bvs);
-                    for (int w = 0; w < row_bytes / 16; ++w) dp[w] = sp[w];
-                } else
-                    for (int w = 0; w < fa.bvs; ++w) dst[k * fa.bvs + w] = x[src * fa.bvs + w];
-            } else
-                dst[k + v * fa.peer_ld[q]] = x[src + v * fa.ld];
+            if (!by_row) dst[k + v * fa.peer_ld[q]] = x[src + v * fa.ld];  // bvs == 1: v == 0
+            else if (seg == 16) reinterpret_cast<int4 *>(dst + k * fa.bvs)[v] = reinterpret_cast<const int4 *>(x + src * fa.bvs)[v];
+            else dst[k * fa.bvs + v] = x[src * fa.bvs + v];
         }
     }
     return mine;
@@ -173,9 +181,8 @@ __device__ __forceinline__ unsigned int fused_push_stores(const FusedArgs &fa, c
 
 // ONE system-scope fence per warp (every push of this warp is ordered before its counter update), then the warp that completes the
 // count raises the neighbours' `arrived` flags
-__device__ __forceinline__ void fused_push_signal(const FusedArgs &fa, const unsigned int mine, const int lane, const unsigned int epoch_e) {
-    const bool by_row = fa.bvs > 1 && fa.layout == 1;
-    const long units = by_row ? fa.n_send : fa.n_send * fa.bvs;
+__device__ __forceinline__ void fused_push_signal(const FusedArgs &fa, const long units, const unsigned int mine, const int lane,
+                                                  const unsigned int epoch_e) {
     const unsigned int n_push_warps = (unsigned int)((units + 31) / 32);
     __threadfence_system();
     __syncwarp();
@@ -196,7 +203,7 @@ template <typename VT>
 __device__ __forceinline__ void fused_push(const FusedArgs &fa, const VT *__restrict__ x, const long gw, const long W, const int lane,
                                            const unsigned int epoch_e) {
     const unsigned int mine = fused_push_stores<VT>(fa, x, gw, W, lane, epoch_e);
-    if (mine) fused_push_signal(fa, mine, lane, epoch_e);
+    if (mine) fused_push_signal(fa, fused_push_units<VT>(fa), mine, lane, epoch_e);
 }
 
 // (d) of the fused step: the last warp of the grid acknowledges consumption to the senders and closes the epoch
@@ -285,7 +292,7 @@ struct SpmvBodyFusedStream {
     bool sig_pending, halo_ready, bnd;
     typename A::acc_t acc;
     __device__ __forceinline__ void signal() {
-        fused_push_signal(*fa, mine, lane, epoch_e);
+        fused_push_signal(*fa, fused_push_units<VT>(*fa), mine, lane, epoch_e);
         sig_pending = false;
     }
     __device__ __forceinline__ void begin_chunk(int = 0, const int flags = 0) {
@@ -1531,12 +1538,49 @@ k_csr_stream(long n_rows, const int *__restrict__ row_ptrs, const int *__restric
     }
 }
 
+// One warp's pass over a chunk subset with the SpMMV body: items first, first + W, ... < n (COH: gathers through L2 only, for chunks
+// that read a halo a peer GPU wrote during this kernel).
+template <typename VT, typename A, int LMAX, int D, int BVS, bool ROWWISE, bool USE_WIDE, bool COH>
+__device__ __forceinline__ void mmv_run(unsigned char *base, uint64_t *bars, PieceHdr *hdrs, uint32_t &phase_bits, const int W, const int first,
+                                        const int lane, const int n, const int *__restrict__ list, const int off,
+                                        const int *__restrict__ chunk_ptrs, const int *__restrict__ chunk_lengths,
+                                        const int *__restrict__ col_idxs, const VT *__restrict__ values, const VT *__restrict__ X,
+                                        VT *__restrict__ Y, const long ld, const uint64_t pol) {
+    using Body = std::conditional_t<USE_WIDE, SpmmvBodyRowWide<VT, A, LMAX, BVS, COH>, SpmmvBody<VT, A, LMAX, BVS, ROWWISE, COH>>;
+    Body body;
+    body.X = X; body.Y = Y; body.lane = lane;
+    if constexpr (!USE_WIDE) body.ld = ld;
+    stream_items<VT, LMAX, D>(base, bars, hdrs, phase_bits, W, first, lane, n, list, off, chunk_ptrs, chunk_lengths, col_idxs, values, body, pol);
+}
+
+// The boundary pass of the fused distributed step as an OUT-OF-LINE function, because ptxas is fragile here (B200, 256^3 7-point
+// matrix, one rank without a neighbour so that only the instance is measured; profiles/r02q_mmv_fused_instance.md):
+//   * a second copy of the unrolled body inlined after the main loop changed the schedule of the FIRST one (sp, block_vec_size 8:
+//     one gather in flight per lane instead of two, same instruction count and traffic, 334 -> 419 us);
+//   * publishing the push from the main loop's end_chunk (an out-of-line call taken once) cost dp block_vec_size 8 at its
+//     80-register bound a factor 1.8;
+//   * the warp's first chunk as a call before an inlined main loop: sp block_vec_size 8 +14 %;
+//   * the main loop itself out of line: dp block_vec_size 4 +20 %, dp 8 +47 %.
+// What ships: push + publish inline at the start, the main loop inline (exactly the single-GPU kernel's), the boundary out of line.
+template <typename VT, typename A, int LMAX, int D, int BVS, bool ROWWISE, bool USE_WIDE, bool COH>
+__device__ __noinline__ uint32_t mmv_run_outofline(unsigned char *base, uint64_t *bars, PieceHdr *hdrs, uint32_t phase_bits, const int W,
+                                                   const int gw, const int lane, const int n, const int *list, const int off,
+                                                   const int *chunk_ptrs, const int *chunk_lengths, const int *col_idxs, const VT *values,
+                                                   const VT *X, VT *Y, const long ld, const uint64_t pol) {
+    mmv_run<VT, A, LMAX, D, BVS, ROWWISE, USE_WIDE, COH>(base, bars, hdrs, phase_bits, W, gw, lane, n, list, off, chunk_ptrs, chunk_lengths,
+                                                         col_idxs, values, X, Y, ld, pol);
+    return phase_bits;
+}
+
 // SELL-32 SpMMV through the same per-warp bulk-copy ring (smaller stages: the block vectors want the L1 capacity).
-template <typename VT, typename A, int LMAX, int D, int WARPS, int BVS, bool ROWWISE, bool WIDE, bool FUSED = false>
-__global__ void __launch_bounds__(WARPS * 32)  // ~80 registers, 24 warps/SM: capping at 64 spills and is 30-50 % slower (measured)
+// MINB = minimum resident CTAs per SM handed to __launch_bounds__.  It is NOT cosmetic: with no minimum (MINB = 0) ptxas aims for the
+// smallest register count and re-serialises the gathers the source issues together (sp, block_vec_size 8: 48 registers, ONE or two
+// 128-bit gathers in flight per lane instead of eight); with a minimum it takes the registers the bound allows and keeps them in flight.
+template <typename VT, typename A, int LMAX, int D, int WARPS, int BVS, bool ROWWISE, bool WIDE, bool FUSED = false, int MINB = 0>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
 k_scs32_stream_mmv(long n_items, const int *__restrict__ chunk_list, int chunk_offset, const int *__restrict__ chunk_ptrs,
                    const int *__restrict__ chunk_lengths, const int *__restrict__ col_idxs, const VT *__restrict__ values,
-                   const VT *__restrict__ X, VT *__restrict__ Y, long ld, const FusedArgs fa) {
+                   const VT *__restrict__ X, VT *__restrict__ Y, long ld, const __grid_constant__ FusedArgs fa) {
     using R = WarpRing<VT, LMAX, D>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1555,31 +1599,27 @@ k_scs32_stream_mmv(long n_items, const int *__restrict__ chunk_list, int chunk_o
     uint32_t phase_bits = 0;
     constexpr int ROW_BYTES = BVS * (int)sizeof(VT);
     constexpr bool USE_WIDE = WIDE && ROWWISE && ROW_BYTES >= 32 && ROW_BYTES <= 128 && (ROW_BYTES & (ROW_BYTES - 1)) == 0;
-    auto run = [&](auto coherent, const long n, const int *list, const int off) {
-        constexpr bool COH = decltype(coherent)::value;
-        if constexpr (USE_WIDE) {
-            SpmmvBodyRowWide<VT, A, LMAX, BVS, COH> body;
-            body.X = X; body.Y = Y; body.lane = lane;
-            stream_items<VT, LMAX, D>(base, bars, hdrs, phase_bits, (int)W, (int)gw, lane, (int)n, list, off, chunk_ptrs, chunk_lengths, col_idxs,
-                                      values, body, pol);
-        } else {
-            SpmmvBody<VT, A, LMAX, BVS, ROWWISE, COH> body;
-            body.X = X; body.Y = Y; body.ld = ld; body.lane = lane;
-            stream_items<VT, LMAX, D>(base, bars, hdrs, phase_bits, (int)W, (int)gw, lane, (int)n, list, off, chunk_ptrs, chunk_lengths, col_idxs,
-                                      values, body, pol);
-        }
-    };
     if constexpr (!FUSED) {
-        run(std::false_type{}, n_items, chunk_list, chunk_offset);
+        mmv_run<VT, A, LMAX, D, BVS, ROWWISE, USE_WIDE, false>(base, bars, hdrs, phase_bits, (int)W, (int)gw, lane, (int)n_items, chunk_list,
+                                                               chunk_offset, chunk_ptrs, chunk_lengths, col_idxs, values, X, Y, ld, pol);
     } else {
-        // ONE kernel per distributed SpMMV (see k_scs32_stream): push all block_vec_size values of the halo rows to the neighbours,
-        // interior chunks, wait for the own halo, boundary chunks with L2-coherent gathers, acknowledge
+        // ONE kernel per distributed SpMMV (see k_scs32_stream): (a) store all block_vec_size values of the halo rows into the neighbours'
+        // vectors — 16-byte segments spread over ALL warps, so each warp issues at most a few coalesced stores — and publish them
+        // (system-scope fence + counter; the last pushing warp raises the neighbours' `arrived` flags); (b) the interior chunks;
+        // (c) wait for the own halo, boundary chunks with L2-coherent gathers; (d) acknowledge.
         const unsigned int epoch_e = ld_flag(fa.epoch) + 1u;
-        fused_push<VT>(fa, X, gw, W, lane, epoch_e);
-        run(std::false_type{}, fa.n_int, fa.int_list, fa.int_off);
+        fused_push_stores<VT>(fa, X, gw, W, lane, epoch_e);
+        mmv_run<VT, A, LMAX, D, BVS, ROWWISE, USE_WIDE, false>(base, bars, hdrs, phase_bits, (int)W, (int)gw, lane, (int)fa.n_int, fa.int_list, fa.int_off,
+                                                               chunk_ptrs, chunk_lengths, col_idxs, values, X, Y, ld, pol);
+        {   // publish the push now that its stores have long landed (recomputing the warp's group count keeps the loop's registers free)
+            const long n_push_warps = (fused_push_units<VT>(fa) + 31) / 32;
+            if (gw < n_push_warps) fused_push_signal(fa, fused_push_units<VT>(fa), (unsigned int)((n_push_warps - gw + W - 1) / W), lane, epoch_e);
+        }
         if (gw < fa.n_bnd) {
             warp_wait_flags(fa.arrived, fa.is_sender, fa.P, epoch_e, lane, fa.error);
-            run(std::true_type{}, fa.n_bnd, fa.bnd_list, fa.bnd_off);
+            phase_bits = mmv_run_outofline<VT, A, LMAX, D, BVS, ROWWISE, USE_WIDE, true>(base, bars, hdrs, phase_bits, (int)W, (int)gw, lane,
+                                                                                        (int)fa.n_bnd, fa.bnd_list, fa.bnd_off, chunk_ptrs,
+                                                                                        chunk_lengths, col_idxs, values, X, Y, ld, pol);
         }
         fused_finish(fa, W, lane, epoch_e);
     }

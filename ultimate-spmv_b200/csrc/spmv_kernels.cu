@@ -263,10 +263,13 @@ __global__ void k_flag_boundary_chunks(long n_chunks, int C, int n_local, const 
 // measured best SpMMV variant (scripts/tune_mmv2.py on B200, 256^3 7-pt, profiles/r01m_tune_spmmv_variants.json): 1 = lane per row /
 // 8 warps, 2 = T lanes per row ("wide") / 8 warps, 6 = wide / 24 warps per CTA
 inline int mmv_default_variant(size_t vsize, int bvs, bool rowwise) {
+    // measured on the 256^3 7-point matrix, B200 (profiles/r02r_tune_mmv3.txt); 15-20 = 8-warp CTAs with a register budget
     if (!rowwise) return 1;
     const long row_bytes = (long)vsize * bvs;
-    if (row_bytes < 32) return 1;                  // one 128-bit load per row: nothing to widen
-    if (row_bytes == 64 && vsize == 8) return 6;   // dp bvs 8: 579 vs 593 us
+    if (row_bytes < 32) return (vsize == 2 && bvs == 8) ? 20 : 1;  // one 128-bit load per row: nothing to widen (hp bvs 8: 254 vs 270 us)
+    if (vsize == 8 && (bvs == 8 || bvs == 4)) return 16;           // dp bvs 8: 551 vs 574 us (variant 6), dp bvs 4: 375 vs 378
+    if (vsize == 4 && bvs == 8) return 15;                         // sp bvs 8: 323 vs 333 us
+    if (vsize == 2 && bvs == 16) return 19;                        // hp bvs 16: 418 vs 453 us
     return 2;
 }
 
@@ -624,10 +627,10 @@ struct ScsView {
     const void *vals;
 };
 
-template <typename VT, int BVS, bool ROWWISE, int LMAX, int WARPS, bool WIDE, int D = 2>
+template <typename VT, int BVS, bool ROWWISE, int LMAX, int WARPS, bool WIDE, int D = 2, int MINB = 0>
 void launch_spmmv_stream_v(const ScsView &s, const VT *X, VT *Y, long ld, cudaStream_t st, const ChunkSel &sel) {
     using R = stream::WarpRing<VT, LMAX, D>;
-    auto kern = stream::k_scs32_stream_mmv<VT, Arith<VT>, LMAX, D, WARPS, BVS, ROWWISE, WIDE>;
+    auto kern = stream::k_scs32_stream_mmv<VT, Arith<VT>, LMAX, D, WARPS, BVS, ROWWISE, WIDE, false, MINB>;
     constexpr int smem = WARPS * R::BYTES_ALIGNED;
     static bool configured_on[uspmv::MAX_DEVICES] = {};
     bool &configured = configured_on[uspmv::current_device()];
@@ -652,11 +655,11 @@ void launch_spmmv_stream_v(const ScsView &s, const VT *X, VT *Y, long ld, cudaSt
 
 // ONE kernel per distributed SpMMV (push + interior + wait + boundary + ack): every CTA must be resident, so the grid is exactly
 // SMs x resident CTAs per SM
-template <typename VT, int BVS, bool ROWWISE, int LMAX, int WARPS, bool WIDE>
+template <typename VT, int BVS, bool ROWWISE, int LMAX, int WARPS, bool WIDE, int MINB = 0>
 void launch_spmmv_fused_v(const ScsView &s, const VT *X, VT *Y, long ld, cudaStream_t st, const stream::FusedArgs &fa) {
     constexpr int D = 2;
     using R = stream::WarpRing<VT, LMAX, D>;
-    auto kern = stream::k_scs32_stream_mmv<VT, Arith<VT>, LMAX, D, WARPS, BVS, ROWWISE, WIDE, true>;
+    auto kern = stream::k_scs32_stream_mmv<VT, Arith<VT>, LMAX, D, WARPS, BVS, ROWWISE, WIDE, true, MINB>;
     constexpr int smem = WARPS * R::BYTES_ALIGNED;
     static bool configured_on[uspmv::MAX_DEVICES] = {};
     static int bps_on[uspmv::MAX_DEVICES];
@@ -674,9 +677,21 @@ void launch_spmmv_fused_v(const ScsView &s, const VT *X, VT *Y, long ld, cudaStr
 
 template <typename VT, int BVS, bool ROWWISE>
 void launch_spmmv_fused(const ScsView &s, const VT *X, VT *Y, long ld, cudaStream_t st, const stream::FusedArgs &fa) {
-    switch (mmv_default_variant(sizeof(VT), BVS, ROWWISE)) {  // the tuned instantiation per (precision, block_vec_size, layout)
+    int v = options().mmv_variant;  // 0: the tuned instantiation per (precision, block_vec_size, layout); else forced (A/B runs)
+    if (v == 0) {
+        v = mmv_default_variant(sizeof(VT), BVS, ROWWISE);
+        // dp, block_vec_size 8: at the 80-register bound of variants 16 / 6 the FUSED instance loses 12-75 % to its single-GPU twin
+        // (ptxas), with 128 registers it does not: 610 vs 603 us (profiles/r02w_probe.txt)
+        if (ROWWISE && sizeof(VT) == 8 && BVS == 8) v = 17;
+    }
+    switch (v) {
     case 2: launch_spmmv_fused_v<VT, BVS, ROWWISE, 8, 8, true>(s, X, Y, ld, st, fa); break;
     case 6: launch_spmmv_fused_v<VT, BVS, ROWWISE, 8, 24, true>(s, X, Y, ld, st, fa); break;
+    case 17: launch_spmmv_fused_v<VT, BVS, ROWWISE, 8, 8, true, 2>(s, X, Y, ld, st, fa); break;
+    case 15: launch_spmmv_fused_v<VT, BVS, ROWWISE, 8, 8, true, 4>(s, X, Y, ld, st, fa); break;
+    case 16: launch_spmmv_fused_v<VT, BVS, ROWWISE, 8, 8, true, 3>(s, X, Y, ld, st, fa); break;
+    case 19: launch_spmmv_fused_v<VT, BVS, ROWWISE, 8, 8, false, 3>(s, X, Y, ld, st, fa); break;
+    case 20: launch_spmmv_fused_v<VT, BVS, ROWWISE, 8, 8, true, 5>(s, X, Y, ld, st, fa); break;
     default: launch_spmmv_fused_v<VT, BVS, ROWWISE, 8, 8, false>(s, X, Y, ld, st, fa); break;
     }
 }
@@ -700,6 +715,13 @@ void launch_spmmv_stream(const ScsView &s, const VT *X, VT *Y, long ld, cudaStre
     case 12: launch_spmmv_stream_v<VT, BVS, ROWWISE, 4, 16, true, 3>(s, X, Y, ld, st, sel); break;
     case 13: launch_spmmv_stream_v<VT, BVS, ROWWISE, 4, 32, true>(s, X, Y, ld, st, sel); break;
     case 14: launch_spmmv_stream_v<VT, BVS, ROWWISE, 4, 32, false>(s, X, Y, ld, st, sel); break;
+    // 8-warp CTAs with a minimum of resident CTAs per SM: ptxas then keeps the gathers of a piece in flight (see k_scs32_stream_mmv)
+    case 15: launch_spmmv_stream_v<VT, BVS, ROWWISE, 8, 8, true, 2, 4>(s, X, Y, ld, st, sel); break;   // <= 64 registers
+    case 16: launch_spmmv_stream_v<VT, BVS, ROWWISE, 8, 8, true, 2, 3>(s, X, Y, ld, st, sel); break;   // <= 80
+    case 17: launch_spmmv_stream_v<VT, BVS, ROWWISE, 8, 8, true, 2, 2>(s, X, Y, ld, st, sel); break;   // <= 128
+    case 18: launch_spmmv_stream_v<VT, BVS, ROWWISE, 8, 8, false, 2, 4>(s, X, Y, ld, st, sel); break;
+    case 19: launch_spmmv_stream_v<VT, BVS, ROWWISE, 8, 8, false, 2, 3>(s, X, Y, ld, st, sel); break;
+    case 20: launch_spmmv_stream_v<VT, BVS, ROWWISE, 8, 8, true, 2, 5>(s, X, Y, ld, st, sel); break;   // <= 48, but told so
     default: launch_spmmv_stream_v<VT, BVS, ROWWISE, 8, 8, false>(s, X, Y, ld, st, sel); break;
     }
 }

@@ -683,6 +683,8 @@ void launch_spmmv_fused(const ScsView &s, const VT *X, VT *Y, long ld, cudaStrea
         // dp, block_vec_size 8: at the 80-register bound of variants 16 / 6 the FUSED instance loses 12-75 % to its single-GPU twin
         // (ptxas), with 128 registers it does not: 610 vs 603 us (profiles/r02w_probe.txt)
         if (ROWWISE && sizeof(VT) == 8 && BVS == 8) v = 17;
+        // (16-byte rows, sp bvs 4: the fused instance of variant 1 is 13 % slower than its twin and stating its 48 registers — variant
+        // 20 — does not help: profiles/r02D_probe.txt; the step still equals the multi-kernel one, 282 vs 280 us)
     }
     switch (v) {
     case 2: launch_spmmv_fused_v<VT, BVS, ROWWISE, 8, 8, true>(s, X, Y, ld, st, fa); break;

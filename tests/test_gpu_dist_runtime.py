@@ -70,6 +70,16 @@ def _run_rank(rank, world, port, out_dir, C=32, same_device=False):
             del r
         capi.set_option("push_variant", -1)
         capi.set_option("push_min_elements", 1 << 20)
+        # narrow value types: mode 2 defaults to the push / wait kernels next to the single-GPU interior kernel (the fused instance is
+        # issue-bound there); "fused_narrow" keeps the fused kernel reachable — both against the stencil formula, solve buffers included
+        for vt, tol in (("sp", 1e-5), ("hp", 1e-2)):
+            for narrow in (0, 1):
+                capi.set_option("fused_narrow", narrow)
+                r = d.DistributedSpmv(eng.default_context(dev), 27, n, C, 64, vt, rank, world, overlap=2, halo="p2p")
+                assert r.validate(steps=3) <= tol, (vt, narrow)
+                r.close()
+                del r
+        capi.set_option("fused_narrow", 0)
         base = results["p2p2pv0"]
         for k, v in results.items():
             assert np.array_equal(v, base), k

@@ -105,6 +105,7 @@ struct Options {
     bool scs_stream = true;      // C = 32: bulk-copy streamed kernel (false: direct-load kernel)
     bool scs_stream_wide = true; // C = 64 / 128: wide-chunk streamed kernel (false: direct-load kernel)
     bool narrow_dp = true;       // C = 16 in fp64 through the narrow-chunk streamed kernel (12 warps per CTA)
+    bool fused_narrow = false;       // distributed SELL-32 SpMV in sp / hp through the fused kernel too (default: multi-kernel overlap, see halo.cu)
     bool mmv_push_first = true;      // distributed SpMMV, multi-kernel overlap: launch the push before the interior kernel (see halo.cu)
     int mmv_fused_rowwise = 1;       // distributed SpMMV with row-major block vectors: 1 fused one-kernel step (default), 0 push / wait kernels next to the
                                      // interior kernel, 2 fused even without a neighbour (profiling the instance)

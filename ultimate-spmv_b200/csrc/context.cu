@@ -49,6 +49,7 @@ static void apply_option(Options &c, const char *name, long value, int device) {
         else if (!std::strcmp(name, "pair_hp")) c.pair_hp = value != 0;
         else if (!std::strcmp(name, "mmv_fused_rowwise")) c.mmv_fused_rowwise = (int)value;
         else if (!std::strcmp(name, "mmv_push_first")) c.mmv_push_first = value != 0;
+        else if (!std::strcmp(name, "fused_narrow")) c.fused_narrow = value != 0;
         else if (!std::strcmp(name, "stream_variant")) c.stream_variant = (int)value;
         else if (!std::strcmp(name, "stream_blocks_per_sm")) c.stream_blocks_per_sm = (int)std::max(1L, value);
         else if (!std::strcmp(name, "mmv_variant")) c.mmv_variant = (int)std::max(0L, value);

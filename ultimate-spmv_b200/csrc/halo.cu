@@ -672,8 +672,8 @@ int uspmv_p2p_create_ex(uspmv_halo *plan, int vt, long vec_length, int bvs, int 
             p->error = p->epoch + 1;
             p->block_counter.alloc(1);
             USPMV_CUDA(cudaMemset(p->block_counter.p, 0, sizeof(unsigned int)));
-            p->fused_counters.alloc(2);
-            USPMV_CUDA(cudaMemset(p->fused_counters.p, 0, 2 * sizeof(unsigned int)));
+            p->fused_counters.alloc(4);
+            USPMV_CUDA(cudaMemset(p->fused_counters.p, 0, 4 * sizeof(unsigned int)));
             cudaIpcMemHandle_t h;
             USPMV_CUDA(cudaIpcGetMemHandle(&h, p->arena));
             std::memcpy(ipc_handle64, &h, 64);
@@ -769,7 +769,12 @@ int uspmv_p2p_spmv_buf(uspmv_p2p *p, const uspmv_scs *scs, int x_buf, int y_buf,
         cudaStream_t main = as_stream(stream), comm = as_stream(comm_stream);
         const int P = h->P;
         const void *x = p->buffer(x_buf);
-        if (p->mode == 2 && scs_fused_supported(scs) && P <= 32) {
+        // The fused one-kernel step where it wins.  C = 32 in sp / hp does not: the fused instance of the kernel executes 32 % more
+        // instructions per chunk than the single-GPU loop and the narrow types are issue-bound (scs_stream.cuh, k_scs32_stream), so
+        // they take the push / wait kernels next to the unchanged interior kernel — N = 2, 256^3 slab per rank: sp 0.175 vs 0.210 ms,
+        // hp 0.163 vs 0.203 ms; dp the other way round, 0.253 (fused) vs 0.276 (profiles/r02I_n2_*.json).  "fused_narrow" = 1 forces it.
+        const bool fused_pays = scs->C != 32 || p->vt == USPMV_F64 || options().fused_narrow;
+        if (p->mode == 2 && fused_pays && scs_fused_supported(scs) && P <= 32) {
             stream::FusedArgs fa{};
             fa.n_int = (long)scs->interior_chunks.n;
             fa.n_bnd = (long)scs->boundary_chunks.n;

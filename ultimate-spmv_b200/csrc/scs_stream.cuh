@@ -721,6 +721,16 @@ __device__ __forceinline__ void stream_items_u(unsigned char *base, uint64_t *ba
     }
 }
 
+// FUSED: the fused distributed step, interior and boundary chunks in ONE item stream (SpmvBodyFusedStream).
+// Known cost of the fused instance (one rank, nothing to exchange; profiles/r02G_spmv_fused_probe.txt, ncu
+// r02H_spmv_sp_fused_instance_ncu_summary.txt): it executes 270 instructions per chunk against 204 of the single-GPU loop (flag
+// decoding, the warp-uniform gather branch, a recomputed store address, the two-list producer).  dp is HBM-bound and loses 2 %
+// (250 vs 245 us); sp / hp are ISSUE-bound and lose 25-30 % (203 vs 163, 196 vs 150 us), which is why halo.cu gives them the push /
+// wait kernels next to the single-GPU interior kernel instead.  Tried in round 2 and dropped (profiles/r02J_early_ack.md):
+//   * the boundary chunks in the MIDDLE of the stream with the acknowledgement right behind them, so that neighbours may drift half
+//     a kernel apart: the decoupling is worth 2-3 us per step at N = 2 and N = 8, the extra code in the instance costs the same;
+//   * the step in three PHASES around the unchanged single-GPU loop (push | first chunk | publish | interior | boundary + ack |
+//     interior): ptxas spills 120-320 bytes inside the hot loop at the 64-register bound, boundary pass inlined or not.
 template <typename VT, typename A, int LMAX, int D, int WARPS, bool UNPERM, bool FUSED>
 __global__ void __launch_bounds__(WARPS * 32, (1024 / (WARPS * 32)) > 0 ? (1024 / (WARPS * 32)) : 1)  // <= 64 registers: 32 warps/SM
 k_scs32_stream(long n_items, const int *__restrict__ chunk_list, int chunk_offset, const int *__restrict__ chunk_ptrs,

@@ -62,3 +62,19 @@ def test_product_does_not_touch_the_oracle():
                     if re.search(r"liboracle|oracle\.bindings|from oracle|import oracle|oracle/_ref|uspmv_ref_", txt):
                         bad.append(os.path.join(dp, f))
     assert not bad, bad
+
+
+def test_baseline_drivers_load_without_a_gpu_and_stay_out_of_the_product():
+    """The two GPU baselines (the reference's own CUDA kernels recompiled for sm_100, and cuSPARSE the way the reference's
+    USE_CUSPARSE mode calls it) are measurement infrastructure under oracle/_ref: they must load here (symbols only, no CUDA call) so that
+    bench.py finds them on the GPU box, and the product library must not depend on them or on cuSPARSE."""
+    import subprocess
+    from oracle import bindings
+    if not bindings.cusparse_available():
+        pytest.skip("oracle/_ref/libuspmv_cusparse.so not built")
+    lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "libuspmv_cusparse.so"))
+    assert hasattr(lib, "cusp_spmv") and hasattr(lib, "cusp_last_error")
+    if bindings.ref_gpu_available():
+        ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "libuspmv_ref_gpu.so"))
+    needed = subprocess.run(["ldd", os.path.join(ROOT, "ultimate-spmv_b200", "lib", "libuspmv_b200.so")], capture_output=True, text=True).stdout
+    assert "cusparse" not in needed and "uspmv_ref" not in needed and "oracle" not in needed, needed

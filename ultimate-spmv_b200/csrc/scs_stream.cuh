@@ -1571,7 +1571,8 @@ __device__ __forceinline__ void mmv_run(unsigned char *base, uint64_t *bars, Pie
 //     80-register bound a factor 1.8;
 //   * the warp's first chunk as a call before an inlined main loop: sp block_vec_size 8 +14 %;
 //   * the main loop itself out of line: dp block_vec_size 4 +20 %, dp 8 +47 %.
-// What ships: push + publish inline at the start, the main loop inline (exactly the single-GPU kernel's), the boundary out of line.
+// What ships: the push stores inline at the start, the main loop inline (exactly the single-GPU kernel's), the publish right behind it
+// (published at once after the stores, every step cost 25-35 us more: r02z vs r02A_dist_probe_mmv.txt), the boundary out of line.
 template <typename VT, typename A, int LMAX, int D, int BVS, bool ROWWISE, bool USE_WIDE, bool COH>
 __device__ __noinline__ uint32_t mmv_run_outofline(unsigned char *base, uint64_t *bars, PieceHdr *hdrs, uint32_t phase_bits, const int W,
                                                    const int gw, const int lane, const int n, const int *list, const int off,
@@ -1614,9 +1615,9 @@ k_scs32_stream_mmv(long n_items, const int *__restrict__ chunk_list, int chunk_o
                                                                chunk_offset, chunk_ptrs, chunk_lengths, col_idxs, values, X, Y, ld, pol);
     } else {
         // ONE kernel per distributed SpMMV (see k_scs32_stream): (a) store all block_vec_size values of the halo rows into the neighbours'
-        // vectors — 16-byte segments spread over ALL warps, so each warp issues at most a few coalesced stores — and publish them
-        // (system-scope fence + counter; the last pushing warp raises the neighbours' `arrived` flags); (b) the interior chunks;
-        // (c) wait for the own halo, boundary chunks with L2-coherent gathers; (d) acknowledge.
+        // vectors — 16-byte segments spread over ALL warps, so each warp issues at most a few coalesced stores; (b) the interior
+        // chunks; (c) publish the push (system-scope fence + counter; the last pushing warp raises the neighbours' `arrived` flags);
+        // (d) wait for the own halo, boundary chunks with L2-coherent gathers; (e) acknowledge.
         const unsigned int epoch_e = ld_flag(fa.epoch) + 1u;
         fused_push_stores<VT>(fa, X, gw, W, lane, epoch_e);
         mmv_run<VT, A, LMAX, D, BVS, ROWWISE, USE_WIDE, false>(base, bars, hdrs, phase_bits, (int)W, (int)gw, lane, (int)fa.n_int, fa.int_list, fa.int_off,

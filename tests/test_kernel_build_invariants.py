@@ -58,3 +58,28 @@ def test_streamed_kernels_use_the_bulk_copy_engine():
         sass = subprocess.run([CUOBJDUMP, "-sass", LIB], capture_output=True, text=True, timeout=900).stdout
     assert "UBLKCP.S.G" in sass, "cp.async.bulk global -> shared (TMA bulk copy) missing"
     assert "SYNCS.ARRIVE.TRANS64" in sass and "SYNCS.PHASECHK.TRANS64.TRYWAIT" in sass, "mbarrier expect_tx / try_wait missing"
+
+
+def _gather_destinations(mangled_pattern):
+    """Destination registers of the 128-bit read-only gathers (LDG.E.128.CONSTANT) of one kernel instance, in SASS order."""
+    _, usage = _res_usage()
+    names = [k for k in usage if re.search(mangled_pattern, k)]
+    assert len(names) == 1, (mangled_pattern, names)
+    sass = subprocess.run([CUOBJDUMP, "-sass", "-fun", names[0], LIB], capture_output=True, text=True, timeout=300).stdout
+    return re.findall(r"LDG\.E\.128\.CONSTANT\s+(R\d+)", sass)
+
+
+@pytest.mark.parametrize("what,pattern", [
+    ("sp block_vec_size 8, 8 warps, MINB 4", r"k_scs32_stream_mmvIf.*Li8ELi2ELi8ELi8ELb1ELb1ELb0ELi4E"),
+    ("dp block_vec_size 8, 8 warps, MINB 3", r"k_scs32_stream_mmvId.*Li8ELi2ELi8ELi8ELb1ELb1ELb0ELi3E"),
+    ("dp block_vec_size 4, 8 warps, MINB 3", r"k_scs32_stream_mmvId.*Li8ELi2ELi8ELi4ELb1ELb1ELb0ELi3E"),
+])
+def test_spmmv_kernels_keep_their_gathers_in_flight(what, pattern):
+    """Round 2 (profiles/r02q_mmv_fused_instance.md): without a register budget in __launch_bounds__ ptxas re-serialises the gathers a
+    piece issues together (destinations R16 R16 R16 ... or R20 R16 R20 R16 ...: one or two in flight per lane) and the kernel loses
+    3-25 %.  The shipped row-major SpMMV instances state a budget; here: some run of 8 consecutive gathers lands in >= 6 DIFFERENT
+    registers, i.e. they really are in flight together."""
+    dst = _gather_destinations(pattern)
+    assert len(dst) >= 16, (what, len(dst))
+    best = max(len(set(dst[i:i + 8])) for i in range(len(dst) - 7))
+    assert best >= 6, (what, best, dst[:40])

@@ -48,7 +48,9 @@ long uspmv_kernel_launches(void);
  *   "stream_blocks_per_sm"    persistent CTAs per SM
  *   "strict_reference_halo"   0 (default): padding slots stay local (column 0 of the rank); 1: replicate the reference,
  *                             where padding's column 0 is GLOBAL column 0 and so becomes one spurious halo element
- *                             received from rank 0 on every rank > 0 (utilities.hpp:1991-2002, mpi_funcs.hpp:279-283) */
+ *                             received from rank 0 on every rank > 0 (utilities.hpp:1991-2002, mpi_funcs.hpp:279-283)
+ * The complete table (SpMMV / AP variants, fused vs multi-kernel exchange, push kernels) with defaults: INTEGRATION.md section 7.
+ * No knob changes a result bit. */
 int uspmv_set_option(const char *name, long value);
 /* The knobs are per CONTEXT: uspmv_set_option changes the process defaults AND every live context; uspmv_ctx_set_option changes one
  * context only, so two contexts in one process (two GPUs, two solver instances) can run different variants.  get reads them back
